@@ -1,0 +1,69 @@
+"""ctypes binding of libvfs_b200.so (the C ABI declared in include/vfs_b200.h).
+
+There is deliberately NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+torch is only used by callers for device memory and streams; the ABI itself is torch-free.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_lib', 'libvfs_b200.so')
+
+VFS_OK = 0
+
+
+class VfsConvDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32)
+                for n in ('N', 'H', 'W', 'Cin', 'Cout', 'ksize', 'stride', 'dilation', 'relu')]
+
+
+_vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); every symbol include/vfs_b200.h declares
+PROTOTYPES = {
+    'vfs_last_error_string': (ctypes.c_char_p, []),
+    'vfs_abi_version': (_i, []),
+    'vfs_check_device': (_i, []),
+    'vfs_nchw_f32_to_split': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'vfs_split_to_nchw_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'vfs_stem_workspace_bytes': (_sz, [_i, _i, _i]),
+    'vfs_stem_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'vfs_conv_bn_act': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'vfs_pack_conv_weight': (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    'vfs_debug_conv_bn_act_simt': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} not found: build it with `python -m vfs_b200.build` (no CPU fallback exists)')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != VFS_OK:
+        msg = lib().vfs_last_error_string().decode(errors='replace')
+        raise RuntimeError(f'libvfs_b200 {what} failed with code {rc}: {msg}')
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,135 @@
+// C-ABI surface of libvfs_b200.so (see include/vfs_b200.h) + host helpers.
+#include <stdarg.h>
+
+#include "host_common.h"
+
+namespace vfs {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return VFS_OK;
+  set_last_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return VFS_ECUDA;
+}
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+      set_last_error("cuTensorMapEncodeTiled entry point unavailable (err %d)", static_cast<int>(e));
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return VFS_ECUDA;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                  gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
+                   static_cast<int>(r), rank, (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0),
+                   (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0),
+                   (unsigned long long)(rank > 4 ? gdim[4] : 0), bdim[0], rank > 1 ? bdim[1] : 0,
+                   rank > 2 ? bdim[2] : 0, rank > 3 ? bdim[3] : 0, rank > 4 ? bdim[4] : 0);
+    return VFS_ECUDA;
+  }
+  return VFS_OK;
+}
+
+// implemented in the kernel translation units
+int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
+                   const float* shift, const void* residual_split, void* out_split, float* out_f32,
+                   cudaStream_t stream);
+int conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
+                     const float* shift, const void* residual_split, float* out_f32, cudaStream_t stream);
+int nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, cudaStream_t s);
+int split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H, int W, cudaStream_t s);
+int pack_conv_weight(const float* w, void* w_split, int Cout, int Cin, int k, cudaStream_t s);
+size_t stem_workspace_bytes(int N, int H, int W);
+int stem_forward(const float* in, const float* weight, const float* scale, const float* shift, void* out_split,
+                 void* workspace, int N, int H, int W, cudaStream_t s);
+
+}  // namespace vfs
+
+extern "C" {
+
+const char* vfs_last_error_string(void) { return vfs::g_last_error; }
+int vfs_abi_version(void) { return 1; }
+
+int vfs_check_device(void) {
+  int dev = 0;
+  VFS_CUDA_OK(cudaGetDevice(&dev));
+  int major = 0;
+  VFS_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  VFS_REQUIRE(major == 10, VFS_EARCH, "device compute capability major %d, need 10 (sm_100a)", major);
+  return VFS_OK;
+}
+
+int vfs_nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, vfs_stream_t s) {
+  return vfs::nchw_f32_to_split(in, out_split, N, C, H, W, s);
+}
+int vfs_split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H, int W, vfs_stream_t s) {
+  return vfs::split_to_nchw_f32(in_split, out, N, C, H, W, s);
+}
+size_t vfs_stem_workspace_bytes(int N, int H, int W) { return vfs::stem_workspace_bytes(N, H, W); }
+int vfs_stem_forward(const float* in, const float* weight, const float* scale, const float* shift, void* out_split,
+                     void* workspace, int N, int H, int W, vfs_stream_t s) {
+  return vfs::stem_forward(in, weight, scale, shift, out_split, workspace, N, H, W, s);
+}
+int vfs_conv_bn_act(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
+                    const float* shift, const void* residual_split, void* out_split, float* out_f32_nhwc,
+                    vfs_stream_t s) {
+  return vfs::conv_bn_act_tc(d, in_split, w_split, scale, shift, residual_split, out_split, out_f32_nhwc, s);
+}
+int vfs_pack_conv_weight(const float* w_oihw, void* w_split, int Cout, int Cin, int ksize, vfs_stream_t s) {
+  return vfs::pack_conv_weight(w_oihw, w_split, Cout, Cin, ksize, s);
+}
+int vfs_debug_conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
+                               const float* shift, const void* residual_split, float* out_f32_nhwc,
+                               vfs_stream_t s) {
+  return vfs::conv_bn_act_simt(d, in_split, w_split, scale, shift, residual_split, out_f32_nhwc, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+// Layout boundary kernels (NCHW fp32 <-> split NHWC), weight packing, and the fp32 SIMT conv used as
+// an on-device test instrument.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace vfs {
+
+// ------------------------------------------------------------------------------------------------
+// NCHW fp32 -> split NHWC (tile transpose through shared memory)
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out_hi,
+                                     __nv_bfloat16* __restrict__ out_lo, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* src = in + static_cast<size_t>(n) * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? src[static_cast<size_t>(c) * HW + p] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(tile[threadIdx.x][i], hi, lo);
+      const size_t o = (static_cast<size_t>(n) * HW + p) * C + c;
+      out_hi[o] = hi;
+      out_lo[o] = lo;
+    }
+  }
+}
+
+__global__ void split_to_nchw_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                                     float* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    float v = 0.0f;
+    if (p < HW && c < C) {
+      const size_t o = (static_cast<size_t>(n) * HW + p) * C + c;
+      v = __bfloat162float(in_hi[o]) + __bfloat162float(in_lo[o]);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  float* dst = out + static_cast<size_t>(n) * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) dst[static_cast<size_t>(c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+int nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, cudaStream_t s) {
+  VFS_REQUIRE(in && out_split, VFS_EINVAL, "nchw_f32_to_split: null argument");
+  VFS_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, VFS_ESHAPE, "nchw_f32_to_split: empty tensor");
+  const int HW = H * W;
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out_split);
+  __nv_bfloat16* lo = hi + static_cast<size_t>(N) * HW * C;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  nchw_to_split_kernel<<<grid, block, 0, s>>>(in, hi, lo, C, HW);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+int split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H, int W, cudaStream_t s) {
+  VFS_REQUIRE(in_split && out, VFS_EINVAL, "split_to_nchw_f32: null argument");
+  VFS_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, VFS_ESHAPE, "split_to_nchw_f32: empty tensor");
+  const int HW = H * W;
+  const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(in_split);
+  const __nv_bfloat16* lo = hi + static_cast<size_t>(N) * HW * C;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  split_to_nchw_kernel<<<grid, block, 0, s>>>(hi, lo, out, C, HW);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// OIHW fp32 -> split [2][Cout][(r*k+s)*Cin + ci]
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int k) {
+  const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // destination index i = (co * k*k + tap) * Cin + ci
+    const int ci = static_cast<int>(i % Cin);
+    const size_t t = i / Cin;
+    const int tap = static_cast<int>(t % (k * k));
+    const int co = static_cast<int>(t / (k * k));
+    const float v = w[(static_cast<size_t>(co) * Cin + ci) * k * k + tap];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+int pack_conv_weight(const float* w, void* w_split, int Cout, int Cin, int k, cudaStream_t s) {
+  VFS_REQUIRE(w && w_split, VFS_EINVAL, "pack_conv_weight: null argument");
+  VFS_REQUIRE(Cout > 0 && Cin > 0 && k > 0, VFS_ESHAPE, "pack_conv_weight: bad shape");
+  const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(w_split);
+  const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  pack_weight_kernel<<<blocks, 256, 0, s>>>(w, hi, hi + total, Cout, Cin, k);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 SIMT conv (test instrument): one thread per output element, fixed summation order.
+// ------------------------------------------------------------------------------------------------
+__global__ void conv_simt_kernel(VfsConvDesc d, const __nv_bfloat16* __restrict__ in_hi,
+                                 const __nv_bfloat16* __restrict__ in_lo, const __nv_bfloat16* __restrict__ w_hi,
+                                 const __nv_bfloat16* __restrict__ w_lo, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res_hi,
+                                 const __nv_bfloat16* __restrict__ res_lo, float* __restrict__ out, int Ho, int Wo,
+                                 int pad, int dil) {
+  const size_t total = static_cast<size_t>(d.N) * Ho * Wo * d.Cout;
+  const int k = d.ksize;
+  const size_t Ktot = static_cast<size_t>(k) * k * d.Cin;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % d.Cout);
+    size_t t = i / d.Cout;
+    const int ox = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oy = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float acc = 0.0f;
+    for (int r = 0; r < k; ++r) {
+      const int iy = oy * d.stride + r * dil - pad;
+      if (iy < 0 || iy >= d.H) continue;
+      for (int c = 0; c < k; ++c) {
+        const int ix = ox * d.stride + c * dil - pad;
+        if (ix < 0 || ix >= d.W) continue;
+        const size_t ibase = ((static_cast<size_t>(n) * d.H + iy) * d.W + ix) * d.Cin;
+        const size_t wbase = co * Ktot + static_cast<size_t>(r * k + c) * d.Cin;
+        for (int ci = 0; ci < d.Cin; ++ci) {
+          const float x = __bfloat162float(in_hi[ibase + ci]) + __bfloat162float(in_lo[ibase + ci]);
+          const float ww = __bfloat162float(w_hi[wbase + ci]) + __bfloat162float(w_lo[wbase + ci]);
+          acc = fmaf(x, ww, acc);
+        }
+      }
+    }
+    float y = fmaf(acc, scale[co], shift[co]);
+    if (res_hi) y += __bfloat162float(res_hi[i]) + __bfloat162float(res_lo[i]);
+    if (d.relu) y = fmaxf(y, 0.0f);
+    out[i] = y;
+  }
+}
+
+int conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
+                     const float* shift, const void* residual_split, float* out_f32, cudaStream_t stream) {
+  VFS_REQUIRE(d && in_split && w_split && scale && shift && out_f32, VFS_EINVAL, "conv_simt: null argument");
+  const int k = d->ksize, s = d->stride, dil = (k == 1) ? 1 : d->dilation;
+  const int pad = (k == 1) ? 0 : dil;
+  const int Ho = (d->H + 2 * pad - dil * (k - 1) - 1) / s + 1;
+  const int Wo = (d->W + 2 * pad - dil * (k - 1) - 1) / s + 1;
+  const size_t in_plane = static_cast<size_t>(d->N) * d->H * d->W * d->Cin;
+  const size_t out_plane = static_cast<size_t>(d->N) * Ho * Wo * d->Cout;
+  const size_t w_plane = static_cast<size_t>(d->Cout) * k * k * d->Cin;
+  const __nv_bfloat16* in_hi = reinterpret_cast<const __nv_bfloat16*>(in_split);
+  const __nv_bfloat16* w_hi = reinterpret_cast<const __nv_bfloat16*>(w_split);
+  const __nv_bfloat16* r_hi = reinterpret_cast<const __nv_bfloat16*>(residual_split);
+  const int blocks = static_cast<int>((out_plane + 255) / 256 < 65535 ? (out_plane + 255) / 256 : 65535);
+  conv_simt_kernel<<<blocks, 256, 0, stream>>>(*d, in_hi, in_hi + in_plane, w_hi, w_hi + w_plane, scale, shift, r_hi,
+                                               r_hi ? r_hi + out_plane : nullptr, out_f32, Ho, Wo, pad, dil);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+}  // namespace vfs
