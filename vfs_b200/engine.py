@@ -1,0 +1,133 @@
+"""Host-side executor of the backbone: owns the device-side plan of a ``ResNet`` module (packed split-bf16
+weights, folded BN scale/shift) and walks the block list issuing one fused kernel per ConvModule through the
+C ABI.  It never computes anything in torch: tensors here are only device buffers handed to libvfs_b200.so.
+
+Train-mode batch statistics are not fused yet; in that mode the engine raises (no silent eval-mode result).
+"""
+import torch
+from torch.nn.modules.batchnorm import _BatchNorm
+
+from . import ops
+from .mmcv_lite import ConvModule
+
+
+class _ConvPlan:
+    __slots__ = ('w_split', 'scale', 'shift', 'ksize', 'version')
+
+
+def fold_bn(conv_module, device):
+    """Eval-mode BN folded to y = conv(x) * scale + shift (computed in fp64, stored fp32)."""
+    cout = conv_module.conv.out_channels
+    if conv_module.with_norm:
+        bn = conv_module.norm
+        inv = 1.0 / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        g = bn.weight.detach().double() if bn.weight is not None else torch.ones(cout, dtype=torch.float64)
+        b = bn.bias.detach().double() if bn.bias is not None else torch.zeros(cout, dtype=torch.float64)
+        scale = g.to(inv.device) * inv
+        shift = b.to(inv.device) - bn.running_mean.detach().double() * scale
+    else:
+        scale = torch.ones(cout, dtype=torch.float64)
+        shift = torch.zeros(cout, dtype=torch.float64)
+    if conv_module.conv.bias is not None:
+        shift = shift + conv_module.conv.bias.detach().double().to(shift.device) * scale
+    return (scale.float().to(device).contiguous(), shift.float().to(device).contiguous())
+
+
+class BackboneEngine:
+
+    def __init__(self, resnet):
+        self.net = resnet
+        self._plans = {}
+        self.check_versions = True  # re-pack when parameters were modified in place / reloaded
+
+    # -------------------------------------------------------------- plans
+    @staticmethod
+    def _version(cm):
+        v = cm.conv.weight._version + cm.conv.weight.data_ptr()
+        if cm.with_norm:
+            bn = cm.norm
+            for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var):
+                if t is not None:
+                    v += t._version + t.data_ptr()
+        return v
+
+    def plan(self, cm, device):
+        p = self._plans.get(id(cm))
+        ver = self._version(cm) if (self.check_versions or p is None) else None
+        if p is None or (ver is not None and p.version != ver) or p.scale.device != device:
+            p = _ConvPlan()
+            w = cm.conv.weight.detach().to(device=device, dtype=torch.float32).contiguous()
+            p.ksize = w.shape[2]
+            p.w_split = ops.pack_conv_weight(w) if w.shape[1] % 64 == 0 else w  # stem keeps OIHW fp32
+            p.scale, p.shift = fold_bn(cm, device)
+            p.version = ver if ver is not None else self._version(cm)
+            self._plans[id(cm)] = p
+        return p
+
+    def invalidate(self):
+        self._plans.clear()
+
+    # -------------------------------------------------------------- single fused layer
+    def conv(self, cm, xs, relu, residual=None, want_f32=False):
+        """One ConvModule (+residual, +ReLU) on a split NHWC tensor."""
+        assert isinstance(cm, ConvModule)
+        if cm.with_norm and cm.norm.training:
+            raise NotImplementedError(
+                'vfs_b200: train-mode (batch-statistics) BatchNorm is not implemented in the native engine yet; '
+                'call .eval() on the model or use norm_eval=True')
+        k = cm.conv.kernel_size[0]
+        stride, dil, pad = cm.conv.stride[0], cm.conv.dilation[0], cm.conv.padding[0]
+        assert cm.conv.kernel_size[0] == cm.conv.kernel_size[1] and cm.conv.stride[0] == cm.conv.stride[1]
+        assert cm.conv.groups == 1
+        assert pad == (0 if k == 1 else dil), f'unsupported padding {pad} for k={k}, dilation={dil}'
+        p = self.plan(cm, xs.device)
+        out, out32 = ops.conv_bn_act(xs, p.w_split, p.scale, p.shift, k, stride, dil, relu, residual,
+                                     want_split=not want_f32, want_f32=want_f32)
+        return out32 if want_f32 else out
+
+    def stem(self, x):
+        cm = self.net.conv1
+        if cm.with_norm and cm.norm.training:
+            raise NotImplementedError('vfs_b200: train-mode BatchNorm is not implemented in the native engine yet')
+        assert cm.conv.in_channels == 3 and cm.conv.kernel_size == (7, 7) and cm.conv.stride == (2, 2)
+        p = self.plan(cm, x.device)
+        return ops.stem_forward(x, p.w_split, p.scale, p.shift)
+
+    # -------------------------------------------------------------- whole backbone
+    def forward(self, x, out_indices=None, block_index=None):
+        """Runs stem + residual stages.  Returns a list of NCHW fp32 tensors: the outputs of the stages in
+        ``out_indices`` (reference ResNet.forward, resnet.py:555-575) or of block ``block_index``
+        (forward_block :577-587).  Stages after the last requested one are skipped -- the reference computes
+        and discards them, the results are identical."""
+        if not x.is_cuda:
+            raise RuntimeError('vfs_b200.ResNet needs a CUDA tensor: the B200 path has no CPU fallback '
+                               '(the CPU restatement lives in oracle/ and is test infrastructure only)')
+        x = x.contiguous().float()
+        net = self.net
+        xs = self.stem(x)
+        outs = []
+        last_stage = max(out_indices) if out_indices is not None else len(net.res_layers) - 1
+        bidx = 0
+        for i, name in enumerate(net.res_layers):
+            if i > last_stage:
+                break
+            for block in getattr(net, name):
+                xs = block.native_forward(self, xs)
+                if block_index is not None and bidx == block_index:
+                    return [ops.from_split(xs)]
+                bidx += 1
+            if out_indices is not None and i in out_indices:
+                outs.append(ops.from_split(xs))
+        if block_index is not None:
+            return [None]
+        return outs
+
+    def forward_split(self, x, stage):
+        """Features of stage ``stage`` kept in the library's split NHWC format (for the on-device tracker)."""
+        xs = self.stem(x.contiguous().float())
+        for i, name in enumerate(self.net.res_layers):
+            if i > stage:
+                break
+            for block in getattr(self.net, name):
+                xs = block.native_forward(self, xs)
+        return xs
