@@ -88,6 +88,71 @@ int vfs_debug_conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const
                                const float* shift, const void* residual_split, float* out_f32_nhwc,
                                vfs_stream_t s);
 
+/* ------------------------------------------------------------------------------------------------
+ * Restricted-attention label propagation (DAVIS inference).  Replaces masked_attention_efficient,
+ * mmaction/models/common/local_attention.py:237-348 (F.normalize :277-279, einsum :289-291, masked_fill
+ * :292-313, topk :316, index_select :320-326, softmax + einsum :327-334), with the HW x HW bool mask of
+ * spatial_neighbor (common/affinity_utils.py:119-156) replaced by its analytic predicate.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct VfsAttnDesc {
+  int32_t H, W;         /* feature-map size (queries and keys) */
+  int32_t C;            /* attention channels, multiple of 64 */
+  int32_t Cv;           /* value channels (objects + background) */
+  int32_t T;            /* number of key frames, 1..32 */
+  int32_t topk;         /* 1..16 */
+  int32_t mask_mode;    /* 0 none, 1 circle: dy^2+dx^2 < radius_y^2, 2 square: |dy|<=radius_y && |dx|<=radius_x */
+  int32_t radius_y, radius_x;
+  int32_t non_mask_len; /* leading key frames exempt from the mask */
+  int32_t mode;         /* 0 softmax, 1 cosine (clamp(min=0)^2) */
+  float temperature;    /* > 0 */
+} VfsAttnDesc;
+
+/* NCHW fp32 features [N,C,H,W] -> split NHWC, optionally L2-normalised over C (F.normalize, eps 1e-12).
+ * inv_norm_ws: fp32 [N*H*W] scratch (only when normalize != 0). */
+int vfs_features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
+                          int normalize, vfs_stream_t s);
+/* split NHWC -> L2-normalised split NHWC (plane strides in elements; in == out allowed). */
+int vfs_normalize_split(const void* in_split, void* out_split, long long num_pixels, int C,
+                        long long in_plane_stride, long long out_plane_stride, vfs_stream_t s);
+
+size_t vfs_attention_workspace_bytes(const VfsAttnDesc* d);
+/*   q_split        hi plane of the query frame [H][W][C]; lo plane at +q_plane_stride elements
+ *   k_bank_split   hi plane of a bank of frames [k_bank_frames][H][W][C]; lo plane at +k_plane_stride elements
+ *   key_frame_ids  HOST array [T]: bank frame used by key slot t (a frame may repeat, cf. vanilla_tracker.py:133-149)
+ *   values         fp32; element (slot t, channel c, position p) at values[key_frame_ids[t]*v_frame_stride +
+ *                  c*v_chan_stride + p]
+ *   out            fp32 [Cv][H*W]
+ *   out_topk_val / out_topk_idx   NULL or [topk][H*W]: selected affinities (already / temperature) and flat key
+ *                  indices t*H*W + p, sorted descending -- for index-parity tests */
+int vfs_masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_plane_stride,
+                         const void* k_bank_split, long long k_plane_stride, int k_bank_frames,
+                         const int32_t* key_frame_ids, const float* values, long long v_frame_stride,
+                         long long v_chan_stride, float* out, float* out_topk_val, int32_t* out_topk_idx,
+                         void* workspace, size_t workspace_bytes, vfs_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
+ * SimSiam head + loss.  Replaces SimSiamHead.forward (heads/sim_siam_head.py:143-163: AdaptiveAvgPool2d,
+ * nn.Linear, BatchNorm1d/SyncBatchNorm, ReLU) and CosineSimLoss._forward (losses/sim_loss.py:42-63).
+ * ---------------------------------------------------------------------------------------------- */
+int vfs_global_avg_pool(const float* in_nchw, float* out, int B, int C, int HW, vfs_stream_t s);
+/* y[M,N] = x[M,K] W[N,K]^T + bias */
+int vfs_linear(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, vfs_stream_t s);
+/* in-place BatchNorm1d over y[M,N] (+ReLU); training != 0 uses batch statistics and updates the running ones */
+int vfs_bn1d_act(float* y, int M, int N, const float* gamma, const float* beta, float* running_mean,
+                 float* running_var, float eps, float momentum, int training, int relu, vfs_stream_t s);
+int vfs_relu(float* y, size_t n, vfs_stream_t s);
+/* loss[b] = 2 - 2*cos(p[b], z[b])  (negative != 0: -cos; with_norm == 0: raw dot product) */
+int vfs_cosine_sim_loss(const float* p, const float* z, float* loss, int B, int D, int with_norm, int negative,
+                        vfs_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
+ * SiamFC cross-correlation.  Replaces SiamFC._fast_xcorr (projects/siamfc-pytorch/siamfc/heads.py:16-23).
+ *   z fp32 NHWC [nz,hz,wz,C], x fp32 NHWC [nx,h,w,C] -> out fp32 [nx,1,h-hz+1,w-wz+1], x[i] pairs with z[i % nz]
+ * ---------------------------------------------------------------------------------------------- */
+int vfs_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, vfs_stream_t s);
+int vfs_xcorr_nhwc(const float* z, const float* x, float* out, int nz, int nx, int C, int hz, int wz, int h, int w,
+                   float out_scale, vfs_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,161 @@
+"""Seeded test cases shared by make_golden.py (reference outputs), the oracle tests (CPU) and the GPU parity
+tests.  Everything is reproducible from seeds; only reference OUTPUTS live in vfs_golden.npz."""
+import torch
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------ backbone
+BACKBONE_CASES = {
+    # name: reference-config analogue
+    'r18_default': dict(depth=18, strides=(1, 2, 2, 2), dilations=(1, 1, 1, 1), out_indices=(3, ), seed=1,
+                        shape=(2, 3, 64, 64)),                       # tests/test_models/test_backbone.py:109-113
+    'r50_default': dict(depth=50, strides=(1, 2, 2, 2), dilations=(1, 1, 1, 1), out_indices=(3, ), seed=2,
+                        shape=(2, 3, 64, 64)),                       # test_backbone.py:116-120
+    'r50_davis': dict(depth=50, strides=(1, 2, 1, 1), dilations=(1, 1, 1, 1), out_indices=(2, ), seed=3,
+                      shape=(2, 3, 72, 104)),                        # configs/r50_nc...:27-36 test_cfg
+    'r18_davis': dict(depth=18, strides=(1, 2, 1, 1), dilations=(1, 1, 1, 1), out_indices=(2, ), seed=4,
+                      shape=(1, 3, 75, 91)),                         # odd sizes
+    'r18_siamfc': dict(depth=18, strides=(1, 2, 1, 1), dilations=(1, 1, 2, 4), out_indices=(3, ), seed=5,
+                       shape=(2, 3, 95, 95)),                        # siamfc/default_config_base.py:40-49
+    'r50_siamfc': dict(depth=50, strides=(1, 2, 1, 1), dilations=(1, 1, 2, 4), out_indices=(3, ), seed=6,
+                       shape=(1, 3, 63, 63)),
+    'r50_multi_out': dict(depth=50, strides=(1, 2, 2, 2), dilations=(1, 1, 1, 1), out_indices=(2, ), seed=7,
+                          shape=(3, 3, 96, 64)),
+}
+
+
+def backbone_input(c):
+    return torch.randn(c['shape'], generator=_gen(100 + c['seed']))
+
+
+# ------------------------------------------------------------------ SimSiam head / loss
+HEAD_CASES = {
+    'r18_head': dict(seed=11, B=4, hw=(2, 2),
+                     cfg=dict(in_channels=512, norm_cfg=dict(type='SyncBN'), num_projection_fcs=3,
+                              projection_mid_channels=512, projection_out_channels=512, num_predictor_fcs=2,
+                              predictor_mid_channels=128, predictor_out_channels=512, with_norm=True,
+                              loss_feat=dict(type='CosineSimLoss', negative=False), spatial_type='avg')),
+    'r50_head': dict(seed=12, B=8, hw=(2, 3),
+                     cfg=dict(in_channels=2048, norm_cfg=dict(type='SyncBN'), num_projection_fcs=3,
+                              projection_mid_channels=2048, projection_out_channels=2048, num_predictor_fcs=2,
+                              predictor_mid_channels=512, predictor_out_channels=2048, with_norm=True,
+                              loss_feat=dict(type='CosineSimLoss', negative=False), spatial_type='avg')),
+}
+
+
+def head_inputs(c):
+    g = _gen(200 + c['seed'])
+    shape = (c['B'], c['cfg']['in_channels']) + tuple(c['hw'])
+    return torch.relu(torch.randn(shape, generator=g)), torch.relu(torch.randn(shape, generator=g))
+
+
+def loss_inputs():
+    g = _gen(300)
+    return torch.randn(6, 96, generator=g), torch.randn(6, 96, generator=g)
+
+
+# ------------------------------------------------------------------ full SimSiam forward_train (config dicts)
+def _simsiam_model(depth, in_ch, mid, pred_mid):
+    return dict(
+        type='SimSiamBaseTracker',
+        backbone=dict(type='ResNet', pretrained=None, depth=depth, out_indices=(3, ),
+                      norm_cfg=dict(type='SyncBN', requires_grad=True), norm_eval=False, zero_init_residual=True),
+        img_head=dict(type='SimSiamHead', in_channels=in_ch, norm_cfg=dict(type='SyncBN'), num_projection_fcs=3,
+                      projection_mid_channels=mid, projection_out_channels=mid, num_predictor_fcs=2,
+                      predictor_mid_channels=pred_mid, predictor_out_channels=mid, with_norm=True,
+                      loss_feat=dict(type='CosineSimLoss', negative=False), spatial_type='avg'))
+
+
+TRACKER_TRAIN_CASES = {
+    # configs/r18_nc_sgd_cos_100e_r2_1xNx8_k400.py model dict, intra_video=True, clip_len 2
+    'r18_intra': dict(seed=21, model=_simsiam_model(18, 512, 512, 128), train_cfg=dict(intra_video=True),
+                      shape=(2, 2, 3, 2, 64, 64)),
+    # configs/r50_nc_sgd_cos_100e_r5_1xNx2_k400.py model dict
+    'r50': dict(seed=22, model=_simsiam_model(50, 2048, 2048, 512), train_cfg=dict(intra_video=False),
+                shape=(3, 2, 3, 1, 64, 64)),
+}
+
+
+def tracker_train_input(c):
+    return torch.randn(c['shape'], generator=_gen(400 + c['seed']))
+
+
+# ------------------------------------------------------------------ restricted attention (DAVIS propagation)
+ATTENTION_CASES = {
+    'small_T1': dict(seed=31, C=32, Cv=3, T=1, H=9, W=11, range=8, temperature=0.07, topk=10),
+    'small_T3': dict(seed=32, C=64, Cv=4, T=3, H=12, W=17, range=10, temperature=0.07, topk=10),
+    'small_T3_first_free': dict(seed=33, C=64, Cv=4, T=3, H=12, W=17, range=10, temperature=0.07, topk=10,
+                                non_mask_len=1),
+    'square_mask': dict(seed=34, C=32, Cv=2, T=1, H=10, W=10, range=6, temperature=0.05, topk=5,
+                        mask_mode='square'),
+    'no_mask': dict(seed=35, C=32, Cv=2, T=2, H=8, W=9, range=None, temperature=0.1, topk=10),
+    'cosine_mode': dict(seed=36, C=32, Cv=3, T=2, H=9, W=11, range=8, temperature=1.0, topk=10, mode='cosine'),
+    'dup_first': dict(seed=37, C=64, Cv=4, T=3, H=12, W=17, range=10, temperature=0.07, topk=10, dup_first=True),
+    'mid_T2': dict(seed=38, C=256, Cv=5, T=2, H=30, W=54, range=24, temperature=0.07, topk=10),
+}
+
+
+def attention_inputs(c):
+    g = _gen(500 + c['seed'])
+    q = torch.relu(torch.randn(1, c['C'], c['H'], c['W'], generator=g))
+    k = torch.relu(torch.randn(1, c['C'], c['T'], c['H'], c['W'], generator=g))
+    v = torch.rand(1, c['Cv'], c['T'], c['H'], c['W'], generator=g)
+    if c.get('dup_first'):  # frame 0 appears twice in the key set while frame_idx <= precede_frames
+        k[:, :, 1] = k[:, :, 0]
+        v[:, :, 1] = v[:, :, 0]
+    return q, k, v
+
+
+AFFINITY_CASES = {
+    'dense': dict(seed=41, C=32, Cv=3, B=2, H=7, W=9, temperature=0.07, softmax_dim=1, topk=None),
+    'dense_topk': dict(seed=42, C=32, Cv=3, B=1, H=8, W=8, temperature=0.07, softmax_dim=1, topk=5),
+}
+
+
+def affinity_inputs(c):
+    g = _gen(600 + c['seed'])
+    a = torch.randn(c['B'], c['C'], c['H'], c['W'], generator=g)
+    b = torch.randn(c['B'], c['C'], c['H'], c['W'], generator=g)
+    img = torch.rand(c['B'], c['Cv'], c['H'], c['W'], generator=g)
+    return a, b, img
+
+
+# ------------------------------------------------------------------ SiamFC cross-correlation
+XCORR_CASES = {
+    'z15_x32': dict(seed=51, C=64, nz=1, nx=3, hz=15, hx=32, out_scale=1e-3),  # exemplar_sz=120 default
+    'z16_x32': dict(seed=52, C=64, nz=1, nx=3, hz=16, hx=32, out_scale=1e-3),  # BASELINE cfg-5 (127 px)
+    'z6_x11': dict(seed=53, C=512, nz=1, nx=2, hz=6, hx=11, out_scale=1e-5),
+}
+
+
+def xcorr_inputs(c):
+    g = _gen(700 + c['seed'])
+    z = torch.randn(c['nz'], c['C'], c['hz'], c['hz'], generator=g)
+    x = torch.randn(c['nx'], c['C'], c['hx'], c['hx'], generator=g)
+    return z, x
+
+
+# ------------------------------------------------------------------ DAVIS-style inference (VanillaTracker)
+TRACKER_TEST_CASES = {
+    'r18_clip5': dict(seed=61, T=5, H=64, W=96, num_objs=3,
+                      backbone=dict(type='ResNet', pretrained=None, depth=18, out_indices=(2, ),
+                                    strides=(1, 2, 1, 1), norm_cfg=dict(type='SyncBN', requires_grad=True),
+                                    norm_eval=False, zero_init_residual=True),
+                      test_cfg=dict(precede_frames=2, topk=10, temperature=0.07, strides=(1, 2, 1, 1),
+                                    out_indices=(2, ), neighbor_range=24, with_first=True,
+                                    with_first_neighbor=True, output_dir='eval_results')),
+}
+
+
+def tracker_test_inputs(c):
+    g = _gen(800 + c['seed'])
+    imgs = torch.randn(1, 1, 3, c['T'], c['H'], c['W'], generator=g)
+    seg = torch.zeros(1, c['H'], c['W'])
+    # a few rectangles as first-frame objects
+    for o in range(1, c['num_objs']):
+        y0, x0 = 8 * o, 12 * o
+        seg[0, y0:y0 + 24, x0:x0 + 30] = o
+    return imgs, seg

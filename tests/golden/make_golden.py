@@ -1,0 +1,113 @@
+"""Generates tests/golden/vfs_golden.npz from the UNMODIFIED reference (imported from /root/reference through
+oracle/ref_shim.py).  Run in the authoring container only:
+
+    python tests/golden/make_golden.py
+
+Inputs and weights are reproducible from seeds alone (``oracle.seeded_state_dict`` fills parameters by
+state-dict name), so only the reference's OUTPUTS are stored.  The fixtures pin the oracle (tests/test_oracle_*.py,
+CPU) and the CUDA path (tests/test_gpu_*.py, on the B200 box where /root/reference does not exist).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim, seeded_state_dict  # noqa: E402
+from tests.golden import cases  # noqa: E402
+
+
+def main():
+    ref = ref_shim.load_reference()
+    torch.set_num_threads(8)
+    out = {}
+
+    # ---- backbone (eval and train-mode BN), reference ResNet.forward
+    for name, c in cases.BACKBONE_CASES.items():
+        m = ref.ResNet(c['depth'], norm_cfg=dict(type='SyncBN', requires_grad=True), strides=c['strides'],
+                       dilations=c['dilations'], out_indices=c['out_indices'])
+        m.load_state_dict(seeded_state_dict(m, seed=c['seed']))
+        x = cases.backbone_input(c)
+        with torch.no_grad():
+            m.train(False)
+            y = m(x)
+            out[f'backbone/{name}/eval'] = y.numpy()
+            m.train(True)
+            out[f'backbone/{name}/train'] = m(x).numpy()
+
+    # ---- SimSiam head + loss
+    for name, c in cases.HEAD_CASES.items():
+        h = ref.SimSiamHead(**c['cfg'])
+        h.load_state_dict(seeded_state_dict(h, seed=c['seed']))
+        x1, x2 = cases.head_inputs(c)
+        for mode in ('eval', 'train'):
+            h.train(mode == 'train')
+            with torch.no_grad():
+                z1, p1 = h(x1)
+                z2, p2 = h(x2)
+                loss = h.loss(p1, z1, p2, z2)['loss_feat']
+            out[f'head/{name}/{mode}/z1'] = z1.numpy()
+            out[f'head/{name}/{mode}/p1'] = p1.numpy()
+            out[f'head/{name}/{mode}/loss'] = loss.numpy()
+    p, z = cases.loss_inputs()
+    for neg in (False, True):
+        out[f'loss/cosine/neg{int(neg)}'] = ref.CosineSimLoss(negative=neg)(p, z).numpy()
+
+    # ---- full SimSiam forward_train through the reference tracker + config dict
+    for name, c in cases.TRACKER_TRAIN_CASES.items():
+        model = ref.build_model(c['model'], train_cfg=c['train_cfg'], test_cfg=None)
+        model.load_state_dict(seeded_state_dict(model, seed=c['seed']))
+        model.train()
+        imgs = cases.tracker_train_input(c)
+        with torch.no_grad():
+            losses = model.forward_train(imgs)
+        for k, v in losses.items():
+            out[f'tracker_train/{name}/{k}'] = v.numpy()
+
+    # ---- restricted attention / affinity
+    for name, c in cases.ATTENTION_CASES.items():
+        q, k, v = cases.attention_inputs(c)
+        mask = ref.spatial_neighbor(1, c['H'], c['W'], neighbor_range=c['range'], device='cpu', dtype=torch.float32,
+                                    mode=c.get('mask_mode', 'circle')) if c['range'] else None
+        if mask is not None:
+            out[f'attention/{name}/mask_packed'] = np.packbits(mask.numpy())
+        o = ref.masked_attention_efficient(q, k, v, mask, temperature=c['temperature'], topk=c['topk'],
+                                           non_mask_len=c.get('non_mask_len', 0), mode=c.get('mode', 'softmax'))
+        out[f'attention/{name}/out'] = o.numpy()
+    for name, c in cases.AFFINITY_CASES.items():
+        a, b, img = cases.affinity_inputs(c)
+        aff = ref.compute_affinity(a, b, temperature=c['temperature'], softmax_dim=c['softmax_dim'])
+        out[f'affinity/{name}/aff'] = aff.numpy()
+        out[f'affinity/{name}/prop'] = ref.propagate(img, aff.clone(), topk=c['topk']).numpy()
+
+    # ---- SiamFC heads
+    for name, c in cases.XCORR_CASES.items():
+        z, x = cases.xcorr_inputs(c)
+        out[f'xcorr/{name}/siamfc'] = ref.siamfc_heads.SiamFC(out_scale=c['out_scale'])(z, x).numpy()
+        m = ref.siamfc_heads.SiamConvFC(c['C'], c['C'], out_scale=c['out_scale'])
+        m.load_state_dict(seeded_state_dict(m, seed=c['seed']))
+        with torch.no_grad():
+            out[f'xcorr/{name}/siamconvfc'] = m(z, x).numpy()
+
+    # ---- DAVIS-style inference through the reference VanillaTracker
+    for name, c in cases.TRACKER_TEST_CASES.items():
+        tr = ref.VanillaTracker(backbone=c['backbone'], test_cfg=ref_shim.sys.modules['mmcv'].ConfigDict(c['test_cfg']))
+        tr.backbone.load_state_dict(seeded_state_dict(tr.backbone, seed=c['seed']))
+        tr.eval()
+        imgs, seg = cases.tracker_test_inputs(c)
+        with torch.no_grad():
+            preds = tr.forward_test(imgs, seg, [dict(original_shape=(c['H'], c['W'], 3))])
+        out[f'tracker_test/{name}/preds'] = np.asarray(preds[0]).astype(np.uint8)
+
+    path = os.path.join(ROOT, 'tests', 'golden', 'vfs_golden.npz')
+    np.savez_compressed(path, **out)
+    print(f'wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB')
+    for k in sorted(out):
+        print(f'  {k:48s} {out[k].dtype} {out[k].shape}')
+
+
+if __name__ == '__main__':
+    main()

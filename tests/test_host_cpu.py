@@ -1,0 +1,226 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol, and the host-side mirror of the reference
+interface (registries, configs, module/state-dict contract, layout helpers) behaves like the reference."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CONFIGS = '/root/reference/configs'
+
+
+def test_library_exports_every_declared_symbol():
+    from vfs_b200 import _native
+    header = open(os.path.join(ROOT, 'include', 'vfs_b200.h')).read()
+    declared = set(re.findall(r'\b(vfs_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations found'
+    lib = _native.lib()
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/vfs_b200.h but not exported'
+    assert declared == set(_native.PROTOTYPES), declared ^ set(_native.PROTOTYPES)
+    assert lib.vfs_abi_version() == 1
+
+
+def test_library_reports_errors_without_gpu():
+    from vfs_b200 import _native
+    lib = _native.lib()
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    assert lib.vfs_check_device() != 0
+    assert len(lib.vfs_last_error_string()) > 0
+    with pytest.raises(RuntimeError):
+        _native.check(lib.vfs_check_device(), 'check_device')
+
+
+def test_registry_and_build_from_cfg():
+    from vfs_b200.mmcv_lite import Registry, build_from_cfg
+    R = Registry('thing')
+
+    @R.register_module()
+    class A:
+        def __init__(self, x, y=2):
+            self.x, self.y = x, y
+
+    with pytest.raises(KeyError):
+        R.register_module()(A)
+    R.register_module(force=True)(A)
+    a = build_from_cfg(dict(type='A', x=1), R, default_args=dict(y=5, x=9))
+    assert (a.x, a.y) == (1, 5)
+    assert isinstance(build_from_cfg(dict(type=A, x=3), R), A)
+    with pytest.raises(KeyError):
+        build_from_cfg(dict(type='B'), R)
+    with pytest.raises(KeyError):
+        build_from_cfg(dict(x=1), R)
+    with pytest.raises(TypeError):
+        build_from_cfg([], R)
+    assert 'A' in R and 'B' not in R and len(R) == 1
+
+
+def test_registries_hold_the_reference_type_names():
+    import vfs_b200
+    assert vfs_b200.BACKBONES.get('ResNet') is not None
+    assert vfs_b200.HEADS.get('SimSiamHead') is not None
+    assert vfs_b200.LOSSES.get('CosineSimLoss') is not None
+    assert vfs_b200.TRACKERS.get('SimSiamBaseTracker') is not None
+    assert vfs_b200.TRACKERS.get('VanillaTracker') is not None
+    with pytest.raises(KeyError):
+        vfs_b200.build_model(dict(type='NoSuchModel'))
+
+
+def _config_files():
+    files = [os.path.join(ROOT, 'tests', 'data', 'sample_simsiam_config.py')]
+    if os.path.isdir(REF_CONFIGS):
+        files += sorted(os.path.join(REF_CONFIGS, f) for f in os.listdir(REF_CONFIGS) if f.endswith('.py'))
+    return files
+
+
+@pytest.mark.parametrize('path', _config_files())
+def test_configs_build_unchanged(path):
+    """The reference's configs/*.py (when /root/reference is present) and the local fixture load through Config and
+    build through build_model; tools/test.py:129-133's VanillaTracker rebuild works too."""
+    import vfs_b200
+    cfg = vfs_b200.Config.fromfile(path)
+    assert cfg.model.type == 'SimSiamBaseTracker'
+    cfg.merge_from_dict({'model.backbone.norm_eval': True, 'optimizer.lr': 0.1})
+    assert cfg.model.backbone.norm_eval is True and cfg.optimizer.lr == 0.1
+    model = vfs_b200.build_model(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+    depth = cfg.model.backbone.depth
+    n_params = sum(p.numel() for p in model.parameters())
+    assert n_params == {18: 12099520, 50: 38210112}[depth]
+    assert model.intra_video == cfg.train_cfg.get('intra_video', False)
+    assert float(model.iteration) == 0.0
+    backbone_cfg = cfg.model.backbone.copy()
+    backbone_cfg['out_indices'] = cfg.test_cfg.out_indices
+    backbone_cfg['strides'] = cfg.test_cfg.strides
+    tracker = vfs_b200.build_model(dict(type='VanillaTracker', backbone=backbone_cfg), train_cfg=None,
+                                   test_cfg=cfg.test_cfg)
+    assert tracker.stride == 8
+    assert tracker.backbone.layer3[0].conv2.conv.stride == (1, 1) if depth == 50 else True
+
+
+def test_resnet_state_dict_contract_matches_torchvision_mapping():
+    """Checkpoint key names are part of the drop-in contract: they must map 1:1 onto torchvision's
+    through the convert_to_pretrained.py renaming."""
+    import torchvision
+    from vfs_b200.backbones import ResNet
+    for depth, tv in ((18, torchvision.models.resnet18), (50, torchvision.models.resnet50)):
+        ours = ResNet(depth).state_dict()
+        theirs = {k: v for k, v in tv(weights=None).state_dict().items() if not k.startswith('fc.')}
+
+        def to_tv(k):
+            k = re.sub(r'^conv1\.conv\.', 'conv1.', k)
+            k = re.sub(r'^conv1\.bn\.', 'bn1.', k)
+            k = re.sub(r'\.downsample\.conv\.', '.downsample.0.', k)
+            k = re.sub(r'\.downsample\.bn\.', '.downsample.1.', k)
+            k = re.sub(r'\.conv(\d)\.conv\.', r'.conv\1.', k)
+            k = re.sub(r'\.conv(\d)\.bn\.', r'.bn\1.', k)
+            return k
+
+        mapped = {to_tv(k): v.shape for k, v in ours.items()}
+        assert mapped == {k: v.shape for k, v in theirs.items()}
+        # and the loader accepts a torchvision state dict
+        net = ResNet(depth)
+        left = net._load_torchvision_checkpoint(dict(tv(weights=None).state_dict()))
+        assert left == ['fc.bias', 'fc.weight']
+
+
+def test_head_state_dict_indices():
+    from vfs_b200.heads import SimSiamHead
+    keys = set(SimSiamHead(in_channels=64, projection_mid_channels=32, projection_out_channels=32,
+                           predictor_mid_channels=16, predictor_out_channels=32).state_dict())
+    for i in (0, 1, 3, 4, 6, 7):
+        assert f'projection_fcs.{i}.weight' in keys
+    for i in (0, 1, 3):
+        assert f'predictor_fcs.{i}.weight' in keys
+    assert 'projection_fcs.2.weight' not in keys
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    from vfs_b200.backbones import ResNet
+    from vfs_b200.losses import CosineSimLoss
+    net = ResNet(18)
+    net.train(False)
+    with pytest.raises(RuntimeError):
+        net(torch.randn(1, 3, 64, 64))
+    with pytest.raises(RuntimeError):
+        CosineSimLoss()(torch.randn(2, 8), torch.randn(2, 8))
+    with pytest.raises(RuntimeError):
+        net.conv1(torch.randn(1, 3, 64, 64))  # ConvModule is a parameter container
+
+
+def test_resnet_constructor_errors():
+    from vfs_b200.backbones import ResNet
+    with pytest.raises(KeyError):
+        ResNet(20)
+    with pytest.raises(AssertionError):
+        ResNet(50, num_stages=0)
+    with pytest.raises(AssertionError):
+        ResNet(50, num_stages=5)
+    with pytest.raises(AssertionError):
+        ResNet(50, strides=(1, ), dilations=(1, 1), num_stages=3)
+    with pytest.raises(AssertionError):
+        ResNet(18, style='tensorflow')
+    with pytest.raises(TypeError):
+        ResNet(50, pretrained=0).init_weights()
+    net = ResNet(50, zero_init_residual=True)
+    net.init_weights()
+    assert float(net.layer1[0].conv3.bn.weight.abs().sum()) == 0.0
+    assert net.output_stride == 32 and net.feat_dim == 2048
+    assert ResNet(18, dilations=(1, 1, 2, 4)).layer4[0].conv1.conv.dilation == (2, 2)   # dilation // 2 (:285)
+    assert ResNet(18, dilations=(1, 1, 2, 4)).layer4[1].conv1.conv.dilation == (4, 4)
+
+
+def test_neighbor_mask_equals_oracle_and_layout_helpers():
+    import oracle
+    from vfs_b200.common import images2video, spatial_neighbor, video2images
+    for (h, w, r, mode) in ((9, 11, 8, 'circle'), (12, 17, 10, 'circle'), (10, 10, 6, 'square'), (60, 107, 36, 'circle')):
+        ours = spatial_neighbor(1, h, w, r, mode=mode).dense()
+        ref = oracle.spatial_neighbor(h, w, r, mode=mode)
+        assert torch.equal(ours, ref)
+    m = spatial_neighbor(1, 60, 107, 36).dense()
+    assert int(m[30 * 107 + 50].sum()) == 1005                      # interior query: 1005 neighbours
+    x = torch.randn(2, 3, 4, 5, 6)
+    assert torch.equal(images2video(video2images(x), 4), x)
+    assert video2images(x[:, :, :1]).shape == (2, 3, 5, 6)
+
+
+def test_pil_nearest_matches_pillow():
+    from PIL import Image
+    from vfs_b200.common import pil_nearest_interpolate
+    g = torch.Generator().manual_seed(0)
+    for (h, w, oh, ow) in ((480, 854, 60, 107), (64, 96, 8, 12), (37, 53, 10, 7), (480, 910, 60, 114)):
+        seg = torch.randint(0, 5, (1, 1, h, w), generator=g).float()
+        ours = pil_nearest_interpolate(seg, (oh, ow))[0, 0].numpy()
+        pil = np.array(Image.fromarray(seg[0, 0].numpy()).resize((ow, oh), Image.NEAREST))
+        np.testing.assert_array_equal(ours, pil)
+
+
+def _parse_losses_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from vfs_b200.trackers import BaseTracker
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    losses = {'img_head.0.loss_feat': torch.full((4, ), float(rank + 1)), 'acc': torch.tensor([0.5 * (rank + 1)])}
+    loss, log_vars = BaseTracker._parse_losses(losses)
+    q.put((rank, float(loss), dict(log_vars)))
+    dist.destroy_process_group()
+
+
+def test_parse_losses_averages_over_ranks_gloo_world2():
+    """world_size-2 gloo: logged scalars are the rank average (reference base.py:103-108); the loss tensor used
+    for backward stays local."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_parse_losses_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [1.0, 2.0]
+    for _, _, lv in res:
+        assert abs(lv['img_head.0.loss_feat'] - 1.5) < 1e-6 and abs(lv['loss'] - 1.5) < 1e-6
+        assert abs(lv['acc'] - 0.75) < 1e-6

@@ -17,8 +17,14 @@ class VfsConvDesc(ctypes.Structure):
                 for n in ('N', 'H', 'W', 'Cin', 'Cout', 'ksize', 'stride', 'dilation', 'relu')]
 
 
+class VfsAttnDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ('H', 'W', 'C', 'Cv', 'T', 'topk', 'mask_mode', 'radius_y', 'radius_x',
+                                              'non_mask_len', 'mode')] + [('temperature', ctypes.c_float)]
+
+
 _vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
-_sz = ctypes.c_size_t
+_sz, _ll = ctypes.c_size_t, ctypes.c_longlong
+_attn_p = ctypes.POINTER(VfsAttnDesc)
 
 # name -> (restype, argtypes); every symbol include/vfs_b200.h declares
 PROTOTYPES = {
@@ -32,6 +38,18 @@ PROTOTYPES = {
     'vfs_conv_bn_act': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'vfs_pack_conv_weight': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'vfs_debug_conv_bn_act_simt': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'vfs_features_to_split': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'vfs_normalize_split': (_i, [_vp, _vp, _ll, _i, _ll, _ll, _vp]),
+    'vfs_attention_workspace_bytes': (_sz, [_attn_p]),
+    'vfs_masked_attention': (_i, [_attn_p, _vp, _ll, _vp, _ll, _i, ctypes.POINTER(ctypes.c_int32), _vp, _ll, _ll,
+                                  _vp, _vp, _vp, _vp, _sz, _vp]),
+    'vfs_global_avg_pool': (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    'vfs_linear': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'vfs_bn1d_act': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _vp]),
+    'vfs_relu': (_i, [_vp, _sz, _vp]),
+    'vfs_cosine_sim_loss': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'vfs_nchw_to_nhwc_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'vfs_xcorr_nhwc': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
 }
 
 _lib = None

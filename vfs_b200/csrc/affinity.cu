@@ -1,0 +1,571 @@
+// Fused restricted-attention label propagation for sm_100a (DAVIS inference hot loop).
+//
+// Replaces the reference's per-32-query chunk loop  einsum -> /T -> masked_fill(-inf) -> topk -> index_select ->
+// softmax -> einsum  (mmaction/models/common/local_attention.py:287-342) by two kernels:
+//
+//  A  attn_scores_topk_kernel : S = Q K^T on tcgen05 (split-bf16 operands, 3 products per K-chunk, fp32 TMEM
+//     accumulators), for one tile of 128 queries (8 rows x 16 cols of the feature map) against 128-key tiles
+//     (8 x 16) that intersect the query tile's neighbour window -- key tiles outside the window are never loaded.
+//     Each epilogue thread owns one query row of the accumulator and keeps a sorted top-k (value, key index) list
+//     in registers; the radius mask is an integer predicate on (dy, dx), the HW x T*HW affinity never exists in
+//     memory.  Work is split into units (query tile, key frame, window slice) so that all 148 SMs are busy even
+//     for a single frame pair; every unit writes its partial top-k.
+//  B  attn_merge_propagate_kernel : per query, merge the partial lists, scale by 1/temperature, softmax over
+//     the k survivors (or clamp^2, mode 'cosine'), gather the k value vectors and write the propagated labels.
+//
+// plus the feature preparation (L2 normalisation over channels fused with the NCHW->split-NHWC transpose,
+// local_attention.py:277-279).
+#include <math.h>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace vfs {
+
+constexpr int kQTileW = 16, kQTileH = 8;  // 128 queries / keys per tile
+constexpr int kAttnStages = 3;
+constexpr int kAttnStageBytes = 4 * 16384;  // Q hi, Q lo, K hi, K lo (each 128 rows x 128 B)
+constexpr int kAttnSmemBytes = kAttnStages * kAttnStageBytes + 256 + 1024;
+constexpr int kAttnThreads = 192;
+constexpr int kMaxKeyFrames = 32;
+
+struct alignas(64) AttnParams {
+  CUtensorMap tmap_q;  // {C, W, H, 1, 2}
+  CUtensorMap tmap_k;  // {C, W, H, frames, 2}
+  int H, W, kchunks;
+  int T;  // number of key frame slots
+  int frame_ids[kMaxKeyFrames];
+  int mask_mode;  // 0 none, 1 circle (dy^2+dx^2 < ry^2), 2 square (|dy| <= ry, |dx| <= rx)
+  int ry, rx;
+  int non_mask_len;
+  int q_tiles_x, q_tiles_y, splits;
+  int num_units;
+  float* part_val;  // [T*splits][KMAX][HW]
+  int* part_idx;
+};
+
+struct KeyWindow {
+  int wy0, wx0, ny, nx;  // origin and number of key tiles
+};
+
+__device__ __forceinline__ KeyWindow key_window(const AttnParams& p, int qy0, int qx0, int t) {
+  KeyWindow w;
+  int wy1, wx1;
+  if (p.mask_mode == 0 || t < p.non_mask_len) {
+    w.wy0 = 0; w.wx0 = 0; wy1 = p.H - 1; wx1 = p.W - 1;
+  } else {
+    const int ey = (p.mask_mode == 1) ? p.ry - 1 : p.ry;
+    const int ex = (p.mask_mode == 1) ? p.ry - 1 : p.rx;
+    w.wy0 = max(0, qy0 - ey);
+    w.wx0 = max(0, qx0 - ex);
+    wy1 = min(p.H - 1, min(qy0 + kQTileH - 1, p.H - 1) + ey);
+    wx1 = min(p.W - 1, min(qx0 + kQTileW - 1, p.W - 1) + ex);
+  }
+  const int wh = wy1 - w.wy0 + 1, ww = wx1 - w.wx0 + 1;
+  w.ny = wh > 0 ? (wh + kQTileH - 1) / kQTileH : 0;
+  w.nx = ww > 0 ? (ww + kQTileW - 1) / kQTileW : 0;
+  if (w.ny == 0 || w.nx == 0) {
+    w.ny = 0;
+    w.nx = 1;  // keeps j / nx well defined for the (empty) tile loop
+  }
+  return w;
+}
+
+struct UnitInfo {
+  int qy0, qx0, t, j_begin, j_end;
+  KeyWindow w;
+};
+
+__device__ __forceinline__ UnitInfo decode_unit(const AttnParams& p, int unit) {
+  UnitInfo u;
+  const int s = unit % p.splits;
+  const int r = unit / p.splits;
+  u.t = r % p.T;
+  const int qt = r / p.T;
+  u.qx0 = (qt % p.q_tiles_x) * kQTileW;
+  u.qy0 = (qt / p.q_tiles_x) * kQTileH;
+  u.w = key_window(p, u.qy0, u.qx0, u.t);
+  const int n = u.w.ny * u.w.nx;
+  const int per = (n + p.splits - 1) / p.splits;
+  u.j_begin = min(n, s * per);
+  u.j_end = min(n, u.j_begin + per);
+  return u;
+}
+
+template <int KMAX>
+__device__ __forceinline__ void topk_insert(float (&v)[KMAX], int (&id)[KMAX], float x, int idx) {
+#pragma unroll
+  for (int i = KMAX - 1; i >= 0; --i) {
+    if (i > 0 && x > v[i - 1]) {
+      v[i] = v[i - 1];
+      id[i] = id[i - 1];
+    } else if (x > v[i]) {
+      v[i] = x;
+      id[i] = idx;
+    }
+  }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kAttnStages * kAttnStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kAttnStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kAttnStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kAttnStages + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kAttnStages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 256;  // 2 accumulator stages x 128 key columns
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_q);
+    tma_prefetch_desc(&p.tmap_k);
+    for (int s = 0; s < kAttnStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_addr, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      const UnitInfo u = decode_unit(p, unit);
+      const int frame = p.frame_ids[u.t];
+      for (int j = u.j_begin; j < u.j_end; ++j) {
+        const int ky0 = u.w.wy0 + (j / u.w.nx) * kQTileH;
+        const int kx0 = u.w.wx0 + (j % u.w.nx) * kQTileW;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
+          if (lane == 0) {
+            const uint32_t sq = smem_base + stage * kAttnStageBytes;
+            mbar_arrive_expect_tx(full_bar(stage), kAttnStageBytes);
+            tma_load_5d(sq, &p.tmap_q, full_bar(stage), kc * 64, u.qx0, u.qy0, 0, 0);
+            tma_load_5d(sq + 32768, &p.tmap_k, full_bar(stage), kc * 64, kx0, ky0, frame, 0);
+          }
+          __syncwarp();
+          if (++stage == kAttnStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 128);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      const UnitInfo u = decode_unit(p, unit);
+      for (int j = u.j_begin; j < u.j_end; ++j) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u, 200 + as);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 128;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(full_bar(stage), phase, 300 + stage);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t q_hi = smem_base + stage * kAttnStageBytes, q_lo = q_hi + 16384;
+            const uint32_t k_hi = q_hi + 32768, k_lo = k_hi + 16384;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t koff = k * 32;
+              const uint64_t dq_hi = umma_desc_sw128_kmajor(q_hi + koff), dq_lo = umma_desc_sw128_kmajor(q_lo + koff);
+              const uint64_t dk_hi = umma_desc_sw128_kmajor(k_hi + koff), dk_lo = umma_desc_sw128_kmajor(k_lo + koff);
+              umma_bf16(d_tmem, dq_lo, dk_hi, idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, dq_hi, dk_lo, idesc, 1u);
+              umma_bf16(d_tmem, dq_hi, dk_hi, idesc, 1u);
+            }
+            umma_commit(empty_bar(stage));
+            if (kc == p.kchunks - 1) umma_commit(tfull_bar(as));
+          }
+          __syncwarp();
+          if (++stage == kAttnStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ======================= epilogue: per-query running top-k =======================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int dqx = row % kQTileW, dqy = row / kQTileW;
+    const int HW = p.H * p.W;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      const UnitInfo u = decode_unit(p, unit);
+      const int qy = u.qy0 + dqy, qx = u.qx0 + dqx;
+      const bool q_valid = (qy < p.H) && (qx < p.W);
+      const bool masked = (p.mask_mode != 0) && (u.t >= p.non_mask_len);
+      const int r2 = p.ry * p.ry;
+      float tv[KMAX];
+      int ti[KMAX];
+#pragma unroll
+      for (int i = 0; i < KMAX; ++i) {
+        tv[i] = -INFINITY;
+        ti[i] = 0;
+      }
+      for (int j = u.j_begin; j < u.j_end; ++j) {
+        const int ky0 = u.w.wy0 + (j / u.w.nx) * kQTileH;
+        const int kx0 = u.w.wx0 + (j % u.w.nx) * kQTileW;
+        mbar_wait(tfull_bar(as), aphase, 400 + as);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 128;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(t_row + c0, acc);
+          tmem_ld_wait();
+          // 32 columns = 2 key rows x 16 key columns
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int ky = ky0 + ((c0 + jj) >> 4);
+            const int kx = kx0 + ((c0 + jj) & 15);
+            const int dy = ky - qy, dx = kx - qx;
+            bool ok = (ky < p.H) && (kx < p.W);
+            if (masked) {
+              ok = ok && ((p.mask_mode == 1) ? (dy * dy + dx * dx < r2) : (abs(dy) <= p.ry && abs(dx) <= p.rx));
+            }
+            const float s = __uint_as_float(acc[jj]);
+            if (ok && s > tv[KMAX - 1]) topk_insert<KMAX>(tv, ti, s, u.t * HW + ky * p.W + kx);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1u;
+        }
+      }
+      if (q_valid) {
+        const int slot = u.t * p.splits + (unit % p.splits);
+        const size_t base = static_cast<size_t>(slot) * KMAX * HW + static_cast<size_t>(qy) * p.W + qx;
+#pragma unroll
+        for (int i = 0; i < KMAX; ++i) {
+          p.part_val[base + static_cast<size_t>(i) * HW] = tv[i];
+          p.part_idx[base + static_cast<size_t>(i) * HW] = ti[i];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel B: merge partial lists, softmax over the k survivors, gather values.
+// ------------------------------------------------------------------------------------------------
+struct MergeParams {
+  const float* part_val;
+  const int* part_idx;
+  int slots, HW, topk, mode;  // mode 0 softmax, 1 cosine
+  float temperature;
+  const float* values;  // element (slot t, channel c, pos) at values[frame_ids[t]*v_frame_stride + c*v_chan_stride + pos]
+  long long v_frame_stride, v_chan_stride;
+  int Cv;
+  int frame_ids[kMaxKeyFrames];
+  float* out;      // [Cv][HW]
+  float* out_val;  // optional [topk][HW] (affinity / temperature of the selected keys)
+  int* out_idx;    // optional [topk][HW] (flat key index slot*HW + pos)
+};
+
+template <int KMAX>
+__global__ void attn_merge_propagate_kernel(const MergeParams p) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= p.HW) return;
+  float tv[KMAX];
+  int ti[KMAX];
+#pragma unroll
+  for (int i = 0; i < KMAX; ++i) {
+    tv[i] = -INFINITY;
+    ti[i] = 0;
+  }
+  for (int s = 0; s < p.slots; ++s) {
+    const size_t base = static_cast<size_t>(s) * KMAX * p.HW + qi;
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      const float v = p.part_val[base + static_cast<size_t>(i) * p.HW];
+      if (v > tv[KMAX - 1]) topk_insert<KMAX>(tv, ti, v, p.part_idx[base + static_cast<size_t>(i) * p.HW]);
+    }
+  }
+  float w[KMAX];
+  float wsum = 0.0f;
+  const float vmax = __fdiv_rn(tv[0], p.temperature);
+#pragma unroll
+  for (int i = 0; i < KMAX; ++i) {
+    const float a = __fdiv_rn(tv[i], p.temperature);  // reference divides the whole affinity by temperature
+    if (i < p.topk) {
+      if (p.out_val) p.out_val[static_cast<size_t>(i) * p.HW + qi] = a;
+      if (p.out_idx) p.out_idx[static_cast<size_t>(i) * p.HW + qi] = ti[i];
+      if (p.mode == 0) {
+        w[i] = expf(a - vmax);
+      } else {
+        const float c = fmaxf(a, 0.0f);
+        w[i] = c * c;
+      }
+      wsum += w[i];
+    } else {
+      w[i] = 0.0f;
+    }
+  }
+  const float inv = (p.mode == 0) ? __fdiv_rn(1.0f, wsum) : 1.0f;
+  for (int c = 0; c < p.Cv; ++c) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      if (i < p.topk) {
+        const int slot = ti[i] / p.HW, pos = ti[i] - slot * p.HW;
+        const float val = p.values[p.frame_ids[slot] * p.v_frame_stride + c * p.v_chan_stride + pos];
+        acc = fmaf(val, (p.mode == 0) ? w[i] * inv : w[i], acc);
+      }
+    }
+    p.out[static_cast<size_t>(c) * p.HW + qi] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Feature preparation: optional L2 normalisation over channels (F.normalize, eps 1e-12) fused with the
+// conversion to split NHWC.
+// ------------------------------------------------------------------------------------------------
+__global__ void pixel_inv_norm_nchw_kernel(const float* __restrict__ in, float* __restrict__ inv, int C, int HW) {
+  const int n = blockIdx.y;
+  const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pidx >= HW) return;
+  const float* src = in + static_cast<size_t>(n) * C * HW + pidx;
+  float s = 0.0f;
+  for (int c = 0; c < C; ++c) {
+    const float x = src[static_cast<size_t>(c) * HW];
+    s = fmaf(x, x, s);
+  }
+  inv[static_cast<size_t>(n) * HW + pidx] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+}
+
+__global__ void nchw_to_split_scaled_kernel(const float* __restrict__ in, const float* __restrict__ pix_scale,
+                                            __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                            int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* src = in + static_cast<size_t>(n) * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, pp = p0 + threadIdx.x;
+    float v = 0.0f;
+    if (c < C && pp < HW) {
+      v = src[static_cast<size_t>(c) * HW + pp];
+      if (pix_scale) v *= pix_scale[static_cast<size_t>(n) * HW + pp];
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, c = c0 + threadIdx.x;
+    if (pp < HW && c < C) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(tile[threadIdx.x][i], hi, lo);
+      const size_t o = (static_cast<size_t>(n) * HW + pp) * C + c;
+      out_hi[o] = hi;
+      out_lo[o] = lo;
+    }
+  }
+}
+
+// split NHWC -> L2-normalised split NHWC; one warp per pixel, C multiple of 64.
+__global__ void normalize_split_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                       size_t num_pixels, int C) {
+  const size_t pix = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pix >= num_pixels) return;
+  const size_t base = pix * C;
+  float s = 0.0f;
+  for (int c = lane * 2; c < C; c += 64) {
+    const uint32_t h = *reinterpret_cast<const uint32_t*>(in_hi + base + c);
+    const uint32_t l = *reinterpret_cast<const uint32_t*>(in_lo + base + c);
+    const float a = bf16_lo_to_float(h) + bf16_lo_to_float(l);
+    const float b = bf16_hi_to_float(h) + bf16_hi_to_float(l);
+    s = fmaf(a, a, s);
+    s = fmaf(b, b, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  for (int c = lane * 2; c < C; c += 64) {
+    const uint32_t h = *reinterpret_cast<const uint32_t*>(in_hi + base + c);
+    const uint32_t l = *reinterpret_cast<const uint32_t*>(in_lo + base + c);
+    const float a = (bf16_lo_to_float(h) + bf16_lo_to_float(l)) * inv;
+    const float b = (bf16_hi_to_float(h) + bf16_hi_to_float(l)) * inv;
+    __nv_bfloat16 ah, al, bh, bl;
+    split_bf16(a, ah, al);
+    split_bf16(b, bh, bl);
+    *reinterpret_cast<uint32_t*>(out_hi + base + c) = pack_bf16x2(ah, bh);
+    *reinterpret_cast<uint32_t*>(out_lo + base + c) = pack_bf16x2(al, bl);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
+                      int normalize, cudaStream_t s) {
+  VFS_REQUIRE(in_nchw && out_split, VFS_EINVAL, "features_to_split: null argument");
+  VFS_REQUIRE(!normalize || inv_norm_ws, VFS_EINVAL, "features_to_split: normalisation needs a workspace");
+  VFS_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, VFS_ESHAPE, "features_to_split: empty tensor");
+  const int HW = H * W;
+  float* inv = reinterpret_cast<float*>(inv_norm_ws);
+  if (normalize) {
+    dim3 grid((HW + 127) / 128, N);
+    pixel_inv_norm_nchw_kernel<<<grid, 128, 0, s>>>(in_nchw, inv, C, HW);
+    VFS_CUDA_OK(cudaGetLastError());
+  }
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out_split);
+  __nv_bfloat16* lo = hi + static_cast<size_t>(N) * HW * C;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  nchw_to_split_scaled_kernel<<<grid, block, 0, s>>>(in_nchw, normalize ? inv : nullptr, hi, lo, C, HW);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+int normalize_split(const void* in_split, void* out_split, long long num_pixels, int C, long long in_plane_stride,
+                    long long out_plane_stride, cudaStream_t s) {
+  VFS_REQUIRE(in_split && out_split, VFS_EINVAL, "normalize_split: null argument");
+  VFS_REQUIRE(C % 64 == 0 && num_pixels > 0, VFS_ESHAPE, "normalize_split: C must be a multiple of 64");
+  const __nv_bfloat16* ih = reinterpret_cast<const __nv_bfloat16*>(in_split);
+  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(out_split);
+  const long long threads = num_pixels * 32;
+  const int blocks = static_cast<int>((threads + 255) / 256);
+  normalize_split_kernel<<<blocks, 256, 0, s>>>(ih, ih + in_plane_stride, oh, oh + out_plane_stride,
+                                                static_cast<size_t>(num_pixels), C);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+static int attn_kmax(int topk) { return topk <= 10 ? 10 : 16; }
+
+static int attn_splits(const VfsAttnDesc* d) {
+  const int q_tiles = ((d->W + kQTileW - 1) / kQTileW) * ((d->H + kQTileH - 1) / kQTileH);
+  const int target = 2 * device_sm_count();
+  int splits = (target + q_tiles * d->T - 1) / (q_tiles * d->T);
+  if (splits < 1) splits = 1;
+  if (splits > 8) splits = 8;
+  return splits;
+}
+
+size_t attention_workspace_bytes(const VfsAttnDesc* d) {
+  if (!d || d->T <= 0) return 0;
+  const size_t slots = static_cast<size_t>(d->T) * attn_splits(d);
+  return slots * attn_kmax(d->topk) * d->H * d->W * (sizeof(float) + sizeof(int));
+}
+
+int masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_plane_stride, const void* k_bank_split,
+                     long long k_plane_stride, int k_bank_frames, const int* key_frame_ids, const float* values,
+                     long long v_frame_stride, long long v_chan_stride, float* out, float* out_topk_val,
+                     int* out_topk_idx, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  VFS_REQUIRE(d && q_split && k_bank_split && key_frame_ids && values && out && workspace, VFS_EINVAL,
+              "masked_attention: null argument");
+  VFS_REQUIRE(d->H > 0 && d->W > 0 && d->C > 0 && d->C % 64 == 0, VFS_ESHAPE,
+              "masked_attention: C=%d must be a positive multiple of 64", d->C);
+  VFS_REQUIRE(d->T >= 1 && d->T <= kMaxKeyFrames, VFS_ESHAPE, "masked_attention: T=%d outside [1,%d]", d->T,
+              kMaxKeyFrames);
+  VFS_REQUIRE(d->topk >= 1 && d->topk <= 16, VFS_ESHAPE, "masked_attention: topk=%d outside [1,16]", d->topk);
+  VFS_REQUIRE(d->temperature > 0.0f, VFS_EINVAL, "masked_attention: temperature must be positive");
+  VFS_REQUIRE(d->mask_mode >= 0 && d->mask_mode <= 2, VFS_EINVAL, "masked_attention: bad mask_mode");
+  VFS_REQUIRE(d->non_mask_len >= 0 && d->non_mask_len < d->T, VFS_EINVAL, "masked_attention: bad non_mask_len");
+  VFS_REQUIRE(d->Cv >= 1, VFS_ESHAPE, "masked_attention: Cv must be >= 1");
+  VFS_REQUIRE(workspace_bytes >= attention_workspace_bytes(d), VFS_EINVAL, "masked_attention: workspace too small");
+  for (int t = 0; t < d->T; ++t)
+    VFS_REQUIRE(key_frame_ids[t] >= 0 && key_frame_ids[t] < k_bank_frames, VFS_EINVAL,
+                "masked_attention: key frame id %d out of range", key_frame_ids[t]);
+
+  const int HW = d->H * d->W;
+  const int KMAX = attn_kmax(d->topk);
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = d->H; p.W = d->W; p.kchunks = d->C / 64; p.T = d->T;
+  for (int t = 0; t < d->T; ++t) p.frame_ids[t] = key_frame_ids[t];
+  p.mask_mode = d->mask_mode; p.ry = d->radius_y; p.rx = d->radius_x; p.non_mask_len = d->non_mask_len;
+  p.q_tiles_x = (d->W + kQTileW - 1) / kQTileW;
+  p.q_tiles_y = (d->H + kQTileH - 1) / kQTileH;
+  p.splits = attn_splits(d);
+  p.num_units = p.q_tiles_x * p.q_tiles_y * d->T * p.splits;
+  const size_t slots = static_cast<size_t>(d->T) * p.splits;
+  p.part_val = reinterpret_cast<float*>(workspace);
+  p.part_idx = reinterpret_cast<int*>(p.part_val + slots * KMAX * HW);
+  {
+    const uint64_t dims[5] = {static_cast<uint64_t>(d->C), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H), 1, 2};
+    const uint64_t strides[4] = {static_cast<uint64_t>(d->C) * 2, static_cast<uint64_t>(d->W) * d->C * 2,
+                                 static_cast<uint64_t>(HW) * d->C * 2, static_cast<uint64_t>(q_plane_stride) * 2};
+    const uint32_t box[5] = {64, kQTileW, kQTileH, 1, 2};
+    int rc = make_tmap_bf16_sw128(&p.tmap_q, q_split, 5, dims, strides, box);
+    if (rc != VFS_OK) return rc;
+  }
+  {
+    const uint64_t dims[5] = {static_cast<uint64_t>(d->C), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+                              static_cast<uint64_t>(k_bank_frames), 2};
+    const uint64_t strides[4] = {static_cast<uint64_t>(d->C) * 2, static_cast<uint64_t>(d->W) * d->C * 2,
+                                 static_cast<uint64_t>(HW) * d->C * 2, static_cast<uint64_t>(k_plane_stride) * 2};
+    const uint32_t box[5] = {64, kQTileW, kQTileH, 1, 2};
+    int rc = make_tmap_bf16_sw128(&p.tmap_k, k_bank_split, 5, dims, strides, box);
+    if (rc != VFS_OK) return rc;
+  }
+  const int sms = device_sm_count();
+  const int grid = p.num_units < sms ? p.num_units : sms;
+  static bool configured = false;
+  if (!configured) {
+    VFS_CUDA_OK(cudaFuncSetAttribute(attn_scores_topk_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kAttnSmemBytes));
+    VFS_CUDA_OK(cudaFuncSetAttribute(attn_scores_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kAttnSmemBytes));
+    configured = true;
+  }
+  if (KMAX == 10) attn_scores_topk_kernel<10><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
+  else attn_scores_topk_kernel<16><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
+  VFS_CUDA_OK(cudaGetLastError());
+
+  MergeParams m;
+  memset(&m, 0, sizeof(m));
+  m.part_val = p.part_val; m.part_idx = p.part_idx;
+  m.slots = static_cast<int>(slots); m.HW = HW; m.topk = d->topk; m.mode = d->mode; m.temperature = d->temperature;
+  m.values = values; m.v_frame_stride = v_frame_stride; m.v_chan_stride = v_chan_stride; m.Cv = d->Cv;
+  for (int t = 0; t < d->T; ++t) m.frame_ids[t] = key_frame_ids[t];
+  m.out = out; m.out_val = out_topk_val; m.out_idx = out_topk_idx;
+  const int blocks = (HW + 127) / 128;
+  if (KMAX == 10) attn_merge_propagate_kernel<10><<<blocks, 128, 0, stream>>>(m);
+  else attn_merge_propagate_kernel<16><<<blocks, 128, 0, stream>>>(m);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+}  // namespace vfs

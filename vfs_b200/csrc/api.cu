@@ -91,6 +91,26 @@ size_t stem_workspace_bytes(int N, int H, int W);
 int stem_forward(const float* in, const float* weight, const float* scale, const float* shift, void* out_split,
                  void* workspace, int N, int H, int W, cudaStream_t s);
 
+int features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
+                      int normalize, cudaStream_t s);
+int normalize_split(const void* in_split, void* out_split, long long num_pixels, int C, long long in_plane_stride,
+                    long long out_plane_stride, cudaStream_t s);
+size_t attention_workspace_bytes(const VfsAttnDesc* d);
+int masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_plane_stride, const void* k_bank_split,
+                     long long k_plane_stride, int k_bank_frames, const int* key_frame_ids, const float* values,
+                     long long v_frame_stride, long long v_chan_stride, float* out, float* out_topk_val,
+                     int* out_topk_idx, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int global_avg_pool_nchw(const float* in, float* out, int B, int C, int HW, cudaStream_t s);
+int linear_forward(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, cudaStream_t s);
+int bn1d_act(float* y, int M, int N, const float* gamma, const float* beta, float* running_mean, float* running_var,
+             float eps, float momentum, int training, int relu, cudaStream_t s);
+int relu_inplace(float* y, size_t n, cudaStream_t s);
+int cosine_sim_loss(const float* p, const float* z, float* loss, int B, int D, int with_norm, int negative,
+                    cudaStream_t s);
+int nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, cudaStream_t s);
+int xcorr_nhwc(const float* z, const float* x, float* out, int nz, int nx, int C, int hz, int wz, int h, int w,
+               float out_scale, cudaStream_t s);
+
 }  // namespace vfs
 
 extern "C" {
@@ -130,6 +150,47 @@ int vfs_debug_conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const
                                const float* shift, const void* residual_split, float* out_f32_nhwc,
                                vfs_stream_t s) {
   return vfs::conv_bn_act_simt(d, in_split, w_split, scale, shift, residual_split, out_f32_nhwc, s);
+}
+
+int vfs_features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
+                          int normalize, vfs_stream_t s) {
+  return vfs::features_to_split(in_nchw, out_split, inv_norm_ws, N, C, H, W, normalize, s);
+}
+int vfs_normalize_split(const void* in_split, void* out_split, long long num_pixels, int C,
+                        long long in_plane_stride, long long out_plane_stride, vfs_stream_t s) {
+  return vfs::normalize_split(in_split, out_split, num_pixels, C, in_plane_stride, out_plane_stride, s);
+}
+size_t vfs_attention_workspace_bytes(const VfsAttnDesc* d) { return vfs::attention_workspace_bytes(d); }
+int vfs_masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_plane_stride,
+                         const void* k_bank_split, long long k_plane_stride, int k_bank_frames,
+                         const int32_t* key_frame_ids, const float* values, long long v_frame_stride,
+                         long long v_chan_stride, float* out, float* out_topk_val, int32_t* out_topk_idx,
+                         void* workspace, size_t workspace_bytes, vfs_stream_t s) {
+  return vfs::masked_attention(d, q_split, q_plane_stride, k_bank_split, k_plane_stride, k_bank_frames,
+                               key_frame_ids, values, v_frame_stride, v_chan_stride, out, out_topk_val, out_topk_idx,
+                               workspace, workspace_bytes, s);
+}
+int vfs_global_avg_pool(const float* in_nchw, float* out, int B, int C, int HW, vfs_stream_t s) {
+  return vfs::global_avg_pool_nchw(in_nchw, out, B, C, HW, s);
+}
+int vfs_linear(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, vfs_stream_t s) {
+  return vfs::linear_forward(x, W, bias, y, M, N, K, s);
+}
+int vfs_bn1d_act(float* y, int M, int N, const float* gamma, const float* beta, float* running_mean,
+                 float* running_var, float eps, float momentum, int training, int relu, vfs_stream_t s) {
+  return vfs::bn1d_act(y, M, N, gamma, beta, running_mean, running_var, eps, momentum, training, relu, s);
+}
+int vfs_relu(float* y, size_t n, vfs_stream_t s) { return vfs::relu_inplace(y, n, s); }
+int vfs_cosine_sim_loss(const float* p, const float* z, float* loss, int B, int D, int with_norm, int negative,
+                        vfs_stream_t s) {
+  return vfs::cosine_sim_loss(p, z, loss, B, D, with_norm, negative, s);
+}
+int vfs_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, vfs_stream_t s) {
+  return vfs::nchw_to_nhwc_f32(in, out, N, C, H, W, s);
+}
+int vfs_xcorr_nhwc(const float* z, const float* x, float* out, int nz, int nx, int C, int hz, int wz, int h, int w,
+                   float out_scale, vfs_stream_t s) {
+  return vfs::xcorr_nhwc(z, x, out, nz, nx, C, hz, wz, h, w, out_scale, s);
 }
 
 }  // extern "C"

@@ -105,3 +105,205 @@ def stem_forward(x, weight, scale, shift):
     check(nat.lib().vfs_stem_forward(ptr(x), ptr(weight), ptr(scale), ptr(shift), ptr(out), ptr(ws), N, H, W,
                                      current_stream()), 'stem_forward')
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SimSiam head / loss
+# ---------------------------------------------------------------------------------------------------------
+def _f32c(t, name):
+    _require_cuda(t, name)
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'{name} must be float32')
+    return t
+
+
+def global_avg_pool(x):
+    """[B,C,h,w] fp32 NCHW -> [B,C]."""
+    x = _f32c(x.contiguous(), 'x')
+    B, C = x.shape[:2]
+    HW = x[0, 0].numel()
+    out = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    check(nat.lib().vfs_global_avg_pool(ptr(x), ptr(out), B, C, HW, current_stream()), 'global_avg_pool')
+    return out
+
+
+def linear_bn_act(x, lin, bn=None, relu=False):
+    """y = relu?(bn?(x @ W^T + b)) with ``lin`` an nn.Linear and ``bn`` a BatchNorm1d/SyncBatchNorm module (its
+    running statistics are updated in training mode exactly like torch does, single process)."""
+    x = _f32c(x.contiguous(), 'x')
+    M, K = x.shape
+    N = lin.out_features
+    w = lin.weight.detach()
+    _f32c(w, 'weight')
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    b = lin.bias.detach() if lin.bias is not None else None
+    check(nat.lib().vfs_linear(ptr(x), ptr(w.contiguous()), ptr(b), ptr(y), M, N, K, current_stream()), 'linear')
+    if bn is not None:
+        training = bn.training or (bn.running_mean is None)
+        if training and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1 and isinstance(bn, torch.nn.SyncBatchNorm):
+            raise NotImplementedError('vfs_b200: cross-rank SyncBN statistics are not implemented yet')
+        momentum = 0.1 if bn.momentum is None else bn.momentum
+        check(nat.lib().vfs_bn1d_act(ptr(y), M, N, ptr(bn.weight.detach()) if bn.affine else None,
+                                     ptr(bn.bias.detach()) if bn.affine else None, ptr(bn.running_mean),
+                                     ptr(bn.running_var), float(bn.eps), float(momentum), int(training), int(relu),
+                                     current_stream()), 'bn1d_act')
+        if training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+    elif relu:
+        check(nat.lib().vfs_relu(ptr(y), y.numel(), current_stream()), 'relu')
+    return y
+
+
+def cosine_sim_loss(p, z, with_norm=True, negative=False):
+    """Per-sample 2 - 2*cos(p, z) (or -cos) for [B, D] inputs."""
+    p = _f32c(p.contiguous(), 'cls_score')
+    z = _f32c(z.contiguous(), 'label')
+    assert p.shape == z.shape and p.ndim == 2, (p.shape, z.shape)
+    B, D = p.shape
+    loss = torch.empty((B, ), dtype=torch.float32, device=p.device)
+    check(nat.lib().vfs_cosine_sim_loss(ptr(p), ptr(z), ptr(loss), B, D, int(with_norm), int(negative),
+                                        current_stream()), 'cosine_sim_loss')
+    return loss
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SiamFC
+# ---------------------------------------------------------------------------------------------------------
+def nchw_to_nhwc(x):
+    x = _f32c(x.contiguous(), 'x')
+    N, C, H, W = x.shape
+    out = torch.empty((N, H, W, C), dtype=torch.float32, device=x.device)
+    check(nat.lib().vfs_nchw_to_nhwc_f32(ptr(x), ptr(out), N, C, H, W, current_stream()), 'nchw_to_nhwc_f32')
+    return out
+
+
+def xcorr_nhwc(z, x, out_scale):
+    """z [nz,hz,wz,C], x [nx,h,w,C] fp32 NHWC -> [nx,1,ho,wo]."""
+    _f32c(z, 'z')
+    _f32c(x, 'x')
+    nz, hz, wz, C = z.shape
+    nx, h, w, C2 = x.shape
+    assert C == C2
+    out = torch.empty((nx, 1, h - hz + 1, w - wz + 1), dtype=torch.float32, device=x.device)
+    check(nat.lib().vfs_xcorr_nhwc(ptr(z), ptr(x), ptr(out), nz, nx, C, hz, wz, h, w, float(out_scale),
+                                   current_stream()), 'xcorr_nhwc')
+    return out
+
+
+def xcorr(z, x, out_scale):
+    """NCHW inputs (reference SiamFC.forward signature)."""
+    return xcorr_nhwc(nchw_to_nhwc(z), nchw_to_nhwc(x), out_scale)
+
+
+def conv_stack_nhwc(x, convs):
+    """Apply a Sequential of biased 1x1 nn.Conv2d (SiamConvFC adapters, heads.py:40-48) through the tcgen05 conv
+    kernel; NCHW fp32 in, NHWC fp32 out."""
+    mods = list(convs)
+    if not mods:
+        return nchw_to_nhwc(x)
+    xs = to_split(_f32c(x.contiguous(), 'x'))
+    out32 = None
+    for i, m in enumerate(mods):
+        assert isinstance(m, torch.nn.Conv2d) and m.kernel_size == (1, 1) and m.stride == (1, 1), \
+            'vfs_b200 SiamConvFC supports 1x1 adapters (the reference default)'
+        w = pack_conv_weight(m.weight.detach().float().contiguous())
+        scale = torch.ones(m.out_channels, dtype=torch.float32, device=x.device)
+        shift = (m.bias.detach().float() if m.bias is not None else torch.zeros_like(scale)).contiguous()
+        last = i == len(mods) - 1
+        xs, out32 = conv_bn_act(xs, w, scale, shift, 1, 1, 1, relu=False, want_split=not last, want_f32=last)
+    return out32
+
+
+# ---------------------------------------------------------------------------------------------------------
+# restricted attention (DAVIS label propagation)
+# ---------------------------------------------------------------------------------------------------------
+def features_to_split(x, normalize=True):
+    """NCHW fp32 [N,C,H,W] -> (optionally L2-normalised over C) split NHWC [2,N,H,W,C]."""
+    x = _f32c(x.contiguous(), 'x')
+    N, C, H, W = x.shape
+    out = torch.empty((2, N, H, W, C), dtype=torch.bfloat16, device=x.device)
+    ws = torch.empty((N * H * W, ), dtype=torch.float32, device=x.device) if normalize else None
+    check(nat.lib().vfs_features_to_split(ptr(x), ptr(out), ptr(ws), N, C, H, W, int(normalize), current_stream()),
+          'features_to_split')
+    return out
+
+
+def normalize_split(xs, out=None):
+    """split NHWC [2,N,H,W,C] -> L2-normalised over C (into ``out`` [2,N',H,W,C] slice-compatible buffer)."""
+    _require_cuda(xs, 'xs')
+    _, N, H, W, C = xs.shape
+    if out is None:
+        out = torch.empty_like(xs)
+    check(nat.lib().vfs_normalize_split(ptr(xs), ptr(out), N * H * W, C, xs.stride(0), out.stride(0),
+                                        current_stream()), 'normalize_split')
+    return out
+
+
+_MASK_MODES = {None: 0, 'circle': 1, 'square': 2}
+
+
+def attention_bank(q_split, k_bank, key_frame_ids, values, v_frame_stride, v_chan_stride, Cv, mask, temperature,
+                   topk, non_mask_len=0, mode='softmax', return_topk=False):
+    """Core call: ``q_split`` [2,1,H,W,C] view (may be a slice of the bank), ``k_bank`` [2,F,H,W,C] normalised split
+    bank, ``key_frame_ids`` python list of bank frames, ``values`` fp32 tensor addressed by the given strides.
+    Returns out [Cv, H*W] (and top-k values / indices [topk, H*W])."""
+    from ._native import VfsAttnDesc
+    _require_cuda(k_bank, 'k_bank')
+    assert q_split.dtype == torch.bfloat16 and k_bank.dtype == torch.bfloat16
+    _, F, H, W, C = k_bank.shape
+    assert q_split.shape[2:] == (H, W, C), (q_split.shape, k_bank.shape)
+    assert q_split[0].is_contiguous() and k_bank[0].is_contiguous()
+    T = len(key_frame_ids)
+    d = VfsAttnDesc(H=H, W=W, C=C, Cv=Cv, T=T, topk=topk,
+                    mask_mode=_MASK_MODES[mask.mode if mask is not None else None],
+                    radius_y=mask.radius_y if mask is not None else 0,
+                    radius_x=mask.radius_x if mask is not None else 0, non_mask_len=non_mask_len,
+                    mode=0 if mode == 'softmax' else 1, temperature=float(temperature))
+    ws_bytes = nat.lib().vfs_attention_workspace_bytes(ctypes.byref(d))
+    ws = torch.empty((ws_bytes, ), dtype=torch.uint8, device=k_bank.device)
+    out = torch.empty((Cv, H * W), dtype=torch.float32, device=k_bank.device)
+    tv = torch.empty((topk, H * W), dtype=torch.float32, device=k_bank.device) if return_topk else None
+    ti = torch.empty((topk, H * W), dtype=torch.int32, device=k_bank.device) if return_topk else None
+    ids = (ctypes.c_int32 * T)(*[int(i) for i in key_frame_ids])
+    check(nat.lib().vfs_masked_attention(ctypes.byref(d), ptr(q_split), q_split.stride(0), ptr(k_bank),
+                                         k_bank.stride(0), F, ids, ptr(values), int(v_frame_stride),
+                                         int(v_chan_stride), ptr(out), ptr(tv), ptr(ti), ptr(ws), ws_bytes,
+                                         current_stream()), 'masked_attention')
+    if return_topk:
+        return out, tv, ti
+    return out
+
+
+def masked_attention(query, key, value, mask, temperature, topk, normalize=True, non_mask_len=0, mode='softmax',
+                     return_topk=False):
+    """Reference-shaped call: query [N,C,H,W], key [N,C,T,H,W], value [N,Cv,T,H,W] fp32 CUDA -> [N,Cv,H,W]."""
+    for t, n in ((query, 'query'), (key, 'key'), (value, 'value')):
+        _require_cuda(t, n)
+    N, C, H, W = query.shape
+    T, Cv = key.shape[2], value.shape[1]
+    assert key.shape[3:] == (H, W), 'vfs_b200: query and key feature maps must have the same size'
+    HW = H * W
+    outs, tvs, tis = [], [], []
+    for b in range(N):
+        qs = features_to_split(query[b:b + 1].float(), normalize)                       # [2,1,H,W,C]
+        ks = features_to_split(key[b].float().transpose(0, 1).contiguous(), normalize)  # [2,T,H,W,C]
+        v = value[b].float().contiguous()                                               # [Cv,T,H,W]
+        r = attention_bank(qs, ks, list(range(T)), v, HW, T * HW, Cv, mask, temperature, topk, non_mask_len, mode,
+                           return_topk)
+        if return_topk:
+            outs.append(r[0]); tvs.append(r[1]); tis.append(r[2])
+        else:
+            outs.append(r)
+    out = torch.stack(outs).reshape(N, Cv, H, W)
+    if return_topk:
+        return out, torch.stack(tvs), torch.stack(tis)
+    return out
+
+
+def dense_affinity(src_img, dst_img, temperature=1., normalize=True, softmax_dim=None, mask=None):
+    raise NotImplementedError('vfs_b200.compute_affinity: dense HWxHW affinity kernel not implemented yet')
+
+
+def propagate_dense(img, affinity, topk=None):
+    raise NotImplementedError('vfs_b200.propagate: dense propagate kernel not implemented yet')

@@ -1,0 +1,143 @@
+"""DAVIS-style label propagation tracker -- interface of mmaction/models/trackers/vanilla_tracker.py:16-206.
+
+Where the reference parks every feature map and every propagated label map on the CPU and copies ~552 MB back
+to the GPU per frame (vanilla_tracker.py:67,131-149,160), this implementation keeps a device-resident bank:
+
+  * all frame features stay on the GPU as L2-normalised split-bf16 NHWC tensors (the fused attention kernel's
+    operand format), written once per frame by the backbone engine;
+  * the propagated label maps stay on the GPU in a [T, Cv, h*w] fp32 bank; a key set {0} U [f-20, f) is a list of
+    bank frame indices handed to the kernel (no concatenation, frame 0 may appear twice exactly like the
+    reference's key set while f <= precede_frames);
+  * predictions are copied to the host once per video.
+"""
+import os.path as osp
+import tempfile
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from ..backbones import ResNet
+from ..common import pil_nearest_interpolate, spatial_neighbor, video2images
+from ..registry import TRACKERS
+from .base import BaseTracker
+
+
+@TRACKERS.register_module()
+class VanillaTracker(BaseTracker):
+    """Pixel tracker: first-frame labels are propagated frame by frame through restricted attention."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.save_np = self.test_cfg.get('save_np', False)
+
+    @property
+    def stride(self):
+        assert isinstance(self.backbone, ResNet)
+        end_index = self.backbone.original_out_indices[0]
+        return np.prod(self.backbone.strides[:end_index + 1]) * 4
+
+    def extract_feat_test(self, imgs):
+        if self.test_cfg.get('all_blocks', False):
+            raise NotImplementedError('vfs_b200 VanillaTracker: test_cfg.all_blocks is not used by any VFS config')
+        return self.extract_feat(imgs)
+
+    def extract_single_feat(self, imgs, idx):
+        feats = self.extract_feat_test(imgs)
+        return feats[idx] if isinstance(feats, (tuple, list)) else feats
+
+    # ------------------------------------------------------------------ device-resident feature bank
+    def _feature_stage(self):
+        out_indices = tuple(self.backbone.out_indices)
+        if len(out_indices) != 1:
+            raise NotImplementedError('vfs_b200 VanillaTracker: exactly one backbone out index is supported')
+        return out_indices[0]
+
+    def get_feat_bank(self, imgs):
+        """imgs [1,3,T,H,W] -> normalised split-bf16 bank [2,T,h,w,C] on the device (reference get_feats,
+        vanilla_tracker.py:55-75, chunked by ``batch_step`` frames like the reference)."""
+        assert imgs.shape[0] == 1
+        batch_step = self.test_cfg.get('batch_step', 10)
+        frames = video2images(imgs)
+        clip_len = frames.size(0)
+        stage = self._feature_stage()
+        with_norm = self.test_cfg.get('with_norm', True)
+        bank = None
+        for ptr in range(0, clip_len, batch_step):
+            xs = self.backbone.engine.forward_split(frames[ptr:ptr + batch_step], stage)  # [2,n,h,w,C]
+            if bank is None:
+                bank = torch.empty((2, clip_len) + tuple(xs.shape[2:]), dtype=torch.bfloat16, device=xs.device)
+            dst = bank[:, ptr:ptr + xs.shape[1]]
+            if with_norm:
+                ops.normalize_split(xs, out=dst)
+            else:
+                dst.copy_(xs)
+        return bank
+
+    def forward_train(self, imgs, labels=None):
+        raise NotImplementedError
+
+    def forward_test(self, imgs, ref_seg_map, img_meta):
+        """imgs [1,1,3,T,H,W], ref_seg_map [1,H,W] (label ids) -> list with one uint8 array [T,H,W]."""
+        if not imgs.is_cuda:
+            raise RuntimeError('vfs_b200 VanillaTracker needs CUDA tensors (no CPU fallback)')
+        imgs = imgs.reshape((-1, ) + imgs.shape[2:])
+        clip_len = imgs.size(2)
+        cfg = self.test_cfg
+        bank = self.get_feat_bank(imgs)                      # [2,T,h,w,C]
+        _, _, fh, fw, _ = bank.shape
+        hw = fh * fw
+        orig_hw = tuple(img_meta[0]['original_shape'][:2])
+        ref_seg_map = ref_seg_map.to(imgs.device)
+        input_onehot = ref_seg_map.ndim == 4
+        if not input_onehot:
+            resized = pil_nearest_interpolate(ref_seg_map.unsqueeze(1), size=(fh, fw)).squeeze(1).long()
+            first = F.one_hot(resized).permute(0, 3, 1, 2).float()                       # [1,Cv,h,w]
+            ref_seg_map = F.interpolate(ref_seg_map.unsqueeze(1), size=orig_hw, mode='nearest').squeeze(1)
+        else:
+            first = F.interpolate(ref_seg_map, size=(fh, fw), mode='bilinear', align_corners=False).float()
+            ref_seg_map = F.interpolate(ref_seg_map, size=orig_hw, mode='bilinear', align_corners=False)
+        cv = first.size(1)
+        seg_bank = torch.empty((clip_len, cv, hw), dtype=torch.float32, device=imgs.device)
+        seg_bank[0] = first[0].reshape(cv, hw)
+
+        neighbor_range = cfg.get('neighbor_range', None)
+        mask = spatial_neighbor(1, fh, fw, neighbor_range=neighbor_range, mode='circle') \
+            if neighbor_range is not None else None
+        with_first = cfg.get('with_first', True)
+        non_mask_len = 0 if cfg.get('with_first_neighbor', True) else 1
+
+        seg_preds = [ref_seg_map.detach()]
+        for frame_idx in range(1, clip_len):
+            key_start = max(0, frame_idx - cfg.precede_frames)
+            key_ids = list(range(key_start, frame_idx))
+            if with_first:
+                key_ids = [0] + key_ids
+            seg_logit = ops.attention_bank(bank[:, frame_idx:frame_idx + 1], bank, key_ids, seg_bank, cv * hw, hw, cv,
+                                           mask, cfg.temperature, cfg.topk, non_mask_len=non_mask_len)
+            seg_bank[frame_idx] = seg_logit
+            seg_pred = F.interpolate(seg_logit.view(1, cv, fh, fw), size=orig_hw, mode='bilinear',
+                                     align_corners=False)
+            if not input_onehot:
+                flat = seg_pred.view(1, cv, -1)
+                smin = flat.min(dim=-1)[0].view(1, cv, 1, 1)
+                smax = flat.max(dim=-1)[0].view(1, cv, 1, 1)
+                normalized = (seg_pred - smin) / (smax - smin + 1e-12)
+                seg_pred = torch.where(smax > 0, normalized, seg_pred)
+                seg_pred = seg_pred.argmax(dim=1)
+                seg_pred = F.interpolate(seg_pred.byte().unsqueeze(1), size=orig_hw, mode='nearest').squeeze(1)
+            seg_preds.append(seg_pred.detach())
+
+        # one device->host copy per video; dtype promotion mirrors np.stack over the reference's per-frame arrays
+        seg_preds = np.stack([p.cpu().numpy() for p in seg_preds], axis=1)
+        if self.save_np:
+            assert seg_preds.shape[0] == 1
+            eval_dir = '.eval'
+            import os
+            os.makedirs(eval_dir, exist_ok=True)
+            temp_file = tempfile.NamedTemporaryFile(dir=eval_dir, suffix='.npy', delete=False)
+            file_path = osp.join(eval_dir, temp_file.name)
+            np.save(file_path, seg_preds[0])
+            return [file_path]
+        return list(seg_preds)
