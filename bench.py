@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Bench of the VFS hot path on B200:  frame-pairs/sec (R50 res4 features + affinity/top-k label propagation).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One step = one batch of BASELINE configs[1]-shaped synthetic input per GPU: 8 clips x 2 frames x 256x256
+(fp32, randn).  For every clip the pair is processed like DAVIS inference does it (reference
+VanillaTracker.forward_test with a 2-frame video, tools/test.py:129-133 model): ResNet-50 with the test_cfg strides
+(1,2,1,1) up to res4 (layer3, 1024 ch, stride 8 -> 32x32) for both frames, then restricted attention
+(radius 18, top-k 10, temperature 0.07) propagating a 4-channel one-hot label map from frame 0 to frame 1.
+
+  value      device-timed (CUDA events) throughput with inputs resident in HBM; L2 flushed between steps
+  e2e        the same work through the public plugin API (build_model(VanillaTracker) -> forward_test per clip) with
+             pinned HOST inputs: H2D of the frames and D2H of the predictions inside the timed region (wall clock)
+  roofline   tcgen05 conv kernel: algorithmic conv FLOPs of a step / CUDA-event time of the conv segment
+  cpu_baseline  the CPU oracle (restatement of the reference's torch-CPU path) on a bounded sample, all host cores
+
+`--impl reference` times the reference's CPU implementation of the same step (the oracle port: /root/reference is a
+Python tree that cannot travel to the GPU box and needs mmcv; oracle/ restates it op for op and is pinned to it
+bit-exactly by tests/test_oracle_golden.py) on the host cores.
+
+Multi-GPU: one process per GPU (torchrun), clips are independent -> sharded with no data-path collective
+("weak" scaling: every rank processes its own 8 clips); NCCL is only used for the barrier and the max-over-ranks of
+the timings.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLIPS, FRAMES, SIZE = 8, 2, 256
+CV = 4
+TEST_CFG = dict(precede_frames=20, topk=10, temperature=0.07, strides=(1, 2, 1, 1), out_indices=(2, ),
+                neighbor_range=36, with_first=True, with_first_neighbor=True, output_dir='eval_results')
+BACKBONE_CFG = dict(type='ResNet', pretrained=None, depth=50, out_indices=(2, ), strides=(1, 2, 1, 1),
+                    norm_cfg=dict(type='SyncBN', requires_grad=True), norm_eval=False, zero_init_residual=True)
+WORKLOAD = 'r50_res4_feat+affinity_topk10 8clips x 2frames x 256x256 (BASELINE configs[1] shape, DAVIS test_cfg)'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='vfs_b200', choices=['vfs_b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------- helpers
+def seg_input(gen, torch):
+    """First-frame label map [1,H,W] with CV-1 rectangular objects."""
+    seg = torch.zeros(1, SIZE, SIZE)
+    for o in range(1, CV):
+        y0, x0 = 30 * o, 40 * o
+        seg[0, y0:y0 + 80, x0:x0 + 90] = o
+    return seg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        loaded = [s for s in sm if s > 0.6 * max(sm)] if sm else []
+        return dict(sm_mhz=statistics.median(loaded) if loaded else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def oracle_pair_step(torch, oracle, sd, frames, seg_onehot, mask):
+    """The reference's CPU path for ONE frame pair (oracle restatement): features of both frames, then
+    masked_attention_efficient from frame 0 to frame 1."""
+    with torch.no_grad():
+        feats = oracle.resnet_forward(sd, frames, 50, strides=(1, 2, 1, 1), out_indices=(2, ))
+        q = feats[1:2]
+        k = feats[0:1].unsqueeze(2)
+        return oracle.masked_attention_efficient(q, k, seg_onehot.unsqueeze(2), mask, temperature=0.07, topk=10)
+
+
+def cpu_reference_setup(torch):
+    import oracle
+    from vfs_b200.backbones import ResNet
+    net = ResNet(50, norm_cfg=dict(type='SyncBN', requires_grad=True), strides=(1, 2, 1, 1), out_indices=(2, ))
+    sd = oracle.seeded_state_dict(net, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    frames = torch.randn(FRAMES, 3, SIZE, SIZE, generator=g)
+    fh = SIZE // 8
+    lab = torch.randint(0, CV, (1, fh, fh), generator=g)
+    seg_onehot = torch.nn.functional.one_hot(lab, CV).permute(0, 3, 1, 2).float()
+    mask = oracle.spatial_neighbor(fh, fh, TEST_CFG['neighbor_range'])
+    return oracle, sd, frames, seg_onehot, mask
+
+
+def run_reference_arm(a):
+    """--impl reference: the reference's CPU implementation (oracle port) on the host cores; rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    oracle, sd, frames, seg_onehot, mask = cpu_reference_setup(torch)
+    for _ in range(max(a.warmup, 1)):
+        oracle_pair_step(torch, oracle, sd, frames, seg_onehot, mask)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        oracle_pair_step(torch, oracle, sd, frames, seg_onehot, mask)
+    dt = time.perf_counter() - t0
+    value = a.steps / dt
+    line = dict(metric='frame-pairs/sec (R50 res4 feat+affinity)', value=value, unit='frame-pairs/s', n_gpus=a.gpus,
+                steps=a.steps, warmup=a.warmup, ms_per_step=dt / a.steps * 1e3, higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                config=dict(workload=WORKLOAD, step='1 frame pair per step (bounded sample of the 8-clip batch)',
+                            device='cpu'),
+                cpu_baseline=dict(value=value, unit='frame-pairs/s', cores=cores, kind='port',
+                                  sample=f'{a.steps} frame pairs, torch CPU fp32, {cores} threads'),
+                e2e=dict(value=value, unit='frame-pairs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------- main arm
+def main():
+    a = parse()
+    if a.impl == 'reference':
+        run_reference_arm(a)
+        return
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (the B200 path has no CPU fallback); '
+                         'use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    import oracle
+    import vfs_b200
+    from vfs_b200 import ops
+    from vfs_b200.common import spatial_neighbor
+
+    model = vfs_b200.build_model(dict(type='VanillaTracker', backbone=BACKBONE_CFG), train_cfg=None,
+                                 test_cfg=vfs_b200.ConfigDict(TEST_CFG))
+    model.backbone.load_state_dict(oracle.seeded_state_dict(model.backbone, seed=0))
+    model = model.to(dev)
+    model.eval()
+    eng = model.backbone.engine
+    eng.check_versions = False  # weights are frozen for the whole run
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    imgs_host = torch.randn(CLIPS, 1, 3, FRAMES, SIZE, SIZE, generator=g).pin_memory()   # forward_test layout
+    seg_host = seg_input(g, torch).pin_memory()
+    # device-resident copy in the batched layout [clip][frame] -> frames [16,3,256,256]
+    frames_dev = imgs_host.to(dev)[:, 0].permute(0, 2, 1, 3, 4).reshape(CLIPS * FRAMES, 3, SIZE, SIZE).contiguous()
+    fh = fw = SIZE // 8
+    hw = fh * fw
+    lab = torch.randint(0, CV, (CLIPS, hw), generator=g)
+    seg_bank = torch.zeros(CLIPS * FRAMES, CV, hw, device=dev)
+    seg_bank[0::2] = torch.nn.functional.one_hot(lab, CV).permute(0, 2, 1).float().to(dev)
+    mask = spatial_neighbor(1, fh, fw, TEST_CFG['neighbor_range'])
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    bank = torch.empty((2, CLIPS * FRAMES, fh, fw, 1024), dtype=torch.bfloat16, device=dev)
+    out = torch.empty((CLIPS, CV, hw), dtype=torch.float32, device=dev)
+
+    def step_device():
+        xs = eng.forward_split(frames_dev, 2)                 # 16 frames -> res4, split NHWC
+        ops.normalize_split(xs, out=bank)
+        for c in range(CLIPS):                                # frame 2c = key (labels known), 2c+1 = query
+            out[c] = ops.attention_bank(bank[:, 2 * c + 1:2 * c + 2], bank, [2 * c], seg_bank, CV * hw, hw, CV, mask,
+                                        TEST_CFG['temperature'], TEST_CFG['topk'])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- warm-up
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    barrier()
+
+    # ---------------- timed: K steps, device time per step (CUDA events on the launching stream), L2 flushed between
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    conv_flops = sum(l['flops'] for l in eng.conv_layer_list((CLIPS * FRAMES, 3, SIZE, SIZE), 2))
+    n_conv_launches = len(eng.conv_layer_list((CLIPS * FRAMES, 3, SIZE, SIZE), 2))
+    starts, ends, conv_spans = [], [], []
+    launches0 = ops.LAUNCHES[0]
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(a.steps):
+        flush.fill_(1)                                        # evict L2 (512 MiB > 126 MB); outside the timed span
+        eng.events = []
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step_device()
+        e.record()
+        starts.append(s)
+        ends.append(e)
+        conv_spans.append(dict(eng.events))
+        eng.events = None
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ops.LAUNCHES[0] - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    conv_ms = [sp['convs_begin'].elapsed_time(sp['convs_end']) for sp in conv_spans]
+    stem_ms = [sp['stem_begin'].elapsed_time(sp['convs_begin']) for sp in conv_spans]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    clocks = sampler.stop()
+    value = world * CLIPS * a.steps / (total_ms / 1e3)
+
+    # ---------------- e2e through the public API: per clip forward_test(imgs, ref_seg_map, img_meta), host buffers
+    meta = [dict(original_shape=(SIZE, SIZE, 3))]
+    def step_e2e():
+        res = []
+        for c in range(CLIPS):
+            imgs = imgs_host[c:c + 1].to(dev, non_blocking=True)          # [1,1,3,2,H,W]  H2D
+            seg = seg_host.to(dev, non_blocking=True)
+            res.append(model.forward_test(imgs, seg, meta)[0])             # numpy on the host (D2H inside)
+        return res
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_steps = max(3, min(a.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r = step_e2e()
+    torch.cuda.synchronize()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * CLIPS * e2e_steps / float(e2e_dt)
+    h2d = CLIPS * (imgs_host[0].numel() * 4 + seg_host.numel() * 4)
+    d2h = CLIPS * sum(int(x.nbytes) for x in [r[0]]) if r else 0
+
+    # ---------------- roofline of the dominant kernel (tcgen05 conv): algorithmic FLOPs / CUDA-event time
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh_:
+            peaks = json.load(fh_)
+    except Exception:
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained') or peaks.get('bf16_tflops') or 1590.0
+    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.59 PFLOP/s'
+    conv_med = statistics.median(conv_ms)
+    achieved = conv_flops / (conv_med * 1e-3) / 1e12
+    roofline = dict(bound='tensor', kernel='conv_tc_kernel', achieved=achieved, peak=peak_tf, unit='TFLOP/s',
+                    frac=achieved / peak_tf, traffic=None, peak_source=peak_src,
+                    note='achieved = algorithmic fp32-equivalent conv FLOPs; the kernel issues 3 bf16 MMAs per '
+                         'product (split-bf16), so tensor-pipe work is 3x: frac_of_issued = %.3f' %
+                         (3 * achieved / peak_tf),
+                    launches_per_step=n_conv_launches, segment_ms_median=conv_med,
+                    flops_per_step=conv_flops)
+
+    line = dict(metric='frame-pairs/sec (R50 res4 feat+affinity)', value=value, unit='frame-pairs/s', n_gpus=world,
+                steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=total_ms / a.steps, higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='bf16x3 (split-bf16 operands, fp32 accumulate)',
+                data='synthetic',
+                config=dict(workload=WORKLOAD, clips_per_gpu=CLIPS, l2='flushed (512 MiB write) between steps',
+                            timing='sum of per-step CUDA-event spans, max over ranks',
+                            parallelism=f'dp{world} (clips sharded, no collective)'),
+                clocks=clocks,
+                e2e=dict(value=e2e_value, unit='frame-pairs/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         api='build_model(VanillaTracker).forward_test per 2-frame clip, pinned host inputs',
+                         steps=e2e_steps),
+                gpu_launches=launches,
+                roofline=roofline,
+                breakdown_ms=dict(step_median=statistics.median(step_ms), stem_median=statistics.median(stem_ms),
+                                  convs_median=conv_med,
+                                  rest_median=statistics.median(step_ms) - statistics.median(stem_ms) - conv_med),
+                wall_s_timed_region=wall)
+
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        o, sd, frames, seg_onehot, m = cpu_reference_setup(torch)
+        oracle_pair_step(torch, o, sd, frames, seg_onehot, m)
+        n, t0 = 0, time.perf_counter()
+        while n < 2 or time.perf_counter() - t0 < 10.0:
+            oracle_pair_step(torch, o, sd, frames, seg_onehot, m)
+            n += 1
+        dt = time.perf_counter() - t0
+        line['cpu_baseline'] = dict(value=n / dt, unit='frame-pairs/s', cores=cores, kind='port',
+                                    sample=f'{n} frame pairs (2 frames 256x256 -> res4 + attention), torch CPU fp32')
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -39,6 +39,7 @@ class BackboneEngine:
         self.net = resnet
         self._plans = {}
         self.check_versions = True  # re-pack when parameters were modified in place / reloaded
+        self.events = None          # bench instrumentation: list collecting (tag, cuda event) at phase boundaries
 
     # -------------------------------------------------------------- plans
     @staticmethod
@@ -122,12 +123,53 @@ class BackboneEngine:
             return [None]
         return outs
 
+    def _mark(self, tag):
+        if self.events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.events.append((tag, ev))
+
     def forward_split(self, x, stage):
         """Features of stage ``stage`` kept in the library's split NHWC format (for the on-device tracker)."""
+        if not x.is_cuda:
+            raise RuntimeError('vfs_b200 backbone needs a CUDA tensor: the B200 path has no CPU fallback')
+        self._mark('stem_begin')
         xs = self.stem(x.contiguous().float())
+        self._mark('convs_begin')
         for i, name in enumerate(self.net.res_layers):
             if i > stage:
                 break
             for block in getattr(self.net, name):
                 xs = block.native_forward(self, xs)
+        self._mark('convs_end')
         return xs
+
+    def conv_layer_list(self, in_shape, stage):
+        """Static (Cin, Cout, k, stride, dil, H, W) list of the tcgen05 conv launches of forward_split for an
+        NCHW input shape -- used by bench.py to count algorithmic FLOPs."""
+        from .ops import conv_out_hw
+        N, _, H, W = in_shape
+        H, W = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        H, W = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+        out = []
+
+        def add(cm, h, w):
+            k, s, d = cm.conv.kernel_size[0], cm.conv.stride[0], cm.conv.dilation[0]
+            ho, wo = conv_out_hw(h, w, k, s, d)
+            out.append(dict(Cin=cm.conv.in_channels, Cout=cm.conv.out_channels, k=k, stride=s, dil=d, H=h, W=w,
+                            Ho=ho, Wo=wo, N=N, flops=2.0 * N * ho * wo * cm.conv.out_channels *
+                            cm.conv.in_channels * k * k))
+            return ho, wo
+
+        for i, name in enumerate(self.net.res_layers):
+            if i > stage:
+                break
+            for block in getattr(self.net, name):
+                if block.downsample is not None:
+                    add(block.downsample, H, W)
+                convs = [block.conv1, block.conv2] + ([block.conv3] if hasattr(block, 'conv3') else [])
+                h, w = H, W
+                for cm in convs:
+                    h, w = add(cm, h, w)
+                H, W = h, w
+        return out

@@ -5,7 +5,16 @@ import ctypes
 import torch
 
 from . import _native as nat
-from ._native import VfsConvDesc, check, current_stream, ptr
+from ._native import VfsConvDesc, current_stream, ptr
+
+LAUNCHES = [0]  # kernels of libvfs_b200.so launched through this module (bench.py reports the count)
+_KERNELS_PER_CALL = {'stem_forward': 2, 'masked_attention': 2, 'features_to_split_norm': 2}
+
+
+def check(rc, what=''):
+    """Raise on a non-zero return code, otherwise account the kernels the entry point launched."""
+    nat.check(rc, what)
+    LAUNCHES[0] += _KERNELS_PER_CALL.get(what, 1)
 
 
 def _require_cuda(t, name):
@@ -225,7 +234,7 @@ def features_to_split(x, normalize=True):
     out = torch.empty((2, N, H, W, C), dtype=torch.bfloat16, device=x.device)
     ws = torch.empty((N * H * W, ), dtype=torch.float32, device=x.device) if normalize else None
     check(nat.lib().vfs_features_to_split(ptr(x), ptr(out), ptr(ws), N, C, H, W, int(normalize), current_stream()),
-          'features_to_split')
+          'features_to_split_norm' if normalize else 'features_to_split')
     return out
 
 
