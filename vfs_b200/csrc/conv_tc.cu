@@ -15,6 +15,8 @@
 //              load of the weight tile, into a STAGES-deep 128B-swizzled shared-memory ring.
 //   warp 1     TMEM allocator + MMA issuer (one elected lane), accumulators double-buffered in TMEM.
 //   warps 2-5  epilogue: tcgen05.ld -> scale/shift (+residual) (ReLU) -> split -> global stores.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -54,8 +56,9 @@ template <int BN, int STAGES>
 struct ConvSmem {
   static constexpr int kTileBBytes = BN * kBlockK * 2;                    // one plane of the weight tile
   static constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // hi+lo of A and B
+  static constexpr int kStagingBytes = kBlockM * 64 * 4;  // epilogue transpose buffer: 128 rows x 64 fp32 columns
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024;  // +1024 alignment slack
+  static constexpr int kTotal = STAGES * kStageBytes + kStagingBytes + kBarrierBytes + 1024;  // +1024 align slack
 };
 
 template <int BN, int STAGES>
@@ -63,7 +66,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   using S = ConvSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * S::kStageBytes;
+  const uint32_t stg_base = smem_base + STAGES * S::kStageBytes;
+  const uint32_t bar_base = stg_base + S::kStagingBytes;
   // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr (4 B)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -177,12 +181,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     }
   } else {
     // ======================= epilogue (warps 2..5) =======================
+    // Phase A (thread = accumulator row): TMEM -> scale/shift -> fp32 staging tile in shared memory (16-byte
+    // chunks XOR-swizzled so both phases are bank-conflict free).  Phase B (8 threads per pixel row): staging
+    // -> (+residual) -> ReLU -> split -> global, every warp access covering whole 128-byte lines.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int dw = row % p.tw;
-    const int r2 = row / p.tw;
-    const int dh = r2 % p.th;
-    const int dn = r2 / p.th;
+    const int et = threadIdx.x - 64;         // 0..127 over the epilogue threads
+    const int piece = et & 7, rr = et >> 3;  // phase B: 8-channel piece within the 64-column chunk, first row
+    auto phys_chunk = [](int r, int c) { return (c & 8) | ((c ^ (c >> 3) ^ r) & 7); };
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -192,39 +198,62 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       const int t2 = m_tile / p.tiles_w;
       const int th_i = t2 % p.tiles_h;
       const int tn_i = t2 / p.tiles_h;
-      const int w = tw_i * p.tw + dw, h = th_i * p.th + dh, n = tn_i * p.tn + dn;
-      const bool valid = (w < p.Wo) && (h < p.Ho) && (n < p.N);
-      const size_t pix = (static_cast<size_t>(n) * p.Ho + h) * p.Wo + w;
-      const size_t obase = pix * p.Cout + static_cast<size_t>(n_tile) * BN;
+      const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.tn;
 
       mbar_wait(tfull_bar(as), aphase, 400 + as);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(t_row + c0, acc);
-        tmem_ld_wait();
-        if (valid) {
-          const int cg = n_tile * BN + c0;
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        const int cg = n_tile * BN + c0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffer free
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float y[8];
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + cg + j));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + cg + j + 4));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.shift + cg + j));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.shift + cg + j + 4));
-            y[0] = fmaf(__uint_as_float(acc[j + 0]), s0.x, b0.x);
-            y[1] = fmaf(__uint_as_float(acc[j + 1]), s0.y, b0.y);
-            y[2] = fmaf(__uint_as_float(acc[j + 2]), s0.z, b0.z);
-            y[3] = fmaf(__uint_as_float(acc[j + 3]), s0.w, b0.w);
-            y[4] = fmaf(__uint_as_float(acc[j + 4]), s1.x, b1.x);
-            y[5] = fmaf(__uint_as_float(acc[j + 5]), s1.y, b1.y);
-            y[6] = fmaf(__uint_as_float(acc[j + 6]), s1.z, b1.z);
-            y[7] = fmaf(__uint_as_float(acc[j + 7]), s1.w, b1.w);
+        for (int h = 0; h < 2; ++h) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(t_row + c0 + h * 32, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cg + h * 32 + j * 4));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cg + h * 32 + j * 4));
+            const float y0 = fmaf(__uint_as_float(acc[4 * j + 0]), sc.x, sh.x);
+            const float y1 = fmaf(__uint_as_float(acc[4 * j + 1]), sc.y, sh.y);
+            const float y2 = fmaf(__uint_as_float(acc[4 * j + 2]), sc.z, sh.z);
+            const float y3 = fmaf(__uint_as_float(acc[4 * j + 3]), sc.w, sh.w);
+            const uint32_t addr = stg_base + row * 256 + phys_chunk(row, h * 8 + j) * 16;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(y0), "f"(y1), "f"(y2), "f"(y3)
+                         : "memory");
+          }
+        }
+        if (c0 + 64 >= BN) {  // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffer full
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+          const int r = rr + 16 * i;
+          const int dw = r % p.tw;
+          const int r2 = r / p.tw;
+          const int dh = r2 % p.th;
+          const int dn = r2 / p.th;
+          const int w = w0 + dw, hh = h0 + dh, n = n0 + dn;
+          if ((w < p.Wo) && (hh < p.Ho) && (n < p.N)) {
+            const size_t o = ((static_cast<size_t>(n) * p.Ho + hh) * p.Wo + w) * p.Cout + cg + piece * 8;
+            uint4 rh = make_uint4(0, 0, 0, 0), rl = make_uint4(0, 0, 0, 0);
             if (p.res_hi != nullptr) {
-              const uint4 rh = *reinterpret_cast<const uint4*>(p.res_hi + obase + c0 + j);
-              const uint4 rl = *reinterpret_cast<const uint4*>(p.res_lo + obase + c0 + j);
+              rh = *reinterpret_cast<const uint4*>(p.res_hi + o);
+              rl = *reinterpret_cast<const uint4*>(p.res_lo + o);
+            }
+            float y[8];
+            const uint32_t a0 = stg_base + r * 256 + phys_chunk(r, 2 * piece) * 16;
+            const uint32_t a1 = stg_base + r * 256 + phys_chunk(r, 2 * piece + 1) * 16;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(y[0]), "=f"(y[1]), "=f"(y[2]), "=f"(y[3]) : "r"(a0));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(y[4]), "=f"(y[5]), "=f"(y[6]), "=f"(y[7]) : "r"(a1));
+            if (p.res_hi != nullptr) {
               y[0] += bf16_lo_to_float(rh.x) + bf16_lo_to_float(rl.x);
               y[1] += bf16_hi_to_float(rh.x) + bf16_hi_to_float(rl.x);
               y[2] += bf16_lo_to_float(rh.y) + bf16_lo_to_float(rl.y);
@@ -239,9 +268,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
               for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.0f);
             }
             if (p.out_f32 != nullptr) {
-              float4* o = reinterpret_cast<float4*>(p.out_f32 + obase + c0 + j);
-              o[0] = make_float4(y[0], y[1], y[2], y[3]);
-              o[1] = make_float4(y[4], y[5], y[6], y[7]);
+              float4* of = reinterpret_cast<float4*>(p.out_f32 + o);
+              of[0] = make_float4(y[0], y[1], y[2], y[3]);
+              of[1] = make_float4(y[4], y[5], y[6], y[7]);
             }
             if (p.out_hi != nullptr) {
               __nv_bfloat16 hi[8], lo[8];
@@ -256,15 +285,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
               ol.y = pack_bf16x2(lo[2], lo[3]);
               ol.z = pack_bf16x2(lo[4], lo[5]);
               ol.w = pack_bf16x2(lo[6], lo[7]);
-              *reinterpret_cast<uint4*>(p.out_hi + obase + c0 + j) = oh;
-              *reinterpret_cast<uint4*>(p.out_lo + obase + c0 + j) = ol;
+              *reinterpret_cast<uint4*>(p.out_hi + o) = oh;
+              *reinterpret_cast<uint4*>(p.out_lo + o) = ol;
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
       if (++as == 2) {
         as = 0;
         aphase ^= 1u;
@@ -410,7 +436,15 @@ int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_spl
     if (rc != VFS_OK) return rc;
   }
 
-  const int BN = (Cout % 128 == 0) ? 128 : 64;
+  int BN = (Cout % 128 == 0) ? 128 : 64;
+  {
+    static int forced = -1;  // VFS_CONV_BN=64|128|256 overrides the tile width (experiments)
+    if (forced < 0) {
+      const char* e = getenv("VFS_CONV_BN");
+      forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0 && Cout % forced == 0) BN = forced;
+  }
   p.num_n_tiles = Cout / BN;
   {
     const uint64_t Ktot = static_cast<uint64_t>(k) * k * Cin;
@@ -424,6 +458,7 @@ int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_spl
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int sms = device_sm_count();
   const int grid = num_tiles < sms ? num_tiles : sms;
+  if (BN == 256) return launch<256, 2>(p, grid, stream);
   if (BN == 128) return launch<128, 3>(p, grid, stream);
   return launch<64, 4>(p, grid, stream);
 }
