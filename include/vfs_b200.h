@@ -78,6 +78,32 @@ int vfs_conv_bn_act(const VfsConvDesc* d, const void* in_split, const void* w_sp
                     const float* shift, const void* residual_split, void* out_split, float* out_f32_nhwc,
                     vfs_stream_t s);
 
+/* ------------------------------------------------------------------------------------------------
+ * Train-mode BatchNorm (batch statistics), reference: mmcv ConvModule with norm_cfg SyncBN/BN in training mode
+ * (torch.nn.SyncBatchNorm / BatchNorm2d forward: batch_norm_stats, gather_stats, batch_norm_elemt).
+ *   1. vfs_conv_stats     conv as above (scale/shift normally 1/0) writing the raw fp32 NHWC output AND accumulating
+ *                         per-channel [sum | sum of squares] into stats (fp64 [2*Cout], zero-initialised by the caller;
+ *                         across GPUs the caller all-reduces stats -- that is the SyncBN exchange)
+ *   2. vfs_bn_finalize    stats,count -> scale = gamma*invstd, shift = beta - mean*scale, save_mean/save_invstd,
+ *                         running_mean/var momentum update (unbiased variance), like F.batch_norm(training=True)
+ *   3. vfs_bn_apply       y = z*scale + shift (+residual) (ReLU) -> split NHWC
+ * vfs_channel_stats_f32 accumulates the same statistics for an fp32 [M,C] tensor (stem output).
+ * ---------------------------------------------------------------------------------------------- */
+/* stem in train mode: raw 7x7/s2 conv output (fp32 NHWC [N,Hc,Wc,64], vfs_stem_workspace_bytes) for the batch
+ * statistics, then BN(scale/shift from vfs_bn_finalize)+ReLU fused into the 3x3/s2 max-pool -> split NHWC */
+int vfs_stem_conv_raw(const float* in, const float* weight, void* conv_out_f32_nhwc, int N, int H, int W,
+                      vfs_stream_t s);
+int vfs_stem_bn_relu_pool(const void* conv_out_f32_nhwc, const float* scale, const float* shift, void* out_split,
+                          int N, int H, int W, vfs_stream_t s);
+int vfs_conv_stats(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
+                   const float* shift, float* out_f32_nhwc, double* stats, vfs_stream_t s);
+int vfs_channel_stats_f32(const float* x, double* stats, long long M, int C, vfs_stream_t s);
+int vfs_bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
+                    float* save_invstd, int C, vfs_stream_t s);
+int vfs_bn_apply(const float* z, const float* scale, const float* shift, const void* residual_split,
+                 void* out_split, long long M, int C, int relu, vfs_stream_t s);
+
 /* OIHW fp32 [Cout,Cin,k,k] -> split [2][Cout][k*k*Cin] (device to device). */
 int vfs_pack_conv_weight(const float* w_oihw, void* w_split, int Cout, int Cin, int ksize, vfs_stream_t s);
 
@@ -115,7 +141,7 @@ int vfs_features_to_split(const float* in_nchw, void* out_split, void* inv_norm_
 int vfs_normalize_split(const void* in_split, void* out_split, long long num_pixels, int C,
                         long long in_plane_stride, long long out_plane_stride, vfs_stream_t s);
 
-size_t vfs_attention_workspace_bytes(const VfsAttnDesc* d);
+size_t vfs_attention_workspace_bytes(const VfsAttnDesc* d, int num_problems);
 /*   q_split        hi plane of the query frame [H][W][C]; lo plane at +q_plane_stride elements
  *   k_bank_split   hi plane of a bank of frames [k_bank_frames][H][W][C]; lo plane at +k_plane_stride elements
  *   key_frame_ids  HOST array [T]: bank frame used by key slot t (a frame may repeat, cf. vanilla_tracker.py:133-149)
@@ -129,6 +155,20 @@ int vfs_masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_
                          const int32_t* key_frame_ids, const float* values, long long v_frame_stride,
                          long long v_chan_stride, float* out, float* out_topk_val, int32_t* out_topk_idx,
                          void* workspace, size_t workspace_bytes, vfs_stream_t s);
+
+/* Several independent (query frame, key set) problems of the same shape in ONE launch (e.g. the frame pairs of a
+ * batch of clips, or the N batch items of masked_attention_efficient).  num_problems <= 32, num_problems*T <= 256.
+ *   q_frame_ids [P] (host): query frame of problem p inside q_bank_split [q_bank_frames][H][W][C]
+ *   key_frame_ids [P*T] (host): key bank frame of (p, slot t);  value_frame_ids [P*T]: frame index used to address
+ *   values[p*v_batch_stride + value_frame_ids[p*T+t]*v_frame_stride + c*v_chan_stride + pos]
+ *   out fp32 [P][Cv][H*W]; out_topk_* NULL or [P][topk][H*W] */
+int vfs_masked_attention_batched(const VfsAttnDesc* d, int num_problems, const void* q_bank_split,
+                                 long long q_plane_stride, int q_bank_frames, const int32_t* q_frame_ids,
+                                 const void* k_bank_split, long long k_plane_stride, int k_bank_frames,
+                                 const int32_t* key_frame_ids, const float* values, const int32_t* value_frame_ids,
+                                 long long v_batch_stride, long long v_frame_stride, long long v_chan_stride,
+                                 float* out, float* out_topk_val, int32_t* out_topk_idx, void* workspace,
+                                 size_t workspace_bytes, vfs_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------
  * SimSiam head + loss.  Replaces SimSiamHead.forward (heads/sim_siam_head.py:143-163: AdaptiveAvgPool2d,

@@ -45,6 +45,57 @@ def test_backbone_eval_matches_reference_golden(golden, name):
     assert rel_err(y, ref) < REL_TOL
 
 
+@pytest.mark.parametrize('name', sorted(cases.BACKBONE_CASES))
+def test_backbone_train_mode_bn_matches_reference_golden(golden, name):
+    """Batch-statistics BatchNorm (train mode): outputs and the running-statistics update."""
+    from vfs_b200.backbones import ResNet
+    c = cases.BACKBONE_CASES[name]
+    net = ResNet(c['depth'], norm_cfg=dict(type='SyncBN', requires_grad=True), strides=c['strides'],
+                 dilations=c['dilations'], out_indices=c['out_indices'])
+    sd = oracle.seeded_state_dict(net, seed=c['seed'])
+    net = _load(net, sd)
+    net.train(True)
+    x = cases.backbone_input(c)
+    y = net(x.cuda())
+    ref = golden[f'backbone/{name}/train']
+    assert tuple(y.shape) == ref.shape
+    assert rel_err(y, ref) < REL_TOL
+    # running statistics of the stem BN after one step == torch's update rule on the oracle's stem conv output
+    with torch.no_grad():
+        z = torch.nn.functional.conv2d(x, sd['conv1.conv.weight'], None, 2, 3)
+        exp_mean = 0.9 * sd['conv1.bn.running_mean'] + 0.1 * z.mean(dim=(0, 2, 3))
+        exp_var = 0.9 * sd['conv1.bn.running_var'] + 0.1 * z.var(dim=(0, 2, 3), unbiased=True)
+    assert rel_err(net.conv1.bn.running_mean, exp_mean) < REL_TOL
+    assert rel_err(net.conv1.bn.running_var, exp_var) < REL_TOL
+    assert int(net.conv1.bn.num_batches_tracked) == 1
+    # and switching back to eval uses the UPDATED running statistics (cached folds are refreshed)
+    net.train(False)
+    y_eval = net(x.cuda())
+    sd2 = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        ref_eval = oracle.resnet_forward(sd2, x, c['depth'], c['strides'], c['dilations'], c['out_indices'])
+    assert rel_err(y_eval, ref_eval) < REL_TOL
+
+
+@pytest.mark.parametrize('name', sorted(cases.TRACKER_TRAIN_CASES))
+def test_simsiam_forward_train_matches_reference_golden(golden, name):
+    """SimSiamBaseTracker.forward_train in TRAIN mode (batch-stat BN in backbone and head) built from the
+    reference's model dicts through build_model, against the reference's own losses."""
+    import vfs_b200
+    c = cases.TRACKER_TRAIN_CASES[name]
+    model = vfs_b200.build_model(c['model'], train_cfg=vfs_b200.ConfigDict(c['train_cfg']), test_cfg=None)
+    model.load_state_dict(oracle.seeded_state_dict(model, seed=c['seed']))
+    model = model.cuda()
+    model.train()
+    with torch.no_grad():
+        losses = model.forward_train(cases.tracker_train_input(c).cuda())
+    keys = [k for k in golden if k.startswith(f'tracker_train/{name}/')]
+    assert len(keys) == len(losses)
+    for k in keys:
+        got = losses[k.split('/', 2)[2]]
+        np.testing.assert_allclose(got.cpu().numpy(), golden[k], rtol=REL_TOL, atol=2e-5)
+
+
 @pytest.mark.parametrize('depth,shape,strides,out_indices', [
     (50, (2, 3, 256, 256), (1, 2, 2, 2), (3, )),      # BASELINE cfg-2 frame size
     (50, (1, 3, 240, 432), (1, 2, 1, 1), (2, )),      # DAVIS-style res4, stride 8
@@ -261,6 +312,20 @@ def test_attention_matches_reference_golden(golden, name):
     assert bad == 0, f'{bad}/{n_q} queries selected a different key set outside the near-tie tolerance'
     # selected affinities are sorted and finite
     assert bool((tv[0][:-1] >= tv[0][1:]).all())
+
+
+def test_attention_multi_batch_matches_oracle():
+    """N > 1 batch items (the reference API allows it) run as problems of one launch."""
+    from vfs_b200.common import masked_attention_efficient, spatial_neighbor
+    g = torch.Generator().manual_seed(11)
+    N, C, Cv, T, H, W = 3, 64, 3, 2, 11, 19
+    q = torch.relu(torch.randn(N, C, H, W, generator=g))
+    k = torch.relu(torch.randn(N, C, T, H, W, generator=g))
+    v = torch.rand(N, Cv, T, H, W, generator=g)
+    out = masked_attention_efficient(q.cuda(), k.cuda(), v.cuda(), spatial_neighbor(1, H, W, 12), temperature=0.07,
+                                     topk=10)
+    ref = oracle.masked_attention_efficient(q, k, v, oracle.spatial_neighbor(H, W, 12), temperature=0.07, topk=10)
+    assert rel_err(out, ref) < REL_TOL
 
 
 def test_attention_full_size_properties():

@@ -78,9 +78,13 @@ def main():
                                                                       H * W, Cv, mask, 0.07, 10))
     q = torch.relu(torch.randn(1, C, H, W, device='cuda'))
     res['features_to_split_480p_ms'] = timed(lambda: ops.features_to_split(q, True))
+    lay = res.pop('layers_16x256')
     print(json.dumps(res, indent=1))
+    for l in lay:
+        print(f"k{l['k']} s{l['s']} {l['Cin']:5d}->{l['Cout']:5d} {l['H']:3d}x{l['W']:3d} {l['ms']*1e3:7.1f} us {l['tflops']:6.1f} TF")
+    res['layers_16x256'] = lay
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-    with open(os.path.join(ROOT, 'gpurun_out', 'probe.json'), 'w') as fh:
+    with open(os.path.join(ROOT, 'gpurun_out', os.environ.get('PROBE_OUT', 'probe.json')), 'w') as fh:
         json.dump(res, fh, indent=1)
 
 

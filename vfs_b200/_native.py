@@ -38,9 +38,18 @@ PROTOTYPES = {
     'vfs_conv_bn_act': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'vfs_pack_conv_weight': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'vfs_debug_conv_bn_act_simt': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'vfs_stem_conv_raw': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    'vfs_stem_bn_relu_pool': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'vfs_conv_stats': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'vfs_channel_stats_f32': (_i, [_vp, _vp, _ll, _i, _vp]),
+    'vfs_bn_finalize': (_i, [_vp, ctypes.c_double, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
+    'vfs_bn_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     'vfs_features_to_split': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'vfs_normalize_split': (_i, [_vp, _vp, _ll, _i, _ll, _ll, _vp]),
-    'vfs_attention_workspace_bytes': (_sz, [_attn_p]),
+    'vfs_attention_workspace_bytes': (_sz, [_attn_p, _i]),
+    'vfs_masked_attention_batched': (_i, [_attn_p, _i, _vp, _ll, _i, ctypes.POINTER(ctypes.c_int32), _vp, _ll, _i,
+                                          ctypes.POINTER(ctypes.c_int32), _vp, ctypes.POINTER(ctypes.c_int32), _ll,
+                                          _ll, _ll, _vp, _vp, _vp, _vp, _sz, _vp]),
     'vfs_masked_attention': (_i, [_attn_p, _vp, _ll, _vp, _ll, _i, ctypes.POINTER(ctypes.c_int32), _vp, _ll, _ll,
                                   _vp, _vp, _vp, _vp, _sz, _vp]),
     'vfs_global_avg_pool': (_i, [_vp, _vp, _i, _i, _i, _vp]),

@@ -28,19 +28,23 @@ constexpr int kAttnStageBytes = 4 * 16384;  // Q hi, Q lo, K hi, K lo (each 128 
 constexpr int kAttnSmemBytes = kAttnStages * kAttnStageBytes + 256 + 1024;
 constexpr int kAttnThreads = 192;
 constexpr int kMaxKeyFrames = 32;
+constexpr int kMaxProblems = 32;   // query frames per launch
+constexpr int kMaxKeySlots = 256;  // problems x key frames per launch
 
 struct alignas(64) AttnParams {
-  CUtensorMap tmap_q;  // {C, W, H, 1, 2}
-  CUtensorMap tmap_k;  // {C, W, H, frames, 2}
+  CUtensorMap tmap_q;  // {C, W, H, q frames, 2}
+  CUtensorMap tmap_k;  // {C, W, H, k frames, 2}
   int H, W, kchunks;
-  int T;  // number of key frame slots
-  int frame_ids[kMaxKeyFrames];
+  int T;  // number of key frame slots per problem
+  int num_problems;
+  short q_ids[kMaxProblems];      // bank frame of each problem's query
+  short frame_ids[kMaxKeySlots];  // [problem][slot] -> key bank frame
   int mask_mode;  // 0 none, 1 circle (dy^2+dx^2 < ry^2), 2 square (|dy| <= ry, |dx| <= rx)
   int ry, rx;
   int non_mask_len;
   int q_tiles_x, q_tiles_y, splits;
   int num_units;
-  float* part_val;  // [T*splits][KMAX][HW]
+  float* part_val;  // [problems*T*splits][KMAX][HW]
   int* part_idx;
 };
 
@@ -72,7 +76,7 @@ __device__ __forceinline__ KeyWindow key_window(const AttnParams& p, int qy0, in
 }
 
 struct UnitInfo {
-  int qy0, qx0, t, j_begin, j_end;
+  int b, qy0, qx0, t, j_begin, j_end;
   KeyWindow w;
 };
 
@@ -81,7 +85,10 @@ __device__ __forceinline__ UnitInfo decode_unit(const AttnParams& p, int unit) {
   const int s = unit % p.splits;
   const int r = unit / p.splits;
   u.t = r % p.T;
-  const int qt = r / p.T;
+  const int r3 = r / p.T;
+  const int q_tiles = p.q_tiles_x * p.q_tiles_y;
+  const int qt = r3 % q_tiles;
+  u.b = r3 / q_tiles;
   u.qx0 = (qt % p.q_tiles_x) * kQTileW;
   u.qy0 = (qt / p.q_tiles_x) * kQTileH;
   u.w = key_window(p, u.qy0, u.qx0, u.t);
@@ -148,7 +155,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
     uint32_t phase = 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       const UnitInfo u = decode_unit(p, unit);
-      const int frame = p.frame_ids[u.t];
+      const int frame = p.frame_ids[u.b * p.T + u.t];
+      const int qframe = p.q_ids[u.b];
       for (int j = u.j_begin; j < u.j_end; ++j) {
         const int ky0 = u.w.wy0 + (j / u.w.nx) * kQTileH;
         const int kx0 = u.w.wx0 + (j % u.w.nx) * kQTileW;
@@ -157,7 +165,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
           if (lane == 0) {
             const uint32_t sq = smem_base + stage * kAttnStageBytes;
             mbar_arrive_expect_tx(full_bar(stage), kAttnStageBytes);
-            tma_load_5d(sq, &p.tmap_q, full_bar(stage), kc * 64, u.qx0, u.qy0, 0, 0);
+            tma_load_5d(sq, &p.tmap_q, full_bar(stage), kc * 64, u.qx0, u.qy0, qframe, 0);
             tma_load_5d(sq + 32768, &p.tmap_k, full_bar(stage), kc * 64, kx0, ky0, frame, 0);
           }
           __syncwarp();
@@ -266,7 +274,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
         }
       }
       if (q_valid) {
-        const int slot = u.t * p.splits + (unit % p.splits);
+        const int slot = (u.b * p.T + u.t) * p.splits + (unit % p.splits);
         const size_t base = static_cast<size_t>(slot) * KMAX * HW + static_cast<size_t>(qy) * p.W + qx;
 #pragma unroll
         for (int i = 0; i < KMAX; ++i) {
@@ -291,20 +299,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
 struct MergeParams {
   const float* part_val;
   const int* part_idx;
-  int slots, HW, topk, mode;  // mode 0 softmax, 1 cosine
+  int slots, HW, topk, mode;  // slots per problem; mode 0 softmax, 1 cosine
   float temperature;
-  const float* values;  // element (slot t, channel c, pos) at values[frame_ids[t]*v_frame_stride + c*v_chan_stride + pos]
-  long long v_frame_stride, v_chan_stride;
-  int Cv;
-  int frame_ids[kMaxKeyFrames];
-  float* out;      // [Cv][HW]
-  float* out_val;  // optional [topk][HW] (affinity / temperature of the selected keys)
-  int* out_idx;    // optional [topk][HW] (flat key index slot*HW + pos)
+  // element (problem b, slot t, channel c, pos) at
+  //   values[b*v_batch_stride + val_ids[b*T+t]*v_frame_stride + c*v_chan_stride + pos]
+  const float* values;
+  long long v_batch_stride, v_frame_stride, v_chan_stride;
+  int Cv, T;
+  short val_ids[kMaxKeySlots];
+  float* out;      // [problems][Cv][HW]
+  float* out_val;  // optional [problems][topk][HW] (affinity / temperature of the selected keys)
+  int* out_idx;    // optional [problems][topk][HW] (flat key index slot*HW + pos)
 };
 
 template <int KMAX>
 __global__ void attn_merge_propagate_kernel(const MergeParams p) {
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
   if (qi >= p.HW) return;
   float tv[KMAX];
   int ti[KMAX];
@@ -314,7 +325,7 @@ __global__ void attn_merge_propagate_kernel(const MergeParams p) {
     ti[i] = 0;
   }
   for (int s = 0; s < p.slots; ++s) {
-    const size_t base = static_cast<size_t>(s) * KMAX * p.HW + qi;
+    const size_t base = (static_cast<size_t>(b) * p.slots + s) * KMAX * p.HW + qi;
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
       const float v = p.part_val[base + static_cast<size_t>(i) * p.HW];
@@ -328,8 +339,8 @@ __global__ void attn_merge_propagate_kernel(const MergeParams p) {
   for (int i = 0; i < KMAX; ++i) {
     const float a = __fdiv_rn(tv[i], p.temperature);  // reference divides the whole affinity by temperature
     if (i < p.topk) {
-      if (p.out_val) p.out_val[static_cast<size_t>(i) * p.HW + qi] = a;
-      if (p.out_idx) p.out_idx[static_cast<size_t>(i) * p.HW + qi] = ti[i];
+      if (p.out_val) p.out_val[(static_cast<size_t>(b) * p.topk + i) * p.HW + qi] = a;
+      if (p.out_idx) p.out_idx[(static_cast<size_t>(b) * p.topk + i) * p.HW + qi] = ti[i];
       if (p.mode == 0) {
         w[i] = expf(a - vmax);
       } else {
@@ -348,11 +359,12 @@ __global__ void attn_merge_propagate_kernel(const MergeParams p) {
     for (int i = 0; i < KMAX; ++i) {
       if (i < p.topk) {
         const int slot = ti[i] / p.HW, pos = ti[i] - slot * p.HW;
-        const float val = p.values[p.frame_ids[slot] * p.v_frame_stride + c * p.v_chan_stride + pos];
+        const float val = p.values[b * p.v_batch_stride + p.val_ids[b * p.T + slot] * p.v_frame_stride +
+                                   c * p.v_chan_stride + pos];
         acc = fmaf(val, (p.mode == 0) ? w[i] * inv : w[i], acc);
       }
     }
-    p.out[static_cast<size_t>(c) * p.HW + qi] = acc;
+    p.out[(static_cast<size_t>(b) * p.Cv + c) * p.HW + qi] = acc;
   }
 }
 
@@ -474,61 +486,75 @@ int normalize_split(const void* in_split, void* out_split, long long num_pixels,
 
 static int attn_kmax(int topk) { return topk <= 10 ? 10 : 16; }
 
-static int attn_splits(const VfsAttnDesc* d) {
+static int attn_splits(const VfsAttnDesc* d, int B) {
   const int q_tiles = ((d->W + kQTileW - 1) / kQTileW) * ((d->H + kQTileH - 1) / kQTileH);
   const int target = 2 * device_sm_count();
-  int splits = (target + q_tiles * d->T - 1) / (q_tiles * d->T);
+  const int base = q_tiles * d->T * (B > 0 ? B : 1);
+  int splits = (target + base - 1) / base;
   if (splits < 1) splits = 1;
   if (splits > 8) splits = 8;
   return splits;
 }
 
-size_t attention_workspace_bytes(const VfsAttnDesc* d) {
-  if (!d || d->T <= 0) return 0;
-  const size_t slots = static_cast<size_t>(d->T) * attn_splits(d);
+size_t attention_workspace_bytes(const VfsAttnDesc* d, int B) {
+  if (!d || d->T <= 0 || B <= 0) return 0;
+  const size_t slots = static_cast<size_t>(B) * d->T * attn_splits(d, B);
   return slots * attn_kmax(d->topk) * d->H * d->W * (sizeof(float) + sizeof(int));
 }
 
-int masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_plane_stride, const void* k_bank_split,
-                     long long k_plane_stride, int k_bank_frames, const int* key_frame_ids, const float* values,
-                     long long v_frame_stride, long long v_chan_stride, float* out, float* out_topk_val,
-                     int* out_topk_idx, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  VFS_REQUIRE(d && q_split && k_bank_split && key_frame_ids && values && out && workspace, VFS_EINVAL,
-              "masked_attention: null argument");
+int masked_attention_batched(const VfsAttnDesc* d, int B, const void* q_bank_split, long long q_plane_stride,
+                             int q_bank_frames, const int* q_ids, const void* k_bank_split, long long k_plane_stride,
+                             int k_bank_frames, const int* key_ids, const float* values, const int* val_ids,
+                             long long v_batch_stride, long long v_frame_stride, long long v_chan_stride, float* out,
+                             float* out_topk_val, int* out_topk_idx, void* workspace, size_t workspace_bytes,
+                             cudaStream_t stream) {
+  VFS_REQUIRE(d && q_bank_split && q_ids && k_bank_split && key_ids && values && val_ids && out && workspace,
+              VFS_EINVAL, "masked_attention: null argument");
   VFS_REQUIRE(d->H > 0 && d->W > 0 && d->C > 0 && d->C % 64 == 0, VFS_ESHAPE,
               "masked_attention: C=%d must be a positive multiple of 64", d->C);
   VFS_REQUIRE(d->T >= 1 && d->T <= kMaxKeyFrames, VFS_ESHAPE, "masked_attention: T=%d outside [1,%d]", d->T,
               kMaxKeyFrames);
+  VFS_REQUIRE(B >= 1 && B <= kMaxProblems && B * d->T <= kMaxKeySlots, VFS_ESHAPE,
+              "masked_attention: %d problems x %d key frames exceeds the per-launch limit (%d, %d)", B, d->T,
+              kMaxProblems, kMaxKeySlots);
   VFS_REQUIRE(d->topk >= 1 && d->topk <= 16, VFS_ESHAPE, "masked_attention: topk=%d outside [1,16]", d->topk);
   VFS_REQUIRE(d->temperature > 0.0f, VFS_EINVAL, "masked_attention: temperature must be positive");
   VFS_REQUIRE(d->mask_mode >= 0 && d->mask_mode <= 2, VFS_EINVAL, "masked_attention: bad mask_mode");
   VFS_REQUIRE(d->non_mask_len >= 0 && d->non_mask_len < d->T, VFS_EINVAL, "masked_attention: bad non_mask_len");
   VFS_REQUIRE(d->Cv >= 1, VFS_ESHAPE, "masked_attention: Cv must be >= 1");
-  VFS_REQUIRE(workspace_bytes >= attention_workspace_bytes(d), VFS_EINVAL, "masked_attention: workspace too small");
-  for (int t = 0; t < d->T; ++t)
-    VFS_REQUIRE(key_frame_ids[t] >= 0 && key_frame_ids[t] < k_bank_frames, VFS_EINVAL,
-                "masked_attention: key frame id %d out of range", key_frame_ids[t]);
+  VFS_REQUIRE(q_bank_frames < 32768 && k_bank_frames < 32768, VFS_ESHAPE, "masked_attention: bank too large");
+  VFS_REQUIRE(workspace_bytes >= attention_workspace_bytes(d, B), VFS_EINVAL, "masked_attention: workspace too small");
+  for (int i = 0; i < B; ++i)
+    VFS_REQUIRE(q_ids[i] >= 0 && q_ids[i] < q_bank_frames, VFS_EINVAL, "masked_attention: query frame id %d out of range",
+                q_ids[i]);
+  for (int i = 0; i < B * d->T; ++i) {
+    VFS_REQUIRE(key_ids[i] >= 0 && key_ids[i] < k_bank_frames, VFS_EINVAL,
+                "masked_attention: key frame id %d out of range", key_ids[i]);
+    VFS_REQUIRE(val_ids[i] >= 0 && val_ids[i] < 32768, VFS_EINVAL, "masked_attention: value frame id out of range");
+  }
 
   const int HW = d->H * d->W;
   const int KMAX = attn_kmax(d->topk);
   AttnParams p;
   memset(&p, 0, sizeof(p));
-  p.H = d->H; p.W = d->W; p.kchunks = d->C / 64; p.T = d->T;
-  for (int t = 0; t < d->T; ++t) p.frame_ids[t] = key_frame_ids[t];
+  p.H = d->H; p.W = d->W; p.kchunks = d->C / 64; p.T = d->T; p.num_problems = B;
+  for (int i = 0; i < B; ++i) p.q_ids[i] = static_cast<short>(q_ids[i]);
+  for (int i = 0; i < B * d->T; ++i) p.frame_ids[i] = static_cast<short>(key_ids[i]);
   p.mask_mode = d->mask_mode; p.ry = d->radius_y; p.rx = d->radius_x; p.non_mask_len = d->non_mask_len;
   p.q_tiles_x = (d->W + kQTileW - 1) / kQTileW;
   p.q_tiles_y = (d->H + kQTileH - 1) / kQTileH;
-  p.splits = attn_splits(d);
-  p.num_units = p.q_tiles_x * p.q_tiles_y * d->T * p.splits;
-  const size_t slots = static_cast<size_t>(d->T) * p.splits;
+  p.splits = attn_splits(d, B);
+  p.num_units = B * p.q_tiles_x * p.q_tiles_y * d->T * p.splits;
+  const size_t slots = static_cast<size_t>(B) * d->T * p.splits;
   p.part_val = reinterpret_cast<float*>(workspace);
   p.part_idx = reinterpret_cast<int*>(p.part_val + slots * KMAX * HW);
+  const uint32_t box[5] = {64, kQTileW, kQTileH, 1, 2};
   {
-    const uint64_t dims[5] = {static_cast<uint64_t>(d->C), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H), 1, 2};
+    const uint64_t dims[5] = {static_cast<uint64_t>(d->C), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+                              static_cast<uint64_t>(q_bank_frames), 2};
     const uint64_t strides[4] = {static_cast<uint64_t>(d->C) * 2, static_cast<uint64_t>(d->W) * d->C * 2,
                                  static_cast<uint64_t>(HW) * d->C * 2, static_cast<uint64_t>(q_plane_stride) * 2};
-    const uint32_t box[5] = {64, kQTileW, kQTileH, 1, 2};
-    int rc = make_tmap_bf16_sw128(&p.tmap_q, q_split, 5, dims, strides, box);
+    int rc = make_tmap_bf16_sw128(&p.tmap_q, q_bank_split, 5, dims, strides, box);
     if (rc != VFS_OK) return rc;
   }
   {
@@ -536,7 +562,6 @@ int masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_plan
                               static_cast<uint64_t>(k_bank_frames), 2};
     const uint64_t strides[4] = {static_cast<uint64_t>(d->C) * 2, static_cast<uint64_t>(d->W) * d->C * 2,
                                  static_cast<uint64_t>(HW) * d->C * 2, static_cast<uint64_t>(k_plane_stride) * 2};
-    const uint32_t box[5] = {64, kQTileW, kQTileH, 1, 2};
     int rc = make_tmap_bf16_sw128(&p.tmap_k, k_bank_split, 5, dims, strides, box);
     if (rc != VFS_OK) return rc;
   }
@@ -557,15 +582,26 @@ int masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_plan
   MergeParams m;
   memset(&m, 0, sizeof(m));
   m.part_val = p.part_val; m.part_idx = p.part_idx;
-  m.slots = static_cast<int>(slots); m.HW = HW; m.topk = d->topk; m.mode = d->mode; m.temperature = d->temperature;
-  m.values = values; m.v_frame_stride = v_frame_stride; m.v_chan_stride = v_chan_stride; m.Cv = d->Cv;
-  for (int t = 0; t < d->T; ++t) m.frame_ids[t] = key_frame_ids[t];
+  m.slots = d->T * p.splits; m.HW = HW; m.topk = d->topk; m.mode = d->mode; m.temperature = d->temperature;
+  m.values = values; m.v_batch_stride = v_batch_stride; m.v_frame_stride = v_frame_stride;
+  m.v_chan_stride = v_chan_stride; m.Cv = d->Cv; m.T = d->T;
+  for (int i = 0; i < B * d->T; ++i) m.val_ids[i] = static_cast<short>(val_ids[i]);
   m.out = out; m.out_val = out_topk_val; m.out_idx = out_topk_idx;
-  const int blocks = (HW + 127) / 128;
-  if (KMAX == 10) attn_merge_propagate_kernel<10><<<blocks, 128, 0, stream>>>(m);
-  else attn_merge_propagate_kernel<16><<<blocks, 128, 0, stream>>>(m);
+  const dim3 mgrid((HW + 127) / 128, B);
+  if (KMAX == 10) attn_merge_propagate_kernel<10><<<mgrid, 128, 0, stream>>>(m);
+  else attn_merge_propagate_kernel<16><<<mgrid, 128, 0, stream>>>(m);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
+}
+
+int masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_plane_stride, const void* k_bank_split,
+                     long long k_plane_stride, int k_bank_frames, const int* key_frame_ids, const float* values,
+                     long long v_frame_stride, long long v_chan_stride, float* out, float* out_topk_val,
+                     int* out_topk_idx, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const int q_id = 0;
+  return masked_attention_batched(d, 1, q_split, q_plane_stride, 1, &q_id, k_bank_split, k_plane_stride,
+                                  k_bank_frames, key_frame_ids, values, key_frame_ids, 0, v_frame_stride,
+                                  v_chan_stride, out, out_topk_val, out_topk_idx, workspace, workspace_bytes, stream);
 }
 
 }  // namespace vfs

@@ -81,7 +81,13 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uin
 // implemented in the kernel translation units
 int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
                    const float* shift, const void* residual_split, void* out_split, float* out_f32,
-                   cudaStream_t stream);
+                   double* stats, cudaStream_t stream);
+int channel_stats_f32(const float* x, double* stats, long long M, int C, cudaStream_t s);
+int bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean,
+                float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
+                float* save_invstd, int C, cudaStream_t s);
+int bn_apply(const float* z, const float* scale, const float* shift, const void* residual_split, void* out_split,
+             long long M, int C, int relu, cudaStream_t s);
 int conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
                      const float* shift, const void* residual_split, float* out_f32, cudaStream_t stream);
 int nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, cudaStream_t s);
@@ -91,11 +97,20 @@ size_t stem_workspace_bytes(int N, int H, int W);
 int stem_forward(const float* in, const float* weight, const float* scale, const float* shift, void* out_split,
                  void* workspace, int N, int H, int W, cudaStream_t s);
 
+int stem_conv_raw(const float* in, const float* weight, void* conv_out, int N, int H, int W, cudaStream_t s);
+int stem_bn_relu_pool(const void* conv_out, const float* scale, const float* shift, void* out_split, int N, int H,
+                      int W, cudaStream_t s);
 int features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
                       int normalize, cudaStream_t s);
 int normalize_split(const void* in_split, void* out_split, long long num_pixels, int C, long long in_plane_stride,
                     long long out_plane_stride, cudaStream_t s);
-size_t attention_workspace_bytes(const VfsAttnDesc* d);
+size_t attention_workspace_bytes(const VfsAttnDesc* d, int B);
+int masked_attention_batched(const VfsAttnDesc* d, int B, const void* q_bank_split, long long q_plane_stride,
+                             int q_bank_frames, const int* q_ids, const void* k_bank_split, long long k_plane_stride,
+                             int k_bank_frames, const int* key_ids, const float* values, const int* val_ids,
+                             long long v_batch_stride, long long v_frame_stride, long long v_chan_stride, float* out,
+                             float* out_topk_val, int* out_topk_idx, void* workspace, size_t workspace_bytes,
+                             cudaStream_t stream);
 int masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_plane_stride, const void* k_bank_split,
                      long long k_plane_stride, int k_bank_frames, const int* key_frame_ids, const float* values,
                      long long v_frame_stride, long long v_chan_stride, float* out, float* out_topk_val,
@@ -138,10 +153,35 @@ int vfs_stem_forward(const float* in, const float* weight, const float* scale, c
                      void* workspace, int N, int H, int W, vfs_stream_t s) {
   return vfs::stem_forward(in, weight, scale, shift, out_split, workspace, N, H, W, s);
 }
+int vfs_stem_conv_raw(const float* in, const float* weight, void* conv_out_f32_nhwc, int N, int H, int W,
+                      vfs_stream_t s) {
+  return vfs::stem_conv_raw(in, weight, conv_out_f32_nhwc, N, H, W, s);
+}
+int vfs_stem_bn_relu_pool(const void* conv_out_f32_nhwc, const float* scale, const float* shift, void* out_split,
+                          int N, int H, int W, vfs_stream_t s) {
+  return vfs::stem_bn_relu_pool(conv_out_f32_nhwc, scale, shift, out_split, N, H, W, s);
+}
 int vfs_conv_bn_act(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
                     const float* shift, const void* residual_split, void* out_split, float* out_f32_nhwc,
                     vfs_stream_t s) {
-  return vfs::conv_bn_act_tc(d, in_split, w_split, scale, shift, residual_split, out_split, out_f32_nhwc, s);
+  return vfs::conv_bn_act_tc(d, in_split, w_split, scale, shift, residual_split, out_split, out_f32_nhwc, nullptr, s);
+}
+int vfs_conv_stats(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
+                   const float* shift, float* out_f32_nhwc, double* stats, vfs_stream_t s) {
+  return vfs::conv_bn_act_tc(d, in_split, w_split, scale, shift, nullptr, nullptr, out_f32_nhwc, stats, s);
+}
+int vfs_channel_stats_f32(const float* x, double* stats, long long M, int C, vfs_stream_t s) {
+  return vfs::channel_stats_f32(x, stats, M, C, s);
+}
+int vfs_bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
+                    float* save_invstd, int C, vfs_stream_t s) {
+  return vfs::bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift,
+                          save_mean, save_invstd, C, s);
+}
+int vfs_bn_apply(const float* z, const float* scale, const float* shift, const void* residual_split,
+                 void* out_split, long long M, int C, int relu, vfs_stream_t s) {
+  return vfs::bn_apply(z, scale, shift, residual_split, out_split, M, C, relu, s);
 }
 int vfs_pack_conv_weight(const float* w_oihw, void* w_split, int Cout, int Cin, int ksize, vfs_stream_t s) {
   return vfs::pack_conv_weight(w_oihw, w_split, Cout, Cin, ksize, s);
@@ -160,7 +200,21 @@ int vfs_normalize_split(const void* in_split, void* out_split, long long num_pix
                         long long in_plane_stride, long long out_plane_stride, vfs_stream_t s) {
   return vfs::normalize_split(in_split, out_split, num_pixels, C, in_plane_stride, out_plane_stride, s);
 }
-size_t vfs_attention_workspace_bytes(const VfsAttnDesc* d) { return vfs::attention_workspace_bytes(d); }
+size_t vfs_attention_workspace_bytes(const VfsAttnDesc* d, int num_problems) {
+  return vfs::attention_workspace_bytes(d, num_problems);
+}
+int vfs_masked_attention_batched(const VfsAttnDesc* d, int num_problems, const void* q_bank_split,
+                                 long long q_plane_stride, int q_bank_frames, const int32_t* q_frame_ids,
+                                 const void* k_bank_split, long long k_plane_stride, int k_bank_frames,
+                                 const int32_t* key_frame_ids, const float* values, const int32_t* value_frame_ids,
+                                 long long v_batch_stride, long long v_frame_stride, long long v_chan_stride,
+                                 float* out, float* out_topk_val, int32_t* out_topk_idx, void* workspace,
+                                 size_t workspace_bytes, vfs_stream_t s) {
+  return vfs::masked_attention_batched(d, num_problems, q_bank_split, q_plane_stride, q_bank_frames, q_frame_ids,
+                                       k_bank_split, k_plane_stride, k_bank_frames, key_frame_ids, values,
+                                       value_frame_ids, v_batch_stride, v_frame_stride, v_chan_stride, out,
+                                       out_topk_val, out_topk_idx, workspace, workspace_bytes, s);
+}
 int vfs_masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_plane_stride,
                          const void* k_bank_split, long long k_plane_stride, int k_bank_frames,
                          const int32_t* key_frame_ids, const float* values, long long v_frame_stride,

@@ -1,0 +1,136 @@
+// Train-mode BatchNorm pieces around the tcgen05 conv: per-channel statistics of an fp32 tensor, finalisation
+// (mean / invstd / running-stat update, exactly F.batch_norm(training=True)'s bookkeeping) and the normalise +
+// residual + ReLU + split pass.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace vfs {
+
+// x fp32 [M, C] (C multiple of 4): block = 256 threads covering C/4 float4 columns x row groups
+__global__ void channel_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, long long M, int C) {
+  const int c4 = C / 4;
+  const int col = threadIdx.x % c4;          // float4 column
+  const int rgrp = threadIdx.x / c4;         // row group inside the block
+  const int rows_per_block = blockDim.x / c4;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (rgrp < rows_per_block) {
+    for (long long r = static_cast<long long>(blockIdx.x) * rows_per_block + rgrp; r < M;
+         r += static_cast<long long>(gridDim.x) * rows_per_block) {
+      const float4 v = *reinterpret_cast<const float4*>(x + r * C + col * 4);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]);
+      q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      atomicAdd(stats + col * 4 + e, static_cast<double>(s[e]));
+      atomicAdd(stats + C + col * 4 + e, static_cast<double>(q[e]));
+    }
+  }
+}
+
+__global__ void bn_finalize_kernel(double* __restrict__ stats, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = stats[c] / count;
+  double var = stats[C + c] / count - mean * mean;  // biased variance, fp64 so the subtraction is benign
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = b - static_cast<float>(mean) * sc;
+  if (save_mean) save_mean[c] = static_cast<float>(mean);
+  if (save_invstd) save_invstd[c] = invstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+// y = z*scale + shift (+res) (relu) -> split; one thread per 8 channels
+__global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res_hi,
+                                const __nv_bfloat16* __restrict__ res_lo, __nv_bfloat16* __restrict__ out_hi,
+                                __nv_bfloat16* __restrict__ out_lo, long long total8, int C, int relu) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long o = i * 8;
+    const int c = static_cast<int>(o % C);
+    const float4 a = *reinterpret_cast<const float4*>(z + o), b = *reinterpret_cast<const float4*>(z + o + 4);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
+    float y[8] = {fmaf(a.x, s0.x, h0.x), fmaf(a.y, s0.y, h0.y), fmaf(a.z, s0.z, h0.z), fmaf(a.w, s0.w, h0.w),
+                  fmaf(b.x, s1.x, h1.x), fmaf(b.y, s1.y, h1.y), fmaf(b.z, s1.z, h1.z), fmaf(b.w, s1.w, h1.w)};
+    if (res_hi) {
+      const uint4 rh = *reinterpret_cast<const uint4*>(res_hi + o), rl = *reinterpret_cast<const uint4*>(res_lo + o);
+      y[0] += bf16_lo_to_float(rh.x) + bf16_lo_to_float(rl.x);
+      y[1] += bf16_hi_to_float(rh.x) + bf16_hi_to_float(rl.x);
+      y[2] += bf16_lo_to_float(rh.y) + bf16_lo_to_float(rl.y);
+      y[3] += bf16_hi_to_float(rh.y) + bf16_hi_to_float(rl.y);
+      y[4] += bf16_lo_to_float(rh.z) + bf16_lo_to_float(rl.z);
+      y[5] += bf16_hi_to_float(rh.z) + bf16_hi_to_float(rl.z);
+      y[6] += bf16_lo_to_float(rh.w) + bf16_lo_to_float(rl.w);
+      y[7] += bf16_hi_to_float(rh.w) + bf16_hi_to_float(rl.w);
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.0f);
+    }
+    __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_bf16(y[e], hi[e], lo[e]);
+    uint4 oh, ol;
+    oh.x = pack_bf16x2(hi[0], hi[1]); oh.y = pack_bf16x2(hi[2], hi[3]);
+    oh.z = pack_bf16x2(hi[4], hi[5]); oh.w = pack_bf16x2(hi[6], hi[7]);
+    ol.x = pack_bf16x2(lo[0], lo[1]); ol.y = pack_bf16x2(lo[2], lo[3]);
+    ol.z = pack_bf16x2(lo[4], lo[5]); ol.w = pack_bf16x2(lo[6], lo[7]);
+    *reinterpret_cast<uint4*>(out_hi + o) = oh;
+    *reinterpret_cast<uint4*>(out_lo + o) = ol;
+  }
+}
+
+int channel_stats_f32(const float* x, double* stats, long long M, int C, cudaStream_t s) {
+  VFS_REQUIRE(x && stats, VFS_EINVAL, "channel_stats: null argument");
+  VFS_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && C / 4 <= 256, VFS_ESHAPE, "channel_stats: C=%d unsupported", C);
+  const int c4 = C / 4;
+  const int rows_per_block = 256 / c4;
+  long long blocks = (M + rows_per_block - 1) / rows_per_block;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  channel_stats_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(x, stats, M, C);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+int bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean,
+                float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
+                float* save_invstd, int C, cudaStream_t s) {
+  VFS_REQUIRE(stats && scale && shift, VFS_EINVAL, "bn_finalize: null argument");
+  VFS_REQUIRE(count > 1.0, VFS_ESHAPE, "bn_finalize: Expected more than 1 value per channel when training");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, count, gamma, beta, running_mean, running_var, momentum,
+                                                     eps, scale, shift, save_mean, save_invstd, C);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+int bn_apply(const float* z, const float* scale, const float* shift, const void* residual_split, void* out_split,
+             long long M, int C, int relu, cudaStream_t s) {
+  VFS_REQUIRE(z && scale && shift && out_split, VFS_EINVAL, "bn_apply: null argument");
+  VFS_REQUIRE(M > 0 && C > 0 && C % 8 == 0, VFS_ESHAPE, "bn_apply: C=%d must be a multiple of 8", C);
+  const long long total8 = M * C / 8;
+  const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(residual_split);
+  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(out_split);
+  long long blocks = (total8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bn_apply_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(z, scale, shift, rh, rh ? rh + M * C : nullptr, oh,
+                                                           oh + M * C, total8, C, relu);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+}  // namespace vfs

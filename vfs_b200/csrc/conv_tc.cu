@@ -50,6 +50,8 @@ struct alignas(64) ConvKernelParams {
   __nv_bfloat16* out_lo;
   float* out_f32;  // nullable, NHWC fp32
   int relu;
+  double* stat_sum;    // nullable: per-channel sum / sum of squares of the epilogue output over all valid pixels
+  double* stat_sqsum;  // (train-mode BatchNorm statistics; accumulated with fp64 atomics)
 };
 
 template <int BN, int STAGES>
@@ -206,6 +208,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 64) {
         const int cg = n_tile * BN + c0;
+        // Prefetch this thread's residual pieces for phase B now, so their HBM/L2 latency is hidden behind the
+        // TMEM reads and the staging pass (the epilogue was long-scoreboard bound on these loads).
+        uint4 pre_h[8], pre_l[8];
+        if (p.res_hi != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rr + 16 * i;
+            const int dw = r % p.tw;
+            const int r2 = r / p.tw;
+            const int w = w0 + dw, hh = h0 + r2 % p.th, n = n0 + r2 / p.th;
+            pre_h[i] = make_uint4(0, 0, 0, 0);
+            pre_l[i] = make_uint4(0, 0, 0, 0);
+            if ((w < p.Wo) && (hh < p.Ho) && (n < p.N)) {
+              const size_t o = ((static_cast<size_t>(n) * p.Ho + hh) * p.Wo + w) * p.Cout + cg + piece * 8;
+              pre_h[i] = *reinterpret_cast<const uint4*>(p.res_hi + o);
+              pre_l[i] = *reinterpret_cast<const uint4*>(p.res_lo + o);
+            }
+          }
+        }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffer free
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -231,7 +252,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffer full
-#pragma unroll 2
+        float st_s[8], st_q[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) st_s[e] = st_q[e] = 0.0f;
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = rr + 16 * i;
           const int dw = r % p.tw;
@@ -241,11 +265,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           const int w = w0 + dw, hh = h0 + dh, n = n0 + dn;
           if ((w < p.Wo) && (hh < p.Ho) && (n < p.N)) {
             const size_t o = ((static_cast<size_t>(n) * p.Ho + hh) * p.Wo + w) * p.Cout + cg + piece * 8;
-            uint4 rh = make_uint4(0, 0, 0, 0), rl = make_uint4(0, 0, 0, 0);
-            if (p.res_hi != nullptr) {
-              rh = *reinterpret_cast<const uint4*>(p.res_hi + o);
-              rl = *reinterpret_cast<const uint4*>(p.res_lo + o);
-            }
+            const uint4 rh = pre_h[i], rl = pre_l[i];
             float y[8];
             const uint32_t a0 = stg_base + r * 256 + phys_chunk(r, 2 * piece) * 16;
             const uint32_t a1 = stg_base + r * 256 + phys_chunk(r, 2 * piece + 1) * 16;
@@ -267,6 +287,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
               for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.0f);
             }
+            if (p.stat_sum != nullptr) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                st_s[e] += y[e];
+                st_q[e] = fmaf(y[e], y[e], st_q[e]);
+              }
+            }
             if (p.out_f32 != nullptr) {
               float4* of = reinterpret_cast<float4*>(p.out_f32 + o);
               of[0] = make_float4(y[0], y[1], y[2], y[3]);
@@ -287,6 +314,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
               ol.w = pack_bf16x2(lo[6], lo[7]);
               *reinterpret_cast<uint4*>(p.out_hi + o) = oh;
               *reinterpret_cast<uint4*>(p.out_lo + o) = ol;
+            }
+          }
+        }
+        if (p.stat_sum != nullptr) {
+          // lanes {l, l+8, l+16, l+24} hold the same 8 channels for different rows: fold them, then one fp64
+          // atomic per channel and warp
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            st_s[e] += __shfl_xor_sync(0xffffffffu, st_s[e], 8);
+            st_q[e] += __shfl_xor_sync(0xffffffffu, st_q[e], 8);
+            st_s[e] += __shfl_xor_sync(0xffffffffu, st_s[e], 16);
+            st_q[e] += __shfl_xor_sync(0xffffffffu, st_q[e], 16);
+          }
+          if (lane < 8) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              atomicAdd(p.stat_sum + cg + piece * 8 + e, static_cast<double>(st_s[e]));
+              atomicAdd(p.stat_sqsum + cg + piece * 8 + e, static_cast<double>(st_q[e]));
             }
           }
         }
@@ -349,7 +394,7 @@ int launch(const ConvKernelParams& p, int grid, cudaStream_t stream) {
 
 int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
                    const float* shift, const void* residual_split, void* out_split, float* out_f32,
-                   cudaStream_t stream) {
+                   double* stats, cudaStream_t stream) {
   VFS_REQUIRE(d && in_split && w_split && scale && shift, VFS_EINVAL, "conv_bn_act: null argument");
   VFS_REQUIRE(out_split || out_f32, VFS_EINVAL, "conv_bn_act: no output buffer");
   VFS_REQUIRE(d->ksize == 1 || d->ksize == 3, VFS_ESHAPE, "conv_bn_act: ksize %d unsupported", d->ksize);
@@ -375,6 +420,10 @@ int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_spl
   p.shift = shift;
   p.relu = d->relu;
   p.out_f32 = out_f32;
+  if (stats) {
+    p.stat_sum = stats;
+    p.stat_sqsum = stats + Cout;
+  }
   if (out_split) {
     p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_split);
     p.out_lo = p.out_hi + out_plane;

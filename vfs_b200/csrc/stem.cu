@@ -73,20 +73,25 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     float4* dst = reinterpret_cast<float4*>(out + ((static_cast<size_t>(n) * Hc + oy) * Wc + ox) * 64);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + j);
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + j);
       float4 y;
-      y.x = fmaxf(fmaf(acc[4 * j + 0], sc.x, sh.x), 0.0f);
-      y.y = fmaxf(fmaf(acc[4 * j + 1], sc.y, sh.y), 0.0f);
-      y.z = fmaxf(fmaf(acc[4 * j + 2], sc.z, sh.z), 0.0f);
-      y.w = fmaxf(fmaf(acc[4 * j + 3], sc.w, sh.w), 0.0f);
+      if (scale != nullptr) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + j);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + j);
+        y.x = fmaxf(fmaf(acc[4 * j + 0], sc.x, sh.x), 0.0f);
+        y.y = fmaxf(fmaf(acc[4 * j + 1], sc.y, sh.y), 0.0f);
+        y.z = fmaxf(fmaf(acc[4 * j + 2], sc.z, sh.z), 0.0f);
+        y.w = fmaxf(fmaf(acc[4 * j + 3], sc.w, sh.w), 0.0f);
+      } else {  // raw convolution output (train-mode BN: statistics are taken before normalisation)
+        y = make_float4(acc[4 * j + 0], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+      }
       dst[j] = y;
     }
   }
 }
 
 // maxpool 3x3/s2/p1 over fp32 NHWC (C = 64) -> split NHWC.  One thread per (pixel, 8 channels).
-__global__ void stem_pool_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out_hi,
+__global__ void stem_pool_kernel(const float* __restrict__ in, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, __nv_bfloat16* __restrict__ out_hi,
                                  __nv_bfloat16* __restrict__ out_lo, int N, int Hc, int Wc, int Hp, int Wp) {
   const size_t total = static_cast<size_t>(N) * Hp * Wp * 8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -108,7 +113,17 @@ __global__ void stem_pool_kernel(const float* __restrict__ in, __nv_bfloat16* __
         if (x < 0 || x >= Wc) continue;
         const float4* src =
             reinterpret_cast<const float4*>(in + ((static_cast<size_t>(n) * Hc + y) * Wc + x) * 64 + g * 8);
-        const float4 a = src[0], b = src[1];
+        float4 a = src[0], b = src[1];
+        if (scale != nullptr) {  // BN(batch statistics) + ReLU applied on the fly to the raw conv output
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + g * 8));
+          const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + g * 8 + 4));
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + g * 8));
+          const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + g * 8 + 4));
+          a = make_float4(fmaxf(fmaf(a.x, s0.x, h0.x), 0.f), fmaxf(fmaf(a.y, s0.y, h0.y), 0.f),
+                          fmaxf(fmaf(a.z, s0.z, h0.z), 0.f), fmaxf(fmaf(a.w, s0.w, h0.w), 0.f));
+          b = make_float4(fmaxf(fmaf(b.x, s1.x, h1.x), 0.f), fmaxf(fmaf(b.y, s1.y, h1.y), 0.f),
+                          fmaxf(fmaf(b.z, s1.z, h1.z), 0.f), fmaxf(fmaf(b.w, s1.w, h1.w), 0.f));
+        }
         m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
         m[4] = fmaxf(m[4], b.x); m[5] = fmaxf(m[5], b.y); m[6] = fmaxf(m[6], b.z); m[7] = fmaxf(m[7], b.w);
       }
@@ -140,10 +155,8 @@ size_t stem_workspace_bytes(int N, int H, int W) {
   return static_cast<size_t>(N) * Hc * Wc * 64 * sizeof(float);
 }
 
-int stem_forward(const float* in, const float* weight, const float* scale, const float* shift, void* out_split,
-                 void* workspace, int N, int H, int W, cudaStream_t s) {
-  VFS_REQUIRE(in && weight && scale && shift && out_split && workspace, VFS_EINVAL, "stem_forward: null argument");
-  VFS_REQUIRE(N > 0 && H >= 7 && W >= 7, VFS_ESHAPE, "stem_forward: input %dx%dx%d too small", N, H, W);
+static int stem_conv_launch(const float* in, const float* weight, const float* scale, const float* shift,
+                            float* conv_out, int N, int H, int W, cudaStream_t s) {
   int Hc, Wc, Hp, Wp;
   stem_dims(H, W, &Hc, &Wc, &Hp, &Wp);
   static bool configured = false;
@@ -152,17 +165,46 @@ int stem_forward(const float* in, const float* weight, const float* scale, const
     VFS_CUDA_OK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
-  float* conv_out = reinterpret_cast<float*>(workspace);
   dim3 grid((Wc + kStemTileW - 1) / kStemTileW, (Hc + kStemTileH - 1) / kStemTileH, N);
   stem_conv_kernel<<<grid, 256, smem_bytes, s>>>(in, weight, scale, shift, conv_out, H, W, Hc, Wc);
   VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+static int stem_pool_launch(const float* conv_out, const float* scale, const float* shift, void* out_split, int N,
+                            int H, int W, cudaStream_t s) {
+  int Hc, Wc, Hp, Wp;
+  stem_dims(H, W, &Hc, &Wc, &Hp, &Wp);
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out_split);
   __nv_bfloat16* lo = hi + static_cast<size_t>(N) * Hp * Wp * 64;
   const size_t total = static_cast<size_t>(N) * Hp * Wp * 8;
   const int blocks = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  stem_pool_kernel<<<blocks, 256, 0, s>>>(conv_out, hi, lo, N, Hc, Wc, Hp, Wp);
+  stem_pool_kernel<<<blocks, 256, 0, s>>>(conv_out, scale, shift, hi, lo, N, Hc, Wc, Hp, Wp);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
+}
+
+int stem_forward(const float* in, const float* weight, const float* scale, const float* shift, void* out_split,
+                 void* workspace, int N, int H, int W, cudaStream_t s) {
+  VFS_REQUIRE(in && weight && scale && shift && out_split && workspace, VFS_EINVAL, "stem_forward: null argument");
+  VFS_REQUIRE(N > 0 && H >= 7 && W >= 7, VFS_ESHAPE, "stem_forward: input %dx%dx%d too small", N, H, W);
+  float* conv_out = reinterpret_cast<float*>(workspace);
+  int rc = stem_conv_launch(in, weight, scale, shift, conv_out, N, H, W, s);
+  if (rc != VFS_OK) return rc;
+  return stem_pool_launch(conv_out, nullptr, nullptr, out_split, N, H, W, s);
+}
+
+// train-mode pieces: raw conv output (statistics are computed on it), then BN+ReLU fused into the max-pool
+int stem_conv_raw(const float* in, const float* weight, void* conv_out, int N, int H, int W, cudaStream_t s) {
+  VFS_REQUIRE(in && weight && conv_out, VFS_EINVAL, "stem_conv_raw: null argument");
+  VFS_REQUIRE(N > 0 && H >= 7 && W >= 7, VFS_ESHAPE, "stem_conv_raw: input %dx%dx%d too small", N, H, W);
+  return stem_conv_launch(in, weight, nullptr, nullptr, reinterpret_cast<float*>(conv_out), N, H, W, s);
+}
+
+int stem_bn_relu_pool(const void* conv_out, const float* scale, const float* shift, void* out_split, int N, int H,
+                      int W, cudaStream_t s) {
+  VFS_REQUIRE(conv_out && scale && shift && out_split, VFS_EINVAL, "stem_bn_relu_pool: null argument");
+  return stem_pool_launch(reinterpret_cast<const float*>(conv_out), scale, shift, out_split, N, H, W, s);
 }
 
 }  // namespace vfs

@@ -2,7 +2,7 @@
 weights, folded BN scale/shift) and walks the block list issuing one fused kernel per ConvModule through the
 C ABI.  It never computes anything in torch: tensors here are only device buffers handed to libvfs_b200.so.
 
-Train-mode batch statistics are not fused yet; in that mode the engine raises (no silent eval-mode result).
+Train-mode BatchNorm (batch statistics, SyncBN exchange) runs as conv+stats -> finalise -> normalise kernels.
 """
 import torch
 from torch.nn.modules.batchnorm import _BatchNorm
@@ -40,6 +40,7 @@ class BackboneEngine:
         self._plans = {}
         self.check_versions = True  # re-pack when parameters were modified in place / reloaded
         self.events = None          # bench instrumentation: list collecting (tag, cuda event) at phase boundaries
+        self.tape = None            # training: list recording what backward needs (set by the autograd wrapper)
         self._graphs = {}           # (input shape, stage, normalize) -> captured CUDA graph over static buffers
         self._tensors = None
 
@@ -49,7 +50,7 @@ class BackboneEngine:
         v = cm.conv.weight._version + cm.conv.weight.data_ptr()
         if cm.with_norm:
             bn = cm.norm
-            for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var):
+            for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked):
                 if t is not None:
                     v += t._version + t.data_ptr()
         return v
@@ -81,26 +82,40 @@ class BackboneEngine:
     def conv(self, cm, xs, relu, residual=None, want_f32=False):
         """One ConvModule (+residual, +ReLU) on a split NHWC tensor."""
         assert isinstance(cm, ConvModule)
-        if cm.with_norm and cm.norm.training:
-            raise NotImplementedError(
-                'vfs_b200: train-mode (batch-statistics) BatchNorm is not implemented in the native engine yet; '
-                'call .eval() on the model or use norm_eval=True')
         k = cm.conv.kernel_size[0]
         stride, dil, pad = cm.conv.stride[0], cm.conv.dilation[0], cm.conv.padding[0]
         assert cm.conv.kernel_size[0] == cm.conv.kernel_size[1] and cm.conv.stride[0] == cm.conv.stride[1]
         assert cm.conv.groups == 1
         assert pad == (0 if k == 1 else dil), f'unsupported padding {pad} for k={k}, dilation={dil}'
         p = self.plan(cm, xs.device)
+        if cm.with_norm and cm.norm.training:
+            # batch statistics: conv (+ per-channel sums in the epilogue) -> finalise (+ SyncBN all-reduce,
+            # running-stat update) -> normalise + residual + ReLU
+            assert not want_f32
+            z, stats = ops.conv_stats(xs, p.w_split, k, stride, dil)
+            scale, shift, mean, invstd = ops.bn_finalize(stats, z.numel() // z.shape[-1], cm.norm)
+            y = ops.bn_apply(z, scale, shift, residual, relu)
+            if self.tape is not None:
+                self.tape.append(dict(cm=cm, xs=xs, z=z, mean=mean, invstd=invstd, y=y, relu=relu,
+                                      residual=residual, k=k, stride=stride, dil=dil))
+            return y
         out, out32 = ops.conv_bn_act(xs, p.w_split, p.scale, p.shift, k, stride, dil, relu, residual,
                                      want_split=not want_f32, want_f32=want_f32)
         return out32 if want_f32 else out
 
     def stem(self, x):
         cm = self.net.conv1
-        if cm.with_norm and cm.norm.training:
-            raise NotImplementedError('vfs_b200: train-mode BatchNorm is not implemented in the native engine yet')
         assert cm.conv.in_channels == 3 and cm.conv.kernel_size == (7, 7) and cm.conv.stride == (2, 2)
         p = self.plan(cm, x.device)
+        if cm.with_norm and cm.norm.training:
+            z = ops.stem_conv_raw(x, p.w_split)
+            stats = ops.channel_stats(z)
+            scale, shift, mean, invstd = ops.bn_finalize(stats, z.numel() // 64, cm.norm)
+            y = ops.stem_bn_relu_pool(z, scale, shift, x.shape[2:])
+            if self.tape is not None:
+                self.tape.append(dict(cm=cm, stem=True, x=x, z=z, mean=mean, invstd=invstd, scale=scale,
+                                      shift=shift, y=y))
+            return y
         return ops.stem_forward(x, p.w_split, p.scale, p.shift)
 
     # -------------------------------------------------------------- whole backbone
@@ -119,8 +134,8 @@ class BackboneEngine:
         last_stage = max(out_indices) if out_indices is not None else len(net.res_layers) - 1
         bidx = 0
         for i, name in enumerate(net.res_layers):
-            if i > last_stage:
-                break
+            if i > last_stage and not net.training:
+                break  # in train mode the reference's later stages still update their BN running statistics
             for block in getattr(net, name):
                 xs = block.native_forward(self, xs)
                 if block_index is not None and bidx == block_index:

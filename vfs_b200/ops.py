@@ -117,6 +117,97 @@ def stem_forward(x, weight, scale, shift):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# train-mode BatchNorm around the conv kernel (batch statistics; SyncBN exchange = one all-reduce of the stats)
+# ---------------------------------------------------------------------------------------------------------
+_CONST_CACHE = {}
+
+
+def _const_vec(value, n, device):
+    key = (float(value), int(n), str(device))
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        t = torch.full((n, ), float(value), dtype=torch.float32, device=device)
+        _CONST_CACHE[key] = t
+    return t
+
+
+def conv_stats(xs, w_split, ksize, stride=1, dilation=1):
+    """Raw conv output (fp32 NHWC) + per-channel [sum | sum of squares] (fp64 [2*Cout]) in one kernel."""
+    Cout = w_split.shape[1]
+    _, N, H, W, Cin = xs.shape
+    Ho, Wo = conv_out_hw(H, W, ksize, stride, dilation)
+    z = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=xs.device)
+    stats = torch.zeros((2 * Cout, ), dtype=torch.float64, device=xs.device)
+    d = _desc(xs, Cout, ksize, stride, dilation, False)
+    check(nat.lib().vfs_conv_stats(ctypes.byref(d), ptr(xs), ptr(w_split), ptr(_const_vec(1, Cout, xs.device)),
+                                   ptr(_const_vec(0, Cout, xs.device)), ptr(z), ptr(stats), current_stream()),
+          'conv_stats')
+    return z, stats
+
+
+def channel_stats(z):
+    """fp32 [..., C] -> fp64 [2*C] per-channel sum | sum of squares."""
+    C = z.shape[-1]
+    stats = torch.zeros((2 * C, ), dtype=torch.float64, device=z.device)
+    check(nat.lib().vfs_channel_stats_f32(ptr(z), ptr(stats), z.numel() // C, C, current_stream()), 'channel_stats')
+    return stats
+
+
+def bn_finalize(stats, count, bn):
+    """Batch statistics -> (scale, shift, save_mean, save_invstd); updates bn.running_* like torch.  With
+    SyncBatchNorm in an initialised multi-rank process group the statistics are all-reduced first (that IS the
+    SyncBN exchange: [sum, sum of squares] is equivalent to torch's gather of mean/invstd/count)."""
+    C = stats.numel() // 2
+    import torch.distributed as dist
+    if isinstance(bn, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() \
+            and dist.get_world_size() > 1:
+        dist.all_reduce(stats)
+        count = count * dist.get_world_size()
+    dev = stats.device
+    scale = torch.empty((C, ), dtype=torch.float32, device=dev)
+    shift = torch.empty_like(scale)
+    mean = torch.empty_like(scale)
+    invstd = torch.empty_like(scale)
+    track = bn.track_running_stats and bn.running_mean is not None
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    check(nat.lib().vfs_bn_finalize(ptr(stats), float(count), ptr(bn.weight.detach()) if bn.affine else None,
+                                    ptr(bn.bias.detach()) if bn.affine else None,
+                                    ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
+                                    float(momentum), float(bn.eps), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), C,
+                                    current_stream()), 'bn_finalize')
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1   # also bumps a tensor version so cached eval-mode folds are refreshed
+    return scale, shift, mean, invstd
+
+
+def bn_apply(z, scale, shift, residual=None, relu=True):
+    """fp32 NHWC z -> split NHWC relu?(z*scale + shift (+residual))."""
+    N, H, W, C = z.shape
+    out = torch.empty((2, N, H, W, C), dtype=torch.bfloat16, device=z.device)
+    check(nat.lib().vfs_bn_apply(ptr(z), ptr(scale), ptr(shift), ptr(residual), ptr(out), N * H * W, C, int(relu),
+                                 current_stream()), 'bn_apply')
+    return out
+
+
+def stem_conv_raw(x, weight):
+    N, C, H, W = x.shape
+    Hc, Wc = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    z = torch.empty((N, Hc, Wc, 64), dtype=torch.float32, device=x.device)
+    check(nat.lib().vfs_stem_conv_raw(ptr(x), ptr(weight), ptr(z), N, H, W, current_stream()), 'stem_conv_raw')
+    return z
+
+
+def stem_bn_relu_pool(z, scale, shift, in_hw):
+    N, Hc, Wc, _ = z.shape
+    H, W = in_hw
+    Hp, Wp = (Hc + 2 - 3) // 2 + 1, (Wc + 2 - 3) // 2 + 1
+    out = torch.empty((2, N, Hp, Wp, 64), dtype=torch.bfloat16, device=z.device)
+    check(nat.lib().vfs_stem_bn_relu_pool(ptr(z), ptr(scale), ptr(shift), ptr(out), N, H, W, current_stream()),
+          'stem_bn_relu_pool')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
 # SimSiam head / loss
 # ---------------------------------------------------------------------------------------------------------
 def _f32c(t, name):
@@ -252,61 +343,84 @@ def normalize_split(xs, out=None):
 _MASK_MODES = {None: 0, 'circle': 1, 'square': 2}
 
 
-def attention_bank(q_split, k_bank, key_frame_ids, values, v_frame_stride, v_chan_stride, Cv, mask, temperature,
-                   topk, non_mask_len=0, mode='softmax', return_topk=False):
-    """Core call: ``q_split`` [2,1,H,W,C] view (may be a slice of the bank), ``k_bank`` [2,F,H,W,C] normalised split
-    bank, ``key_frame_ids`` python list of bank frames, ``values`` fp32 tensor addressed by the given strides.
-    Returns out [Cv, H*W] (and top-k values / indices [topk, H*W])."""
+def attention_bank_batched(q_bank, q_ids, k_bank, key_ids, values, val_ids, v_batch_stride, v_frame_stride,
+                           v_chan_stride, Cv, mask, temperature, topk, non_mask_len=0, mode='softmax',
+                           return_topk=False):
+    """P independent (query frame, key set) problems in one launch.  ``q_bank`` [2,Fq,H,W,C] / ``k_bank`` [2,Fk,H,W,C]
+    normalised split banks; ``q_ids`` [P], ``key_ids`` [P][T] bank frames; ``val_ids`` [P][T] frame indices used to
+    address ``values`` (see include/vfs_b200.h).  Returns out [P,Cv,H*W] (+ top-k values / indices [P,topk,H*W])."""
     from ._native import VfsAttnDesc
     _require_cuda(k_bank, 'k_bank')
-    assert q_split.dtype == torch.bfloat16 and k_bank.dtype == torch.bfloat16
-    _, F, H, W, C = k_bank.shape
-    assert q_split.shape[2:] == (H, W, C), (q_split.shape, k_bank.shape)
-    assert q_split[0].is_contiguous() and k_bank[0].is_contiguous()
-    T = len(key_frame_ids)
+    assert q_bank.dtype == torch.bfloat16 and k_bank.dtype == torch.bfloat16
+    _, Fk, H, W, C = k_bank.shape
+    Fq = q_bank.shape[1]
+    assert q_bank.shape[2:] == (H, W, C), (q_bank.shape, k_bank.shape)
+    assert q_bank[0].is_contiguous() and k_bank[0].is_contiguous()
+    P = len(q_ids)
+    T = len(key_ids[0])
+    assert len(key_ids) == P and len(val_ids) == P and all(len(k) == T for k in key_ids)
     d = VfsAttnDesc(H=H, W=W, C=C, Cv=Cv, T=T, topk=topk,
                     mask_mode=_MASK_MODES[mask.mode if mask is not None else None],
                     radius_y=mask.radius_y if mask is not None else 0,
                     radius_x=mask.radius_x if mask is not None else 0, non_mask_len=non_mask_len,
                     mode=0 if mode == 'softmax' else 1, temperature=float(temperature))
-    ws_bytes = nat.lib().vfs_attention_workspace_bytes(ctypes.byref(d))
+    ws_bytes = nat.lib().vfs_attention_workspace_bytes(ctypes.byref(d), P)
     ws = torch.empty((ws_bytes, ), dtype=torch.uint8, device=k_bank.device)
-    out = torch.empty((Cv, H * W), dtype=torch.float32, device=k_bank.device)
-    tv = torch.empty((topk, H * W), dtype=torch.float32, device=k_bank.device) if return_topk else None
-    ti = torch.empty((topk, H * W), dtype=torch.int32, device=k_bank.device) if return_topk else None
-    ids = (ctypes.c_int32 * T)(*[int(i) for i in key_frame_ids])
-    check(nat.lib().vfs_masked_attention(ctypes.byref(d), ptr(q_split), q_split.stride(0), ptr(k_bank),
-                                         k_bank.stride(0), F, ids, ptr(values), int(v_frame_stride),
-                                         int(v_chan_stride), ptr(out), ptr(tv), ptr(ti), ptr(ws), ws_bytes,
-                                         current_stream()), 'masked_attention')
+    out = torch.empty((P, Cv, H * W), dtype=torch.float32, device=k_bank.device)
+    tv = torch.empty((P, topk, H * W), dtype=torch.float32, device=k_bank.device) if return_topk else None
+    ti = torch.empty((P, topk, H * W), dtype=torch.int32, device=k_bank.device) if return_topk else None
+    qarr = (ctypes.c_int32 * P)(*[int(i) for i in q_ids])
+    karr = (ctypes.c_int32 * (P * T))(*[int(i) for row in key_ids for i in row])
+    varr = (ctypes.c_int32 * (P * T))(*[int(i) for row in val_ids for i in row])
+    check(nat.lib().vfs_masked_attention_batched(
+        ctypes.byref(d), P, ptr(q_bank), q_bank.stride(0), Fq, qarr, ptr(k_bank), k_bank.stride(0), Fk, karr,
+        ptr(values), varr, int(v_batch_stride), int(v_frame_stride), int(v_chan_stride), ptr(out), ptr(tv), ptr(ti),
+        ptr(ws), ws_bytes, current_stream()), 'masked_attention')
     if return_topk:
         return out, tv, ti
     return out
 
 
+def attention_bank(q_split, k_bank, key_frame_ids, values, v_frame_stride, v_chan_stride, Cv, mask, temperature,
+                   topk, non_mask_len=0, mode='softmax', return_topk=False):
+    """One query frame: ``q_split`` [2,1,H,W,C] view (may be a slice of the bank), ``k_bank`` [2,F,H,W,C] normalised
+    split bank, ``key_frame_ids`` python list of bank frames, ``values`` fp32 tensor addressed by the given strides.
+    Returns out [Cv, H*W] (and top-k values / indices [topk, H*W])."""
+    ids = [list(key_frame_ids)]
+    r = attention_bank_batched(q_split, [0], k_bank, ids, values, ids, 0, v_frame_stride, v_chan_stride, Cv, mask,
+                               temperature, topk, non_mask_len, mode, return_topk)
+    if return_topk:
+        return r[0][0], r[1][0], r[2][0]
+    return r[0]
+
+
 def masked_attention(query, key, value, mask, temperature, topk, normalize=True, non_mask_len=0, mode='softmax',
                      return_topk=False):
-    """Reference-shaped call: query [N,C,H,W], key [N,C,T,H,W], value [N,Cv,T,H,W] fp32 CUDA -> [N,Cv,H,W]."""
+    """Reference-shaped call: query [N,C,H,W], key [N,C,T,H,W], value [N,Cv,T,H,W] fp32 CUDA -> [N,Cv,H,W].
+    All N batch items run in one launch (chunks of 32 items / 256 key frames)."""
     for t, n in ((query, 'query'), (key, 'key'), (value, 'value')):
         _require_cuda(t, n)
     N, C, H, W = query.shape
     T, Cv = key.shape[2], value.shape[1]
     assert key.shape[3:] == (H, W), 'vfs_b200: query and key feature maps must have the same size'
     HW = H * W
+    qs = features_to_split(query.float(), normalize)                                              # [2,N,H,W,C]
+    ks = features_to_split(key.float().transpose(1, 2).reshape(N * T, C, H, W).contiguous(), normalize)
+    v = value.float().contiguous()                                                                # [N,Cv,T,H,W]
+    per = max(1, min(32, 256 // T))
     outs, tvs, tis = [], [], []
-    for b in range(N):
-        qs = features_to_split(query[b:b + 1].float(), normalize)                       # [2,1,H,W,C]
-        ks = features_to_split(key[b].float().transpose(0, 1).contiguous(), normalize)  # [2,T,H,W,C]
-        v = value[b].float().contiguous()                                               # [Cv,T,H,W]
-        r = attention_bank(qs, ks, list(range(T)), v, HW, T * HW, Cv, mask, temperature, topk, non_mask_len, mode,
-                           return_topk)
+    for b0 in range(0, N, per):
+        bs = list(range(b0, min(N, b0 + per)))
+        r = attention_bank_batched(qs, bs, ks, [[b * T + t for t in range(T)] for b in bs], v[b0:],
+                                   [list(range(T)) for _ in bs], Cv * T * HW, HW, T * HW, Cv, mask, temperature, topk,
+                                   non_mask_len, mode, return_topk)
         if return_topk:
             outs.append(r[0]); tvs.append(r[1]); tis.append(r[2])
         else:
             outs.append(r)
-    out = torch.stack(outs).reshape(N, Cv, H, W)
+    out = torch.cat(outs).reshape(N, Cv, H, W)
     if return_topk:
-        return out, torch.stack(tvs), torch.stack(tis)
+        return out, torch.cat(tvs), torch.cat(tis)
     return out
 
 
