@@ -104,6 +104,19 @@ int vfs_bn_finalize(double* stats, double count, const float* gamma, const float
 int vfs_bn_apply(const float* z, const float* scale, const float* shift, const void* residual_split,
                  void* out_split, long long M, int C, int relu, vfs_stream_t s);
 
+/* ------------------------------------------------------------------------------------------------
+ * Backward of the convolution w.r.t. its input (training): dX = conv_transpose(dZ, W) (+ add), the same tcgen05
+ * implicit-GEMM kernel with the roles of Cin/Cout swapped and a flipped kernel; stride-2 layers are evaluated per
+ * output-parity class.  Replaces torch autograd's cudnn_convolution_backward_input for the ConvModules of
+ * resnet.py.  `d` is the FORWARD descriptor (N,H,W = forward input extent).
+ *   dz_split  split NHWC [N,Ho,Wo,Cout]     wt_split  split [2][Cin][k*k*Cout] (vfs_pack_conv_weight_dgrad)
+ *   ones/zeros fp32 [Cin] constant vectors  add_split NULL or split NHWC [N,H,W,Cin] (gradient of another branch)
+ *   dx_split  split NHWC [N,H,W,Cin]
+ * ---------------------------------------------------------------------------------------------- */
+int vfs_conv_dgrad(const VfsConvDesc* d, const void* dz_split, const void* wt_split, const float* ones,
+                   const float* zeros, const void* add_split, void* dx_split, vfs_stream_t s);
+int vfs_pack_conv_weight_dgrad(const float* w_oihw, void* wt_split, int Cout, int Cin, int ksize, vfs_stream_t s);
+
 /* OIHW fp32 [Cout,Cin,k,k] -> split [2][Cout][k*k*Cin] (device to device). */
 int vfs_pack_conv_weight(const float* w_oihw, void* w_split, int Cout, int Cin, int ksize, vfs_stream_t s);
 

@@ -197,6 +197,37 @@ def test_conv_bn_act_against_fp64_and_simt(case):
     assert rel_err(out32, simt) < 5e-5
 
 
+DGRAD_CASES = [
+    # N, H, W, Cin, Cout, k, stride, dil, with_add
+    (2, 16, 16, 64, 128, 1, 1, 1, 0), (2, 16, 16, 64, 64, 3, 1, 1, 1), (1, 15, 13, 128, 64, 3, 1, 1, 0),
+    (2, 16, 16, 64, 128, 3, 2, 1, 1), (1, 15, 13, 64, 64, 3, 2, 1, 0), (2, 16, 16, 128, 256, 1, 2, 1, 1),
+    (1, 15, 13, 64, 128, 1, 2, 1, 0), (1, 20, 20, 64, 64, 3, 1, 2, 0), (4, 8, 8, 256, 256, 3, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize('case', DGRAD_CASES)
+def test_conv_dgrad_matches_autograd(case):
+    """Data gradient of the conv (training backward) against torch autograd in fp64 on the CPU."""
+    import torch.nn.functional as F
+    from vfs_b200 import ops
+    N, H, W, Cin, Cout, k, stride, dil, with_add = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k)**0.5
+    Ho, Wo = ops.conv_out_hw(H, W, k, stride, dil)
+    dz = torch.randn(N, Cout, Ho, Wo, generator=g)
+    add = torch.randn(N, Cin, H, W, generator=g) if with_add else None
+    dzs = ops.to_split(dz.cuda())
+    wt = ops.pack_conv_weight_dgrad(w.cuda())
+    adds = ops.to_split(add.cuda()) if with_add else None
+    dx = ops.from_split(ops.conv_dgrad(dzs, wt, (H, W), k, stride, dil, adds))
+    x = torch.zeros(N, Cin, H, W, dtype=torch.float64, requires_grad=True)
+    z = F.conv2d(x, w.double(), stride=stride, padding=0 if k == 1 else dil, dilation=dil if k == 3 else 1)
+    (ref, ) = torch.autograd.grad(z, x, ops.from_split(dzs).cpu().double())
+    if with_add:
+        ref = ref + ops.from_split(adds).cpu().double()
+    assert rel_err(dx, ref) < 5e-5
+
+
 def test_layout_roundtrip_and_stem():
     import torch.nn.functional as F
     from vfs_b200 import ops

@@ -82,6 +82,9 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uin
 int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
                    const float* shift, const void* residual_split, void* out_split, float* out_f32,
                    double* stats, cudaStream_t stream);
+int conv_dgrad_tc(const VfsConvDesc* d, const void* dz_split, const void* wt_split, const float* ones,
+                  const float* zeros, const void* add_split, void* dx_split, cudaStream_t stream);
+int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, int k, cudaStream_t s);
 int channel_stats_f32(const float* x, double* stats, long long M, int C, cudaStream_t s);
 int bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean,
                 float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
@@ -169,6 +172,13 @@ int vfs_conv_bn_act(const VfsConvDesc* d, const void* in_split, const void* w_sp
 int vfs_conv_stats(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
                    const float* shift, float* out_f32_nhwc, double* stats, vfs_stream_t s) {
   return vfs::conv_bn_act_tc(d, in_split, w_split, scale, shift, nullptr, nullptr, out_f32_nhwc, stats, s);
+}
+int vfs_conv_dgrad(const VfsConvDesc* d, const void* dz_split, const void* wt_split, const float* ones,
+                   const float* zeros, const void* add_split, void* dx_split, vfs_stream_t s) {
+  return vfs::conv_dgrad_tc(d, dz_split, wt_split, ones, zeros, add_split, dx_split, s);
+}
+int vfs_pack_conv_weight_dgrad(const float* w_oihw, void* wt_split, int Cout, int Cin, int ksize, vfs_stream_t s) {
+  return vfs::pack_conv_weight_dgrad(w_oihw, wt_split, Cout, Cin, ksize, s);
 }
 int vfs_channel_stats_f32(const float* x, double* stats, long long M, int C, vfs_stream_t s) {
   return vfs::channel_stats_f32(x, stats, M, C, s);

@@ -42,6 +42,10 @@ struct alignas(64) ConvKernelParams {
   int tap_view[kMaxTaps];
   int tap_dh[kMaxTaps];
   int tap_dw[kMaxTaps];
+  int tap_koff[kMaxTaps];  // K coordinate (elements) of this tap's first channel chunk in the weight operand
+  // output / residual addressing: pixel (n, h, w) of this launch lives at
+  //   ((n*out_H + h*out_sy + out_oy)*out_W + w*out_sx + out_ox) * Cout   (strided views are used by stride-2 dgrad)
+  int out_H, out_W, out_sy, out_sx, out_oy, out_ox;
   const float* scale;
   const float* shift;
   const __nv_bfloat16* res_hi;  // nullable
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
           tma_load_5d(sa, &p.tmap_a[p.tap_view[tap]], full_bar(stage), c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap],
                       n0, 0);
-          tma_load_3d(sb, &p.tmap_b, full_bar(stage), kc * kBlockK, n_tile * BN, 0);
+          tma_load_3d(sb, &p.tmap_b, full_bar(stage), p.tap_koff[tap] + c0, n_tile * BN, 0);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -221,7 +225,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
             pre_h[i] = make_uint4(0, 0, 0, 0);
             pre_l[i] = make_uint4(0, 0, 0, 0);
             if ((w < p.Wo) && (hh < p.Ho) && (n < p.N)) {
-              const size_t o = ((static_cast<size_t>(n) * p.Ho + hh) * p.Wo + w) * p.Cout + cg + piece * 8;
+              const size_t o = ((static_cast<size_t>(n) * p.out_H + hh * p.out_sy + p.out_oy) * p.out_W +
+                                w * p.out_sx + p.out_ox) * p.Cout + cg + piece * 8;
               pre_h[i] = *reinterpret_cast<const uint4*>(p.res_hi + o);
               pre_l[i] = *reinterpret_cast<const uint4*>(p.res_lo + o);
             }
@@ -264,7 +269,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           const int dn = r2 / p.th;
           const int w = w0 + dw, hh = h0 + dh, n = n0 + dn;
           if ((w < p.Wo) && (hh < p.Ho) && (n < p.N)) {
-            const size_t o = ((static_cast<size_t>(n) * p.Ho + hh) * p.Wo + w) * p.Cout + cg + piece * 8;
+            const size_t o = ((static_cast<size_t>(n) * p.out_H + hh * p.out_sy + p.out_oy) * p.out_W +
+                              w * p.out_sx + p.out_ox) * p.Cout + cg + piece * 8;
             const uint4 rh = pre_h[i], rl = pre_l[i];
             float y[8];
             const uint32_t a0 = stg_base + r * 256 + phys_chunk(r, 2 * piece) * 16;
@@ -392,124 +398,284 @@ int launch(const ConvKernelParams& p, int grid, cudaStream_t stream) {
 
 }  // namespace
 
-int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
-                   const float* shift, const void* residual_split, void* out_split, float* out_f32,
-                   double* stats, cudaStream_t stream) {
-  VFS_REQUIRE(d && in_split && w_split && scale && shift, VFS_EINVAL, "conv_bn_act: null argument");
-  VFS_REQUIRE(out_split || out_f32, VFS_EINVAL, "conv_bn_act: no output buffer");
-  VFS_REQUIRE(d->ksize == 1 || d->ksize == 3, VFS_ESHAPE, "conv_bn_act: ksize %d unsupported", d->ksize);
-  VFS_REQUIRE(d->stride == 1 || d->stride == 2, VFS_ESHAPE, "conv_bn_act: stride %d unsupported", d->stride);
-  VFS_REQUIRE(d->dilation >= 1, VFS_ESHAPE, "conv_bn_act: dilation %d", d->dilation);
-  VFS_REQUIRE(d->Cin % 64 == 0 && d->Cout % 64 == 0, VFS_ESHAPE, "conv_bn_act: Cin/Cout must be multiples of 64");
-  VFS_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, VFS_ESHAPE, "conv_bn_act: empty input");
+struct TapSpec {
+  int view, dh, dw, koff;
+};
 
-  const int N = d->N, H = d->H, W = d->W, Cin = d->Cin, Cout = d->Cout;
-  const int k = d->ksize, s = d->stride, dil = (k == 1) ? 1 : d->dilation;
-  const int pad = (k == 1) ? 0 : dil;
-  const int Ho = (H + 2 * pad - dil * (k - 1) - 1) / s + 1;
-  const int Wo = (W + 2 * pad - dil * (k - 1) - 1) / s + 1;
-  const size_t in_plane = static_cast<size_t>(N) * H * W * Cin;
-  const size_t out_plane = static_cast<size_t>(N) * Ho * Wo * Cout;
+// One launch of the implicit-GEMM kernel: A = pixels of a split NHWC tensor (optionally through stride-parity
+// views), B = [2][Nout][Ktot] split weights, output pixels written through a (possibly strided) view.
+struct ConvSpec {
+  const void* a_split;
+  size_t a_plane;
+  int N, H, W, C;
+  int view_stride;
+  bool flat;
+  int num_taps;
+  TapSpec taps[kMaxTaps];
+  const void* b_split;
+  int Nout;
+  uint64_t Ktot;
+  int Ho, Wo;
+  int out_H, out_W, out_sy, out_sx, out_oy, out_ox;
+  const float* scale;
+  const float* shift;
+  const void* res_split;
+  void* out_split;
+  size_t out_plane;
+  float* out_f32;
+  double* stats;
+  int relu;
+};
 
+static int run_spec(const ConvSpec& c, cudaStream_t stream) {
   ConvKernelParams p;
   memset(&p, 0, sizeof(p));
-  p.Cout = Cout;
-  p.kchunks_per_tap = Cin / 64;
-  p.num_taps = k * k;
-  p.scale = scale;
-  p.shift = shift;
-  p.relu = d->relu;
-  p.out_f32 = out_f32;
-  if (stats) {
-    p.stat_sum = stats;
-    p.stat_sqsum = stats + Cout;
+  p.Cout = c.Nout;
+  p.kchunks_per_tap = c.C / 64;
+  p.num_taps = c.num_taps;
+  p.scale = c.scale;
+  p.shift = c.shift;
+  p.relu = c.relu;
+  p.out_f32 = c.out_f32;
+  if (c.stats) {
+    p.stat_sum = c.stats;
+    p.stat_sqsum = c.stats + c.Nout;
   }
-  if (out_split) {
-    p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_split);
-    p.out_lo = p.out_hi + out_plane;
+  if (c.out_split) {
+    p.out_hi = reinterpret_cast<__nv_bfloat16*>(c.out_split);
+    p.out_lo = p.out_hi + c.out_plane;
   }
-  if (residual_split) {
-    p.res_hi = reinterpret_cast<const __nv_bfloat16*>(residual_split);
-    p.res_lo = p.res_hi + out_plane;
+  if (c.res_split) {
+    p.res_hi = reinterpret_cast<const __nv_bfloat16*>(c.res_split);
+    p.res_lo = p.res_hi + c.out_plane;
   }
-
-  const bool flat = (k == 1 && s == 1);
-  if (flat) {
-    // 1x1/s1: the pixel axis is one flat dimension, no spatial waste
+  const int s = c.view_stride;
+  if (c.flat) {
     p.tw = 128; p.th = 1; p.tn = 1;
-    p.Wo = N * H * W; p.Ho = 1; p.N = 1;
+    p.Wo = c.N * c.H * c.W; p.Ho = 1; p.N = 1;
+    p.out_H = 1; p.out_W = p.Wo; p.out_sy = 1; p.out_sx = 1; p.out_oy = 0; p.out_ox = 0;
   } else {
-    choose_tile(Wo, Ho, N, &p.tw, &p.th, &p.tn);
-    p.Wo = Wo; p.Ho = Ho; p.N = N;
+    choose_tile(c.Wo, c.Ho, c.N, &p.tw, &p.th, &p.tn);
+    p.Wo = c.Wo; p.Ho = c.Ho; p.N = c.N;
+    p.out_H = c.out_H; p.out_W = c.out_W; p.out_sy = c.out_sy; p.out_sx = c.out_sx;
+    p.out_oy = c.out_oy; p.out_ox = c.out_ox;
   }
   p.tiles_w = (p.Wo + p.tw - 1) / p.tw;
   p.tiles_h = (p.Ho + p.th - 1) / p.th;
   const int tiles_n = (p.N + p.tn - 1) / p.tn;
   p.num_m_tiles = p.tiles_w * p.tiles_h * tiles_n;
 
-  // activation views, one per stride parity (ph, pw): view[y', x'] = in[s*y' + ph, s*x' + pw]
   const uint32_t box_a[5] = {64u, static_cast<uint32_t>(p.tw), static_cast<uint32_t>(p.th),
                              static_cast<uint32_t>(p.tn), 2u};
-  const char* in_base = reinterpret_cast<const char*>(in_split);
+  const char* in_base = reinterpret_cast<const char*>(c.a_split);
   bool view_used[kMaxViews] = {false, false, false, false};
-  for (int r = 0; r < k; ++r) {
-    for (int c = 0; c < k; ++c) {
-      const int oh = r * dil - pad, ow = c * dil - pad;
-      const int ph = ((oh % s) + s) % s, pw = ((ow % s) + s) % s;
-      const int t = r * k + c;
-      p.tap_view[t] = ph * 2 + pw;
-      p.tap_dh[t] = floordiv(oh - ph, s);
-      p.tap_dw[t] = floordiv(ow - pw, s);
-      view_used[ph * 2 + pw] = true;
-    }
+  for (int t = 0; t < c.num_taps; ++t) {
+    p.tap_view[t] = c.taps[t].view;
+    p.tap_dh[t] = c.taps[t].dh;
+    p.tap_dw[t] = c.taps[t].dw;
+    p.tap_koff[t] = c.taps[t].koff;
+    view_used[c.taps[t].view] = true;
   }
+  int first_valid = -1;
   for (int v = 0; v < kMaxViews; ++v) {
     const int ph = v / 2, pw = v % 2;
-    int rc;
-    if (flat) {
-      const uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(N) * H * W, 1, 1, 2};
-      const uint64_t strides[4] = {static_cast<uint64_t>(Cin) * 2, in_plane * 2, in_plane * 2, in_plane * 2};
+    int rc = VFS_OK;
+    if (c.flat) {
+      const uint64_t dims[5] = {static_cast<uint64_t>(c.C), static_cast<uint64_t>(c.N) * c.H * c.W, 1, 1, 2};
+      const uint64_t strides[4] = {static_cast<uint64_t>(c.C) * 2, c.a_plane * 2, c.a_plane * 2, c.a_plane * 2};
       rc = make_tmap_bf16_sw128(&p.tmap_a[v], in_base, 5, dims, strides, box_a);
-    } else if (view_used[v] && ph < H && pw < W) {
-      const int Hv = (H - ph + s - 1) / s, Wv = (W - pw + s - 1) / s;
-      const uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Wv), static_cast<uint64_t>(Hv),
-                                static_cast<uint64_t>(N), 2};
-      const uint64_t strides[4] = {static_cast<uint64_t>(s) * Cin * 2, static_cast<uint64_t>(s) * W * Cin * 2,
-                                   static_cast<uint64_t>(H) * W * Cin * 2, in_plane * 2};
-      rc = make_tmap_bf16_sw128(&p.tmap_a[v], in_base + (static_cast<size_t>(ph) * W + pw) * Cin * 2, 5, dims,
+      if (first_valid < 0) first_valid = v;
+    } else if (view_used[v] && ph < c.H && pw < c.W && (s > 1 || v == 0)) {
+      const int Hv = (c.H - ph + s - 1) / s, Wv = (c.W - pw + s - 1) / s;
+      const uint64_t dims[5] = {static_cast<uint64_t>(c.C), static_cast<uint64_t>(Wv), static_cast<uint64_t>(Hv),
+                                static_cast<uint64_t>(c.N), 2};
+      const uint64_t strides[4] = {static_cast<uint64_t>(s) * c.C * 2, static_cast<uint64_t>(s) * c.W * c.C * 2,
+                                   static_cast<uint64_t>(c.H) * c.W * c.C * 2, c.a_plane * 2};
+      rc = make_tmap_bf16_sw128(&p.tmap_a[v], in_base + (static_cast<size_t>(ph) * c.W + pw) * c.C * 2, 5, dims,
                                 strides, box_a);
-    } else {
-      p.tmap_a[v] = p.tmap_a[0];  // never dereferenced with a valid tap; keep a valid descriptor for prefetch
-      rc = VFS_OK;
+      if (first_valid < 0) first_valid = v;
     }
     if (rc != VFS_OK) return rc;
   }
+  VFS_REQUIRE(first_valid >= 0, VFS_EINVAL, "conv: no usable input view");
+  for (int v = 0; v < kMaxViews; ++v) {
+    const bool built = c.flat || (view_used[v] && (v / 2) < c.H && (v % 2) < c.W && (s > 1 || v == 0));
+    if (!built) p.tmap_a[v] = p.tmap_a[first_valid];  // never used by a tap; keeps the prefetch valid
+  }
 
-  int BN = (Cout % 128 == 0) ? 128 : 64;
+  int BN = (c.Nout % 128 == 0) ? 128 : 64;
   {
     static int forced = -1;  // VFS_CONV_BN=64|128|256 overrides the tile width (experiments)
     if (forced < 0) {
       const char* e = getenv("VFS_CONV_BN");
       forced = e ? atoi(e) : 0;
     }
-    if (forced > 0 && Cout % forced == 0) BN = forced;
+    if (forced > 0 && c.Nout % forced == 0) BN = forced;
   }
-  p.num_n_tiles = Cout / BN;
+  p.num_n_tiles = c.Nout / BN;
   {
-    const uint64_t Ktot = static_cast<uint64_t>(k) * k * Cin;
-    const uint64_t dims[3] = {Ktot, static_cast<uint64_t>(Cout), 2};
-    const uint64_t strides[2] = {Ktot * 2, Ktot * Cout * 2};
+    const uint64_t dims[3] = {c.Ktot, static_cast<uint64_t>(c.Nout), 2};
+    const uint64_t strides[2] = {c.Ktot * 2, c.Ktot * c.Nout * 2};
     const uint32_t box_b[3] = {64u, static_cast<uint32_t>(BN), 2u};
-    int rc = make_tmap_bf16_sw128(&p.tmap_b, w_split, 3, dims, strides, box_b);
+    int rc = make_tmap_bf16_sw128(&p.tmap_b, c.b_split, 3, dims, strides, box_b);
     if (rc != VFS_OK) return rc;
   }
-
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int sms = device_sm_count();
   const int grid = num_tiles < sms ? num_tiles : sms;
   if (BN == 256) return launch<256, 2>(p, grid, stream);
   if (BN == 128) return launch<128, 3>(p, grid, stream);
   return launch<64, 4>(p, grid, stream);
+}
+
+static int check_desc(const VfsConvDesc* d, const char* who) {
+  VFS_REQUIRE(d->ksize == 1 || d->ksize == 3, VFS_ESHAPE, "%s: ksize %d unsupported", who, d->ksize);
+  VFS_REQUIRE(d->stride == 1 || d->stride == 2, VFS_ESHAPE, "%s: stride %d unsupported", who, d->stride);
+  VFS_REQUIRE(d->dilation >= 1, VFS_ESHAPE, "%s: dilation %d", who, d->dilation);
+  VFS_REQUIRE(d->Cin % 64 == 0 && d->Cout % 64 == 0, VFS_ESHAPE, "%s: Cin/Cout must be multiples of 64", who);
+  VFS_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, VFS_ESHAPE, "%s: empty input", who);
+  return VFS_OK;
+}
+
+int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
+                   const float* shift, const void* residual_split, void* out_split, float* out_f32,
+                   double* stats, cudaStream_t stream) {
+  VFS_REQUIRE(d && in_split && w_split && scale && shift, VFS_EINVAL, "conv_bn_act: null argument");
+  VFS_REQUIRE(out_split || out_f32, VFS_EINVAL, "conv_bn_act: no output buffer");
+  int rc = check_desc(d, "conv_bn_act");
+  if (rc != VFS_OK) return rc;
+  const int N = d->N, H = d->H, W = d->W, Cin = d->Cin, Cout = d->Cout;
+  const int k = d->ksize, s = d->stride, dil = (k == 1) ? 1 : d->dilation;
+  const int pad = (k == 1) ? 0 : dil;
+  const int Ho = (H + 2 * pad - dil * (k - 1) - 1) / s + 1;
+  const int Wo = (W + 2 * pad - dil * (k - 1) - 1) / s + 1;
+
+  ConvSpec c;
+  memset(&c, 0, sizeof(c));
+  c.a_split = in_split;
+  c.a_plane = static_cast<size_t>(N) * H * W * Cin;
+  c.N = N; c.H = H; c.W = W; c.C = Cin;
+  c.view_stride = s;
+  c.flat = (k == 1 && s == 1);
+  c.num_taps = k * k;
+  // activation views, one per stride parity (ph, pw): view[y', x'] = in[s*y' + ph, s*x' + pw]
+  for (int r = 0; r < k; ++r) {
+    for (int q = 0; q < k; ++q) {
+      const int oh = r * dil - pad, ow = q * dil - pad;
+      const int ph = ((oh % s) + s) % s, pw = ((ow % s) + s) % s;
+      TapSpec& t = c.taps[r * k + q];
+      t.view = ph * 2 + pw;
+      t.dh = floordiv(oh - ph, s);
+      t.dw = floordiv(ow - pw, s);
+      t.koff = (r * k + q) * Cin;
+    }
+  }
+  c.b_split = w_split;
+  c.Nout = Cout;
+  c.Ktot = static_cast<uint64_t>(k) * k * Cin;
+  c.Ho = Ho; c.Wo = Wo;
+  c.out_H = Ho; c.out_W = Wo; c.out_sy = 1; c.out_sx = 1;
+  c.scale = scale; c.shift = shift;
+  c.res_split = residual_split;
+  c.out_split = out_split;
+  c.out_plane = static_cast<size_t>(N) * Ho * Wo * Cout;
+  c.out_f32 = out_f32;
+  c.stats = stats;
+  c.relu = d->relu;
+  return run_spec(c, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Data gradient of the same convolution (training backward): dX = conv_transpose(dZ, W).
+//   d          forward descriptor (N, H, W = forward INPUT extent; Cin, Cout forward channels)
+//   dz_split   split NHWC [N, Ho, Wo, Cout]
+//   wt_split   split [2][Cin][k*k*Cout], K index = (r'*k + s')*Cout + co with the kernel flipped:
+//              wt[ci][r'][s'][co] = w[co][ci][k-1-r'][k-1-s']        (vfs_pack_conv_weight_dgrad)
+//   add_split  NULL or split NHWC [N,H,W,Cin] added to the result (gradient arriving through the other branch)
+//   dx_split   split NHWC [N, H, W, Cin]
+// Stride 1 is one launch of the forward kernel with the roles of Cin/Cout swapped.  Stride 2 is the sum over the
+// four output-parity classes (dX[2a+pa, 2b+pb] only receives the taps with matching parity), each one launch that
+// writes its strided view of dX; positions no tap reaches get the plain `add` term (or zero).
+// ------------------------------------------------------------------------------------------------
+int conv_dgrad_tc(const VfsConvDesc* d, const void* dz_split, const void* wt_split, const float* ones,
+                  const float* zeros, const void* add_split, void* dx_split, cudaStream_t stream) {
+  VFS_REQUIRE(d && dz_split && wt_split && ones && zeros && dx_split, VFS_EINVAL, "conv_dgrad: null argument");
+  int rc = check_desc(d, "conv_dgrad");
+  if (rc != VFS_OK) return rc;
+  const int N = d->N, H = d->H, W = d->W, Cin = d->Cin, Cout = d->Cout;
+  const int k = d->ksize, s = d->stride, dil = (k == 1) ? 1 : d->dilation;
+  const int pad = (k == 1) ? 0 : dil;
+  const int Ho = (H + 2 * pad - dil * (k - 1) - 1) / s + 1;
+  const int Wo = (W + 2 * pad - dil * (k - 1) - 1) / s + 1;
+  VFS_REQUIRE(s == 1 || dil == 1, VFS_ESHAPE, "conv_dgrad: stride 2 with dilation > 1 unsupported");
+
+  ConvSpec c;
+  memset(&c, 0, sizeof(c));
+  c.a_split = dz_split;
+  c.a_plane = static_cast<size_t>(N) * Ho * Wo * Cout;
+  c.N = N; c.H = Ho; c.W = Wo; c.C = Cout;
+  c.view_stride = 1;
+  c.b_split = wt_split;
+  c.Nout = Cin;
+  c.Ktot = static_cast<uint64_t>(k) * k * Cout;
+  c.scale = ones; c.shift = zeros;
+  c.res_split = add_split;
+  c.out_split = dx_split;
+  c.out_plane = static_cast<size_t>(N) * H * W * Cin;
+  c.out_H = H; c.out_W = W;
+  if (s == 1) {
+    // dX[h] = sum_r' dZ[h + (r'-c)*dil] * wt[r'] : a same-size correlation with the flipped kernel
+    c.flat = (k == 1);
+    c.num_taps = k * k;
+    for (int r = 0; r < k; ++r)
+      for (int q = 0; q < k; ++q) {
+        TapSpec& t = c.taps[r * k + q];
+        t.view = 0;
+        t.dh = r * dil - pad;
+        t.dw = q * dil - pad;
+        t.koff = (r * k + q) * Cout;
+      }
+    c.Ho = H; c.Wo = W;
+    c.out_sy = 1; c.out_sx = 1; c.out_oy = 0; c.out_ox = 0;
+    return run_spec(c, stream);
+  }
+  if (k == 1) {
+    // only the (even, even) positions receive a tap; everything else is the `add` term (or zero)
+    const size_t bytes = 2 * c.out_plane * sizeof(__nv_bfloat16);
+    if (add_split) VFS_CUDA_OK(cudaMemcpyAsync(dx_split, add_split, bytes, cudaMemcpyDeviceToDevice, stream));
+    else VFS_CUDA_OK(cudaMemsetAsync(dx_split, 0, bytes, stream));
+  }
+  // stride 2: forward z[ho] += x[2*ho + r - pad] * w[r]  =>  dX[i] = sum_{r : (i + pad - r) even} dZ[(i+pad-r)/2] * w[r]
+  // in flipped-kernel coordinates r' = k-1-r the weight chunk of forward tap r is (k-1-r).
+  for (int pa = 0; pa < 2; ++pa) {
+    for (int pb = 0; pb < 2; ++pb) {
+      const int Hc = (H - pa + 1) / 2, Wc = (W - pb + 1) / 2;  // number of positions 2a+pa < H
+      if (Hc <= 0 || Wc <= 0) continue;
+      int nt = 0;
+      int rs[3], dhs[3], qs[3], dws[3];
+      int nr = 0, nq = 0;
+      for (int r = 0; r < k; ++r)
+        if (((pa + pad - r) % 2 + 2) % 2 == 0) { rs[nr] = r; dhs[nr] = floordiv(pa + pad - r, 2); ++nr; }
+      for (int q = 0; q < k; ++q)
+        if (((pb + pad - q) % 2 + 2) % 2 == 0) { qs[nq] = q; dws[nq] = floordiv(pb + pad - q, 2); ++nq; }
+      for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < nq; ++j) {
+          TapSpec& t = c.taps[nt++];
+          t.view = 0;
+          t.dh = dhs[i];
+          t.dw = dws[j];
+          t.koff = ((k - 1 - rs[i]) * k + (k - 1 - qs[j])) * Cout;
+        }
+      c.flat = false;
+      c.Ho = Hc; c.Wo = Wc;
+      c.out_sy = 2; c.out_sx = 2; c.out_oy = pa; c.out_ox = pb;
+      if (nt == 0) continue;  // no tap reaches this parity class (1x1/s2): pre-filled below
+      c.num_taps = nt;
+      rc = run_spec(c, stream);
+      if (rc != VFS_OK) return rc;
+    }
+  }
+  return VFS_OK;
 }
 
 }  // namespace vfs

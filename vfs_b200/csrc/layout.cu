@@ -98,6 +98,37 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// OIHW fp32 -> split [2][Cin][(r'*k+s')*Cout + co] with the kernel flipped (operand of the data-gradient conv)
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int k) {
+  const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // destination index i = (ci * k*k + tap') * Cout + co
+    const int co = static_cast<int>(i % Cout);
+    const size_t t = i / Cout;
+    const int tap = static_cast<int>(t % (k * k));
+    const int ci = static_cast<int>(t / (k * k));
+    const int src_tap = k * k - 1 - tap;  // (k-1-r', k-1-s')
+    const float v = w[(static_cast<size_t>(co) * Cin + ci) * k * k + src_tap];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, int k, cudaStream_t s) {
+  VFS_REQUIRE(w && wt_split, VFS_EINVAL, "pack_conv_weight_dgrad: null argument");
+  VFS_REQUIRE(Cout > 0 && Cin > 0 && k > 0, VFS_ESHAPE, "pack_conv_weight_dgrad: bad shape");
+  const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(wt_split);
+  const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  pack_weight_dgrad_kernel<<<blocks, 256, 0, s>>>(w, hi, hi + total, Cout, Cin, k);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
 int pack_conv_weight(const float* w, void* w_split, int Cout, int Cin, int k, cudaStream_t s) {
   VFS_REQUIRE(w && w_split, VFS_EINVAL, "pack_conv_weight: null argument");
   VFS_REQUIRE(Cout > 0 && Cin > 0 && k > 0, VFS_ESHAPE, "pack_conv_weight: bad shape");

@@ -8,7 +8,7 @@ from . import _native as nat
 from ._native import VfsConvDesc, current_stream, ptr
 
 LAUNCHES = [0]  # kernels of libvfs_b200.so launched through this module (bench.py reports the count)
-_KERNELS_PER_CALL = {'stem_forward': 2, 'masked_attention': 2, 'features_to_split_norm': 2}
+_KERNELS_PER_CALL = {'stem_forward': 2, 'masked_attention': 2, 'features_to_split_norm': 2, 'conv_dgrad': 1}
 
 
 def check(rc, what=''):
@@ -205,6 +205,33 @@ def stem_bn_relu_pool(z, scale, shift, in_hw):
     check(nat.lib().vfs_stem_bn_relu_pool(ptr(z), ptr(scale), ptr(shift), ptr(out), N, H, W, current_stream()),
           'stem_bn_relu_pool')
     return out
+
+
+def pack_conv_weight_dgrad(w):
+    """OIHW fp32 -> split [2, Cin, k*k*Cout] (flipped kernel, roles of Cin/Cout swapped) for conv_dgrad."""
+    _require_cuda(w, 'w')
+    Cout, Cin, k, _ = w.shape
+    out = torch.empty((2, Cin, k * k * Cout), dtype=torch.bfloat16, device=w.device)
+    check(nat.lib().vfs_pack_conv_weight_dgrad(ptr(w), ptr(out), Cout, Cin, k, current_stream()),
+          'pack_conv_weight_dgrad')
+    return out
+
+
+def conv_dgrad(dz, wt_split, in_hw, ksize, stride=1, dilation=1, add=None):
+    """dX = conv_transpose(dZ, W) (+ add): ``dz`` split [2,N,Ho,Wo,Cout], ``wt_split`` from pack_conv_weight_dgrad,
+    ``in_hw`` the forward input (H, W); returns split [2,N,H,W,Cin]."""
+    _, N, Ho, Wo, Cout = dz.shape
+    Cin = wt_split.shape[1]
+    H, W = in_hw
+    assert conv_out_hw(H, W, ksize, stride, dilation) == (Ho, Wo), (in_hw, dz.shape)
+    dx = torch.empty((2, N, H, W, Cin), dtype=torch.bfloat16, device=dz.device)
+    if add is not None:
+        assert tuple(add.shape) == tuple(dx.shape)
+    d = VfsConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, ksize=ksize, stride=stride, dilation=dilation, relu=0)
+    check(nat.lib().vfs_conv_dgrad(ctypes.byref(d), ptr(dz), ptr(wt_split), ptr(_const_vec(1, Cin, dz.device)),
+                                   ptr(_const_vec(0, Cin, dz.device)), ptr(add), ptr(dx), current_stream()),
+          'conv_dgrad')
+    return dx
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -411,8 +438,11 @@ def masked_attention(query, key, value, mask, temperature, topk, normalize=True,
     outs, tvs, tis = [], [], []
     for b0 in range(0, N, per):
         bs = list(range(b0, min(N, b0 + per)))
-        r = attention_bank_batched(qs, bs, ks, [[b * T + t for t in range(T)] for b in bs], v[b0:],
-                                   [list(range(T)) for _ in bs], Cv * T * HW, HW, T * HW, Cv, mask, temperature, topk,
+        # NOTE reference quirk kept for parity: local_attention.py:320-326 flattens value_vec over the batch and
+        # gathers with per-item indices that are NOT offset by the batch, so every batch item reads the value
+        # maps of batch item 0 (invisible in VFS, which always calls with N == 1) -> v_batch_stride = 0.
+        r = attention_bank_batched(qs, bs, ks, [[b * T + t for t in range(T)] for b in bs], v,
+                                   [list(range(T)) for _ in bs], 0, HW, T * HW, Cv, mask, temperature, topk,
                                    non_mask_len, mode, return_topk)
         if return_topk:
             outs.append(r[0]); tvs.append(r[1]); tis.append(r[2])
