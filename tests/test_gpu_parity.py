@@ -228,6 +228,36 @@ def test_conv_dgrad_matches_autograd(case):
     assert rel_err(dx, ref) < 5e-5
 
 
+WGRAD_CASES = [
+    # N, H, W, Cin, Cout, k, stride, dil
+    (2, 16, 16, 64, 128, 1, 1, 1), (2, 16, 16, 128, 128, 3, 1, 1), (1, 15, 13, 64, 64, 3, 1, 1),
+    (2, 16, 16, 64, 128, 3, 2, 1), (1, 15, 13, 128, 256, 3, 2, 1), (2, 16, 16, 256, 512, 1, 2, 1),
+    (1, 20, 20, 64, 128, 3, 1, 2), (8, 32, 32, 256, 256, 3, 1, 1), (4, 8, 8, 512, 128, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize('case', WGRAD_CASES)
+def test_conv_wgrad_matches_autograd(case):
+    """Weight gradient of the conv (tcgen05, MN-major operands) against torch autograd in fp64 on the CPU."""
+    import torch.nn.functional as F
+    from vfs_b200 import ops
+    N, H, W, Cin, Cout, k, stride, dil = case
+    g = torch.Generator().manual_seed(sum(case) + 2)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    Ho, Wo = ops.conv_out_hw(H, W, k, stride, dil)
+    dz = torch.randn(N, Cout, Ho, Wo, generator=g)
+    xs, dzs = ops.to_split(x.cuda()), ops.to_split(dz.cuda())
+    dw = ops.conv_wgrad(xs, dzs, k, stride, dil)
+    w = torch.zeros(Cout, Cin, k, k, dtype=torch.float64, requires_grad=True)
+    z = F.conv2d(ops.from_split(xs).cpu().double(), w, stride=stride, padding=0 if k == 1 else dil,
+                 dilation=dil if k == 3 else 1)
+    (ref, ) = torch.autograd.grad(z, w, ops.from_split(dzs).cpu().double())
+    assert rel_err(dw, ref) < 5e-5
+    # accumulate into an existing gradient (second view of the SimSiam step)
+    dw2 = ops.conv_wgrad(xs, dzs, k, stride, dil, out=dw.clone(), accumulate=True)
+    assert rel_err(dw2, 2 * ref) < 5e-5
+
+
 def test_layout_roundtrip_and_stem():
     import torch.nn.functional as F
     from vfs_b200 import ops

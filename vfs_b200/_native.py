@@ -43,6 +43,8 @@ PROTOTYPES = {
     'vfs_conv_stats': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'vfs_conv_dgrad': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'vfs_pack_conv_weight_dgrad': (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    'vfs_conv_wgrad_workspace_bytes': (_sz, [_i, _i, _i]),
+    'vfs_conv_wgrad': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _i, _vp]),
     'vfs_channel_stats_f32': (_i, [_vp, _vp, _ll, _i, _vp]),
     'vfs_bn_finalize': (_i, [_vp, ctypes.c_double, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     'vfs_bn_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),

@@ -85,6 +85,9 @@ int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_spl
 int conv_dgrad_tc(const VfsConvDesc* d, const void* dz_split, const void* wt_split, const float* ones,
                   const float* zeros, const void* add_split, void* dx_split, cudaStream_t stream);
 int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, int k, cudaStream_t s);
+size_t wgrad_workspace_bytes(int Cout, int Cin, int ksize);
+int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_split, void* workspace, float* dw_oihw,
+                  int accumulate, cudaStream_t stream);
 int channel_stats_f32(const float* x, double* stats, long long M, int C, cudaStream_t s);
 int bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean,
                 float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
@@ -179,6 +182,13 @@ int vfs_conv_dgrad(const VfsConvDesc* d, const void* dz_split, const void* wt_sp
 }
 int vfs_pack_conv_weight_dgrad(const float* w_oihw, void* wt_split, int Cout, int Cin, int ksize, vfs_stream_t s) {
   return vfs::pack_conv_weight_dgrad(w_oihw, wt_split, Cout, Cin, ksize, s);
+}
+size_t vfs_conv_wgrad_workspace_bytes(int Cout, int Cin, int ksize) {
+  return vfs::wgrad_workspace_bytes(Cout, Cin, ksize);
+}
+int vfs_conv_wgrad(const VfsConvDesc* d, const void* x_split, const void* dz_split, void* workspace, float* dw_oihw,
+                   int accumulate, vfs_stream_t s) {
+  return vfs::conv_wgrad_tc(d, x_split, dz_split, workspace, dw_oihw, accumulate, s);
 }
 int vfs_channel_stats_f32(const float* x, double* stats, long long M, int C, vfs_stream_t s) {
   return vfs::channel_stats_f32(x, stats, M, C, s);

@@ -135,6 +135,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
   return d;
 }
 
+// Shared-memory matrix descriptor for an MN-major operand tile stored with the 128-byte swizzle: rows are K
+// indices (128 B = 64 consecutive M/N elements per row, 8-row swizzle atoms of 1024 B stacked along K),
+// 64-element M/N blocks are `lbo_bytes` apart.  Canonical layout (CUTLASS mma_traits_sm100.hpp, make_umma_desc
+// <Major::MN>):  Swizzle<3,4,3> o ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO))  in 16-byte units of bf16.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16 : A,B = BF16 (K-major), D = F32, shape M x N (K = 16).
 // Field positions follow cute::UMMA::InstrDescriptor.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
@@ -143,6 +157,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
          | (1u << 10)              // b_format = BF16
          | (0u << 15) | (0u << 16) // a_major = K, b_major = K
          | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// Same with both operands MN-major (a_major = b_major = 1): D[m,n] += sum_k A[k][m] * B[k][n].
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_mn(int M, int N) {
+  return umma_idesc_bf16_f32(M, N) | (1u << 15) | (1u << 16);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
@@ -174,6 +193,11 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// vector fp32 reduction to global memory (no return value): 4 consecutive floats, 16-byte aligned
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 // ----------------------------------------------------------------------------------------------
 // split-bf16 ("bf16x2") representation of an fp32 value: x ~= hi + lo, |err| <~ 2^-17 |x|

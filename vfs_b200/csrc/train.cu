@@ -1,0 +1,640 @@
+// Backward-pass kernels around the tensor-core dgrad/wgrad convolutions: BatchNorm(+ReLU) backward on split NHWC
+// activations, stem (max-pool / BN / 7x7 weight gradient), SimSiam head (Linear, BatchNorm1d, avg-pool, cosine loss)
+// and the fused SGD-momentum update.  All exact fp32 (fp64 for cross-pixel reductions), fixed formulas of
+// torch.nn.functional.batch_norm / max_pool2d / linear backward.
+#include <math.h>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace vfs {
+
+__device__ __forceinline__ void unpack8(const uint4 h, const uint4 l, float (&v)[8]) {
+  v[0] = bf16_lo_to_float(h.x) + bf16_lo_to_float(l.x);
+  v[1] = bf16_hi_to_float(h.x) + bf16_hi_to_float(l.x);
+  v[2] = bf16_lo_to_float(h.y) + bf16_lo_to_float(l.y);
+  v[3] = bf16_hi_to_float(h.y) + bf16_hi_to_float(l.y);
+  v[4] = bf16_lo_to_float(h.z) + bf16_lo_to_float(l.z);
+  v[5] = bf16_hi_to_float(h.z) + bf16_hi_to_float(l.z);
+  v[6] = bf16_lo_to_float(h.w) + bf16_lo_to_float(l.w);
+  v[7] = bf16_hi_to_float(h.w) + bf16_hi_to_float(l.w);
+}
+__device__ __forceinline__ void pack8(const float (&v)[8], uint4& h, uint4& l) {
+  __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) split_bf16(v[e], hi[e], lo[e]);
+  h.x = pack_bf16x2(hi[0], hi[1]); h.y = pack_bf16x2(hi[2], hi[3]);
+  h.z = pack_bf16x2(hi[4], hi[5]); h.w = pack_bf16x2(hi[6], hi[7]);
+  l.x = pack_bf16x2(lo[0], lo[1]); l.y = pack_bf16x2(lo[2], lo[3]);
+  l.z = pack_bf16x2(lo[4], lo[5]); l.w = pack_bf16x2(lo[6], lo[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm (+ReLU, +residual fan-out) backward on [M, C] activations.
+//   g  = dY * 1[y > 0]            (relu; y = forward output of the layer)
+//   reduce: sums[c] = sum g, sums[C + c] = sum g * xhat,  xhat = (z - mean) * invstd
+//   apply : dz = gamma * invstd * (g - sums[c]/M - xhat * sums[C+c]/M)     -> split;  optionally also g -> split
+// ------------------------------------------------------------------------------------------------
+struct BnBwdArgs {
+  const __nv_bfloat16* dy_hi; const __nv_bfloat16* dy_lo;  // split dY (or null when dy_f32 is used)
+  const float* dy_f32;
+  const __nv_bfloat16* y_hi; const __nv_bfloat16* y_lo;    // forward output for the ReLU mask (null: no ReLU)
+  const float* z;                                          // raw conv output fp32 [M, C]
+  const float* mean; const float* invstd; const float* gamma;
+  double* sums;                                            // [2C] (reduce: accumulated; apply: read)
+  double count;
+  __nv_bfloat16* dz_hi; __nv_bfloat16* dz_lo;              // split dz (or null)
+  float* dz_f32;                                           // fp32 dz (stem)
+  __nv_bfloat16* g_hi; __nv_bfloat16* g_lo;                // optional: masked gradient for the residual branch
+  long long M; int C;
+};
+
+__device__ __forceinline__ void bn_bwd_load_g(const BnBwdArgs& a, long long o, float (&g)[8]) {
+  if (a.dy_f32) {
+    const float4 p = *reinterpret_cast<const float4*>(a.dy_f32 + o), q = *reinterpret_cast<const float4*>(a.dy_f32 + o + 4);
+    g[0] = p.x; g[1] = p.y; g[2] = p.z; g[3] = p.w; g[4] = q.x; g[5] = q.y; g[6] = q.z; g[7] = q.w;
+  } else {
+    unpack8(*reinterpret_cast<const uint4*>(a.dy_hi + o), *reinterpret_cast<const uint4*>(a.dy_lo + o), g);
+  }
+  if (a.y_hi) {
+    float y[8];
+    unpack8(*reinterpret_cast<const uint4*>(a.y_hi + o), *reinterpret_cast<const uint4*>(a.y_lo + o), y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.0f) ? g[e] : 0.0f;
+  }
+}
+
+__global__ void bn_bwd_reduce_kernel(const BnBwdArgs a) {
+  const int pieces = a.C / 8;
+  const int piece = threadIdx.x % pieces, rgrp = threadIdx.x / pieces;
+  const int rows_per_block = blockDim.x / pieces;
+  if (rgrp >= rows_per_block) return;
+  const int c = piece * 8;
+  float sg[8], sx[8], mu[8], is[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sg[e] = sx[e] = 0.0f;
+    mu[e] = a.mean[c + e];
+    is[e] = a.invstd[c + e];
+  }
+  for (long long r = static_cast<long long>(blockIdx.x) * rows_per_block + rgrp; r < a.M;
+       r += static_cast<long long>(gridDim.x) * rows_per_block) {
+    const long long o = r * a.C + c;
+    float g[8];
+    bn_bwd_load_g(a, o, g);
+    const float4 z0 = *reinterpret_cast<const float4*>(a.z + o), z1 = *reinterpret_cast<const float4*>(a.z + o + 4);
+    const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sg[e] += g[e];
+      sx[e] = fmaf(g[e], (zz[e] - mu[e]) * is[e], sx[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    atomicAdd(a.sums + c + e, static_cast<double>(sg[e]));
+    atomicAdd(a.sums + a.C + c + e, static_cast<double>(sx[e]));
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(const BnBwdArgs a) {
+  const long long total8 = a.M * a.C / 8;
+  const float inv_count = static_cast<float>(1.0 / a.count);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long o = i * 8;
+    const int c = static_cast<int>(o % a.C);
+    float g[8];
+    bn_bwd_load_g(a, o, g);
+    const float4 z0 = *reinterpret_cast<const float4*>(a.z + o), z1 = *reinterpret_cast<const float4*>(a.z + o + 4);
+    const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+    float dz[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float is = a.invstd[c + e];
+      const float xhat = (zz[e] - a.mean[c + e]) * is;
+      const float sgm = static_cast<float>(a.sums[c + e]) * inv_count;
+      const float sxm = static_cast<float>(a.sums[a.C + c + e]) * inv_count;
+      const float gam = a.gamma ? a.gamma[c + e] : 1.0f;
+      dz[e] = gam * is * (g[e] - sgm - xhat * sxm);
+    }
+    if (a.dz_hi) {
+      uint4 h, l;
+      pack8(dz, h, l);
+      *reinterpret_cast<uint4*>(a.dz_hi + o) = h;
+      *reinterpret_cast<uint4*>(a.dz_lo + o) = l;
+    }
+    if (a.dz_f32) {
+      *reinterpret_cast<float4*>(a.dz_f32 + o) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+      *reinterpret_cast<float4*>(a.dz_f32 + o + 4) = make_float4(dz[4], dz[5], dz[6], dz[7]);
+    }
+    if (a.g_hi) {
+      uint4 h, l;
+      pack8(g, h, l);
+      *reinterpret_cast<uint4*>(a.g_hi + o) = h;
+      *reinterpret_cast<uint4*>(a.g_lo + o) = l;
+    }
+  }
+}
+
+// sums fp64 [2C] -> dgamma/dbeta fp32 (optionally accumulated)
+__global__ void bn_bwd_param_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int C, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float dg = static_cast<float>(sums[C + c]), db = static_cast<float>(sums[c]);
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + db : db;
+}
+
+static int bn_bwd_fill(BnBwdArgs& a, const void* dy_split, const float* dy_f32, const void* y_split, const float* z,
+                       const float* mean, const float* invstd, const float* gamma, double* sums, double count,
+                       void* dz_split, float* dz_f32, void* g_split, long long M, int C) {
+  memset(&a, 0, sizeof(a));
+  const long long plane = M * C;
+  if (dy_split) {
+    a.dy_hi = reinterpret_cast<const __nv_bfloat16*>(dy_split);
+    a.dy_lo = a.dy_hi + plane;
+  }
+  a.dy_f32 = dy_f32;
+  if (y_split) {
+    a.y_hi = reinterpret_cast<const __nv_bfloat16*>(y_split);
+    a.y_lo = a.y_hi + plane;
+  }
+  a.z = z; a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.sums = sums; a.count = count;
+  if (dz_split) {
+    a.dz_hi = reinterpret_cast<__nv_bfloat16*>(dz_split);
+    a.dz_lo = a.dz_hi + plane;
+  }
+  a.dz_f32 = dz_f32;
+  if (g_split) {
+    a.g_hi = reinterpret_cast<__nv_bfloat16*>(g_split);
+    a.g_lo = a.g_hi + plane;
+  }
+  a.M = M; a.C = C;
+  return VFS_OK;
+}
+
+int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
+                  const float* invstd, double* sums, long long M, int C, cudaStream_t s) {
+  VFS_REQUIRE((dy_split || dy_f32) && z && mean && invstd && sums, VFS_EINVAL, "bn_bwd_reduce: null argument");
+  VFS_REQUIRE(M > 0 && C % 8 == 0 && C / 8 <= 256, VFS_ESHAPE, "bn_bwd_reduce: C=%d unsupported", C);
+  BnBwdArgs a;
+  bn_bwd_fill(a, dy_split, dy_f32, y_split, z, mean, invstd, nullptr, sums, 1.0, nullptr, nullptr, nullptr, M, C);
+  const int rows_per_block = 256 / (C / 8);
+  long long blocks = (M + rows_per_block - 1) / rows_per_block;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bn_bwd_reduce_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(a);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
+                 const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
+                 float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, long long M, int C,
+                 cudaStream_t s) {
+  VFS_REQUIRE((dy_split || dy_f32) && z && mean && invstd && sums && (dz_split || dz_f32), VFS_EINVAL,
+              "bn_bwd_apply: null argument");
+  VFS_REQUIRE(M > 0 && C % 8 == 0 && count > 0, VFS_ESHAPE, "bn_bwd_apply: bad shape");
+  BnBwdArgs a;
+  bn_bwd_fill(a, dy_split, dy_f32, y_split, z, mean, invstd, gamma, const_cast<double*>(sums), count, dz_split, dz_f32,
+              g_split, M, C);
+  const long long total8 = M * C / 8;
+  long long blocks = (total8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bn_bwd_apply_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(a);
+  VFS_CUDA_OK(cudaGetLastError());
+  if (dgamma || dbeta) {
+    bn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, dgamma, dbeta, C, accumulate);
+    VFS_CUDA_OK(cudaGetLastError());
+  }
+  return VFS_OK;
+}
+
+// masked gradient only (no BN): g = dY * 1[y > 0]  -> split   (blocks whose last op is add+ReLU with eval-mode BN)
+__global__ void relu_bwd_split_kernel(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, const __nv_bfloat16* y_hi,
+                                      const __nv_bfloat16* y_lo, __nv_bfloat16* g_hi, __nv_bfloat16* g_lo,
+                                      long long total8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long o = i * 8;
+    float g[8], y[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy_hi + o), *reinterpret_cast<const uint4*>(dy_lo + o), g);
+    unpack8(*reinterpret_cast<const uint4*>(y_hi + o), *reinterpret_cast<const uint4*>(y_lo + o), y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.0f) ? g[e] : 0.0f;
+    uint4 h, l;
+    pack8(g, h, l);
+    *reinterpret_cast<uint4*>(g_hi + o) = h;
+    *reinterpret_cast<uint4*>(g_lo + o) = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem backward: max-pool(3,2,1) + ReLU backward, then 7x7 weight gradient.
+// ------------------------------------------------------------------------------------------------
+// g[n,y,x,c] = 1[a > 0] * sum over pooling windows whose (first) arg-max is (y,x) of dPool, with a = relu(z*sc+sh)
+__global__ void stem_pool_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dp_hi, const __nv_bfloat16* __restrict__ dp_lo,
+                                          const float* __restrict__ z, const float* __restrict__ scale,
+                                          const float* __restrict__ shift, float* __restrict__ g, int N, int Hc, int Wc,
+                                          int Hp, int Wp) {
+  const size_t total = static_cast<size_t>(N) * Hc * Wc * 8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int grp = static_cast<int>(i & 7);
+    size_t t = i >> 3;
+    const int x = static_cast<int>(t % Wc);
+    t /= Wc;
+    const int y = static_cast<int>(t % Hc);
+    const int n = static_cast<int>(t / Hc);
+    float sc[8], sh[8], acc[8], a0[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = scale[grp * 8 + e];
+      sh[e] = shift[grp * 8 + e];
+      acc[e] = 0.0f;
+    }
+    auto act = [&](int yy, int xx, float (&out)[8]) {
+      const float4* src = reinterpret_cast<const float4*>(z + ((static_cast<size_t>(n) * Hc + yy) * Wc + xx) * 64 + grp * 8);
+      const float4 p = src[0], q = src[1];
+      const float v[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) out[e] = fmaxf(fmaf(v[e], sc[e], sh[e]), 0.0f);
+    };
+    act(y, x, a0);
+    // pooling windows (py, px) containing this pixel: 2*py-1 <= y <= 2*py+1  <=>  y/2 <= py <= (y+1)/2
+    const int py_lo = y / 2, py_hi = (y + 1) / 2;
+    const int px_lo = x / 2, px_hi = (x + 1) / 2;
+    for (int py = py_lo; py <= py_hi; ++py) {
+      if (py >= Hp) continue;
+      for (int px = px_lo; px <= px_hi; ++px) {
+        if (px >= Wp) continue;
+        // is (y, x) the first maximum of window (py, px) in row-major scan order?
+        bool first[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) first[e] = true;
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = 2 * py + dy;
+          if (yy < 0 || yy >= Hc) continue;
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = 2 * px + dx;
+            if (xx < 0 || xx >= Wc || (yy == y && xx == x)) continue;
+            float o[8];
+            act(yy, xx, o);
+            const bool before = (yy < y) || (yy == y && xx < x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) first[e] = first[e] && (before ? (o[e] < a0[e]) : (o[e] <= a0[e]));
+          }
+        }
+        float d[8];
+        const size_t po = ((static_cast<size_t>(n) * Hp + py) * Wp + px) * 64 + grp * 8;
+        unpack8(*reinterpret_cast<const uint4*>(dp_hi + po), *reinterpret_cast<const uint4*>(dp_lo + po), d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += first[e] ? d[e] : 0.0f;
+      }
+    }
+    float out[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = (a0[e] > 0.0f) ? acc[e] : 0.0f;
+    float* dst = g + ((static_cast<size_t>(n) * Hc + y) * Wc + x) * 64 + grp * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(out[4], out[5], out[6], out[7]);
+  }
+}
+
+// dW[co][c][r][s] += sum_{n,oy,ox} dz[n,oy,ox,co] * x[n,c,2oy+r-3,2ox+s-3]; block = strip of conv pixels,
+// thread = (co, 37 k values); partial sums reduced with fp32 atomics.
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                         float* __restrict__ dw, int N, int H, int W, int Hc, int Wc) {
+  __shared__ float patch[3][7][70];   // input rows needed by one output row segment of 32 pixels
+  __shared__ float dzs[32][64];
+  const int co = threadIdx.x & 63, kq = threadIdx.x >> 6;  // kq in 0..3 -> k = kq, kq+4, ...
+  float acc[37];
+#pragma unroll
+  for (int j = 0; j < 37; ++j) acc[j] = 0.0f;
+  const int segs_per_row = (Wc + 31) / 32;
+  const long long total_segs = static_cast<long long>(N) * Hc * segs_per_row;
+  for (long long sidx = blockIdx.x; sidx < total_segs; sidx += gridDim.x) {
+    const int seg = static_cast<int>(sidx % segs_per_row);
+    long long t = sidx / segs_per_row;
+    const int oy = static_cast<int>(t % Hc);
+    const int n = static_cast<int>(t / Hc);
+    const int ox0 = seg * 32;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 7 * 70; i += 256) {
+      const int pc = i % 70, r = (i / 70) % 7, c = i / 490;
+      const int iy = 2 * oy + r - 3, ix = 2 * ox0 + pc - 3;
+      patch[c][r][pc] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[(static_cast<size_t>(n) * 3 + c) * H * W + static_cast<size_t>(iy) * W + ix] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+      const int px = i >> 6, c = i & 63;
+      dzs[px][c] = (ox0 + px < Wc) ? dz[((static_cast<size_t>(n) * Hc + oy) * Wc + ox0 + px) * 64 + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 37; ++j) {
+      const int k = kq + 4 * j;
+      if (k < 147) {
+        const int c = k / 49, r = (k / 7) % 7, s = k % 7;
+        float a = acc[j];
+#pragma unroll 8
+        for (int px = 0; px < 32; ++px) a = fmaf(dzs[px][co], patch[c][r][2 * px + s], a);
+        acc[j] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 37; ++j) {
+    const int k = kq + 4 * j;
+    if (k < 147) atomicAdd(dw + co * 147 + k, acc[j]);
+  }
+}
+
+int stem_pool_relu_bwd(const void* dpool_split, const float* z, const float* scale, const float* shift, float* g,
+                       int N, int H, int W, cudaStream_t s) {
+  VFS_REQUIRE(dpool_split && z && scale && shift && g, VFS_EINVAL, "stem_pool_relu_bwd: null argument");
+  const int Hc = (H + 6 - 7) / 2 + 1, Wc = (W + 6 - 7) / 2 + 1;
+  const int Hp = (Hc + 2 - 3) / 2 + 1, Wp = (Wc + 2 - 3) / 2 + 1;
+  const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(dpool_split);
+  const size_t total = static_cast<size_t>(N) * Hc * Wc * 8;
+  const int blocks = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  stem_pool_relu_bwd_kernel<<<blocks, 256, 0, s>>>(hi, hi + static_cast<size_t>(N) * Hp * Wp * 64, z, scale, shift, g, N,
+                                                   Hc, Wc, Hp, Wp);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+int stem_wgrad(const float* x, const float* dz, float* dw, int accumulate, int N, int H, int W, cudaStream_t s) {
+  VFS_REQUIRE(x && dz && dw, VFS_EINVAL, "stem_wgrad: null argument");
+  const int Hc = (H + 6 - 7) / 2 + 1, Wc = (W + 6 - 7) / 2 + 1;
+  if (!accumulate) VFS_CUDA_OK(cudaMemsetAsync(dw, 0, 64 * 147 * sizeof(float), s));
+  stem_wgrad_kernel<<<148 * 2, 256, 0, s>>>(x, dz, dw, N, H, W, Hc, Wc);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SimSiam head backward
+// ------------------------------------------------------------------------------------------------
+// dX[m, k] = sum_n dY[m, n] W[n, k]; block = 256 consecutive k, rows tiled by 16
+__global__ void __launch_bounds__(256) linear_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ W,
+                                                              float* __restrict__ dx, int M, int N, int K) {
+  __shared__ float dys[16][128];
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  const int m0 = blockIdx.y * 16;
+  float acc[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) acc[m] = 0.0f;
+  for (int n0 = 0; n0 < N; n0 += 128) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16 * 128; i += 256) {
+      const int m = i >> 7, nn = i & 127;
+      dys[m][nn] = (m0 + m < M && n0 + nn < N) ? dy[static_cast<size_t>(m0 + m) * N + n0 + nn] : 0.0f;
+    }
+    __syncthreads();
+    if (k < K) {
+      const int nmax = min(128, N - n0);
+      for (int nn = 0; nn < nmax; ++nn) {
+        const float w = __ldg(W + static_cast<size_t>(n0 + nn) * K + k);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) acc[m] = fmaf(dys[m][nn], w, acc[m]);
+      }
+    }
+  }
+  if (k < K) {
+#pragma unroll
+    for (int m = 0; m < 16; ++m)
+      if (m0 + m < M) dx[static_cast<size_t>(m0 + m) * K + k] = acc[m];
+  }
+}
+
+// dW[n, k] (+)= sum_m dY[m, n] X[m, k];  block = 8 rows n x 256 k; db[n] (+)= sum_m dY[m, n]
+__global__ void __launch_bounds__(256) linear_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                float* __restrict__ dW, float* __restrict__ db, int M,
+                                                                int N, int K, int accumulate) {
+  __shared__ float dys[128][8];
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  const int n0 = blockIdx.y * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  float bsum = 0.0f;
+  for (int m0 = 0; m0 < M; m0 += 128) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * 8; i += 256) {
+      const int m = i >> 3, j = i & 7;
+      dys[m][j] = (m0 + m < M && n0 + j < N) ? dy[static_cast<size_t>(m0 + m) * N + n0 + j] : 0.0f;
+    }
+    __syncthreads();
+    const int mmax = min(128, M - m0);
+    if (k < K) {
+      for (int m = 0; m < mmax; ++m) {
+        const float xv = __ldg(x + static_cast<size_t>(m0 + m) * K + k);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(dys[m][j], xv, acc[j]);
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 8)
+      for (int m = 0; m < mmax; ++m) bsum += dys[m][threadIdx.x];
+  }
+  if (k < K) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (n0 + j < N) {
+        float* d = dW + static_cast<size_t>(n0 + j) * K + k;
+        *d = accumulate ? *d + acc[j] : acc[j];
+      }
+  }
+  if (db && blockIdx.x == 0 && threadIdx.x < 8 && n0 + threadIdx.x < N)
+    db[n0 + threadIdx.x] = accumulate ? db[n0 + threadIdx.x] + bsum : bsum;
+}
+
+// BatchNorm1d (+ReLU) backward, one thread per feature.  pre = linear output before BN, out = layer output.
+__global__ void bn1d_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre,
+                                const float* __restrict__ out, float* __restrict__ dpre, int M, int N,
+                                const float* __restrict__ gamma, const float* __restrict__ mean,
+                                const float* __restrict__ invstd, int training, int relu, float* __restrict__ dgamma,
+                                float* __restrict__ dbeta, int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float mu = mean[n], is = invstd[n], g = gamma ? gamma[n] : 1.0f;
+  float sg = 0.0f, sx = 0.0f;
+  for (int m = 0; m < M; ++m) {
+    const size_t o = static_cast<size_t>(m) * N + n;
+    float d = dy[o];
+    if (relu && !(out[o] > 0.0f)) d = 0.0f;
+    sg += d;
+    sx = fmaf(d, (pre[o] - mu) * is, sx);
+  }
+  const float invM = 1.0f / static_cast<float>(M);
+  for (int m = 0; m < M; ++m) {
+    const size_t o = static_cast<size_t>(m) * N + n;
+    float d = dy[o];
+    if (relu && !(out[o] > 0.0f)) d = 0.0f;
+    const float xhat = (pre[o] - mu) * is;
+    dpre[o] = training ? g * is * (d - sg * invM - xhat * sx * invM) : g * is * d;
+  }
+  if (dgamma) dgamma[n] = accumulate ? dgamma[n] + sx : sx;
+  if (dbeta) dbeta[n] = accumulate ? dbeta[n] + sg : sg;
+}
+
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ out, float* __restrict__ dx,
+                                size_t n) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) dx[i] = (out[i] > 0.0f) ? dy[i] : 0.0f;
+}
+
+// global average pool backward straight into the backbone's gradient format: dY [B, C] -> split NHWC [B, HW, C]
+__global__ void avgpool_bwd_split_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, int B, int HW, int C) {
+  const size_t total8 = static_cast<size_t>(B) * HW * C / 8;
+  const float inv = 1.0f / static_cast<float>(HW);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t o = i * 8;
+    const int c = static_cast<int>(o % C);
+    const int b = static_cast<int>(o / (static_cast<size_t>(HW) * C));
+    const float4 p = *reinterpret_cast<const float4*>(dy + static_cast<size_t>(b) * C + c);
+    const float4 q = *reinterpret_cast<const float4*>(dy + static_cast<size_t>(b) * C + c + 4);
+    const float v[8] = {p.x * inv, p.y * inv, p.z * inv, p.w * inv, q.x * inv, q.y * inv, q.z * inv, q.w * inv};
+    uint4 h, l;
+    pack8(v, h, l);
+    *reinterpret_cast<uint4*>(hi + o) = h;
+    *reinterpret_cast<uint4*>(lo + o) = l;
+  }
+}
+
+// cosine loss backward w.r.t. p (z is detached in SimSiam):  L = 2 - 2 cos  ->  dp = g * (-2) (zhat - phat cos)/|p|
+__global__ void __launch_bounds__(128) cosine_loss_bwd_kernel(const float* __restrict__ p, const float* __restrict__ z,
+                                                              const float* __restrict__ gout, float* __restrict__ dp,
+                                                              int D, int with_norm, int negative) {
+  __shared__ float red[3][4];
+  __shared__ float bc[3];
+  const int b = blockIdx.x;
+  const float* pp = p + static_cast<size_t>(b) * D;
+  const float* zz = z + static_cast<size_t>(b) * D;
+  float spp = 0.0f, szz = 0.0f, spz = 0.0f;
+  for (int i = threadIdx.x; i < D; i += 128) {
+    const float a = pp[i], c = zz[i];
+    spp = fmaf(a, a, spp);
+    szz = fmaf(c, c, szz);
+    spz = fmaf(a, c, spz);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    spp += __shfl_xor_sync(0xffffffffu, spp, o);
+    szz += __shfl_xor_sync(0xffffffffu, szz, o);
+    spz += __shfl_xor_sync(0xffffffffu, spz, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = spp;
+    red[1][threadIdx.x >> 5] = szz;
+    red[2][threadIdx.x >> 5] = spz;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bc[0] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    bc[1] = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    bc[2] = red[2][0] + red[2][1] + red[2][2] + red[2][3];
+  }
+  __syncthreads();
+  const float coef = (negative ? -1.0f : -2.0f) * gout[b];
+  if (!with_norm) {
+    for (int i = threadIdx.x; i < D; i += 128) dp[static_cast<size_t>(b) * D + i] = coef * zz[i];
+    return;
+  }
+  const float np = fmaxf(sqrtf(bc[0]), 1e-12f), nz = fmaxf(sqrtf(bc[1]), 1e-12f);
+  const float cosv = bc[2] / (np * nz);
+  for (int i = threadIdx.x; i < D; i += 128)
+    dp[static_cast<size_t>(b) * D + i] = coef * (zz[i] / nz - pp[i] / np * cosv) / np;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SGD with momentum and weight decay (torch.optim.SGD semantics, dampening 0, no nesterov):
+//   g' = g + wd * p ;  buf = first ? g' : momentum * buf + g' ;  p -= lr * buf
+// ------------------------------------------------------------------------------------------------
+__global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                                    size_t n, float lr, float momentum, float wd, int first, float grad_scale) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float gg = fmaf(wd, p[i], g[i] * grad_scale);
+    const float b = first ? gg : fmaf(momentum, buf[i], gg);
+    buf[i] = b;
+    p[i] = p[i] - lr * b;
+  }
+}
+
+int relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, long long elems, cudaStream_t s) {
+  VFS_REQUIRE(dy_split && y_split && g_split && elems % 8 == 0, VFS_EINVAL, "relu_bwd_split: bad argument");
+  const __nv_bfloat16* dh = reinterpret_cast<const __nv_bfloat16*>(dy_split);
+  const __nv_bfloat16* yh = reinterpret_cast<const __nv_bfloat16*>(y_split);
+  __nv_bfloat16* gh = reinterpret_cast<__nv_bfloat16*>(g_split);
+  long long blocks = (elems / 8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  relu_bwd_split_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(dh, dh + elems, yh, yh + elems, gh, gh + elems, elems / 8);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+int linear_backward(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db, int M, int N,
+                    int K, int accumulate, cudaStream_t s) {
+  VFS_REQUIRE(dy && x && W, VFS_EINVAL, "linear_backward: null argument");
+  VFS_REQUIRE(M > 0 && N > 0 && K > 0, VFS_ESHAPE, "linear_backward: bad shape");
+  if (dx) {
+    linear_bwd_data_kernel<<<dim3((K + 255) / 256, (M + 15) / 16), 256, 0, s>>>(dy, W, dx, M, N, K);
+    VFS_CUDA_OK(cudaGetLastError());
+  }
+  if (dW) {
+    linear_bwd_weight_kernel<<<dim3((K + 255) / 256, (N + 7) / 8), 256, 0, s>>>(dy, x, dW, db, M, N, K, accumulate);
+    VFS_CUDA_OK(cudaGetLastError());
+  }
+  return VFS_OK;
+}
+
+int bn1d_backward(const float* dy, const float* pre, const float* out, float* dpre, int M, int N, const float* gamma,
+                  const float* mean, const float* invstd, int training, int relu, float* dgamma, float* dbeta,
+                  int accumulate, cudaStream_t s) {
+  VFS_REQUIRE(dy && pre && out && dpre && mean && invstd, VFS_EINVAL, "bn1d_backward: null argument");
+  bn1d_bwd_kernel<<<(N + 127) / 128, 128, 0, s>>>(dy, pre, out, dpre, M, N, gamma, mean, invstd, training, relu, dgamma,
+                                                  dbeta, accumulate);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+int relu_backward(const float* dy, const float* out, float* dx, size_t n, cudaStream_t s) {
+  VFS_REQUIRE(dy && out && dx, VFS_EINVAL, "relu_backward: null argument");
+  relu_bwd_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(dy, out, dx, n);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+int avgpool_backward_split(const float* dy, void* out_split, int B, int HW, int C, cudaStream_t s) {
+  VFS_REQUIRE(dy && out_split && C % 8 == 0, VFS_EINVAL, "avgpool_backward: bad argument");
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out_split);
+  const size_t total8 = static_cast<size_t>(B) * HW * C / 8;
+  const int blocks = static_cast<int>((total8 + 255) / 256 < 148 * 16 ? (total8 + 255) / 256 : 148 * 16);
+  avgpool_bwd_split_kernel<<<blocks, 256, 0, s>>>(dy, hi, hi + static_cast<size_t>(B) * HW * C, B, HW, C);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+int cosine_loss_backward(const float* p, const float* z, const float* gout, float* dp, int B, int D, int with_norm,
+                         int negative, cudaStream_t s) {
+  VFS_REQUIRE(p && z && gout && dp, VFS_EINVAL, "cosine_loss_backward: null argument");
+  cosine_loss_bwd_kernel<<<B, 128, 0, s>>>(p, z, gout, dp, D, with_norm, negative);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+int sgd_momentum_step(float* p, const float* g, float* buf, size_t n, float lr, float momentum, float wd, int first,
+                      float grad_scale, cudaStream_t s) {
+  VFS_REQUIRE(p && g && buf, VFS_EINVAL, "sgd_momentum_step: null argument");
+  if (n == 0) return VFS_OK;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sgd_momentum_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(p, g, buf, n, lr, momentum, wd, first, grad_scale);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+}  // namespace vfs

@@ -8,7 +8,7 @@ from . import _native as nat
 from ._native import VfsConvDesc, current_stream, ptr
 
 LAUNCHES = [0]  # kernels of libvfs_b200.so launched through this module (bench.py reports the count)
-_KERNELS_PER_CALL = {'stem_forward': 2, 'masked_attention': 2, 'features_to_split_norm': 2, 'conv_dgrad': 1}
+_KERNELS_PER_CALL = {'stem_forward': 2, 'masked_attention': 2, 'features_to_split_norm': 2, 'conv_dgrad': 1, 'conv_wgrad': 2}
 
 
 def check(rc, what=''):
@@ -232,6 +232,23 @@ def conv_dgrad(dz, wt_split, in_hw, ksize, stride=1, dilation=1, add=None):
                                    ptr(_const_vec(0, Cin, dz.device)), ptr(add), ptr(dx), current_stream()),
           'conv_dgrad')
     return dx
+
+
+def conv_wgrad(xs, dz, ksize, stride=1, dilation=1, out=None, accumulate=False):
+    """dW (OIHW fp32) of the conv with forward input ``xs`` split [2,N,H,W,Cin] and output gradient ``dz`` split
+    [2,N,Ho,Wo,Cout].  ``out``: existing gradient tensor to overwrite / accumulate into."""
+    _, N, H, W, Cin = xs.shape
+    Cout = dz.shape[-1]
+    assert conv_out_hw(H, W, ksize, stride, dilation) == tuple(dz.shape[2:4]), (xs.shape, dz.shape)
+    if out is None:
+        out = torch.empty((Cout, Cin, ksize, ksize), dtype=torch.float32, device=xs.device)
+        accumulate = False
+    ws = torch.empty((nat.lib().vfs_conv_wgrad_workspace_bytes(Cout, Cin, ksize) // 4, ), dtype=torch.float32,
+                     device=xs.device)
+    d = VfsConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, ksize=ksize, stride=stride, dilation=dilation, relu=0)
+    check(nat.lib().vfs_conv_wgrad(ctypes.byref(d), ptr(xs), ptr(dz), ptr(ws), ptr(out), int(accumulate),
+                                   current_stream()), 'conv_wgrad')
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
