@@ -236,7 +236,7 @@ def main():
     mask = spatial_neighbor(1, fh, fw, TEST_CFG['neighbor_range'])
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    bank = torch.empty((2, CLIPS * FRAMES, fh, fw, 1024), dtype=torch.bfloat16, device=dev)
+    bank = torch.empty((2, CLIPS * FRAMES, fh, fw, 1024), dtype=torch.float16, device=dev)
     out = torch.empty((CLIPS, CV, hw), dtype=torch.float32, device=dev)
 
     # The step is three CUDA graphs (stem | tcgen05 conv stages | normalise + attention) captured once over static
@@ -354,14 +354,14 @@ def main():
     roofline = dict(bound='tensor', kernel='conv_tc_kernel', achieved=achieved, peak=peak_tf, unit='TFLOP/s',
                     frac=achieved / peak_tf, traffic=None, peak_source=peak_src,
                     note='achieved = algorithmic fp32-equivalent conv FLOPs; the kernel issues 3 bf16 MMAs per '
-                         'product (split-bf16), so tensor-pipe work is 3x: frac_of_issued = %.3f' %
+                         'product (split-fp16), so tensor-pipe work is 3x: frac_of_issued = %.3f' %
                          (3 * achieved / peak_tf),
                     launches_per_step=n_conv_launches, segment_ms_median=conv_med,
                     flops_per_step=conv_flops)
 
     line = dict(metric='frame-pairs/sec (R50 res4 feat+affinity)', value=value, unit='frame-pairs/s', n_gpus=world,
                 steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=total_ms / a.steps, higher_is_better=True,
-                scaling='weak', vs_baseline=None, dtype='bf16x3 (split-bf16 operands, fp32 accumulate)',
+                scaling='weak', vs_baseline=None, dtype='fp16x3 (split-fp16 operands, fp32 accumulate)',
                 data='synthetic',
                 config=dict(workload=WORKLOAD, clips_per_gpu=CLIPS, l2='flushed (512 MiB write) between steps',
                             timing='sum of per-step CUDA-event spans (3 CUDA graphs per step), max over ranks',

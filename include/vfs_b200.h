@@ -7,10 +7,12 @@
  *     callbacks inside; everything is enqueued on the caller's stream.
  *   - return value: VFS_OK (0) or a negative error code; vfs_last_error_string() describes the last
  *     failure of the calling thread.  Nothing throws across the boundary.
- *   - "split" tensors are the library's activation format: fp32 values stored as two bf16 planes
- *     (hi, lo with x ~= hi + lo, relative error <= 2^-16), layout [2][N][H][W][C] (plane-major NHWC).
- *     They feed the tcgen05 tensor cores three products at a time (hi*hi + hi*lo + lo*hi), which
- *     keeps fp32-level accuracy (the reference computes in fp32; parity bar 1e-3).
+ *   - "split" tensors are the library's activation format: fp32 values stored as two IEEE-half planes
+ *     (hi, lo with x ~= hi + lo: 22 significant bits, relative error <= 2^-22 for |x| >~ 0.1, absolute error
+ *     <= 3e-8 below), layout [2][N][H][W][C] (plane-major NHWC).  They feed the tcgen05 tensor cores three
+ *     products at a time (lo*hi + hi*lo + hi*hi, fp32 accumulation), which keeps fp32-class accuracy (the
+ *     reference computes in fp32; parity bar 1e-3, exact top-k indices).  Values must stay inside the fp16 range
+ *     (|x| <= 65504); violations are counted, see vfs_overflow_count().
  */
 #ifndef VFS_B200_H_
 #define VFS_B200_H_
@@ -34,12 +36,17 @@ const char* vfs_last_error_string(void);
 int vfs_abi_version(void);
 /* VFS_OK iff the current device is compute capability 10.x. */
 int vfs_check_device(void);
+/* Values that left the fp16 range while being split since the last reset (synchronises the device). */
+unsigned int vfs_overflow_count(int reset);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout boundary.  Reference tensors are NCHW fp32 contiguous.
  * ---------------------------------------------------------------------------------------------- */
 /* NCHW fp32 -> split NHWC.  C must be a multiple of 8. */
 int vfs_nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, vfs_stream_t s);
+/* same, of scale * in (used to enter the backward pass with power-of-two scaled gradients). */
+int vfs_nchw_f32_to_split_scaled(const float* in, void* out_split, int N, int C, int H, int W, float scale,
+                                 vfs_stream_t s);
 /* split NHWC -> NCHW fp32 (hi + lo). */
 int vfs_split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H, int W, vfs_stream_t s);
 
@@ -124,7 +131,40 @@ int vfs_pack_conv_weight_dgrad(const float* w_oihw, void* wt_split, int Cout, in
  *   dw_oihw fp32 [Cout,Cin,k,k]: overwritten, or accumulated into when accumulate != 0 (second SimSiam view). */
 size_t vfs_conv_wgrad_workspace_bytes(int Cout, int Cin, int ksize);
 int vfs_conv_wgrad(const VfsConvDesc* d, const void* x_split, const void* dz_split, void* workspace, float* dw_oihw,
-                   int accumulate, vfs_stream_t s);
+                   int accumulate, float out_scale, vfs_stream_t s);
+
+/* BatchNorm(+ReLU) backward around the conv gradients (torch batch_norm_backward_reduce / _elemt):
+ *   g = dY * 1[y > 0];  sums = [sum g | sum g*xhat] (fp64, caller zero-initialises; all-reduced across ranks for
+ *   SyncBN);  dz = gamma*invstd*(g - sums0/count - xhat*sums1/count);  dgamma = param_scale*sums1, dbeta = param_scale*sums0.
+ * dY comes as a split tensor or as fp32 (stem); dz goes out split (residual stages) and/or fp32 (stem); g_split
+ * (optional) is the masked gradient that also flows into the block's identity branch. */
+int vfs_bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* z,
+                      const float* mean, const float* invstd, double* sums, long long M, int C, vfs_stream_t s);
+int vfs_bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
+                     const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
+                     float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
+                     long long M, int C, vfs_stream_t s);
+int vfs_relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, long long elems, vfs_stream_t s);
+/* stem backward: max-pool(3,2,1)+ReLU backward onto the raw conv output grid (g fp32 [N,Hc,Wc,64]), and the 7x7
+ * weight gradient dw[64,3,7,7] (+)= out_scale * sum dz * x */
+int vfs_stem_pool_relu_bwd(const void* dpool_split, const float* z, const float* scale, const float* shift, float* g,
+                           int N, int H, int W, vfs_stream_t s);
+int vfs_stem_wgrad(const float* x, const float* dz, float* dw, int accumulate, float out_scale, int N, int H, int W,
+                   vfs_stream_t s);
+/* SimSiam head / loss backward and the optimiser update */
+int vfs_linear_backward(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db, int M,
+                        int N, int K, int accumulate, vfs_stream_t s);
+int vfs_bn1d_backward(const float* dy, const float* pre, const float* out, float* dpre, int M, int N,
+                      const float* gamma, const float* mean, const float* invstd, int training, int relu,
+                      float* dgamma, float* dbeta, int accumulate, vfs_stream_t s);
+int vfs_relu_backward(const float* dy, const float* out, float* dx, size_t n, vfs_stream_t s);
+int vfs_avgpool_backward(const float* dy, float* dx_nchw, int B, int C, int HW, vfs_stream_t s);
+int vfs_cosine_loss_backward(const float* p, const float* z, const float* gout, float* dp, int B, int D,
+                             int with_norm, int negative, vfs_stream_t s);
+/* torch.optim.SGD update (momentum, weight decay, dampening 0): g' = grad_scale*g + wd*p; buf = first ? g' :
+ * momentum*buf + g'; p -= lr*buf.  Replaces the optimizer step of mmcv's OptimizerHook (configs/*:134). */
+int vfs_sgd_momentum_step(float* p, const float* g, float* buf, size_t n, float lr, float momentum, float wd,
+                          int first, float grad_scale, vfs_stream_t s);
 
 /* OIHW fp32 [Cout,Cin,k,k] -> split [2][Cout][k*k*Cin] (device to device). */
 int vfs_pack_conv_weight(const float* w_oihw, void* w_split, int Cout, int Cin, int ksize, vfs_stream_t s);
@@ -201,7 +241,8 @@ int vfs_global_avg_pool(const float* in_nchw, float* out, int B, int C, int HW, 
 int vfs_linear(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, vfs_stream_t s);
 /* in-place BatchNorm1d over y[M,N] (+ReLU); training != 0 uses batch statistics and updates the running ones */
 int vfs_bn1d_act(float* y, int M, int N, const float* gamma, const float* beta, float* running_mean,
-                 float* running_var, float eps, float momentum, int training, int relu, vfs_stream_t s);
+                 float* running_var, float eps, float momentum, int training, int relu, float* save_mean,
+                 float* save_invstd, vfs_stream_t s);
 int vfs_relu(float* y, size_t n, vfs_stream_t s);
 /* loss[b] = 2 - 2*cos(p[b], z[b])  (negative != 0: -cos; with_norm == 0: raw dot product) */
 int vfs_cosine_sim_loss(const float* p, const float* z, float* loss, int B, int D, int with_norm, int negative,

@@ -491,3 +491,72 @@ def test_simsiam_forward_eval_mode_matches_oracle(name):
     out = model.train_step(dict(imgs=imgs.cuda()), None)
     assert set(out) == {'loss', 'log_vars', 'num_samples'} and out['num_samples'] == imgs.shape[0]
     assert abs(out['log_vars']['loss'] - float(sum(v.mean() for v in exp.values()))) < 1e-3
+
+
+# --------------------------------------------------------------------------------------------- training step
+def _oracle_train_reference(c, sd, imgs):
+    """Loss and parameter gradients of SimSiamBaseTracker.forward_train by torch autograd through the oracle
+    (CPU fp32; the oracle functions are plain differentiable torch code)."""
+    from vfs_b200.common import images2video, video2images
+    params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in sd.items()}
+    depth = c['model']['backbone']['depth']
+    bsd = {k[len('backbone.'):]: v for k, v in params.items() if k.startswith('backbone.')}
+    hsd = {k[len('img_head.'):]: v for k, v in params.items() if k.startswith('img_head.')}
+    clip_len = imgs.size(3)
+    i1 = video2images(imgs[:, 0].contiguous().reshape(-1, *imgs.shape[2:]))
+    i2 = video2images(imgs[:, 1].contiguous().reshape(-1, *imgs.shape[2:]))
+    z1, p1 = oracle.simsiam_head_forward(hsd, oracle.resnet_forward(bsd, i1, depth, bn_training=True), bn_training=True)
+    z2, p2 = oracle.simsiam_head_forward(hsd, oracle.resnet_forward(bsd, i2, depth, bn_training=True), bn_training=True)
+    intra = c['train_cfg'].get('intra_video', False)
+    w = 1. / clip_len if intra else 1.
+    losses = [oracle.simsiam_loss(p1, z1, p2, z2, weight=w)]
+    if intra:
+        z2v, p2v = images2video(z2, clip_len), images2video(p2, clip_len)
+        for i in range(1, clip_len):
+            losses.append(oracle.simsiam_loss(p1, z1, video2images(p2v.roll(i, dims=2)),
+                                              video2images(z2v.roll(i, dims=2)), weight=w))
+    loss = sum(l.mean() for l in losses)
+    loss.backward()
+    return float(loss), {k: v.grad for k, v in params.items() if v.requires_grad and v.grad is not None}
+
+
+@pytest.mark.parametrize('name', sorted(cases.TRACKER_TRAIN_CASES))
+def test_train_step_gradients_match_oracle_autograd(name):
+    """Full SimSiam training step through the public API (train_step -> loss.backward()): every parameter gradient
+    against torch autograd over the CPU oracle, then one native SGD update against torch.optim.SGD's rule."""
+    import vfs_b200
+    from vfs_b200 import ops
+    from vfs_b200.optim import SGD
+    c = cases.TRACKER_TRAIN_CASES[name]
+    model = vfs_b200.build_model(c['model'], train_cfg=vfs_b200.ConfigDict(c['train_cfg']), test_cfg=None)
+    sd = oracle.seeded_state_dict(model, seed=c['seed'])
+    model.load_state_dict(sd)
+    model = model.cuda()
+    model.train()
+    imgs = cases.tracker_train_input(c)
+    ref_loss, ref_grads = _oracle_train_reference(c, sd, imgs)
+
+    opt = SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    opt.zero_grad()
+    out = model.train_step(dict(imgs=imgs.cuda()), opt)
+    assert abs(out['log_vars']['loss'] - ref_loss) < 1e-3 * max(1.0, abs(ref_loss))
+    out['loss'].backward()
+    assert ops.overflow_count() == 0
+    got = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert set(got) == set(ref_grads), set(got) ^ set(ref_grads)
+    worst = []
+    for k, g in got.items():
+        r = ref_grads[k]
+        worst.append((float((g.cpu().double() - r.double()).abs().max() / r.abs().max().clamp_min(1e-12)), k))
+    worst.sort(reverse=True)
+    assert worst[0][0] < 2e-2, worst[:5]          # every tensor within 2e-2 of its own max ...
+    assert sum(w for w, _ in worst) / len(worst) < 2e-3, worst[:5]   # ... and 2e-3 on average
+
+    # one SGD step (first step: momentum buffer = g + wd*p)
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    opt.step()
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        exp = before[k] - 0.05 * (p.grad + 1e-4 * before[k])
+        assert rel_err(p.detach(), exp) < 1e-5, k

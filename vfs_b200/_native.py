@@ -31,7 +31,9 @@ PROTOTYPES = {
     'vfs_last_error_string': (ctypes.c_char_p, []),
     'vfs_abi_version': (_i, []),
     'vfs_check_device': (_i, []),
+    'vfs_overflow_count': (ctypes.c_uint, [_i]),
     'vfs_nchw_f32_to_split': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'vfs_nchw_f32_to_split_scaled': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     'vfs_split_to_nchw_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'vfs_stem_workspace_bytes': (_sz, [_i, _i, _i]),
     'vfs_stem_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -44,7 +46,19 @@ PROTOTYPES = {
     'vfs_conv_dgrad': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'vfs_pack_conv_weight_dgrad': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'vfs_conv_wgrad_workspace_bytes': (_sz, [_i, _i, _i]),
-    'vfs_conv_wgrad': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _i, _vp]),
+    'vfs_conv_wgrad': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _i, _f, _vp]),
+    'vfs_bn_bwd_reduce': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
+    'vfs_bn_bwd_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _i,
+                              _f, _ll, _i, _vp]),
+    'vfs_relu_bwd_split': (_i, [_vp, _vp, _vp, _ll, _vp]),
+    'vfs_stem_pool_relu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'vfs_stem_wgrad': (_i, [_vp, _vp, _vp, _i, _f, _i, _i, _i, _vp]),
+    'vfs_linear_backward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'vfs_bn1d_backward': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    'vfs_relu_backward': (_i, [_vp, _vp, _vp, _sz, _vp]),
+    'vfs_avgpool_backward': (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    'vfs_cosine_loss_backward': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'vfs_sgd_momentum_step': (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _i, _f, _vp]),
     'vfs_channel_stats_f32': (_i, [_vp, _vp, _ll, _i, _vp]),
     'vfs_bn_finalize': (_i, [_vp, ctypes.c_double, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     'vfs_bn_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
@@ -58,7 +72,7 @@ PROTOTYPES = {
                                   _vp, _vp, _vp, _vp, _sz, _vp]),
     'vfs_global_avg_pool': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'vfs_linear': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    'vfs_bn1d_act': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _vp]),
+    'vfs_bn1d_act': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp]),
     'vfs_relu': (_i, [_vp, _sz, _vp]),
     'vfs_cosine_sim_loss': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'vfs_nchw_to_nhwc_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

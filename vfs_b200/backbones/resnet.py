@@ -207,9 +207,28 @@ class ResNet(nn.Module):
                 yield i, block
 
     def forward(self, x):
-        """NCHW fp32 CUDA tensor -> stage outputs listed in ``out_indices`` (tensor if one, else tuple)."""
-        outs = self.engine.forward(x, out_indices=tuple(self.out_indices))
+        """NCHW fp32 CUDA tensor -> stage outputs listed in ``out_indices`` (tensor if one, else tuple).  With
+        gradients enabled and trainable parameters the call is recorded for the native backward pass
+        (vfs_b200/autograd.py: BN/ReLU backward, tcgen05 dgrad + wgrad)."""
+        out_indices = tuple(self.out_indices)
+        params = [p for p in self.parameters() if p.requires_grad]
+        if torch.is_grad_enabled() and params and self.training:
+            # (a module in eval mode is treated as inference: its outputs carry no autograd history)
+            self._check_trainable()
+            from ..autograd import BackboneFunction
+            outs = BackboneFunction.apply(x, self.engine, out_indices, *params)
+        else:
+            outs = self.engine.forward(x, out_indices=out_indices)
         return outs[0] if len(outs) == 1 else tuple(outs)
+
+    def _check_trainable(self):
+        """The native backward pass covers the reference's pre-training setting (every BN in batch-statistics mode,
+        configs/*:9-11).  Eval-mode BN inside a trainable layer has no backward kernel yet: fail loudly."""
+        for m in self.modules():
+            if isinstance(m, ConvModule) and m.conv.weight.requires_grad and m.with_norm and not m.norm.training:
+                raise NotImplementedError('vfs_b200: backward through an eval-mode BatchNorm (norm_eval / partial_bn '
+                                          'with trainable convs) is not implemented; freeze the layer or call '
+                                          'under torch.no_grad()')
 
     def forward_block(self, x, index):
         return self.engine.forward(x, block_index=index)[0]

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 128);
+    constexpr uint32_t idesc = umma_idesc_f16_f32(128, 128);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -200,9 +200,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
               const uint32_t koff = k * 32;
               const uint64_t dq_hi = umma_desc_sw128_kmajor(q_hi + koff), dq_lo = umma_desc_sw128_kmajor(q_lo + koff);
               const uint64_t dk_hi = umma_desc_sw128_kmajor(k_hi + koff), dk_lo = umma_desc_sw128_kmajor(k_lo + koff);
-              umma_bf16(d_tmem, dq_lo, dk_hi, idesc, (kc | k) != 0 ? 1u : 0u);
-              umma_bf16(d_tmem, dq_hi, dk_lo, idesc, 1u);
-              umma_bf16(d_tmem, dq_hi, dk_hi, idesc, 1u);
+              umma_f16(d_tmem, dq_lo, dk_hi, idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, dq_hi, dk_lo, idesc, 1u);
+              umma_f16(d_tmem, dq_hi, dk_hi, idesc, 1u);
             }
             umma_commit(empty_bar(stage));
             if (kc == p.kchunks - 1) umma_commit(tfull_bar(as));
@@ -386,7 +386,7 @@ __global__ void pixel_inv_norm_nchw_kernel(const float* __restrict__ in, float* 
 }
 
 __global__ void nchw_to_split_scaled_kernel(const float* __restrict__ in, const float* __restrict__ pix_scale,
-                                            __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                            h16* __restrict__ out_hi, h16* __restrict__ out_lo,
                                             int C, int HW) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -405,8 +405,8 @@ __global__ void nchw_to_split_scaled_kernel(const float* __restrict__ in, const 
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int pp = p0 + i, c = c0 + threadIdx.x;
     if (pp < HW && c < C) {
-      __nv_bfloat16 hi, lo;
-      split_bf16(tile[threadIdx.x][i], hi, lo);
+      h16 hi, lo;
+      split16(tile[threadIdx.x][i], hi, lo);
       const size_t o = (static_cast<size_t>(n) * HW + pp) * C + c;
       out_hi[o] = hi;
       out_lo[o] = lo;
@@ -415,8 +415,8 @@ __global__ void nchw_to_split_scaled_kernel(const float* __restrict__ in, const 
 }
 
 // split NHWC -> L2-normalised split NHWC; one warp per pixel, C multiple of 64.
-__global__ void normalize_split_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
-                                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+__global__ void normalize_split_kernel(const h16* __restrict__ in_hi, const h16* __restrict__ in_lo,
+                                       h16* __restrict__ out_hi, h16* __restrict__ out_lo,
                                        size_t num_pixels, int C) {
   const size_t pix = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -426,8 +426,8 @@ __global__ void normalize_split_kernel(const __nv_bfloat16* __restrict__ in_hi, 
   for (int c = lane * 2; c < C; c += 64) {
     const uint32_t h = *reinterpret_cast<const uint32_t*>(in_hi + base + c);
     const uint32_t l = *reinterpret_cast<const uint32_t*>(in_lo + base + c);
-    const float a = bf16_lo_to_float(h) + bf16_lo_to_float(l);
-    const float b = bf16_hi_to_float(h) + bf16_hi_to_float(l);
+    const float a = lo16_to_float(h) + lo16_to_float(l);
+    const float b = hi16_to_float(h) + hi16_to_float(l);
     s = fmaf(a, a, s);
     s = fmaf(b, b, s);
   }
@@ -437,13 +437,13 @@ __global__ void normalize_split_kernel(const __nv_bfloat16* __restrict__ in_hi, 
   for (int c = lane * 2; c < C; c += 64) {
     const uint32_t h = *reinterpret_cast<const uint32_t*>(in_hi + base + c);
     const uint32_t l = *reinterpret_cast<const uint32_t*>(in_lo + base + c);
-    const float a = (bf16_lo_to_float(h) + bf16_lo_to_float(l)) * inv;
-    const float b = (bf16_hi_to_float(h) + bf16_hi_to_float(l)) * inv;
-    __nv_bfloat16 ah, al, bh, bl;
-    split_bf16(a, ah, al);
-    split_bf16(b, bh, bl);
-    *reinterpret_cast<uint32_t*>(out_hi + base + c) = pack_bf16x2(ah, bh);
-    *reinterpret_cast<uint32_t*>(out_lo + base + c) = pack_bf16x2(al, bl);
+    const float a = (lo16_to_float(h) + lo16_to_float(l)) * inv;
+    const float b = (hi16_to_float(h) + hi16_to_float(l)) * inv;
+    h16 ah, al, bh, bl;
+    split16(a, ah, al);
+    split16(b, bh, bl);
+    *reinterpret_cast<uint32_t*>(out_hi + base + c) = pack16x2(ah, bh);
+    *reinterpret_cast<uint32_t*>(out_lo + base + c) = pack16x2(al, bl);
   }
 }
 
@@ -462,8 +462,8 @@ int features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, 
     pixel_inv_norm_nchw_kernel<<<grid, 128, 0, s>>>(in_nchw, inv, C, HW);
     VFS_CUDA_OK(cudaGetLastError());
   }
-  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out_split);
-  __nv_bfloat16* lo = hi + static_cast<size_t>(N) * HW * C;
+  h16* hi = reinterpret_cast<h16*>(out_split);
+  h16* lo = hi + static_cast<size_t>(N) * HW * C;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
   nchw_to_split_scaled_kernel<<<grid, block, 0, s>>>(in_nchw, normalize ? inv : nullptr, hi, lo, C, HW);
   VFS_CUDA_OK(cudaGetLastError());
@@ -474,8 +474,8 @@ int normalize_split(const void* in_split, void* out_split, long long num_pixels,
                     long long out_plane_stride, cudaStream_t s) {
   VFS_REQUIRE(in_split && out_split, VFS_EINVAL, "normalize_split: null argument");
   VFS_REQUIRE(C % 64 == 0 && num_pixels > 0, VFS_ESHAPE, "normalize_split: C must be a multiple of 64");
-  const __nv_bfloat16* ih = reinterpret_cast<const __nv_bfloat16*>(in_split);
-  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(out_split);
+  const h16* ih = reinterpret_cast<const h16*>(in_split);
+  h16* oh = reinterpret_cast<h16*>(out_split);
   const long long threads = num_pixels * 32;
   const int blocks = static_cast<int>((threads + 255) / 256);
   normalize_split_kernel<<<blocks, 256, 0, s>>>(ih, ih + in_plane_stride, oh, oh + out_plane_stride,
@@ -554,7 +554,7 @@ int masked_attention_batched(const VfsAttnDesc* d, int B, const void* q_bank_spl
                               static_cast<uint64_t>(q_bank_frames), 2};
     const uint64_t strides[4] = {static_cast<uint64_t>(d->C) * 2, static_cast<uint64_t>(d->W) * d->C * 2,
                                  static_cast<uint64_t>(HW) * d->C * 2, static_cast<uint64_t>(q_plane_stride) * 2};
-    int rc = make_tmap_bf16_sw128(&p.tmap_q, q_bank_split, 5, dims, strides, box);
+    int rc = make_tmap_16b_sw128(&p.tmap_q, q_bank_split, 5, dims, strides, box);
     if (rc != VFS_OK) return rc;
   }
   {
@@ -562,7 +562,7 @@ int masked_attention_batched(const VfsAttnDesc* d, int B, const void* q_bank_spl
                               static_cast<uint64_t>(k_bank_frames), 2};
     const uint64_t strides[4] = {static_cast<uint64_t>(d->C) * 2, static_cast<uint64_t>(d->W) * d->C * 2,
                                  static_cast<uint64_t>(HW) * d->C * 2, static_cast<uint64_t>(k_plane_stride) * 2};
-    int rc = make_tmap_bf16_sw128(&p.tmap_k, k_bank_split, 5, dims, strides, box);
+    int rc = make_tmap_16b_sw128(&p.tmap_k, k_bank_split, 5, dims, strides, box);
     if (rc != VFS_OK) return rc;
   }
   const int sms = device_sm_count();
@@ -603,5 +603,7 @@ int masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_plan
                                   k_bank_frames, key_frame_ids, values, key_frame_ids, 0, v_frame_stride,
                                   v_chan_stride, out, out_topk_val, out_topk_idx, workspace, workspace_bytes, stream);
 }
+
+VFS_DEFINE_OVERFLOW_ACCESSOR(overflow_affinity)
 
 }  // namespace vfs

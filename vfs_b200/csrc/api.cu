@@ -50,7 +50,7 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+int make_tmap_16b_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return VFS_ECUDA;
@@ -64,7 +64,7 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uin
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
                   gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -87,7 +87,29 @@ int conv_dgrad_tc(const VfsConvDesc* d, const void* dz_split, const void* wt_spl
 int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, int k, cudaStream_t s);
 size_t wgrad_workspace_bytes(int Cout, int Cin, int ksize);
 int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_split, void* workspace, float* dw_oihw,
-                  int accumulate, cudaStream_t stream);
+                  int accumulate, float out_scale, cudaStream_t stream);
+int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
+                  const float* invstd, double* sums, long long M, int C, cudaStream_t s);
+int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
+                 const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
+                 float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
+                 long long M, int C, cudaStream_t s);
+int relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, long long elems, cudaStream_t s);
+int stem_pool_relu_bwd(const void* dpool_split, const float* z, const float* scale, const float* shift, float* g,
+                       int N, int H, int W, cudaStream_t s);
+int stem_wgrad(const float* x, const float* dz, float* dw, int accumulate, float out_scale, int N, int H, int W,
+               cudaStream_t s);
+int linear_backward(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db, int M, int N,
+                    int K, int accumulate, cudaStream_t s);
+int bn1d_backward(const float* dy, const float* pre, const float* out, float* dpre, int M, int N, const float* gamma,
+                  const float* mean, const float* invstd, int training, int relu, float* dgamma, float* dbeta,
+                  int accumulate, cudaStream_t s);
+int relu_backward(const float* dy, const float* out, float* dx, size_t n, cudaStream_t s);
+int avgpool_backward_nchw(const float* dy, float* dx, int B, int C, int HW, cudaStream_t s);
+int cosine_loss_backward(const float* p, const float* z, const float* gout, float* dp, int B, int D, int with_norm,
+                         int negative, cudaStream_t s);
+int sgd_momentum_step(float* p, const float* g, float* buf, size_t n, float lr, float momentum, float wd, int first,
+                      float grad_scale, cudaStream_t s);
 int channel_stats_f32(const float* x, double* stats, long long M, int C, cudaStream_t s);
 int bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean,
                 float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
@@ -96,7 +118,7 @@ int bn_apply(const float* z, const float* scale, const float* shift, const void*
              long long M, int C, int relu, cudaStream_t s);
 int conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
                      const float* shift, const void* residual_split, float* out_f32, cudaStream_t stream);
-int nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, cudaStream_t s);
+int nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, float scale, cudaStream_t s);
 int split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H, int W, cudaStream_t s);
 int pack_conv_weight(const float* w, void* w_split, int Cout, int Cin, int k, cudaStream_t s);
 size_t stem_workspace_bytes(int N, int H, int W);
@@ -124,7 +146,7 @@ int masked_attention(const VfsAttnDesc* d, const void* q_split, long long q_plan
 int global_avg_pool_nchw(const float* in, float* out, int B, int C, int HW, cudaStream_t s);
 int linear_forward(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, cudaStream_t s);
 int bn1d_act(float* y, int M, int N, const float* gamma, const float* beta, float* running_mean, float* running_var,
-             float eps, float momentum, int training, int relu, cudaStream_t s);
+             float eps, float momentum, int training, int relu, float* save_mean, float* save_invstd, cudaStream_t s);
 int relu_inplace(float* y, size_t n, cudaStream_t s);
 int cosine_sim_loss(const float* p, const float* z, float* loss, int B, int D, int with_norm, int negative,
                     cudaStream_t s);
@@ -132,12 +154,22 @@ int nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, cu
 int xcorr_nhwc(const float* z, const float* x, float* out, int nz, int nx, int C, int hz, int wz, int h, int w,
                float out_scale, cudaStream_t s);
 
+unsigned int overflow_conv(int), overflow_layout(int), overflow_stem(int), overflow_affinity(int), overflow_bn(int),
+    overflow_train(int);
+
 }  // namespace vfs
 
 extern "C" {
 
 const char* vfs_last_error_string(void) { return vfs::g_last_error; }
 int vfs_abi_version(void) { return 1; }
+
+/* Number of values that exceeded the fp16 range (|x| > 65504) when a tensor was split since the last reset.
+ * Synchronises the device. */
+unsigned int vfs_overflow_count(int reset) {
+  return vfs::overflow_conv(reset) + vfs::overflow_layout(reset) + vfs::overflow_stem(reset) +
+         vfs::overflow_affinity(reset) + vfs::overflow_bn(reset) + vfs::overflow_train(reset);
+}
 
 int vfs_check_device(void) {
   int dev = 0;
@@ -149,7 +181,11 @@ int vfs_check_device(void) {
 }
 
 int vfs_nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, vfs_stream_t s) {
-  return vfs::nchw_f32_to_split(in, out_split, N, C, H, W, s);
+  return vfs::nchw_f32_to_split(in, out_split, N, C, H, W, 1.0f, s);
+}
+int vfs_nchw_f32_to_split_scaled(const float* in, void* out_split, int N, int C, int H, int W, float scale,
+                                 vfs_stream_t s) {
+  return vfs::nchw_f32_to_split(in, out_split, N, C, H, W, scale, s);
 }
 int vfs_split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H, int W, vfs_stream_t s) {
   return vfs::split_to_nchw_f32(in_split, out, N, C, H, W, s);
@@ -187,8 +223,53 @@ size_t vfs_conv_wgrad_workspace_bytes(int Cout, int Cin, int ksize) {
   return vfs::wgrad_workspace_bytes(Cout, Cin, ksize);
 }
 int vfs_conv_wgrad(const VfsConvDesc* d, const void* x_split, const void* dz_split, void* workspace, float* dw_oihw,
-                   int accumulate, vfs_stream_t s) {
-  return vfs::conv_wgrad_tc(d, x_split, dz_split, workspace, dw_oihw, accumulate, s);
+                   int accumulate, float out_scale, vfs_stream_t s) {
+  return vfs::conv_wgrad_tc(d, x_split, dz_split, workspace, dw_oihw, accumulate, out_scale, s);
+}
+int vfs_bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* z,
+                      const float* mean, const float* invstd, double* sums, long long M, int C, vfs_stream_t s) {
+  return vfs::bn_bwd_reduce(dy_split, dy_f32, y_split, z, mean, invstd, sums, M, C, s);
+}
+int vfs_bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
+                     const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
+                     float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
+                     long long M, int C, vfs_stream_t s) {
+  return vfs::bn_bwd_apply(dy_split, dy_f32, y_split, z, mean, invstd, gamma, sums, count, dz_split, dz_f32, g_split,
+                           dgamma, dbeta, accumulate, param_scale, M, C, s);
+}
+int vfs_relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, long long elems, vfs_stream_t s) {
+  return vfs::relu_bwd_split(dy_split, y_split, g_split, elems, s);
+}
+int vfs_stem_pool_relu_bwd(const void* dpool_split, const float* z, const float* scale, const float* shift, float* g,
+                           int N, int H, int W, vfs_stream_t s) {
+  return vfs::stem_pool_relu_bwd(dpool_split, z, scale, shift, g, N, H, W, s);
+}
+int vfs_stem_wgrad(const float* x, const float* dz, float* dw, int accumulate, float out_scale, int N, int H, int W,
+                   vfs_stream_t s) {
+  return vfs::stem_wgrad(x, dz, dw, accumulate, out_scale, N, H, W, s);
+}
+int vfs_linear_backward(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db, int M,
+                        int N, int K, int accumulate, vfs_stream_t s) {
+  return vfs::linear_backward(dy, x, W, dx, dW, db, M, N, K, accumulate, s);
+}
+int vfs_bn1d_backward(const float* dy, const float* pre, const float* out, float* dpre, int M, int N,
+                      const float* gamma, const float* mean, const float* invstd, int training, int relu,
+                      float* dgamma, float* dbeta, int accumulate, vfs_stream_t s) {
+  return vfs::bn1d_backward(dy, pre, out, dpre, M, N, gamma, mean, invstd, training, relu, dgamma, dbeta, accumulate, s);
+}
+int vfs_relu_backward(const float* dy, const float* out, float* dx, size_t n, vfs_stream_t s) {
+  return vfs::relu_backward(dy, out, dx, n, s);
+}
+int vfs_avgpool_backward(const float* dy, float* dx_nchw, int B, int C, int HW, vfs_stream_t s) {
+  return vfs::avgpool_backward_nchw(dy, dx_nchw, B, C, HW, s);
+}
+int vfs_cosine_loss_backward(const float* p, const float* z, const float* gout, float* dp, int B, int D,
+                             int with_norm, int negative, vfs_stream_t s) {
+  return vfs::cosine_loss_backward(p, z, gout, dp, B, D, with_norm, negative, s);
+}
+int vfs_sgd_momentum_step(float* p, const float* g, float* buf, size_t n, float lr, float momentum, float wd,
+                          int first, float grad_scale, vfs_stream_t s) {
+  return vfs::sgd_momentum_step(p, g, buf, n, lr, momentum, wd, first, grad_scale, s);
 }
 int vfs_channel_stats_f32(const float* x, double* stats, long long M, int C, vfs_stream_t s) {
   return vfs::channel_stats_f32(x, stats, M, C, s);
@@ -251,8 +332,10 @@ int vfs_linear(const float* x, const float* W, const float* bias, float* y, int 
   return vfs::linear_forward(x, W, bias, y, M, N, K, s);
 }
 int vfs_bn1d_act(float* y, int M, int N, const float* gamma, const float* beta, float* running_mean,
-                 float* running_var, float eps, float momentum, int training, int relu, vfs_stream_t s) {
-  return vfs::bn1d_act(y, M, N, gamma, beta, running_mean, running_var, eps, momentum, training, relu, s);
+                 float* running_var, float eps, float momentum, int training, int relu, float* save_mean,
+                 float* save_invstd, vfs_stream_t s) {
+  return vfs::bn1d_act(y, M, N, gamma, beta, running_mean, running_var, eps, momentum, training, relu, save_mean,
+                       save_invstd, s);
 }
 int vfs_relu(float* y, size_t n, vfs_stream_t s) { return vfs::relu_inplace(y, n, s); }
 int vfs_cosine_sim_loss(const float* p, const float* z, float* loss, int B, int D, int with_norm, int negative,

@@ -55,9 +55,9 @@ __global__ void bn_finalize_kernel(double* __restrict__ stats, double count, con
 
 // y = z*scale + shift (+res) (relu) -> split; one thread per 8 channels
 __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale,
-                                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res_hi,
-                                const __nv_bfloat16* __restrict__ res_lo, __nv_bfloat16* __restrict__ out_hi,
-                                __nv_bfloat16* __restrict__ out_lo, long long total8, int C, int relu) {
+                                const float* __restrict__ shift, const h16* __restrict__ res_hi,
+                                const h16* __restrict__ res_lo, h16* __restrict__ out_hi,
+                                h16* __restrict__ out_lo, long long total8, int C, int relu) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long o = i * 8;
@@ -69,27 +69,27 @@ __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __rest
                   fmaf(b.x, s1.x, h1.x), fmaf(b.y, s1.y, h1.y), fmaf(b.z, s1.z, h1.z), fmaf(b.w, s1.w, h1.w)};
     if (res_hi) {
       const uint4 rh = *reinterpret_cast<const uint4*>(res_hi + o), rl = *reinterpret_cast<const uint4*>(res_lo + o);
-      y[0] += bf16_lo_to_float(rh.x) + bf16_lo_to_float(rl.x);
-      y[1] += bf16_hi_to_float(rh.x) + bf16_hi_to_float(rl.x);
-      y[2] += bf16_lo_to_float(rh.y) + bf16_lo_to_float(rl.y);
-      y[3] += bf16_hi_to_float(rh.y) + bf16_hi_to_float(rl.y);
-      y[4] += bf16_lo_to_float(rh.z) + bf16_lo_to_float(rl.z);
-      y[5] += bf16_hi_to_float(rh.z) + bf16_hi_to_float(rl.z);
-      y[6] += bf16_lo_to_float(rh.w) + bf16_lo_to_float(rl.w);
-      y[7] += bf16_hi_to_float(rh.w) + bf16_hi_to_float(rl.w);
+      y[0] += lo16_to_float(rh.x) + lo16_to_float(rl.x);
+      y[1] += hi16_to_float(rh.x) + hi16_to_float(rl.x);
+      y[2] += lo16_to_float(rh.y) + lo16_to_float(rl.y);
+      y[3] += hi16_to_float(rh.y) + hi16_to_float(rl.y);
+      y[4] += lo16_to_float(rh.z) + lo16_to_float(rl.z);
+      y[5] += hi16_to_float(rh.z) + hi16_to_float(rl.z);
+      y[6] += lo16_to_float(rh.w) + lo16_to_float(rl.w);
+      y[7] += hi16_to_float(rh.w) + hi16_to_float(rl.w);
     }
     if (relu) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.0f);
     }
-    __nv_bfloat16 hi[8], lo[8];
+    h16 hi[8], lo[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) split_bf16(y[e], hi[e], lo[e]);
+    for (int e = 0; e < 8; ++e) split16(y[e], hi[e], lo[e]);
     uint4 oh, ol;
-    oh.x = pack_bf16x2(hi[0], hi[1]); oh.y = pack_bf16x2(hi[2], hi[3]);
-    oh.z = pack_bf16x2(hi[4], hi[5]); oh.w = pack_bf16x2(hi[6], hi[7]);
-    ol.x = pack_bf16x2(lo[0], lo[1]); ol.y = pack_bf16x2(lo[2], lo[3]);
-    ol.z = pack_bf16x2(lo[4], lo[5]); ol.w = pack_bf16x2(lo[6], lo[7]);
+    oh.x = pack16x2(hi[0], hi[1]); oh.y = pack16x2(hi[2], hi[3]);
+    oh.z = pack16x2(hi[4], hi[5]); oh.w = pack16x2(hi[6], hi[7]);
+    ol.x = pack16x2(lo[0], lo[1]); ol.y = pack16x2(lo[2], lo[3]);
+    ol.z = pack16x2(lo[4], lo[5]); ol.w = pack16x2(lo[6], lo[7]);
     *reinterpret_cast<uint4*>(out_hi + o) = oh;
     *reinterpret_cast<uint4*>(out_lo + o) = ol;
   }
@@ -123,8 +123,8 @@ int bn_apply(const float* z, const float* scale, const float* shift, const void*
   VFS_REQUIRE(z && scale && shift && out_split, VFS_EINVAL, "bn_apply: null argument");
   VFS_REQUIRE(M > 0 && C > 0 && C % 8 == 0, VFS_ESHAPE, "bn_apply: C=%d must be a multiple of 8", C);
   const long long total8 = M * C / 8;
-  const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(residual_split);
-  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(out_split);
+  const h16* rh = reinterpret_cast<const h16*>(residual_split);
+  h16* oh = reinterpret_cast<h16*>(out_split);
   long long blocks = (total8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   bn_apply_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(z, scale, shift, rh, rh ? rh + M * C : nullptr, oh,
@@ -132,5 +132,7 @@ int bn_apply(const float* z, const float* scale, const float* shift, const void*
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }
+
+VFS_DEFINE_OVERFLOW_ACCESSOR(overflow_bn)
 
 }  // namespace vfs

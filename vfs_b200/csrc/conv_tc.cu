@@ -48,10 +48,10 @@ struct alignas(64) ConvKernelParams {
   int out_H, out_W, out_sy, out_sx, out_oy, out_ox;
   const float* scale;
   const float* shift;
-  const __nv_bfloat16* res_hi;  // nullable
-  const __nv_bfloat16* res_lo;
-  __nv_bfloat16* out_hi;  // nullable
-  __nv_bfloat16* out_lo;
+  const h16* res_hi;  // nullable
+  const h16* res_lo;
+  h16* out_hi;  // nullable
+  h16* out_lo;
   float* out_f32;  // nullable, NHWC fp32
   int relu;
   double* stat_sum;    // nullable: per-channel sum / sum of squares of the epilogue output over all valid pixels
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(kBlockM, BN);
+    constexpr uint32_t idesc = umma_idesc_f16_f32(kBlockM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -167,9 +167,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
             const uint64_t da_lo = umma_desc_sw128_kmajor(a_lo + koff);
             const uint64_t db_hi = umma_desc_sw128_kmajor(b_hi + koff);
             const uint64_t db_lo = umma_desc_sw128_kmajor(b_lo + koff);
-            umma_bf16(d_tmem, da_lo, db_hi, idesc, (kc | k) != 0 ? 1u : 0u);  // small terms first
-            umma_bf16(d_tmem, da_hi, db_lo, idesc, 1u);
-            umma_bf16(d_tmem, da_hi, db_hi, idesc, 1u);
+            umma_f16(d_tmem, da_lo, db_hi, idesc, (kc | k) != 0 ? 1u : 0u);  // small terms first
+            umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+            umma_f16(d_tmem, da_hi, db_hi, idesc, 1u);
           }
           umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
           if (kc == num_kchunks - 1) umma_commit(tfull_bar(as));
@@ -280,14 +280,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(y[4]), "=f"(y[5]), "=f"(y[6]), "=f"(y[7]) : "r"(a1));
             if (p.res_hi != nullptr) {
-              y[0] += bf16_lo_to_float(rh.x) + bf16_lo_to_float(rl.x);
-              y[1] += bf16_hi_to_float(rh.x) + bf16_hi_to_float(rl.x);
-              y[2] += bf16_lo_to_float(rh.y) + bf16_lo_to_float(rl.y);
-              y[3] += bf16_hi_to_float(rh.y) + bf16_hi_to_float(rl.y);
-              y[4] += bf16_lo_to_float(rh.z) + bf16_lo_to_float(rl.z);
-              y[5] += bf16_hi_to_float(rh.z) + bf16_hi_to_float(rl.z);
-              y[6] += bf16_lo_to_float(rh.w) + bf16_lo_to_float(rl.w);
-              y[7] += bf16_hi_to_float(rh.w) + bf16_hi_to_float(rl.w);
+              y[0] += lo16_to_float(rh.x) + lo16_to_float(rl.x);
+              y[1] += hi16_to_float(rh.x) + hi16_to_float(rl.x);
+              y[2] += lo16_to_float(rh.y) + lo16_to_float(rl.y);
+              y[3] += hi16_to_float(rh.y) + hi16_to_float(rl.y);
+              y[4] += lo16_to_float(rh.z) + lo16_to_float(rl.z);
+              y[5] += hi16_to_float(rh.z) + hi16_to_float(rl.z);
+              y[6] += lo16_to_float(rh.w) + lo16_to_float(rl.w);
+              y[7] += hi16_to_float(rh.w) + hi16_to_float(rl.w);
             }
             if (p.relu) {
 #pragma unroll
@@ -306,18 +306,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
               of[1] = make_float4(y[4], y[5], y[6], y[7]);
             }
             if (p.out_hi != nullptr) {
-              __nv_bfloat16 hi[8], lo[8];
+              h16 hi[8], lo[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) split_bf16(y[e], hi[e], lo[e]);
+              for (int e = 0; e < 8; ++e) split16(y[e], hi[e], lo[e]);
               uint4 oh, ol;
-              oh.x = pack_bf16x2(hi[0], hi[1]);
-              oh.y = pack_bf16x2(hi[2], hi[3]);
-              oh.z = pack_bf16x2(hi[4], hi[5]);
-              oh.w = pack_bf16x2(hi[6], hi[7]);
-              ol.x = pack_bf16x2(lo[0], lo[1]);
-              ol.y = pack_bf16x2(lo[2], lo[3]);
-              ol.z = pack_bf16x2(lo[4], lo[5]);
-              ol.w = pack_bf16x2(lo[6], lo[7]);
+              oh.x = pack16x2(hi[0], hi[1]);
+              oh.y = pack16x2(hi[2], hi[3]);
+              oh.z = pack16x2(hi[4], hi[5]);
+              oh.w = pack16x2(hi[6], hi[7]);
+              ol.x = pack16x2(lo[0], lo[1]);
+              ol.y = pack16x2(lo[2], lo[3]);
+              ol.z = pack16x2(lo[4], lo[5]);
+              ol.w = pack16x2(lo[6], lo[7]);
               *reinterpret_cast<uint4*>(p.out_hi + o) = oh;
               *reinterpret_cast<uint4*>(p.out_lo + o) = ol;
             }
@@ -442,11 +442,11 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
     p.stat_sqsum = c.stats + c.Nout;
   }
   if (c.out_split) {
-    p.out_hi = reinterpret_cast<__nv_bfloat16*>(c.out_split);
+    p.out_hi = reinterpret_cast<h16*>(c.out_split);
     p.out_lo = p.out_hi + c.out_plane;
   }
   if (c.res_split) {
-    p.res_hi = reinterpret_cast<const __nv_bfloat16*>(c.res_split);
+    p.res_hi = reinterpret_cast<const h16*>(c.res_split);
     p.res_lo = p.res_hi + c.out_plane;
   }
   const int s = c.view_stride;
@@ -483,7 +483,7 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
     if (c.flat) {
       const uint64_t dims[5] = {static_cast<uint64_t>(c.C), static_cast<uint64_t>(c.N) * c.H * c.W, 1, 1, 2};
       const uint64_t strides[4] = {static_cast<uint64_t>(c.C) * 2, c.a_plane * 2, c.a_plane * 2, c.a_plane * 2};
-      rc = make_tmap_bf16_sw128(&p.tmap_a[v], in_base, 5, dims, strides, box_a);
+      rc = make_tmap_16b_sw128(&p.tmap_a[v], in_base, 5, dims, strides, box_a);
       if (first_valid < 0) first_valid = v;
     } else if (view_used[v] && ph < c.H && pw < c.W && (s > 1 || v == 0)) {
       const int Hv = (c.H - ph + s - 1) / s, Wv = (c.W - pw + s - 1) / s;
@@ -491,7 +491,7 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
                                 static_cast<uint64_t>(c.N), 2};
       const uint64_t strides[4] = {static_cast<uint64_t>(s) * c.C * 2, static_cast<uint64_t>(s) * c.W * c.C * 2,
                                    static_cast<uint64_t>(c.H) * c.W * c.C * 2, c.a_plane * 2};
-      rc = make_tmap_bf16_sw128(&p.tmap_a[v], in_base + (static_cast<size_t>(ph) * c.W + pw) * c.C * 2, 5, dims,
+      rc = make_tmap_16b_sw128(&p.tmap_a[v], in_base + (static_cast<size_t>(ph) * c.W + pw) * c.C * 2, 5, dims,
                                 strides, box_a);
       if (first_valid < 0) first_valid = v;
     }
@@ -517,7 +517,7 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
     const uint64_t dims[3] = {c.Ktot, static_cast<uint64_t>(c.Nout), 2};
     const uint64_t strides[2] = {c.Ktot * 2, c.Ktot * c.Nout * 2};
     const uint32_t box_b[3] = {64u, static_cast<uint32_t>(BN), 2u};
-    int rc = make_tmap_bf16_sw128(&p.tmap_b, c.b_split, 3, dims, strides, box_b);
+    int rc = make_tmap_16b_sw128(&p.tmap_b, c.b_split, 3, dims, strides, box_b);
     if (rc != VFS_OK) return rc;
   }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -641,7 +641,7 @@ int conv_dgrad_tc(const VfsConvDesc* d, const void* dz_split, const void* wt_spl
   }
   if (k == 1) {
     // only the (even, even) positions receive a tap; everything else is the `add` term (or zero)
-    const size_t bytes = 2 * c.out_plane * sizeof(__nv_bfloat16);
+    const size_t bytes = 2 * c.out_plane * sizeof(h16);
     if (add_split) VFS_CUDA_OK(cudaMemcpyAsync(dx_split, add_split, bytes, cudaMemcpyDeviceToDevice, stream));
     else VFS_CUDA_OK(cudaMemsetAsync(dx_split, 0, bytes, stream));
   }
@@ -677,5 +677,7 @@ int conv_dgrad_tc(const VfsConvDesc* d, const void* dz_split, const void* wt_spl
   }
   return VFS_OK;
 }
+
+VFS_DEFINE_OVERFLOW_ACCESSOR(overflow_conv)
 
 }  // namespace vfs

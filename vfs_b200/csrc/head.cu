@@ -94,13 +94,13 @@ __global__ void bn1d_act_kernel(float* __restrict__ y, int M, int N, const float
       running_mean[n] = (1.0f - momentum) * running_mean[n] + momentum * mean;
       running_var[n] = (1.0f - momentum) * running_var[n] + momentum * unbiased;
     }
-    if (save_mean) save_mean[n] = mean;
-    if (save_var) save_var[n] = var;
   } else {
     mean = running_mean[n];
     var = running_var[n];
   }
   const float invstd = 1.0f / sqrtf(var + eps);
+  if (save_mean) save_mean[n] = mean;
+  if (save_var) save_var[n] = invstd;  // inverse standard deviation (what the backward pass needs)
   const float g = gamma ? gamma[n] : 1.0f, b = beta ? beta[n] : 0.0f;
   for (int m = 0; m < M; ++m) {
     float v = (y[static_cast<size_t>(m) * N + n] - mean) * invstd * g + b;
@@ -176,13 +176,13 @@ int linear_forward(const float* x, const float* W, const float* bias, float* y, 
 }
 
 int bn1d_act(float* y, int M, int N, const float* gamma, const float* beta, float* running_mean, float* running_var,
-             float eps, float momentum, int training, int relu, cudaStream_t s) {
+             float eps, float momentum, int training, int relu, float* save_mean, float* save_invstd, cudaStream_t s) {
   VFS_REQUIRE(y, VFS_EINVAL, "bn1d_act: null argument");
   VFS_REQUIRE(training || (running_mean && running_var), VFS_EINVAL, "bn1d_act: eval mode needs running stats");
   VFS_REQUIRE(!training || M > 1, VFS_ESHAPE,
               "bn1d_act: Expected more than 1 value per channel when training, got M=%d", M);
   bn1d_act_kernel<<<(N + 127) / 128, 128, 0, s>>>(y, M, N, gamma, beta, running_mean, running_var, eps, momentum,
-                                                  training, relu, nullptr, nullptr);
+                                                  training, relu, save_mean, save_invstd);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }

@@ -30,7 +30,7 @@ int check_cuda(cudaError_t e, const char* what);  // returns VFS_OK or VFS_ECUDA
 
 // Encodes a bf16 tiled tensor map with 128-byte swizzle.  dims/box innermost-first; strides_bytes has
 // rank-1 entries (stride of dim 1.. rank-1).  Returns VFS_OK or an error code.
-int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+int make_tmap_16b_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box);
 
 int device_sm_count();

@@ -8,22 +8,22 @@ namespace vfs {
 // ------------------------------------------------------------------------------------------------
 // NCHW fp32 -> split NHWC (tile transpose through shared memory)
 // ------------------------------------------------------------------------------------------------
-__global__ void nchw_to_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out_hi,
-                                     __nv_bfloat16* __restrict__ out_lo, int C, int HW) {
+__global__ void nchw_to_split_kernel(const float* __restrict__ in, h16* __restrict__ out_hi,
+                                     h16* __restrict__ out_lo, int C, int HW, float scale) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float* src = in + static_cast<size_t>(n) * C * HW;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, p = p0 + threadIdx.x;
-    tile[i][threadIdx.x] = (c < C && p < HW) ? src[static_cast<size_t>(c) * HW + p] : 0.0f;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? src[static_cast<size_t>(c) * HW + p] * scale : 0.0f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int p = p0 + i, c = c0 + threadIdx.x;
     if (p < HW && c < C) {
-      __nv_bfloat16 hi, lo;
-      split_bf16(tile[threadIdx.x][i], hi, lo);
+      h16 hi, lo;
+      split16(tile[threadIdx.x][i], hi, lo);
       const size_t o = (static_cast<size_t>(n) * HW + p) * C + c;
       out_hi[o] = hi;
       out_lo[o] = lo;
@@ -31,7 +31,7 @@ __global__ void nchw_to_split_kernel(const float* __restrict__ in, __nv_bfloat16
   }
 }
 
-__global__ void split_to_nchw_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+__global__ void split_to_nchw_kernel(const h16* __restrict__ in_hi, const h16* __restrict__ in_lo,
                                      float* __restrict__ out, int C, int HW) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -41,7 +41,7 @@ __global__ void split_to_nchw_kernel(const __nv_bfloat16* __restrict__ in_hi, co
     float v = 0.0f;
     if (p < HW && c < C) {
       const size_t o = (static_cast<size_t>(n) * HW + p) * C + c;
-      v = __bfloat162float(in_hi[o]) + __bfloat162float(in_lo[o]);
+      v = h16_to_float(in_hi[o]) + h16_to_float(in_lo[o]);
     }
     tile[i][threadIdx.x] = v;
   }
@@ -53,14 +53,14 @@ __global__ void split_to_nchw_kernel(const __nv_bfloat16* __restrict__ in_hi, co
   }
 }
 
-int nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, cudaStream_t s) {
+int nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, float scale, cudaStream_t s) {
   VFS_REQUIRE(in && out_split, VFS_EINVAL, "nchw_f32_to_split: null argument");
   VFS_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, VFS_ESHAPE, "nchw_f32_to_split: empty tensor");
   const int HW = H * W;
-  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out_split);
-  __nv_bfloat16* lo = hi + static_cast<size_t>(N) * HW * C;
+  h16* hi = reinterpret_cast<h16*>(out_split);
+  h16* lo = hi + static_cast<size_t>(N) * HW * C;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
-  nchw_to_split_kernel<<<grid, block, 0, s>>>(in, hi, lo, C, HW);
+  nchw_to_split_kernel<<<grid, block, 0, s>>>(in, hi, lo, C, HW, scale);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }
@@ -69,8 +69,8 @@ int split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H, int
   VFS_REQUIRE(in_split && out, VFS_EINVAL, "split_to_nchw_f32: null argument");
   VFS_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, VFS_ESHAPE, "split_to_nchw_f32: empty tensor");
   const int HW = H * W;
-  const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(in_split);
-  const __nv_bfloat16* lo = hi + static_cast<size_t>(N) * HW * C;
+  const h16* hi = reinterpret_cast<const h16*>(in_split);
+  const h16* lo = hi + static_cast<size_t>(N) * HW * C;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
   split_to_nchw_kernel<<<grid, block, 0, s>>>(hi, lo, out, C, HW);
   VFS_CUDA_OK(cudaGetLastError());
@@ -80,8 +80,8 @@ int split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H, int
 // ------------------------------------------------------------------------------------------------
 // OIHW fp32 -> split [2][Cout][(r*k+s)*Cin + ci]
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
-                                   __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int k) {
+__global__ void pack_weight_kernel(const float* __restrict__ w, h16* __restrict__ hi,
+                                   h16* __restrict__ lo, int Cout, int Cin, int k) {
   const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -91,16 +91,16 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int tap = static_cast<int>(t % (k * k));
     const int co = static_cast<int>(t / (k * k));
     const float v = w[(static_cast<size_t>(co) * Cin + ci) * k * k + tap];
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
+    h16 h, l;
+    split16(v, h, l);
     hi[i] = h;
     lo[i] = l;
   }
 }
 
 // OIHW fp32 -> split [2][Cin][(r'*k+s')*Cout + co] with the kernel flipped (operand of the data-gradient conv)
-__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
-                                         __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int k) {
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, h16* __restrict__ hi,
+                                         h16* __restrict__ lo, int Cout, int Cin, int k) {
   const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -111,8 +111,8 @@ __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, __nv_bfloa
     const int ci = static_cast<int>(t / (k * k));
     const int src_tap = k * k - 1 - tap;  // (k-1-r', k-1-s')
     const float v = w[(static_cast<size_t>(co) * Cin + ci) * k * k + src_tap];
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
+    h16 h, l;
+    split16(v, h, l);
     hi[i] = h;
     lo[i] = l;
   }
@@ -122,7 +122,7 @@ int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, in
   VFS_REQUIRE(w && wt_split, VFS_EINVAL, "pack_conv_weight_dgrad: null argument");
   VFS_REQUIRE(Cout > 0 && Cin > 0 && k > 0, VFS_ESHAPE, "pack_conv_weight_dgrad: bad shape");
   const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
-  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(wt_split);
+  h16* hi = reinterpret_cast<h16*>(wt_split);
   const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   pack_weight_dgrad_kernel<<<blocks, 256, 0, s>>>(w, hi, hi + total, Cout, Cin, k);
   VFS_CUDA_OK(cudaGetLastError());
@@ -133,7 +133,7 @@ int pack_conv_weight(const float* w, void* w_split, int Cout, int Cin, int k, cu
   VFS_REQUIRE(w && w_split, VFS_EINVAL, "pack_conv_weight: null argument");
   VFS_REQUIRE(Cout > 0 && Cin > 0 && k > 0, VFS_ESHAPE, "pack_conv_weight: bad shape");
   const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
-  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(w_split);
+  h16* hi = reinterpret_cast<h16*>(w_split);
   const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   pack_weight_kernel<<<blocks, 256, 0, s>>>(w, hi, hi + total, Cout, Cin, k);
   VFS_CUDA_OK(cudaGetLastError());
@@ -143,11 +143,11 @@ int pack_conv_weight(const float* w, void* w_split, int Cout, int Cin, int k, cu
 // ------------------------------------------------------------------------------------------------
 // fp32 SIMT conv (test instrument): one thread per output element, fixed summation order.
 // ------------------------------------------------------------------------------------------------
-__global__ void conv_simt_kernel(VfsConvDesc d, const __nv_bfloat16* __restrict__ in_hi,
-                                 const __nv_bfloat16* __restrict__ in_lo, const __nv_bfloat16* __restrict__ w_hi,
-                                 const __nv_bfloat16* __restrict__ w_lo, const float* __restrict__ scale,
-                                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res_hi,
-                                 const __nv_bfloat16* __restrict__ res_lo, float* __restrict__ out, int Ho, int Wo,
+__global__ void conv_simt_kernel(VfsConvDesc d, const h16* __restrict__ in_hi,
+                                 const h16* __restrict__ in_lo, const h16* __restrict__ w_hi,
+                                 const h16* __restrict__ w_lo, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, const h16* __restrict__ res_hi,
+                                 const h16* __restrict__ res_lo, float* __restrict__ out, int Ho, int Wo,
                                  int pad, int dil) {
   const size_t total = static_cast<size_t>(d.N) * Ho * Wo * d.Cout;
   const int k = d.ksize;
@@ -170,14 +170,14 @@ __global__ void conv_simt_kernel(VfsConvDesc d, const __nv_bfloat16* __restrict_
         const size_t ibase = ((static_cast<size_t>(n) * d.H + iy) * d.W + ix) * d.Cin;
         const size_t wbase = co * Ktot + static_cast<size_t>(r * k + c) * d.Cin;
         for (int ci = 0; ci < d.Cin; ++ci) {
-          const float x = __bfloat162float(in_hi[ibase + ci]) + __bfloat162float(in_lo[ibase + ci]);
-          const float ww = __bfloat162float(w_hi[wbase + ci]) + __bfloat162float(w_lo[wbase + ci]);
+          const float x = h16_to_float(in_hi[ibase + ci]) + h16_to_float(in_lo[ibase + ci]);
+          const float ww = h16_to_float(w_hi[wbase + ci]) + h16_to_float(w_lo[wbase + ci]);
           acc = fmaf(x, ww, acc);
         }
       }
     }
     float y = fmaf(acc, scale[co], shift[co]);
-    if (res_hi) y += __bfloat162float(res_hi[i]) + __bfloat162float(res_lo[i]);
+    if (res_hi) y += h16_to_float(res_hi[i]) + h16_to_float(res_lo[i]);
     if (d.relu) y = fmaxf(y, 0.0f);
     out[i] = y;
   }
@@ -193,14 +193,16 @@ int conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const void* w_s
   const size_t in_plane = static_cast<size_t>(d->N) * d->H * d->W * d->Cin;
   const size_t out_plane = static_cast<size_t>(d->N) * Ho * Wo * d->Cout;
   const size_t w_plane = static_cast<size_t>(d->Cout) * k * k * d->Cin;
-  const __nv_bfloat16* in_hi = reinterpret_cast<const __nv_bfloat16*>(in_split);
-  const __nv_bfloat16* w_hi = reinterpret_cast<const __nv_bfloat16*>(w_split);
-  const __nv_bfloat16* r_hi = reinterpret_cast<const __nv_bfloat16*>(residual_split);
+  const h16* in_hi = reinterpret_cast<const h16*>(in_split);
+  const h16* w_hi = reinterpret_cast<const h16*>(w_split);
+  const h16* r_hi = reinterpret_cast<const h16*>(residual_split);
   const int blocks = static_cast<int>((out_plane + 255) / 256 < 65535 ? (out_plane + 255) / 256 : 65535);
   conv_simt_kernel<<<blocks, 256, 0, stream>>>(*d, in_hi, in_hi + in_plane, w_hi, w_hi + w_plane, scale, shift, r_hi,
                                                r_hi ? r_hi + out_plane : nullptr, out_f32, Ho, Wo, pad, dil);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }
+
+VFS_DEFINE_OVERFLOW_ACCESSOR(overflow_layout)
 
 }  // namespace vfs

@@ -2,7 +2,7 @@
 // Everything here is device-side and header-only.  No CUTLASS dependency.
 #pragma once
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -120,7 +120,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 
 // Shared-memory matrix descriptor for a K-major operand tile stored with the 128-byte swizzle
-// (rows of 128 B = 64 bf16, 8-row swizzle atoms of 1024 B, atoms stacked along M/N).
+// (rows of 128 B = 64 halves, 8-row swizzle atoms of 1024 B, atoms stacked along M/N).
 //   bits [0,14)  start address >> 4          bits [16,30) leading byte offset >> 4 (ignored for SW128 K-major; 1)
 //   bits [32,46) stride byte offset >> 4 (1024 B between 8-row groups)
 //   bits [46,48) descriptor version = 1 (Blackwell)      bits [61,64) layout type = 2 (SWIZZLE_128B)
@@ -138,7 +138,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
 // Shared-memory matrix descriptor for an MN-major operand tile stored with the 128-byte swizzle: rows are K
 // indices (128 B = 64 consecutive M/N elements per row, 8-row swizzle atoms of 1024 B stacked along K),
 // 64-element M/N blocks are `lbo_bytes` apart.  Canonical layout (CUTLASS mma_traits_sm100.hpp, make_umma_desc
-// <Major::MN>):  Swizzle<3,4,3> o ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO))  in 16-byte units of bf16.
+// <Major::MN>):  Swizzle<3,4,3> o ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO))  in 16-byte units of fp16.
 __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
@@ -149,23 +149,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
   return d;
 }
 
-// Instruction descriptor, kind::f16 : A,B = BF16 (K-major), D = F32, shape M x N (K = 16).
-// Field positions follow cute::UMMA::InstrDescriptor.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
+// Instruction descriptor, kind::f16 : A,B = FP16 (K-major), D = F32, shape M x N (K = 16).
+// Field positions follow cute::UMMA::InstrDescriptor (a_format/b_format: 0 = F16, 1 = BF16, 2 = TF32).
+__host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int M, int N) {
   return (1u << 4)                 // c_format = F32
-         | (1u << 7)               // a_format = BF16
-         | (1u << 10)              // b_format = BF16
+         | (0u << 7)               // a_format = F16
+         | (0u << 10)              // b_format = F16
          | (0u << 15) | (0u << 16) // a_major = K, b_major = K
          | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // Same with both operands MN-major (a_major = b_major = 1): D[m,n] += sum_k A[k][m] * B[k][n].
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_mn(int M, int N) {
-  return umma_idesc_bf16_f32(M, N) | (1u << 15) | (1u << 16);
+__host__ __device__ constexpr uint32_t umma_idesc_f16_f32_mn(int M, int N) {
+  return umma_idesc_f16_f32(M, N) | (1u << 15) | (1u << 16);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -200,16 +200,42 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 // ----------------------------------------------------------------------------------------------
-// split-bf16 ("bf16x2") representation of an fp32 value: x ~= hi + lo, |err| <~ 2^-17 |x|
+// split-fp16 ("fp16x2") representation of an fp32 value: x ~= hi + lo with hi, lo IEEE half.
+// 11 + 11 significant bits: relative error <= 2^-22 while lo is a normal half (|x| >~ 0.12) and an absolute error
+// <= 3e-8 below that -- fp32-class accuracy for the tensor-core operands.  |x| must stay below 65504 (fp16 range);
+// activations of a batch-normalised ResNet and L2-normalised features are far inside it, and an overflow is
+// recorded in a device flag instead of silently producing inf (vfs_overflow_count).
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+using h16 = __half;
+
+static __device__ unsigned int g_split_overflow = 0;  // values that left the fp16 range (one counter per .cu)
+
+// Every translation unit that splits values exposes its counter to the host (summed by vfs_overflow_count()).
+#define VFS_DEFINE_OVERFLOW_ACCESSOR(name)                                                  \
+  unsigned int name(int reset) {                                                            \
+    unsigned int v = 0;                                                                     \
+    cudaMemcpyFromSymbol(&v, g_split_overflow, sizeof(v));                                  \
+    if (reset && v) {                                                                       \
+      const unsigned int z = 0;                                                             \
+      cudaMemcpyToSymbol(g_split_overflow, &z, sizeof(z));                                  \
+    }                                                                                       \
+    return v;                                                                               \
+  }
+
+__device__ __forceinline__ void split16(float x, h16& hi, h16& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+  if (!(fabsf(x) <= 65504.0f)) atomicAdd(&g_split_overflow, 1u);
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+__device__ __forceinline__ uint32_t pack16x2(h16 a, h16 b) {
+  return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
 }
-__device__ __forceinline__ float bf16_lo_to_float(uint32_t packed) { return __uint_as_float(packed << 16); }
-__device__ __forceinline__ float bf16_hi_to_float(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
+__device__ __forceinline__ float h16_to_float(h16 v) { return __half2float(v); }
+__device__ __forceinline__ float lo16_to_float(uint32_t packed) {
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(packed & 0xFFFFu)));
+}
+__device__ __forceinline__ float hi16_to_float(uint32_t packed) {
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(packed >> 16)));
+}
 
 }  // namespace vfs

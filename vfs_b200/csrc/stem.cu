@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 
 // maxpool 3x3/s2/p1 over fp32 NHWC (C = 64) -> split NHWC.  One thread per (pixel, 8 channels).
 __global__ void stem_pool_kernel(const float* __restrict__ in, const float* __restrict__ scale,
-                                 const float* __restrict__ shift, __nv_bfloat16* __restrict__ out_hi,
-                                 __nv_bfloat16* __restrict__ out_lo, int N, int Hc, int Wc, int Hp, int Wp) {
+                                 const float* __restrict__ shift, h16* __restrict__ out_hi,
+                                 h16* __restrict__ out_lo, int N, int Hc, int Wc, int Hp, int Wp) {
   const size_t total = static_cast<size_t>(N) * Hp * Wp * 8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -128,14 +128,14 @@ __global__ void stem_pool_kernel(const float* __restrict__ in, const float* __re
         m[4] = fmaxf(m[4], b.x); m[5] = fmaxf(m[5], b.y); m[6] = fmaxf(m[6], b.z); m[7] = fmaxf(m[7], b.w);
       }
     }
-    __nv_bfloat16 hi[8], lo[8];
+    h16 hi[8], lo[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) split_bf16(m[e], hi[e], lo[e]);
+    for (int e = 0; e < 8; ++e) split16(m[e], hi[e], lo[e]);
     uint4 oh, ol;
-    oh.x = pack_bf16x2(hi[0], hi[1]); oh.y = pack_bf16x2(hi[2], hi[3]);
-    oh.z = pack_bf16x2(hi[4], hi[5]); oh.w = pack_bf16x2(hi[6], hi[7]);
-    ol.x = pack_bf16x2(lo[0], lo[1]); ol.y = pack_bf16x2(lo[2], lo[3]);
-    ol.z = pack_bf16x2(lo[4], lo[5]); ol.w = pack_bf16x2(lo[6], lo[7]);
+    oh.x = pack16x2(hi[0], hi[1]); oh.y = pack16x2(hi[2], hi[3]);
+    oh.z = pack16x2(hi[4], hi[5]); oh.w = pack16x2(hi[6], hi[7]);
+    ol.x = pack16x2(lo[0], lo[1]); ol.y = pack16x2(lo[2], lo[3]);
+    ol.z = pack16x2(lo[4], lo[5]); ol.w = pack16x2(lo[6], lo[7]);
     const size_t o = ((static_cast<size_t>(n) * Hp + py) * Wp + px) * 64 + g * 8;
     *reinterpret_cast<uint4*>(out_hi + o) = oh;
     *reinterpret_cast<uint4*>(out_lo + o) = ol;
@@ -175,8 +175,8 @@ static int stem_pool_launch(const float* conv_out, const float* scale, const flo
                             int H, int W, cudaStream_t s) {
   int Hc, Wc, Hp, Wp;
   stem_dims(H, W, &Hc, &Wc, &Hp, &Wp);
-  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out_split);
-  __nv_bfloat16* lo = hi + static_cast<size_t>(N) * Hp * Wp * 64;
+  h16* hi = reinterpret_cast<h16*>(out_split);
+  h16* lo = hi + static_cast<size_t>(N) * Hp * Wp * 64;
   const size_t total = static_cast<size_t>(N) * Hp * Wp * 8;
   const int blocks = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   stem_pool_kernel<<<blocks, 256, 0, s>>>(conv_out, scale, shift, hi, lo, N, Hc, Wc, Hp, Wp);
@@ -206,5 +206,7 @@ int stem_bn_relu_pool(const void* conv_out, const float* scale, const float* shi
   VFS_REQUIRE(conv_out && scale && shift && out_split, VFS_EINVAL, "stem_bn_relu_pool: null argument");
   return stem_pool_launch(reinterpret_cast<const float*>(conv_out), scale, shift, out_split, N, H, W, s);
 }
+
+VFS_DEFINE_OVERFLOW_ACCESSOR(overflow_stem)
 
 }  // namespace vfs

@@ -10,23 +10,23 @@
 namespace vfs {
 
 __device__ __forceinline__ void unpack8(const uint4 h, const uint4 l, float (&v)[8]) {
-  v[0] = bf16_lo_to_float(h.x) + bf16_lo_to_float(l.x);
-  v[1] = bf16_hi_to_float(h.x) + bf16_hi_to_float(l.x);
-  v[2] = bf16_lo_to_float(h.y) + bf16_lo_to_float(l.y);
-  v[3] = bf16_hi_to_float(h.y) + bf16_hi_to_float(l.y);
-  v[4] = bf16_lo_to_float(h.z) + bf16_lo_to_float(l.z);
-  v[5] = bf16_hi_to_float(h.z) + bf16_hi_to_float(l.z);
-  v[6] = bf16_lo_to_float(h.w) + bf16_lo_to_float(l.w);
-  v[7] = bf16_hi_to_float(h.w) + bf16_hi_to_float(l.w);
+  v[0] = lo16_to_float(h.x) + lo16_to_float(l.x);
+  v[1] = hi16_to_float(h.x) + hi16_to_float(l.x);
+  v[2] = lo16_to_float(h.y) + lo16_to_float(l.y);
+  v[3] = hi16_to_float(h.y) + hi16_to_float(l.y);
+  v[4] = lo16_to_float(h.z) + lo16_to_float(l.z);
+  v[5] = hi16_to_float(h.z) + hi16_to_float(l.z);
+  v[6] = lo16_to_float(h.w) + lo16_to_float(l.w);
+  v[7] = hi16_to_float(h.w) + hi16_to_float(l.w);
 }
 __device__ __forceinline__ void pack8(const float (&v)[8], uint4& h, uint4& l) {
-  __nv_bfloat16 hi[8], lo[8];
+  h16 hi[8], lo[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) split_bf16(v[e], hi[e], lo[e]);
-  h.x = pack_bf16x2(hi[0], hi[1]); h.y = pack_bf16x2(hi[2], hi[3]);
-  h.z = pack_bf16x2(hi[4], hi[5]); h.w = pack_bf16x2(hi[6], hi[7]);
-  l.x = pack_bf16x2(lo[0], lo[1]); l.y = pack_bf16x2(lo[2], lo[3]);
-  l.z = pack_bf16x2(lo[4], lo[5]); l.w = pack_bf16x2(lo[6], lo[7]);
+  for (int e = 0; e < 8; ++e) split16(v[e], hi[e], lo[e]);
+  h.x = pack16x2(hi[0], hi[1]); h.y = pack16x2(hi[2], hi[3]);
+  h.z = pack16x2(hi[4], hi[5]); h.w = pack16x2(hi[6], hi[7]);
+  l.x = pack16x2(lo[0], lo[1]); l.y = pack16x2(lo[2], lo[3]);
+  l.z = pack16x2(lo[4], lo[5]); l.w = pack16x2(lo[6], lo[7]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -36,16 +36,16 @@ __device__ __forceinline__ void pack8(const float (&v)[8], uint4& h, uint4& l) {
 //   apply : dz = gamma * invstd * (g - sums[c]/M - xhat * sums[C+c]/M)     -> split;  optionally also g -> split
 // ------------------------------------------------------------------------------------------------
 struct BnBwdArgs {
-  const __nv_bfloat16* dy_hi; const __nv_bfloat16* dy_lo;  // split dY (or null when dy_f32 is used)
+  const h16* dy_hi; const h16* dy_lo;  // split dY (or null when dy_f32 is used)
   const float* dy_f32;
-  const __nv_bfloat16* y_hi; const __nv_bfloat16* y_lo;    // forward output for the ReLU mask (null: no ReLU)
+  const h16* y_hi; const h16* y_lo;    // forward output for the ReLU mask (null: no ReLU)
   const float* z;                                          // raw conv output fp32 [M, C]
   const float* mean; const float* invstd; const float* gamma;
   double* sums;                                            // [2C] (reduce: accumulated; apply: read)
   double count;
-  __nv_bfloat16* dz_hi; __nv_bfloat16* dz_lo;              // split dz (or null)
+  h16* dz_hi; h16* dz_lo;              // split dz (or null)
   float* dz_f32;                                           // fp32 dz (stem)
-  __nv_bfloat16* g_hi; __nv_bfloat16* g_lo;                // optional: masked gradient for the residual branch
+  h16* g_hi; h16* g_lo;                // optional: masked gradient for the residual branch
   long long M; int C;
 };
 
@@ -139,10 +139,10 @@ __global__ void bn_bwd_apply_kernel(const BnBwdArgs a) {
 
 // sums fp64 [2C] -> dgamma/dbeta fp32 (optionally accumulated)
 __global__ void bn_bwd_param_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int C, int accumulate) {
+                                    float* __restrict__ dbeta, int C, int accumulate, float out_scale) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float dg = static_cast<float>(sums[C + c]), db = static_cast<float>(sums[c]);
+  const float dg = static_cast<float>(sums[C + c]) * out_scale, db = static_cast<float>(sums[c]) * out_scale;
   if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + db : db;
 }
@@ -153,22 +153,22 @@ static int bn_bwd_fill(BnBwdArgs& a, const void* dy_split, const float* dy_f32, 
   memset(&a, 0, sizeof(a));
   const long long plane = M * C;
   if (dy_split) {
-    a.dy_hi = reinterpret_cast<const __nv_bfloat16*>(dy_split);
+    a.dy_hi = reinterpret_cast<const h16*>(dy_split);
     a.dy_lo = a.dy_hi + plane;
   }
   a.dy_f32 = dy_f32;
   if (y_split) {
-    a.y_hi = reinterpret_cast<const __nv_bfloat16*>(y_split);
+    a.y_hi = reinterpret_cast<const h16*>(y_split);
     a.y_lo = a.y_hi + plane;
   }
   a.z = z; a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.sums = sums; a.count = count;
   if (dz_split) {
-    a.dz_hi = reinterpret_cast<__nv_bfloat16*>(dz_split);
+    a.dz_hi = reinterpret_cast<h16*>(dz_split);
     a.dz_lo = a.dz_hi + plane;
   }
   a.dz_f32 = dz_f32;
   if (g_split) {
-    a.g_hi = reinterpret_cast<__nv_bfloat16*>(g_split);
+    a.g_hi = reinterpret_cast<h16*>(g_split);
     a.g_lo = a.g_hi + plane;
   }
   a.M = M; a.C = C;
@@ -191,8 +191,8 @@ int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split
 
 int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
                  const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
-                 float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, long long M, int C,
-                 cudaStream_t s) {
+                 float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
+                 long long M, int C, cudaStream_t s) {
   VFS_REQUIRE((dy_split || dy_f32) && z && mean && invstd && sums && (dz_split || dz_f32), VFS_EINVAL,
               "bn_bwd_apply: null argument");
   VFS_REQUIRE(M > 0 && C % 8 == 0 && count > 0, VFS_ESHAPE, "bn_bwd_apply: bad shape");
@@ -205,15 +205,15 @@ int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split,
   bn_bwd_apply_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(a);
   VFS_CUDA_OK(cudaGetLastError());
   if (dgamma || dbeta) {
-    bn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, dgamma, dbeta, C, accumulate);
+    bn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, dgamma, dbeta, C, accumulate, param_scale);
     VFS_CUDA_OK(cudaGetLastError());
   }
   return VFS_OK;
 }
 
 // masked gradient only (no BN): g = dY * 1[y > 0]  -> split   (blocks whose last op is add+ReLU with eval-mode BN)
-__global__ void relu_bwd_split_kernel(const __nv_bfloat16* dy_hi, const __nv_bfloat16* dy_lo, const __nv_bfloat16* y_hi,
-                                      const __nv_bfloat16* y_lo, __nv_bfloat16* g_hi, __nv_bfloat16* g_lo,
+__global__ void relu_bwd_split_kernel(const h16* dy_hi, const h16* dy_lo, const h16* y_hi,
+                                      const h16* y_lo, h16* g_hi, h16* g_lo,
                                       long long total8) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -234,7 +234,7 @@ __global__ void relu_bwd_split_kernel(const __nv_bfloat16* dy_hi, const __nv_bfl
 // Stem backward: max-pool(3,2,1) + ReLU backward, then 7x7 weight gradient.
 // ------------------------------------------------------------------------------------------------
 // g[n,y,x,c] = 1[a > 0] * sum over pooling windows whose (first) arg-max is (y,x) of dPool, with a = relu(z*sc+sh)
-__global__ void stem_pool_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dp_hi, const __nv_bfloat16* __restrict__ dp_lo,
+__global__ void stem_pool_relu_bwd_kernel(const h16* __restrict__ dp_hi, const h16* __restrict__ dp_lo,
                                           const float* __restrict__ z, const float* __restrict__ scale,
                                           const float* __restrict__ shift, float* __restrict__ g, int N, int Hc, int Wc,
                                           int Hp, int Wp) {
@@ -305,7 +305,8 @@ __global__ void stem_pool_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dp_h
 // dW[co][c][r][s] += sum_{n,oy,ox} dz[n,oy,ox,co] * x[n,c,2oy+r-3,2ox+s-3]; block = strip of conv pixels,
 // thread = (co, 37 k values); partial sums reduced with fp32 atomics.
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
-                                                         float* __restrict__ dw, int N, int H, int W, int Hc, int Wc) {
+                                                         float* __restrict__ dw, int N, int H, int W, int Hc, int Wc,
+                                                         float out_scale) {
   __shared__ float patch[3][7][70];   // input rows needed by one output row segment of 32 pixels
   __shared__ float dzs[32][64];
   const int co = threadIdx.x & 63, kq = threadIdx.x >> 6;  // kq in 0..3 -> k = kq, kq+4, ...
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
 #pragma unroll
   for (int j = 0; j < 37; ++j) {
     const int k = kq + 4 * j;
-    if (k < 147) atomicAdd(dw + co * 147 + k, acc[j]);
+    if (k < 147) atomicAdd(dw + co * 147 + k, acc[j] * out_scale);
   }
 }
 
@@ -355,7 +356,7 @@ int stem_pool_relu_bwd(const void* dpool_split, const float* z, const float* sca
   VFS_REQUIRE(dpool_split && z && scale && shift && g, VFS_EINVAL, "stem_pool_relu_bwd: null argument");
   const int Hc = (H + 6 - 7) / 2 + 1, Wc = (W + 6 - 7) / 2 + 1;
   const int Hp = (Hc + 2 - 3) / 2 + 1, Wp = (Wc + 2 - 3) / 2 + 1;
-  const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(dpool_split);
+  const h16* hi = reinterpret_cast<const h16*>(dpool_split);
   const size_t total = static_cast<size_t>(N) * Hc * Wc * 8;
   const int blocks = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   stem_pool_relu_bwd_kernel<<<blocks, 256, 0, s>>>(hi, hi + static_cast<size_t>(N) * Hp * Wp * 64, z, scale, shift, g, N,
@@ -364,11 +365,12 @@ int stem_pool_relu_bwd(const void* dpool_split, const float* z, const float* sca
   return VFS_OK;
 }
 
-int stem_wgrad(const float* x, const float* dz, float* dw, int accumulate, int N, int H, int W, cudaStream_t s) {
+int stem_wgrad(const float* x, const float* dz, float* dw, int accumulate, float out_scale, int N, int H, int W,
+               cudaStream_t s) {
   VFS_REQUIRE(x && dz && dw, VFS_EINVAL, "stem_wgrad: null argument");
   const int Hc = (H + 6 - 7) / 2 + 1, Wc = (W + 6 - 7) / 2 + 1;
   if (!accumulate) VFS_CUDA_OK(cudaMemsetAsync(dw, 0, 64 * 147 * sizeof(float), s));
-  stem_wgrad_kernel<<<148 * 2, 256, 0, s>>>(x, dz, dw, N, H, W, Hc, Wc);
+  stem_wgrad_kernel<<<148 * 2, 256, 0, s>>>(x, dz, dw, N, H, W, Hc, Wc, out_scale);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }
@@ -485,8 +487,8 @@ __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __res
 }
 
 // global average pool backward straight into the backbone's gradient format: dY [B, C] -> split NHWC [B, HW, C]
-__global__ void avgpool_bwd_split_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ hi,
-                                         __nv_bfloat16* __restrict__ lo, int B, int HW, int C) {
+__global__ void avgpool_bwd_split_kernel(const float* __restrict__ dy, h16* __restrict__ hi,
+                                         h16* __restrict__ lo, int B, int HW, int C) {
   const size_t total8 = static_cast<size_t>(B) * HW * C / 8;
   const float inv = 1.0f / static_cast<float>(HW);
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
@@ -502,6 +504,23 @@ __global__ void avgpool_bwd_split_kernel(const float* __restrict__ dy, __nv_bflo
     *reinterpret_cast<uint4*>(hi + o) = h;
     *reinterpret_cast<uint4*>(lo + o) = l;
   }
+}
+
+// global average pool backward in the reference layout: dY [B, C] -> dX NCHW [B, C, HW]
+__global__ void avgpool_bwd_nchw_kernel(const float* __restrict__ dy, float* __restrict__ dx, size_t total, int HW) {
+  const float inv = 1.0f / static_cast<float>(HW);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dx[i] = dy[i / HW] * inv;
+}
+
+int avgpool_backward_nchw(const float* dy, float* dx, int B, int C, int HW, cudaStream_t s) {
+  VFS_REQUIRE(dy && dx, VFS_EINVAL, "avgpool_backward_nchw: null argument");
+  const size_t total = static_cast<size_t>(B) * C * HW;
+  const int blocks = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  avgpool_bwd_nchw_kernel<<<blocks, 256, 0, s>>>(dy, dx, total, HW);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
 }
 
 // cosine loss backward w.r.t. p (z is detached in SimSiam):  L = 2 - 2 cos  ->  dp = g * (-2) (zhat - phat cos)/|p|
@@ -566,9 +585,9 @@ __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restri
 
 int relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, long long elems, cudaStream_t s) {
   VFS_REQUIRE(dy_split && y_split && g_split && elems % 8 == 0, VFS_EINVAL, "relu_bwd_split: bad argument");
-  const __nv_bfloat16* dh = reinterpret_cast<const __nv_bfloat16*>(dy_split);
-  const __nv_bfloat16* yh = reinterpret_cast<const __nv_bfloat16*>(y_split);
-  __nv_bfloat16* gh = reinterpret_cast<__nv_bfloat16*>(g_split);
+  const h16* dh = reinterpret_cast<const h16*>(dy_split);
+  const h16* yh = reinterpret_cast<const h16*>(y_split);
+  h16* gh = reinterpret_cast<h16*>(g_split);
   long long blocks = (elems / 8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   relu_bwd_split_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(dh, dh + elems, yh, yh + elems, gh, gh + elems, elems / 8);
@@ -610,7 +629,7 @@ int relu_backward(const float* dy, const float* out, float* dx, size_t n, cudaSt
 
 int avgpool_backward_split(const float* dy, void* out_split, int B, int HW, int C, cudaStream_t s) {
   VFS_REQUIRE(dy && out_split && C % 8 == 0, VFS_EINVAL, "avgpool_backward: bad argument");
-  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out_split);
+  h16* hi = reinterpret_cast<h16*>(out_split);
   const size_t total8 = static_cast<size_t>(B) * HW * C / 8;
   const int blocks = static_cast<int>((total8 + 255) / 256 < 148 * 16 ? (total8 + 255) / 256 : 148 * 16);
   avgpool_bwd_split_kernel<<<blocks, 256, 0, s>>>(dy, hi, hi + static_cast<size_t>(B) * HW * C, B, HW, C);
@@ -636,5 +655,7 @@ int sgd_momentum_step(float* p, const float* g, float* buf, size_t n, float lr, 
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }
+
+VFS_DEFINE_OVERFLOW_ACCESSOR(overflow_train)
 
 }  // namespace vfs

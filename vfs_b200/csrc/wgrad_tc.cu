@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    const uint32_t idesc = umma_idesc_bf16_f32_mn(128, p.bn);
+    const uint32_t idesc = umma_idesc_f16_f32_mn(128, p.bn);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -145,9 +145,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             const uint64_t da_lo = umma_desc_sw128_mnmajor(a_lo + koff, kWgBoxBytes);
             const uint64_t db_hi = umma_desc_sw128_mnmajor(b_hi + koff, kWgBoxBytes);
             const uint64_t db_lo = umma_desc_sw128_mnmajor(b_lo + koff, kWgBoxBytes);
-            umma_bf16(d_tmem, da_lo, db_hi, idesc, (c > u.c_begin || k > 0) ? 1u : 0u);
-            umma_bf16(d_tmem, da_hi, db_lo, idesc, 1u);
-            umma_bf16(d_tmem, da_hi, db_hi, idesc, 1u);
+            umma_f16(d_tmem, da_lo, db_hi, idesc, (c > u.c_begin || k > 0) ? 1u : 0u);
+            umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+            umma_f16(d_tmem, da_hi, db_hi, idesc, 1u);
           }
           umma_commit(empty_bar(stage));
           if (c == u.c_end - 1) umma_commit(tfull_bar(as));
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 
 // [Cout][taps][Cin] fp32 -> OIHW fp32 (optionally accumulating into an existing gradient)
 __global__ void wgrad_unpack_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin, int kk,
-                                    int accumulate) {
+                                    int accumulate, float out_scale) {
   const size_t total = static_cast<size_t>(Cout) * Cin * kk;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -219,7 +219,7 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ src, float* __rest
     const size_t t = i / kk;
     const int ci = static_cast<int>(t % Cin);
     const int co = static_cast<int>(t / Cin);
-    const float v = src[(static_cast<size_t>(co) * kk + tap) * Cin + ci];
+    const float v = src[(static_cast<size_t>(co) * kk + tap) * Cin + ci] * out_scale;
     dst[i] = accumulate ? dst[i] + v : v;
   }
 }
@@ -246,9 +246,9 @@ size_t wgrad_workspace_bytes(int Cout, int Cin, int ksize) {
 }
 
 // d = forward descriptor.  x_split [N,H,W,Cin], dz_split [N,Ho,Wo,Cout], workspace fp32 [Cout][k*k][Cin],
-// dw_oihw fp32 [Cout][Cin][k][k] (overwritten, or accumulated into when accumulate != 0).
+// dw_oihw fp32 [Cout][Cin][k][k] = out_scale * dW (overwritten, or accumulated into when accumulate != 0).
 int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_split, void* workspace,
-                  float* dw_oihw, int accumulate, cudaStream_t stream) {
+                  float* dw_oihw, int accumulate, float out_scale, cudaStream_t stream) {
   VFS_REQUIRE(d && x_split && dz_split && workspace && dw_oihw, VFS_EINVAL, "conv_wgrad: null argument");
   VFS_REQUIRE(d->ksize == 1 || d->ksize == 3, VFS_ESHAPE, "conv_wgrad: ksize %d unsupported", d->ksize);
   VFS_REQUIRE(d->stride == 1 || d->stride == 2, VFS_ESHAPE, "conv_wgrad: stride %d unsupported", d->stride);
@@ -298,13 +298,13 @@ int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_spli
     if (flat) {
       const uint64_t dims[5] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(N) * Ho * Wo, 1, 1, 2};
       const uint64_t strides[4] = {static_cast<uint64_t>(Cout) * 2, z_plane * 2, z_plane * 2, z_plane * 2};
-      rc = make_tmap_bf16_sw128(&p.tmap_dz, dz_split, 5, dims, strides, box);
+      rc = make_tmap_16b_sw128(&p.tmap_dz, dz_split, 5, dims, strides, box);
     } else {
       const uint64_t dims[5] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
                                 static_cast<uint64_t>(N), 2};
       const uint64_t strides[4] = {static_cast<uint64_t>(Cout) * 2, static_cast<uint64_t>(Wo) * Cout * 2,
                                    static_cast<uint64_t>(Ho) * Wo * Cout * 2, z_plane * 2};
-      rc = make_tmap_bf16_sw128(&p.tmap_dz, dz_split, 5, dims, strides, box);
+      rc = make_tmap_16b_sw128(&p.tmap_dz, dz_split, 5, dims, strides, box);
     }
     if (rc != VFS_OK) return rc;
   }
@@ -328,7 +328,7 @@ int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_spli
     if (flat) {
       const uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(N) * H * W, 1, 1, 2};
       const uint64_t strides[4] = {static_cast<uint64_t>(Cin) * 2, x_plane * 2, x_plane * 2, x_plane * 2};
-      rc = make_tmap_bf16_sw128(&p.tmap_x[v], x_base, 5, dims, strides, box);
+      rc = make_tmap_16b_sw128(&p.tmap_x[v], x_base, 5, dims, strides, box);
       built[v] = true;
     } else if (view_used[v] && ph < H && pw < W) {
       const int Hv = (H - ph + s - 1) / s, Wv = (W - pw + s - 1) / s;
@@ -336,7 +336,7 @@ int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_spli
                                 static_cast<uint64_t>(N), 2};
       const uint64_t strides[4] = {static_cast<uint64_t>(s) * Cin * 2, static_cast<uint64_t>(s) * W * Cin * 2,
                                    static_cast<uint64_t>(H) * W * Cin * 2, x_plane * 2};
-      rc = make_tmap_bf16_sw128(&p.tmap_x[v], x_base + (static_cast<size_t>(ph) * W + pw) * Cin * 2, 5, dims, strides,
+      rc = make_tmap_16b_sw128(&p.tmap_x[v], x_base + (static_cast<size_t>(ph) * W + pw) * Cin * 2, 5, dims, strides,
                                 box);
       built[v] = true;
     }
@@ -358,7 +358,7 @@ int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_spli
   VFS_CUDA_OK(cudaGetLastError());
   const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
   const int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
-  wgrad_unpack_kernel<<<blocks, 256, 0, stream>>>(p.dw, dw_oihw, Cout, Cin, k * k, accumulate);
+  wgrad_unpack_kernel<<<blocks, 256, 0, stream>>>(p.dw, dw_oihw, Cout, Cin, k * k, accumulate, out_scale);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }

@@ -12,7 +12,7 @@ from .mmcv_lite import ConvModule
 
 
 class _ConvPlan:
-    __slots__ = ('w_split', 'scale', 'shift', 'ksize', 'version')
+    __slots__ = ('w_split', 'wt_split', 'scale', 'shift', 'ksize', 'version')
 
 
 def fold_bn(conv_module, device):
@@ -63,6 +63,7 @@ class BackboneEngine:
             w = cm.conv.weight.detach().to(device=device, dtype=torch.float32).contiguous()
             p.ksize = w.shape[2]
             p.w_split = ops.pack_conv_weight(w) if w.shape[1] % 64 == 0 else w  # stem keeps OIHW fp32
+            p.wt_split = None  # dgrad packing, built on first use by the backward pass
             p.scale, p.shift = fold_bn(cm, device)
             p.version = ver if ver is not None else self._version(cm)
             self._plans[id(cm)] = p
@@ -146,6 +147,73 @@ class BackboneEngine:
         if block_index is not None:
             return [None]
         return outs
+
+    # -------------------------------------------------------------- training: taped forward + native backward
+    def forward_taped(self, x, out_indices):
+        """Like ``forward`` but also returns the split tensors behind the outputs (identity keys of the gradient
+        bookkeeping).  ``self.tape`` must be a list; train-mode ConvModules append what their backward needs."""
+        assert self.tape is not None
+        x = x.contiguous().float()
+        xs = self.stem(x)
+        outs, out_splits = [], []
+        for i, name in enumerate(self.net.res_layers):
+            for block in getattr(self.net, name):
+                xs = block.native_forward(self, xs)
+            if i in out_indices:
+                outs.append(ops.from_split(xs))
+                out_splits.append(xs)
+        return outs, out_splits
+
+    def backward(self, tape, out_splits, grad_outs):
+        """Reverse walk over the tape.  Gradients of activations are split tensors scaled by autograd.GRAD_SCALE;
+        returns {id(parameter): fp32 gradient}.  Per ConvModule: BN(+ReLU) backward (two per-channel sums, all-reduced
+        for SyncBN) -> tcgen05 wgrad -> tcgen05 dgrad (+ the gradient already accumulated for that input)."""
+        from .autograd import GRAD_SCALE as S
+        grad = {}
+        for xs, g in zip(out_splits, grad_outs):
+            if g is None:
+                continue
+            gs = ops.to_split_scaled(g.contiguous().float(), S)
+            if id(xs) in grad:
+                raise NotImplementedError('vfs_b200: the same stage output was requested twice')
+            grad[id(xs)] = gs
+        pgrads = {}
+        inv = 1.0 / S
+        for op in reversed(tape):
+            dy = grad.pop(id(op['y']), None)
+            if dy is None:
+                continue  # not on any gradient path (e.g. stages after the last used output)
+            cm = op['cm']
+            bn = cm.norm
+            if op.get('stem'):
+                g32 = ops.stem_pool_relu_backward(dy, op['z'], op['scale'], op['shift'], op['x'].shape[2:])
+                dz32, _, dgam, dbet = ops.bn_backward(g32, None, op['z'], op['mean'], op['invstd'], bn, dy_is_f32=True,
+                                                      want_f32=True, param_scale=inv)
+                if cm.conv.weight.requires_grad:
+                    pgrads[id(cm.conv.weight)] = ops.stem_wgrad(op['x'], dz32, out_scale=inv)
+                if bn.affine and bn.weight.requires_grad:
+                    pgrads[id(bn.weight)], pgrads[id(bn.bias)] = dgam, dbet
+                continue
+            want_g = op['residual'] is not None
+            dz, g, dgam, dbet = ops.bn_backward(dy, op['y'] if op['relu'] else None, op['z'], op['mean'], op['invstd'],
+                                                bn, want_g=want_g, param_scale=inv)
+            if want_g:
+                if id(op['residual']) in grad:
+                    raise NotImplementedError('vfs_b200: unexpected second gradient for a residual input')
+                grad[id(op['residual'])] = g
+            if bn.affine and bn.weight.requires_grad:
+                pgrads[id(bn.weight)], pgrads[id(bn.bias)] = dgam, dbet
+            if cm.conv.weight.requires_grad:
+                pgrads[id(cm.conv.weight)] = ops.conv_wgrad(op['xs'], dz, op['k'], op['stride'], op['dil'],
+                                                            out_scale=inv)
+            plan = self.plan(cm, dz.device)
+            if plan.wt_split is None:
+                plan.wt_split = ops.pack_conv_weight_dgrad(
+                    cm.conv.weight.detach().to(device=dz.device, dtype=torch.float32).contiguous())
+            prev = grad.get(id(op['xs']))
+            grad[id(op['xs'])] = ops.conv_dgrad(dz, plan.wt_split, tuple(op['xs'].shape[2:4]), op['k'], op['stride'],
+                                                op['dil'], add=prev)
+        return pgrads
 
     def _mark(self, tag):
         if self.events is not None:

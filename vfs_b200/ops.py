@@ -37,15 +37,25 @@ def to_split(x):
     _require_cuda(x, 'x')
     assert x.dtype == torch.float32 and x.ndim == 4
     N, C, H, W = x.shape
-    out = torch.empty((2, N, H, W, C), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((2, N, H, W, C), dtype=torch.float16, device=x.device)
     check(nat.lib().vfs_nchw_f32_to_split(ptr(x), ptr(out), N, C, H, W, current_stream()), 'nchw_f32_to_split')
+    return out
+
+
+def to_split_scaled(x, scale):
+    """NCHW fp32 -> split NHWC of ``scale * x`` (gradient entry of the backward pass)."""
+    _require_cuda(x, 'x')
+    N, C, H, W = x.shape
+    out = torch.empty((2, N, H, W, C), dtype=torch.float16, device=x.device)
+    check(nat.lib().vfs_nchw_f32_to_split_scaled(ptr(x), ptr(out), N, C, H, W, float(scale), current_stream()),
+          'nchw_f32_to_split_scaled')
     return out
 
 
 def from_split(xs):
     """split NHWC [2,N,H,W,C] -> NCHW fp32."""
     _require_cuda(xs, 'xs')
-    assert xs.dtype == torch.bfloat16 and xs.ndim == 5 and xs.shape[0] == 2
+    assert xs.dtype == torch.float16 and xs.ndim == 5 and xs.shape[0] == 2
     _, N, H, W, C = xs.shape
     out = torch.empty((N, C, H, W), dtype=torch.float32, device=xs.device)
     check(nat.lib().vfs_split_to_nchw_f32(ptr(xs), ptr(out), N, C, H, W, current_stream()), 'split_to_nchw_f32')
@@ -57,7 +67,7 @@ def pack_conv_weight(w):
     _require_cuda(w, 'w')
     assert w.dtype == torch.float32 and w.ndim == 4 and w.shape[2] == w.shape[3]
     Cout, Cin, k, _ = w.shape
-    out = torch.empty((2, Cout, k * k * Cin), dtype=torch.bfloat16, device=w.device)
+    out = torch.empty((2, Cout, k * k * Cin), dtype=torch.float16, device=w.device)
     check(nat.lib().vfs_pack_conv_weight(ptr(w), ptr(out), Cout, Cin, k, current_stream()), 'pack_conv_weight')
     return out
 
@@ -77,7 +87,7 @@ def conv_bn_act(xs, w_split, scale, shift, ksize, stride=1, dilation=1, relu=Tru
     _, N, H, W, Cin = xs.shape
     assert w_split.shape[2] == ksize * ksize * Cin, (w_split.shape, ksize, Cin)
     Ho, Wo = conv_out_hw(H, W, ksize, stride, dilation)
-    out = torch.empty((2, N, Ho, Wo, Cout), dtype=torch.bfloat16, device=xs.device) if want_split else None
+    out = torch.empty((2, N, Ho, Wo, Cout), dtype=torch.float16, device=xs.device) if want_split else None
     out32 = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=xs.device) if want_f32 else None
     if residual is not None:
         _require_cuda(residual, 'residual')
@@ -110,7 +120,7 @@ def stem_forward(x, weight, scale, shift):
     Hp, Wp = (Hc + 2 - 3) // 2 + 1, (Wc + 2 - 3) // 2 + 1
     ws_bytes = nat.lib().vfs_stem_workspace_bytes(N, H, W)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=x.device)
-    out = torch.empty((2, N, Hp, Wp, 64), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((2, N, Hp, Wp, 64), dtype=torch.float16, device=x.device)
     check(nat.lib().vfs_stem_forward(ptr(x), ptr(weight), ptr(scale), ptr(shift), ptr(out), ptr(ws), N, H, W,
                                      current_stream()), 'stem_forward')
     return out
@@ -183,7 +193,7 @@ def bn_finalize(stats, count, bn):
 def bn_apply(z, scale, shift, residual=None, relu=True):
     """fp32 NHWC z -> split NHWC relu?(z*scale + shift (+residual))."""
     N, H, W, C = z.shape
-    out = torch.empty((2, N, H, W, C), dtype=torch.bfloat16, device=z.device)
+    out = torch.empty((2, N, H, W, C), dtype=torch.float16, device=z.device)
     check(nat.lib().vfs_bn_apply(ptr(z), ptr(scale), ptr(shift), ptr(residual), ptr(out), N * H * W, C, int(relu),
                                  current_stream()), 'bn_apply')
     return out
@@ -201,7 +211,7 @@ def stem_bn_relu_pool(z, scale, shift, in_hw):
     N, Hc, Wc, _ = z.shape
     H, W = in_hw
     Hp, Wp = (Hc + 2 - 3) // 2 + 1, (Wc + 2 - 3) // 2 + 1
-    out = torch.empty((2, N, Hp, Wp, 64), dtype=torch.bfloat16, device=z.device)
+    out = torch.empty((2, N, Hp, Wp, 64), dtype=torch.float16, device=z.device)
     check(nat.lib().vfs_stem_bn_relu_pool(ptr(z), ptr(scale), ptr(shift), ptr(out), N, H, W, current_stream()),
           'stem_bn_relu_pool')
     return out
@@ -211,7 +221,7 @@ def pack_conv_weight_dgrad(w):
     """OIHW fp32 -> split [2, Cin, k*k*Cout] (flipped kernel, roles of Cin/Cout swapped) for conv_dgrad."""
     _require_cuda(w, 'w')
     Cout, Cin, k, _ = w.shape
-    out = torch.empty((2, Cin, k * k * Cout), dtype=torch.bfloat16, device=w.device)
+    out = torch.empty((2, Cin, k * k * Cout), dtype=torch.float16, device=w.device)
     check(nat.lib().vfs_pack_conv_weight_dgrad(ptr(w), ptr(out), Cout, Cin, k, current_stream()),
           'pack_conv_weight_dgrad')
     return out
@@ -224,7 +234,7 @@ def conv_dgrad(dz, wt_split, in_hw, ksize, stride=1, dilation=1, add=None):
     Cin = wt_split.shape[1]
     H, W = in_hw
     assert conv_out_hw(H, W, ksize, stride, dilation) == (Ho, Wo), (in_hw, dz.shape)
-    dx = torch.empty((2, N, H, W, Cin), dtype=torch.bfloat16, device=dz.device)
+    dx = torch.empty((2, N, H, W, Cin), dtype=torch.float16, device=dz.device)
     if add is not None:
         assert tuple(add.shape) == tuple(dx.shape)
     d = VfsConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, ksize=ksize, stride=stride, dilation=dilation, relu=0)
@@ -234,7 +244,7 @@ def conv_dgrad(dz, wt_split, in_hw, ksize, stride=1, dilation=1, add=None):
     return dx
 
 
-def conv_wgrad(xs, dz, ksize, stride=1, dilation=1, out=None, accumulate=False):
+def conv_wgrad(xs, dz, ksize, stride=1, dilation=1, out=None, accumulate=False, out_scale=1.0):
     """dW (OIHW fp32) of the conv with forward input ``xs`` split [2,N,H,W,Cin] and output gradient ``dz`` split
     [2,N,Ho,Wo,Cout].  ``out``: existing gradient tensor to overwrite / accumulate into."""
     _, N, H, W, Cin = xs.shape
@@ -247,7 +257,7 @@ def conv_wgrad(xs, dz, ksize, stride=1, dilation=1, out=None, accumulate=False):
                      device=xs.device)
     d = VfsConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, ksize=ksize, stride=stride, dilation=dilation, relu=0)
     check(nat.lib().vfs_conv_wgrad(ctypes.byref(d), ptr(xs), ptr(dz), ptr(ws), ptr(out), int(accumulate),
-                                   current_stream()), 'conv_wgrad')
+                                   float(out_scale), current_stream()), 'conv_wgrad')
     return out
 
 
@@ -262,7 +272,14 @@ def _f32c(t, name):
 
 
 def global_avg_pool(x):
-    """[B,C,h,w] fp32 NCHW -> [B,C]."""
+    """[B,C,h,w] fp32 NCHW -> [B,C] (differentiable through the native backward kernel)."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        from .autograd import AvgPoolFunction
+        return AvgPoolFunction.apply(x)
+    return global_avg_pool_raw(x)
+
+
+def global_avg_pool_raw(x):
     x = _f32c(x.contiguous(), 'x')
     B, C = x.shape[:2]
     HW = x[0, 0].numel()
@@ -271,36 +288,179 @@ def global_avg_pool(x):
     return out
 
 
-def linear_bn_act(x, lin, bn=None, relu=False):
-    """y = relu?(bn?(x @ W^T + b)) with ``lin`` an nn.Linear and ``bn`` a BatchNorm1d/SyncBatchNorm module (its
-    running statistics are updated in training mode exactly like torch does, single process)."""
+def linear_forward(x, weight, bias):
+    """y = x @ W^T + b (fp32 CUDA tensors)."""
     x = _f32c(x.contiguous(), 'x')
     M, K = x.shape
-    N = lin.out_features
-    w = lin.weight.detach()
-    _f32c(w, 'weight')
+    N = weight.shape[0]
     y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-    b = lin.bias.detach() if lin.bias is not None else None
-    check(nat.lib().vfs_linear(ptr(x), ptr(w.contiguous()), ptr(b), ptr(y), M, N, K, current_stream()), 'linear')
-    if bn is not None:
-        training = bn.training or (bn.running_mean is None)
-        if training and torch.distributed.is_available() and torch.distributed.is_initialized() \
-                and torch.distributed.get_world_size() > 1 and isinstance(bn, torch.nn.SyncBatchNorm):
-            raise NotImplementedError('vfs_b200: cross-rank SyncBN statistics are not implemented yet')
-        momentum = 0.1 if bn.momentum is None else bn.momentum
-        check(nat.lib().vfs_bn1d_act(ptr(y), M, N, ptr(bn.weight.detach()) if bn.affine else None,
-                                     ptr(bn.bias.detach()) if bn.affine else None, ptr(bn.running_mean),
-                                     ptr(bn.running_var), float(bn.eps), float(momentum), int(training), int(relu),
-                                     current_stream()), 'bn1d_act')
-        if training and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
-    elif relu:
-        check(nat.lib().vfs_relu(ptr(y), y.numel(), current_stream()), 'relu')
+    check(nat.lib().vfs_linear(ptr(x), ptr(_f32c(weight.contiguous(), 'weight')), ptr(bias), ptr(y), M, N, K,
+                               current_stream()), 'linear')
     return y
 
 
+def bn1d_forward_(y, bn, relu):
+    """In-place BatchNorm1d(+ReLU) over y [M,N] with torch's running-stat bookkeeping; returns (mean, invstd,
+    training) for the backward pass.  SyncBatchNorm across ranks is not supported for the head yet."""
+    M, N = y.shape
+    training = bn.training or (bn.running_mean is None)
+    if training and isinstance(bn, torch.nn.SyncBatchNorm) and torch.distributed.is_available() \
+            and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        raise NotImplementedError('vfs_b200: cross-rank SyncBN statistics are not implemented for the SimSiam head')
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    mean = torch.empty((N, ), dtype=torch.float32, device=y.device)
+    invstd = torch.empty_like(mean)
+    check(nat.lib().vfs_bn1d_act(ptr(y), M, N, ptr(bn.weight.detach()) if bn.affine else None,
+                                 ptr(bn.bias.detach()) if bn.affine else None, ptr(bn.running_mean),
+                                 ptr(bn.running_var), float(bn.eps), float(momentum), int(training), int(relu),
+                                 ptr(mean), ptr(invstd), current_stream()), 'bn1d_act')
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return mean, invstd, training
+
+
+def relu_(y):
+    check(nat.lib().vfs_relu(ptr(y), y.numel(), current_stream()), 'relu')
+    return y
+
+
+def linear_bn_act(x, lin, bn=None, relu=False):
+    """y = relu?(bn?(x @ W^T + b)) with ``lin`` an nn.Linear and ``bn`` a BatchNorm1d/SyncBatchNorm module.  When
+    gradients are enabled the call goes through the native autograd Function (vfs_b200/autograd.py)."""
+    if torch.is_grad_enabled() and (x.requires_grad or lin.weight.requires_grad):
+        from .autograd import LinearBnActFunction
+        gamma = bn.weight if (bn is not None and bn.affine) else None
+        beta = bn.bias if (bn is not None and bn.affine) else None
+        return LinearBnActFunction.apply(x, lin.weight, lin.bias, gamma, beta, bn, bool(relu))
+    y = linear_forward(x, lin.weight.detach(), lin.bias.detach() if lin.bias is not None else None)
+    if bn is not None:
+        bn1d_forward_(y, bn, relu)
+    elif relu:
+        relu_(y)
+    return y
+
+
+# ---- backward pieces of the head -------------------------------------------------------------------------
+def linear_backward(dy, x, weight, need_dx=True):
+    """Returns (dx | None, dW, db) for y = x W^T + b."""
+    M, N = dy.shape
+    K = x.shape[1]
+    dx = torch.empty((M, K), dtype=torch.float32, device=dy.device) if need_dx else None
+    dW = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+    db = torch.empty((N, ), dtype=torch.float32, device=dy.device)
+    check(nat.lib().vfs_linear_backward(ptr(dy), ptr(x), ptr(weight), ptr(dx), ptr(dW), ptr(db), M, N, K, 0,
+                                        current_stream()), 'linear_backward')
+    LAUNCHES[0] += 1 if need_dx else 0
+    return dx, dW, db
+
+
+def bn1d_backward(dy, pre, out, gamma, mean, invstd, training, relu):
+    """Returns (dpre, dgamma, dbeta)."""
+    M, N = dy.shape
+    dpre = torch.empty_like(dy)
+    dg = torch.empty((N, ), dtype=torch.float32, device=dy.device)
+    db = torch.empty_like(dg)
+    check(nat.lib().vfs_bn1d_backward(ptr(dy), ptr(pre), ptr(out), ptr(dpre), M, N, ptr(gamma), ptr(mean),
+                                      ptr(invstd), int(training), int(relu), ptr(dg), ptr(db), 0, current_stream()),
+          'bn1d_backward')
+    return dpre, dg, db
+
+
+def relu_backward(dy, out):
+    dx = torch.empty_like(dy)
+    check(nat.lib().vfs_relu_backward(ptr(dy), ptr(out), ptr(dx), dy.numel(), current_stream()), 'relu_backward')
+    return dx
+
+
+def avgpool_backward(dy, hw_shape):
+    """dY [B,C] -> dX NCHW [B,C,h,w] = dY / (h*w)."""
+    B, C = dy.shape
+    h, w = hw_shape
+    dx = torch.empty((B, C, h, w), dtype=torch.float32, device=dy.device)
+    check(nat.lib().vfs_avgpool_backward(ptr(dy), ptr(dx), B, C, h * w, current_stream()), 'avgpool_backward')
+    return dx
+
+
+def cosine_loss_backward(p, z, gout, with_norm=True, negative=False):
+    B, D = p.shape
+    dp = torch.empty_like(p)
+    check(nat.lib().vfs_cosine_loss_backward(ptr(p), ptr(z), ptr(gout), ptr(dp), B, D, int(with_norm), int(negative),
+                                             current_stream()), 'cosine_loss_backward')
+    return dp
+
+
+# ---- backward pieces of the backbone ---------------------------------------------------------------------
+def _sync_sums(sums, bn):
+    import torch.distributed as dist
+    if isinstance(bn, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() \
+            and dist.get_world_size() > 1:
+        dist.all_reduce(sums)
+        return dist.get_world_size()
+    return 1
+
+
+def bn_backward(dy, y_for_relu, z, mean, invstd, bn, want_g=False, dy_is_f32=False, want_f32=False,
+                param_scale=1.0):
+    """BatchNorm(+ReLU) backward.  ``dy``: split [2,N,H,W,C] (or fp32 NHWC when dy_is_f32), ``y_for_relu``: forward
+    output (split) or None, ``z`` raw conv output fp32 NHWC.  Returns (dz, g|None, dgamma, dbeta); dz is split (or
+    fp32 when want_f32).  SyncBN: the two per-channel sums are all-reduced across ranks."""
+    N, H, W, C = z.shape
+    M = N * H * W
+    sums = torch.zeros((2 * C, ), dtype=torch.float64, device=z.device)
+    dys, dyf = (None, dy) if dy_is_f32 else (dy, None)
+    check(nat.lib().vfs_bn_bwd_reduce(ptr(dys), ptr(dyf), ptr(y_for_relu), ptr(z), ptr(mean), ptr(invstd), ptr(sums),
+                                      M, C, current_stream()), 'bn_bwd_reduce')
+    count = M * _sync_sums(sums, bn)
+    dz = torch.empty((N, H, W, C), dtype=torch.float32, device=z.device) if want_f32 else \
+        torch.empty((2, N, H, W, C), dtype=torch.float16, device=z.device)
+    g = torch.empty((2, N, H, W, C), dtype=torch.float16, device=z.device) if want_g else None
+    dg = torch.empty((C, ), dtype=torch.float32, device=z.device)
+    db = torch.empty_like(dg)
+    check(nat.lib().vfs_bn_bwd_apply(ptr(dys), ptr(dyf), ptr(y_for_relu), ptr(z), ptr(mean), ptr(invstd),
+                                     ptr(bn.weight.detach()) if bn.affine else None, ptr(sums), float(count),
+                                     None if want_f32 else ptr(dz), ptr(dz) if want_f32 else None, ptr(g), ptr(dg),
+                                     ptr(db), 0, float(param_scale), M, C, current_stream()), 'bn_bwd_apply')
+    LAUNCHES[0] += 1
+    return dz, g, dg, db
+
+
+def stem_pool_relu_backward(dpool, z, scale, shift, in_hw):
+    """dPool split [2,N,Hp,Wp,64] -> gradient w.r.t. the BN output on the conv grid, fp32 [N,Hc,Wc,64]."""
+    N, Hc, Wc, _ = z.shape
+    g = torch.empty_like(z)
+    check(nat.lib().vfs_stem_pool_relu_bwd(ptr(dpool), ptr(z), ptr(scale), ptr(shift), ptr(g), N, in_hw[0], in_hw[1],
+                                           current_stream()), 'stem_pool_relu_bwd')
+    return g
+
+
+def stem_wgrad(x, dz, out_scale=1.0):
+    N, _, H, W = x.shape
+    dw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=x.device)
+    check(nat.lib().vfs_stem_wgrad(ptr(x), ptr(dz), ptr(dw), 0, float(out_scale), N, H, W, current_stream()),
+          'stem_wgrad')
+    return dw
+
+
+def sgd_momentum_step_(p, grad, buf, lr, momentum, weight_decay, first, grad_scale=1.0):
+    check(nat.lib().vfs_sgd_momentum_step(ptr(p), ptr(grad), ptr(buf), p.numel(), float(lr), float(momentum),
+                                          float(weight_decay), int(first), float(grad_scale), current_stream()),
+          'sgd_momentum_step')
+
+
+def overflow_count(reset=True):
+    """Values that left the fp16 range while being split since the last reset (synchronises the device)."""
+    return int(nat.lib().vfs_overflow_count(int(reset)))
+
+
 def cosine_sim_loss(p, z, with_norm=True, negative=False):
-    """Per-sample 2 - 2*cos(p, z) (or -cos) for [B, D] inputs."""
+    """Per-sample 2 - 2*cos(p, z) (or -cos) for [B, D] inputs (differentiable w.r.t. ``p``)."""
+    if torch.is_grad_enabled() and (p.requires_grad or z.requires_grad):
+        from .autograd import CosineLossFunction
+        return CosineLossFunction.apply(p, z, bool(with_norm), bool(negative))
+    return cosine_sim_loss_raw(p, z, with_norm, negative)
+
+
+def cosine_sim_loss_raw(p, z, with_norm=True, negative=False):
     p = _f32c(p.contiguous(), 'cls_score')
     z = _f32c(z.contiguous(), 'label')
     assert p.shape == z.shape and p.ndim == 2, (p.shape, z.shape)
@@ -366,7 +526,7 @@ def features_to_split(x, normalize=True):
     """NCHW fp32 [N,C,H,W] -> (optionally L2-normalised over C) split NHWC [2,N,H,W,C]."""
     x = _f32c(x.contiguous(), 'x')
     N, C, H, W = x.shape
-    out = torch.empty((2, N, H, W, C), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((2, N, H, W, C), dtype=torch.float16, device=x.device)
     ws = torch.empty((N * H * W, ), dtype=torch.float32, device=x.device) if normalize else None
     check(nat.lib().vfs_features_to_split(ptr(x), ptr(out), ptr(ws), N, C, H, W, int(normalize), current_stream()),
           'features_to_split_norm' if normalize else 'features_to_split')
@@ -395,7 +555,7 @@ def attention_bank_batched(q_bank, q_ids, k_bank, key_ids, values, val_ids, v_ba
     address ``values`` (see include/vfs_b200.h).  Returns out [P,Cv,H*W] (+ top-k values / indices [P,topk,H*W])."""
     from ._native import VfsAttnDesc
     _require_cuda(k_bank, 'k_bank')
-    assert q_bank.dtype == torch.bfloat16 and k_bank.dtype == torch.bfloat16
+    assert q_bank.dtype == torch.float16 and k_bank.dtype == torch.float16
     _, Fk, H, W, C = k_bank.shape
     Fq = q_bank.shape[1]
     assert q_bank.shape[2:] == (H, W, C), (q_bank.shape, k_bank.shape)

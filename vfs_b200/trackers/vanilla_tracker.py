@@ -3,7 +3,7 @@
 Where the reference parks every feature map and every propagated label map on the CPU and copies ~552 MB back
 to the GPU per frame (vanilla_tracker.py:67,131-149,160), this implementation keeps a device-resident bank:
 
-  * all frame features stay on the GPU as L2-normalised split-bf16 NHWC tensors (the fused attention kernel's
+  * all frame features stay on the GPU as L2-normalised split-fp16 NHWC tensors (the fused attention kernel's
     operand format), written once per frame by the backbone engine;
   * the propagated label maps stay on the GPU in a [T, Cv, h*w] fp32 bank; a key set {0} U [f-20, f) is a list of
     bank frame indices handed to the kernel (no concatenation, frame 0 may appear twice exactly like the
@@ -55,7 +55,7 @@ class VanillaTracker(BaseTracker):
         return out_indices[0]
 
     def get_feat_bank(self, imgs):
-        """imgs [1,3,T,H,W] -> normalised split-bf16 bank [2,T,h,w,C] on the device (reference get_feats,
+        """imgs [1,3,T,H,W] -> normalised split-fp16 bank [2,T,h,w,C] on the device (reference get_feats,
         vanilla_tracker.py:55-75, chunked by ``batch_step`` frames like the reference)."""
         assert imgs.shape[0] == 1
         batch_step = self.test_cfg.get('batch_step', 10)
@@ -75,7 +75,7 @@ class VanillaTracker(BaseTracker):
                 if with_norm:
                     xs = ops.normalize_split(xs)
             if bank is None:
-                bank = torch.empty((2, clip_len) + tuple(xs.shape[2:]), dtype=torch.bfloat16, device=xs.device)
+                bank = torch.empty((2, clip_len) + tuple(xs.shape[2:]), dtype=torch.float16, device=xs.device)
             bank[:, ptr:ptr + xs.shape[1]].copy_(xs)
         return bank
 
