@@ -19,8 +19,8 @@ REL_TOL = 1e-3  # north_star: "within 1e-3 rel fp32"
 
 
 def rel_err(got, ref):
-    got = torch.as_tensor(got).double().cpu()
-    ref = torch.as_tensor(ref).double().cpu()
+    got = torch.as_tensor(got).detach().double().cpu()
+    ref = torch.as_tensor(ref).detach().double().cpu()
     assert got.shape == ref.shape, (got.shape, ref.shape)
     return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
 
@@ -289,7 +289,8 @@ def test_head_matches_reference_golden(golden, name, mode):
     loss = head.loss(p1, z1, p2, z2)['loss_feat']
     assert rel_err(z1, golden[f'head/{name}/{mode}/z1']) < REL_TOL
     assert rel_err(p1, golden[f'head/{name}/{mode}/p1']) < REL_TOL
-    np.testing.assert_allclose(loss.cpu().numpy(), golden[f'head/{name}/{mode}/loss'], rtol=REL_TOL, atol=1e-5)
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), golden[f'head/{name}/{mode}/loss'], rtol=REL_TOL,
+                               atol=1e-5)
     if mode == 'train':  # running statistics must have been updated like torch's BatchNorm1d does
         with torch.no_grad():
             x = torch.nn.functional.adaptive_avg_pool2d(x1, 1).flatten(1)
@@ -308,7 +309,7 @@ def test_cosine_loss_matches_reference_golden(golden):
     p, z = cases.loss_inputs()
     for neg in (False, True):
         got = CosineSimLoss(negative=neg)(p.cuda(), z.cuda())
-        np.testing.assert_allclose(got.cpu().numpy(), golden[f'loss/cosine/neg{int(neg)}'], rtol=REL_TOL, atol=1e-6)
+        np.testing.assert_allclose(got.detach().cpu().numpy(), golden[f'loss/cosine/neg{int(neg)}'], rtol=REL_TOL, atol=1e-6)
 
 
 # --------------------------------------------------------------------------------------------- attention
@@ -487,7 +488,7 @@ def test_simsiam_forward_eval_mode_matches_oracle(name):
                     p1, z1, video2images(p2v.roll(i, dims=2)), video2images(z2v.roll(i, dims=2)), weight=w)
     assert set(losses) == set(exp)
     for k_ in exp:
-        np.testing.assert_allclose(losses[k_].cpu().numpy(), exp[k_].numpy(), rtol=REL_TOL, atol=2e-5)
+        np.testing.assert_allclose(losses[k_].detach().cpu().numpy(), exp[k_].numpy(), rtol=REL_TOL, atol=2e-5)
     out = model.train_step(dict(imgs=imgs.cuda()), None)
     assert set(out) == {'loss', 'log_vars', 'num_samples'} and out['num_samples'] == imgs.shape[0]
     assert abs(out['log_vars']['loss'] - float(sum(v.mean() for v in exp.values()))) < 1e-3
@@ -533,7 +534,10 @@ def test_train_step_gradients_match_oracle_autograd(name):
     model.load_state_dict(sd)
     model = model.cuda()
     model.train()
-    imgs = cases.tracker_train_input(c)
+    # 8 clips: with the golden fixtures' 2-3 clips the train-mode BatchNorms see 3-12 samples per channel and their
+    # backward (a projection orthogonal to 2 directions of a 3-dimensional space) amplifies fp32 rounding to O(1)
+    shape = (8, ) + tuple(c['shape'][1:])
+    imgs = torch.randn(shape, generator=torch.Generator().manual_seed(900 + c['seed']))
     ref_loss, ref_grads = _oracle_train_reference(c, sd, imgs)
 
     opt = SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
@@ -544,13 +548,20 @@ def test_train_step_gradients_match_oracle_autograd(name):
     assert ops.overflow_count() == 0
     got = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
     assert set(got) == set(ref_grads), set(got) ^ set(ref_grads)
+    # Gradients that are mathematically zero (a bias feeding a train-mode BN) are pure rounding noise in the reference,
+    # so each tensor is judged relative to max(its own max, 1e-3 x the largest gradient of its kind).
+    gmax = {}
+    for k, r in ref_grads.items():
+        kind = 'bn' if r.ndim == 1 else 'w'
+        gmax[kind] = max(gmax.get(kind, 0.0), float(r.abs().max()))
     worst = []
     for k, g in got.items():
         r = ref_grads[k]
-        worst.append((float((g.cpu().double() - r.double()).abs().max() / r.abs().max().clamp_min(1e-12)), k))
+        floor = 1e-3 * gmax['bn' if r.ndim == 1 else 'w']
+        worst.append((float((g.cpu().double() - r.double()).abs().max() / max(float(r.abs().max()), floor)), k))
     worst.sort(reverse=True)
-    assert worst[0][0] < 2e-2, worst[:5]          # every tensor within 2e-2 of its own max ...
-    assert sum(w for w, _ in worst) / len(worst) < 2e-3, worst[:5]   # ... and 2e-3 on average
+    assert worst[0][0] < 2e-2, worst[:8]          # every tensor within 2e-2 ...
+    assert sum(w for w, _ in worst) / len(worst) < 2e-3, worst[:8]   # ... and 2e-3 on average
 
     # one SGD step (first step: momentum buffer = g + wd*p)
     before = {k: p.detach().clone() for k, p in model.named_parameters()}

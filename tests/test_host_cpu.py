@@ -224,3 +224,48 @@ def test_parse_losses_averages_over_ranks_gloo_world2():
     for _, _, lv in res:
         assert abs(lv['img_head.0.loss_feat'] - 1.5) < 1e-6 and abs(lv['loss'] - 1.5) < 1e-6
         assert abs(lv['acc'] - 0.75) < 1e-6
+
+
+def _allreduce_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from vfs_b200.optim import allreduce_grads
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2))]
+    params[0].grad = torch.full((3, 4), float(rank + 1))
+    params[1].grad = torch.arange(5, dtype=torch.float32) * (rank + 1)
+    allreduce_grads(params, average=True)          # params[2] has no gradient: skipped
+    q.put((rank, params[0].grad.clone(), params[1].grad.clone(), params[2].grad))
+    dist.destroy_process_group()
+
+
+def test_allreduce_grads_gloo_world2():
+    """world_size-2 gloo: the data-parallel gradient exchange of the training step (one flat bucket, averaged)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for _, g0, g1, g2 in res:
+        assert torch.equal(g0, torch.full((3, 4), 1.5))
+        assert torch.equal(g1, torch.arange(5, dtype=torch.float32) * 1.5)
+        assert g2 is None
+
+
+def test_sgd_and_autograd_reject_cpu():
+    from vfs_b200.optim import SGD, build_optimizer
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        SGD([p], lr=0.1).step()
+    with pytest.raises(NotImplementedError):
+        SGD([p], lr=0.1, nesterov=True)
+    with pytest.raises(KeyError):
+        build_optimizer(torch.nn.Linear(2, 2), dict(type='Adam', lr=1e-3))
+    opt = build_optimizer(torch.nn.Linear(2, 2), dict(type='SGD', lr=0.05, momentum=0.9, weight_decay=1e-4))
+    assert opt.param_groups[0]['momentum'] == 0.9
