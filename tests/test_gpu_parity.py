@@ -539,6 +539,11 @@ def test_train_step_gradients_match_oracle_autograd(name):
     shape = (8, ) + tuple(c['shape'][1:])
     imgs = torch.randn(shape, generator=torch.Generator().manual_seed(900 + c['seed']))
     ref_loss, ref_grads = _oracle_train_reference(c, sd, imgs)
+    # fp64 run of the same oracle: the yardstick.  ReLU / max-pool make the gradient discontinuous, so single
+    # elements flip under ANY rounding change (the fp32 oracle itself is up to 1e-1 away from fp64 on some tensors);
+    # a tensor passes if its relative L2 error against fp64 is within 5x the fp32 oracle's own error (floor 2e-3).
+    sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    _, ref64 = _oracle_train_reference(c, sd64, imgs.double())
 
     opt = SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
     opt.zero_grad()
@@ -548,20 +553,17 @@ def test_train_step_gradients_match_oracle_autograd(name):
     assert ops.overflow_count() == 0
     got = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
     assert set(got) == set(ref_grads), set(got) ^ set(ref_grads)
-    # Gradients that are mathematically zero (a bias feeding a train-mode BN) are pure rounding noise in the reference,
-    # so each tensor is judged relative to max(its own max, 1e-3 x the largest gradient of its kind).
-    gmax = {}
-    for k, r in ref_grads.items():
-        kind = 'bn' if r.ndim == 1 else 'w'
-        gmax[kind] = max(gmax.get(kind, 0.0), float(r.abs().max()))
-    worst = []
+    gnorm = max(float(r.norm()) for r in ref64.values())
+    failures, ratios = [], []
     for k, g in got.items():
-        r = ref_grads[k]
-        floor = 1e-3 * gmax['bn' if r.ndim == 1 else 'w']
-        worst.append((float((g.cpu().double() - r.double()).abs().max() / max(float(r.abs().max()), floor)), k))
-    worst.sort(reverse=True)
-    assert worst[0][0] < 2e-2, worst[:8]          # every tensor within 2e-2 ...
-    assert sum(w for w, _ in worst) / len(worst) < 2e-3, worst[:8]   # ... and 2e-3 on average
+        r64 = ref64[k]
+        denom = max(float(r64.norm()), 1e-6 * gnorm)   # mathematically-zero gradients (bias before a BN) are noise
+        mine = float((g.cpu().double() - r64).norm()) / denom
+        base = float((ref_grads[k].double() - r64).norm()) / denom
+        ratios.append(mine / max(base, 1e-7))
+        if mine > max(5 * base, 2e-3):
+            failures.append((k, mine, base))
+    assert not failures, failures[:8]
 
     # one SGD step (first step: momentum buffer = g + wd*p)
     before = {k: p.detach().clone() for k, p in model.named_parameters()}

@@ -25,7 +25,7 @@ namespace vfs {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 B = one swizzle row
 constexpr int kTileABytes = kBlockM * kBlockK * 2;  // one plane of the activation tile (16 KB)
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int kMaxTaps = 9;
 constexpr int kMaxViews = 4;
 
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);
     }
     fence_mbar_init();
   }
@@ -186,14 +186,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       }
     }
   } else {
-    // ======================= epilogue (warps 2..5) =======================
-    // Phase A (thread = accumulator row): TMEM -> scale/shift -> fp32 staging tile in shared memory (16-byte
-    // chunks XOR-swizzled so both phases are bank-conflict free).  Phase B (8 threads per pixel row): staging
-    // -> (+residual) -> ReLU -> split -> global, every warp access covering whole 128-byte lines.
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ======================= epilogue (warps 2..9) =======================
+    // Phase A (thread = accumulator row, warp = 32 rows x 32 of the chunk's 64 columns): TMEM -> fp32 staging tile
+    // in shared memory (16-byte chunks XOR-swizzled so both phases are bank-conflict free).
+    // Phase B (8 threads per pixel row, 8 channels each): staging -> scale/shift (+residual) -> ReLU -> split ->
+    // global, every warp access covering whole 128-byte lines.  Residual pieces are prefetched before phase A.
+    const int ew = warp - 2;   // 0..7
+    const int q = warp & 3;    // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+    const int ch = ew >> 2;    // which 32-column half of the 64-column chunk this warp stages
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;         // 0..127 over the epilogue threads
-    const int piece = et & 7, rr = et >> 3;  // phase B: 8-channel piece within the 64-column chunk, first row
+    const int et = threadIdx.x - 64;         // 0..255 over the epilogue threads
+    const int piece = et & 7, rr = et >> 3;  // phase B: 8-channel piece of the chunk, first of 4 rows (stride 32)
     auto phys_chunk = [](int r, int c) { return (c & 8) | ((c ^ (c >> 3) ^ r) & 7); };
     int as = 0;
     uint32_t aphase = 0;
@@ -205,49 +208,52 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       const int th_i = t2 % p.tiles_h;
       const int tn_i = t2 / p.tiles_h;
       const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.tn;
+      // element offsets of this thread's 4 output pixels (index math once per tile, not per chunk)
+      size_t obase[4];
+      bool ok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rr + 32 * i;
+        const int dw = r % p.tw;
+        const int r2 = r / p.tw;
+        const int w = w0 + dw, hh = h0 + r2 % p.th, n = n0 + r2 / p.th;
+        ok[i] = (w < p.Wo) && (hh < p.Ho) && (n < p.N);
+        obase[i] = ((static_cast<size_t>(n) * p.out_H + hh * p.out_sy + p.out_oy) * p.out_W + w * p.out_sx + p.out_ox) *
+                       p.Cout + n_tile * BN + piece * 8;
+      }
 
       mbar_wait(tfull_bar(as), aphase, 400 + as);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 64) {
-        const int cg = n_tile * BN + c0;
-        // Prefetch this thread's residual pieces for phase B now, so their HBM/L2 latency is hidden behind the
-        // TMEM reads and the staging pass (the epilogue was long-scoreboard bound on these loads).
-        uint4 pre_h[8], pre_l[8];
+        const int cg = n_tile * BN + c0 + piece * 8;
+        uint4 pre_h[4], pre_l[4];
         if (p.res_hi != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rr + 16 * i;
-            const int dw = r % p.tw;
-            const int r2 = r / p.tw;
-            const int w = w0 + dw, hh = h0 + r2 % p.th, n = n0 + r2 / p.th;
+          for (int i = 0; i < 4; ++i) {
             pre_h[i] = make_uint4(0, 0, 0, 0);
             pre_l[i] = make_uint4(0, 0, 0, 0);
-            if ((w < p.Wo) && (hh < p.Ho) && (n < p.N)) {
-              const size_t o = ((static_cast<size_t>(n) * p.out_H + hh * p.out_sy + p.out_oy) * p.out_W +
-                                w * p.out_sx + p.out_ox) * p.Cout + cg + piece * 8;
-              pre_h[i] = *reinterpret_cast<const uint4*>(p.res_hi + o);
-              pre_l[i] = *reinterpret_cast<const uint4*>(p.res_lo + o);
+            if (ok[i]) {
+              pre_h[i] = *reinterpret_cast<const uint4*>(p.res_hi + obase[i] + c0);
+              pre_l[i] = *reinterpret_cast<const uint4*>(p.res_lo + obase[i] + c0);
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffer free
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        const float4 sc0 = __ldg(reinterpret_cast<const float4*>(p.scale + cg));
+        const float4 sc1 = __ldg(reinterpret_cast<const float4*>(p.scale + cg + 4));
+        const float4 sh0 = __ldg(reinterpret_cast<const float4*>(p.shift + cg));
+        const float4 sh1 = __ldg(reinterpret_cast<const float4*>(p.shift + cg + 4));
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // staging buffer free
+        {
           uint32_t acc[32];
-          tmem_ld_32x32b_x32(t_row + c0 + h * 32, acc);
+          tmem_ld_32x32b_x32(t_row + c0 + ch * 32, acc);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cg + h * 32 + j * 4));
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cg + h * 32 + j * 4));
-            const float y0 = fmaf(__uint_as_float(acc[4 * j + 0]), sc.x, sh.x);
-            const float y1 = fmaf(__uint_as_float(acc[4 * j + 1]), sc.y, sh.y);
-            const float y2 = fmaf(__uint_as_float(acc[4 * j + 2]), sc.z, sh.z);
-            const float y3 = fmaf(__uint_as_float(acc[4 * j + 3]), sc.w, sh.w);
-            const uint32_t addr = stg_base + row * 256 + phys_chunk(row, h * 8 + j) * 16;
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(y0), "f"(y1), "f"(y2), "f"(y3)
+            const uint32_t addr = stg_base + row * 256 + phys_chunk(row, ch * 8 + j) * 16;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(acc[4 * j]), "r"(acc[4 * j + 1]),
+                         "r"(acc[4 * j + 2]), "r"(acc[4 * j + 3])
                          : "memory");
           }
         }
@@ -256,22 +262,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffer full
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // staging buffer full
         float st_s[8], st_q[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) st_s[e] = st_q[e] = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = rr + 16 * i;
-          const int dw = r % p.tw;
-          const int r2 = r / p.tw;
-          const int dh = r2 % p.th;
-          const int dn = r2 / p.th;
-          const int w = w0 + dw, hh = h0 + dh, n = n0 + dn;
-          if ((w < p.Wo) && (hh < p.Ho) && (n < p.N)) {
-            const size_t o = ((static_cast<size_t>(n) * p.out_H + hh * p.out_sy + p.out_oy) * p.out_W +
-                              w * p.out_sx + p.out_ox) * p.Cout + cg + piece * 8;
-            const uint4 rh = pre_h[i], rl = pre_l[i];
+        for (int i = 0; i < 4; ++i) {
+          if (ok[i]) {
+            const int r = rr + 32 * i;
+            const size_t o = obase[i] + c0;
             float y[8];
             const uint32_t a0 = stg_base + r * 256 + phys_chunk(r, 2 * piece) * 16;
             const uint32_t a1 = stg_base + r * 256 + phys_chunk(r, 2 * piece + 1) * 16;
@@ -279,15 +278,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
                          : "=f"(y[0]), "=f"(y[1]), "=f"(y[2]), "=f"(y[3]) : "r"(a0));
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(y[4]), "=f"(y[5]), "=f"(y[6]), "=f"(y[7]) : "r"(a1));
+            y[0] = fmaf(y[0], sc0.x, sh0.x); y[1] = fmaf(y[1], sc0.y, sh0.y);
+            y[2] = fmaf(y[2], sc0.z, sh0.z); y[3] = fmaf(y[3], sc0.w, sh0.w);
+            y[4] = fmaf(y[4], sc1.x, sh1.x); y[5] = fmaf(y[5], sc1.y, sh1.y);
+            y[6] = fmaf(y[6], sc1.z, sh1.z); y[7] = fmaf(y[7], sc1.w, sh1.w);
             if (p.res_hi != nullptr) {
-              y[0] += lo16_to_float(rh.x) + lo16_to_float(rl.x);
-              y[1] += hi16_to_float(rh.x) + hi16_to_float(rl.x);
-              y[2] += lo16_to_float(rh.y) + lo16_to_float(rl.y);
-              y[3] += hi16_to_float(rh.y) + hi16_to_float(rl.y);
-              y[4] += lo16_to_float(rh.z) + lo16_to_float(rl.z);
-              y[5] += hi16_to_float(rh.z) + hi16_to_float(rl.z);
-              y[6] += lo16_to_float(rh.w) + lo16_to_float(rl.w);
-              y[7] += hi16_to_float(rh.w) + hi16_to_float(rl.w);
+              const uint4 rh = pre_h[i], rl = pre_l[i];
+              const float2 h0f = h2_to_float2(rh.x), l0f = h2_to_float2(rl.x);
+              const float2 h1f = h2_to_float2(rh.y), l1f = h2_to_float2(rl.y);
+              const float2 h2f = h2_to_float2(rh.z), l2f = h2_to_float2(rl.z);
+              const float2 h3f = h2_to_float2(rh.w), l3f = h2_to_float2(rl.w);
+              y[0] += h0f.x + l0f.x; y[1] += h0f.y + l0f.y;
+              y[2] += h1f.x + l1f.x; y[3] += h1f.y + l1f.y;
+              y[4] += h2f.x + l2f.x; y[5] += h2f.y + l2f.y;
+              y[6] += h3f.x + l3f.x; y[7] += h3f.y + l3f.y;
             }
             if (p.relu) {
 #pragma unroll
@@ -306,18 +310,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
               of[1] = make_float4(y[4], y[5], y[6], y[7]);
             }
             if (p.out_hi != nullptr) {
-              h16 hi[8], lo[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) split16(y[e], hi[e], lo[e]);
               uint4 oh, ol;
-              oh.x = pack16x2(hi[0], hi[1]);
-              oh.y = pack16x2(hi[2], hi[3]);
-              oh.z = pack16x2(hi[4], hi[5]);
-              oh.w = pack16x2(hi[6], hi[7]);
-              ol.x = pack16x2(lo[0], lo[1]);
-              ol.y = pack16x2(lo[2], lo[3]);
-              ol.z = pack16x2(lo[4], lo[5]);
-              ol.w = pack16x2(lo[6], lo[7]);
+              split16x2(y[0], y[1], oh.x, ol.x);
+              split16x2(y[2], y[3], oh.y, ol.y);
+              split16x2(y[4], y[5], oh.z, ol.z);
+              split16x2(y[6], y[7], oh.w, ol.w);
+              note_overflow8(y);
               *reinterpret_cast<uint4*>(p.out_hi + o) = oh;
               *reinterpret_cast<uint4*>(p.out_lo + o) = ol;
             }
@@ -336,8 +334,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           if (lane < 8) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              atomicAdd(p.stat_sum + cg + piece * 8 + e, static_cast<double>(st_s[e]));
-              atomicAdd(p.stat_sqsum + cg + piece * 8 + e, static_cast<double>(st_q[e]));
+              atomicAdd(p.stat_sum + cg + e, static_cast<double>(st_s[e]));
+              atomicAdd(p.stat_sqsum + cg + e, static_cast<double>(st_q[e]));
             }
           }
         }

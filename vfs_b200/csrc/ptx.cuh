@@ -227,6 +227,23 @@ __device__ __forceinline__ void split16(float x, h16& hi, h16& lo) {
   lo = __float2half_rn(x - __half2float(hi));
   if (!(fabsf(x) <= 65504.0f)) atomicAdd(&g_split_overflow, 1u);
 }
+// two values at once: packed hi pair and packed lo pair (one cvt.rn.f16x2.f32 each)
+__device__ __forceinline__ void split16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ float2 h2_to_float2(uint32_t packed) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&packed));
+}
+// one range check per 8 values (the hot epilogues use this instead of the per-value check of split16)
+__device__ __forceinline__ void note_overflow8(const float (&y)[8]) {
+  const float m = fmaxf(fmaxf(fmaxf(fabsf(y[0]), fabsf(y[1])), fmaxf(fabsf(y[2]), fabsf(y[3]))),
+                        fmaxf(fmaxf(fabsf(y[4]), fabsf(y[5])), fmaxf(fabsf(y[6]), fabsf(y[7]))));
+  if (!(m <= 65504.0f)) atomicAdd(&g_split_overflow, 1u);
+}
 __device__ __forceinline__ uint32_t pack16x2(h16 a, h16 b) {
   return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
 }
