@@ -199,6 +199,24 @@ typedef struct VfsAttnDesc {
  * inv_norm_ws: fp32 [N*H*W] scratch (only when normalize != 0). */
 int vfs_features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
                           int normalize, vfs_stream_t s);
+/* same with a channel-padded / row-padded destination (pixel rows c_stride >= C elements apart, lo plane at
+ * +plane_stride elements; the caller zero-fills the padding) -- used to feed odd channel counts to the GEMM. */
+int vfs_features_to_split_ex(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
+                             int normalize, int c_stride, long long plane_stride, vfs_stream_t s);
+/* Label post-processing of the tracker (trackers/vanilla_tracker.py:162-181): bilinear upsample (align_corners=False)
+ * of logit fp32 [Cv][h][w] to [H][W], per-channel min-max normalisation where max > 0, arg-max over channels ->
+ * out_labels uint8 [H][W].  workspace: vfs_seg_postprocess_workspace_bytes(Cv). */
+size_t vfs_seg_postprocess_workspace_bytes(int Cv);
+int vfs_seg_postprocess(const float* logit, unsigned char* out_labels, void* workspace, int Cv, int h, int w, int H,
+                        int W, vfs_stream_t s);
+/* Dense helpers of common/affinity_utils.py:6-50 (compute_affinity / propagate; exported by the reference, unused by
+ * its trackers).  The HW x HW GEMM itself is vfs_conv_bn_act with the dst pixels as 1x1 filters; these finish it:
+ *   vfs_masked_softmax  A [B][R][ld] -> out [B][R][Cc]: mask (analytic window, mask[i,j]) to -inf, softmax over
+ *                       dim 1 (rows, per column) / 2 (columns, per row) / 0 (none); fully masked lines -> 0 (or NaN)
+ *   vfs_propagate_dense out[b,c,j] = sum_i img[b,c,i] A'[b,i,j], A' = A or clamp(A - kth_j, 0)/max(sum, 1e-12) */
+int vfs_masked_softmax(const float* A, float* out, int B, int R, int Cc, int ld, int softmax_dim, int mask_mode,
+                       int radius_y, int radius_x, int W, int nan_to_zero, vfs_stream_t s);
+int vfs_propagate_dense(const float* img, const float* A, float* out, int B, int Cv, int HW, int topk, vfs_stream_t s);
 /* split NHWC -> L2-normalised split NHWC (plane strides in elements; in == out allowed). */
 int vfs_normalize_split(const void* in_split, void* out_split, long long num_pixels, int C,
                         long long in_plane_stride, long long out_plane_stride, vfs_stream_t s);

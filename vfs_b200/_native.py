@@ -63,6 +63,11 @@ PROTOTYPES = {
     'vfs_bn_finalize': (_i, [_vp, ctypes.c_double, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     'vfs_bn_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     'vfs_features_to_split': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'vfs_features_to_split_ex': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _vp]),
+    'vfs_seg_postprocess_workspace_bytes': (_sz, [_i]),
+    'vfs_seg_postprocess': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'vfs_masked_softmax': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'vfs_propagate_dense': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'vfs_normalize_split': (_i, [_vp, _vp, _ll, _i, _ll, _ll, _vp]),
     'vfs_attention_workspace_bytes': (_sz, [_attn_p, _i]),
     'vfs_masked_attention_batched': (_i, [_attn_p, _i, _vp, _ll, _i, ctypes.POINTER(ctypes.c_int32), _vp, _ll, _i,

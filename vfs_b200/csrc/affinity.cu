@@ -387,7 +387,7 @@ __global__ void pixel_inv_norm_nchw_kernel(const float* __restrict__ in, float* 
 
 __global__ void nchw_to_split_scaled_kernel(const float* __restrict__ in, const float* __restrict__ pix_scale,
                                             h16* __restrict__ out_hi, h16* __restrict__ out_lo,
-                                            int C, int HW) {
+                                            int C, int HW, int Cs) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -407,7 +407,7 @@ __global__ void nchw_to_split_scaled_kernel(const float* __restrict__ in, const 
     if (pp < HW && c < C) {
       h16 hi, lo;
       split16(tile[threadIdx.x][i], hi, lo);
-      const size_t o = (static_cast<size_t>(n) * HW + pp) * C + c;
+      const size_t o = (static_cast<size_t>(n) * HW + pp) * Cs + c;  // Cs >= C: channel-padded destination rows
       out_hi[o] = hi;
       out_lo[o] = lo;
     }
@@ -451,7 +451,7 @@ __global__ void normalize_split_kernel(const h16* __restrict__ in_hi, const h16*
 // host side
 // ------------------------------------------------------------------------------------------------
 int features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
-                      int normalize, cudaStream_t s) {
+                      int normalize, int c_stride, long long plane_stride, cudaStream_t s) {
   VFS_REQUIRE(in_nchw && out_split, VFS_EINVAL, "features_to_split: null argument");
   VFS_REQUIRE(!normalize || inv_norm_ws, VFS_EINVAL, "features_to_split: normalisation needs a workspace");
   VFS_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, VFS_ESHAPE, "features_to_split: empty tensor");
@@ -462,10 +462,14 @@ int features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, 
     pixel_inv_norm_nchw_kernel<<<grid, 128, 0, s>>>(in_nchw, inv, C, HW);
     VFS_CUDA_OK(cudaGetLastError());
   }
+  if (c_stride <= 0) c_stride = C;
+  if (plane_stride <= 0) plane_stride = static_cast<long long>(N) * HW * c_stride;
+  VFS_REQUIRE(c_stride >= C && plane_stride >= static_cast<long long>(N) * HW * c_stride, VFS_EINVAL,
+              "features_to_split: destination strides smaller than the tensor");
   h16* hi = reinterpret_cast<h16*>(out_split);
-  h16* lo = hi + static_cast<size_t>(N) * HW * C;
+  h16* lo = hi + plane_stride;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
-  nchw_to_split_scaled_kernel<<<grid, block, 0, s>>>(in_nchw, normalize ? inv : nullptr, hi, lo, C, HW);
+  nchw_to_split_scaled_kernel<<<grid, block, 0, s>>>(in_nchw, normalize ? inv : nullptr, hi, lo, C, HW, c_stride);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }

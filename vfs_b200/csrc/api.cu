@@ -129,7 +129,13 @@ int stem_conv_raw(const float* in, const float* weight, void* conv_out, int N, i
 int stem_bn_relu_pool(const void* conv_out, const float* scale, const float* shift, void* out_split, int N, int H,
                       int W, cudaStream_t s);
 int features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
-                      int normalize, cudaStream_t s);
+                      int normalize, int c_stride, long long plane_stride, cudaStream_t s);
+size_t seg_postprocess_workspace_bytes(int Cv);
+int seg_postprocess(const float* logit, unsigned char* out, void* workspace, int Cv, int h, int w, int H, int W,
+                    cudaStream_t s);
+int masked_softmax(const float* A, float* out, int B, int R, int Cc, int ld, int softmax_dim, int mask_mode, int ry,
+                   int rx, int W, int nan_to_zero, cudaStream_t s);
+int propagate_dense(const float* img, const float* A, float* out, int B, int Cv, int HW, int topk, cudaStream_t s);
 int normalize_split(const void* in_split, void* out_split, long long num_pixels, int C, long long in_plane_stride,
                     long long out_plane_stride, cudaStream_t s);
 size_t attention_workspace_bytes(const VfsAttnDesc* d, int B);
@@ -295,7 +301,23 @@ int vfs_debug_conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const
 
 int vfs_features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
                           int normalize, vfs_stream_t s) {
-  return vfs::features_to_split(in_nchw, out_split, inv_norm_ws, N, C, H, W, normalize, s);
+  return vfs::features_to_split(in_nchw, out_split, inv_norm_ws, N, C, H, W, normalize, 0, 0, s);
+}
+int vfs_features_to_split_ex(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
+                             int normalize, int c_stride, long long plane_stride, vfs_stream_t s) {
+  return vfs::features_to_split(in_nchw, out_split, inv_norm_ws, N, C, H, W, normalize, c_stride, plane_stride, s);
+}
+size_t vfs_seg_postprocess_workspace_bytes(int Cv) { return vfs::seg_postprocess_workspace_bytes(Cv); }
+int vfs_seg_postprocess(const float* logit, unsigned char* out_labels, void* workspace, int Cv, int h, int w, int H,
+                        int W, vfs_stream_t s) {
+  return vfs::seg_postprocess(logit, out_labels, workspace, Cv, h, w, H, W, s);
+}
+int vfs_masked_softmax(const float* A, float* out, int B, int R, int Cc, int ld, int softmax_dim, int mask_mode,
+                       int radius_y, int radius_x, int W, int nan_to_zero, vfs_stream_t s) {
+  return vfs::masked_softmax(A, out, B, R, Cc, ld, softmax_dim, mask_mode, radius_y, radius_x, W, nan_to_zero, s);
+}
+int vfs_propagate_dense(const float* img, const float* A, float* out, int B, int Cv, int HW, int topk, vfs_stream_t s) {
+  return vfs::propagate_dense(img, A, out, B, Cv, HW, topk, s);
 }
 int vfs_normalize_split(const void* in_split, void* out_split, long long num_pixels, int C,
                         long long in_plane_stride, long long out_plane_stride, vfs_stream_t s) {

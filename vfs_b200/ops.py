@@ -8,7 +8,7 @@ from . import _native as nat
 from ._native import VfsConvDesc, current_stream, ptr
 
 LAUNCHES = [0]  # kernels of libvfs_b200.so launched through this module (bench.py reports the count)
-_KERNELS_PER_CALL = {'stem_forward': 2, 'masked_attention': 2, 'features_to_split_norm': 2, 'conv_dgrad': 1, 'conv_wgrad': 2}
+_KERNELS_PER_CALL = {'stem_forward': 2, 'masked_attention': 2, 'features_to_split_norm': 2, 'conv_dgrad': 1, 'conv_wgrad': 2, 'seg_postprocess': 3}
 
 
 def check(rc, what=''):
@@ -631,9 +631,68 @@ def masked_attention(query, key, value, mask, temperature, topk, normalize=True,
     return out
 
 
+def seg_postprocess(seg_logit, fh, fw, out_hw, out=None):
+    """Propagated logits fp32 [Cv, fh*fw] -> uint8 label map [H, W] (bilinear upsample + min-max + argmax)."""
+    _require_cuda(seg_logit, 'seg_logit')
+    Cv = seg_logit.shape[0]
+    H, W = out_hw
+    if out is None:
+        out = torch.empty((H, W), dtype=torch.uint8, device=seg_logit.device)
+    ws = torch.empty((2 * Cv, ), dtype=torch.int32, device=seg_logit.device)
+    check(nat.lib().vfs_seg_postprocess(ptr(seg_logit), ptr(out), ptr(ws), Cv, fh, fw, H, W, current_stream()),
+          'seg_postprocess')
+    return out
+
+
 def dense_affinity(src_img, dst_img, temperature=1., normalize=True, softmax_dim=None, mask=None):
-    raise NotImplementedError('vfs_b200.compute_affinity: dense HWxHW affinity kernel not implemented yet')
+    """compute_affinity (affinity_utils.py:6-30): [B,C,h,w] x [B,C,h',w'] -> [B, hw, h'w'] fp32.  The GEMM runs on
+    the tcgen05 conv kernel (src pixels = image, dst pixels = 1x1 filter bank, scale = 1/temperature); the mask fill
+    and the softmax along ``softmax_dim`` are one more kernel."""
+    for t, n in ((src_img, 'src_img'), (dst_img, 'dst_img')):
+        _require_cuda(t, n)
+    B, C = src_img.shape[:2]
+    hs, ws_ = src_img.shape[2:]
+    hd, wd = dst_img.shape[2:]
+    HWs, HWd = hs * ws_, hd * wd
+    if mask is not None:
+        from .common.affinity_utils import NeighborMask
+        if not isinstance(mask, NeighborMask):
+            raise NotImplementedError('vfs_b200.compute_affinity: only masks built by spatial_neighbor() are supported')
+        assert HWs == HWd and (mask.height, mask.width) == (hd, wd)
+    assert softmax_dim in (None, 1, 2)
+    Cp, HWp = -(-C // 64) * 64, -(-HWd // 64) * 64
+    dev = src_img.device
+    out = torch.empty((B, HWs, HWd), dtype=torch.float32, device=dev)
+    scale = torch.full((HWp, ), 1.0 / float(temperature), dtype=torch.float32, device=dev)
+    shift = _const_vec(0, HWp, dev)
+    inv_ws = torch.empty((max(HWs, HWd), ), dtype=torch.float32, device=dev)
+    for b in range(B):
+        a_split = torch.zeros((2, 1, hs, ws_, Cp), dtype=torch.float16, device=dev)
+        w_split = torch.zeros((2, HWp, Cp), dtype=torch.float16, device=dev)
+        check(nat.lib().vfs_features_to_split_ex(ptr(src_img[b:b + 1].float().contiguous()), ptr(a_split), ptr(inv_ws),
+                                                 1, C, hs, ws_, int(normalize), Cp, a_split.stride(0),
+                                                 current_stream()), 'features_to_split_norm' if normalize else
+              'features_to_split')
+        check(nat.lib().vfs_features_to_split_ex(ptr(dst_img[b:b + 1].float().contiguous()), ptr(w_split), ptr(inv_ws),
+                                                 1, C, hd, wd, int(normalize), Cp, w_split.stride(0),
+                                                 current_stream()), 'features_to_split_norm' if normalize else
+              'features_to_split')
+        _, aff = conv_bn_act(a_split, w_split, scale, shift, 1, 1, 1, relu=False, want_split=False, want_f32=True)
+        check(nat.lib().vfs_masked_softmax(ptr(aff), ptr(out[b]), 1, HWs, HWd, HWp, int(softmax_dim or 0),
+                                           _MASK_MODES[mask.mode if mask is not None else None],
+                                           mask.radius_y if mask is not None else 0,
+                                           mask.radius_x if mask is not None else 0, wd, int(mask is not None),
+                                           current_stream()), 'masked_softmax')
+    return out
 
 
 def propagate_dense(img, affinity, topk=None):
-    raise NotImplementedError('vfs_b200.propagate: dense propagate kernel not implemented yet')
+    """propagate (affinity_utils.py:33-50): img [B,Cv,h,w], affinity [B,hw,hw] -> [B,Cv,h,w]."""
+    for t, n in ((img, 'img'), (affinity, 'affinity')):
+        _require_cuda(t, n)
+    B, Cv, h, w = img.shape
+    assert tuple(affinity.shape) == (B, h * w, h * w), (affinity.shape, img.shape)
+    out = torch.empty((B, Cv, h, w), dtype=torch.float32, device=img.device)
+    check(nat.lib().vfs_propagate_dense(ptr(img.float().contiguous()), ptr(affinity.float().contiguous()), ptr(out), B,
+                                        Cv, h * w, int(topk or 0), current_stream()), 'propagate_dense')
+    return out

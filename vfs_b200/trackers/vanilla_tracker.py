@@ -121,16 +121,12 @@ class VanillaTracker(BaseTracker):
             seg_logit = ops.attention_bank(bank[:, frame_idx:frame_idx + 1], bank, key_ids, seg_bank, cv * hw, hw, cv,
                                            mask, cfg.temperature, cfg.topk, non_mask_len=non_mask_len)
             seg_bank[frame_idx] = seg_logit
-            seg_pred = F.interpolate(seg_logit.view(1, cv, fh, fw), size=orig_hw, mode='bilinear',
-                                     align_corners=False)
             if not input_onehot:
-                flat = seg_pred.view(1, cv, -1)
-                smin = flat.min(dim=-1)[0].view(1, cv, 1, 1)
-                smax = flat.max(dim=-1)[0].view(1, cv, 1, 1)
-                normalized = (seg_pred - smin) / (smax - smin + 1e-12)
-                seg_pred = torch.where(smax > 0, normalized, seg_pred)
-                seg_pred = seg_pred.argmax(dim=1)
-                seg_pred = F.interpolate(seg_pred.byte().unsqueeze(1), size=orig_hw, mode='nearest').squeeze(1)
+                # fused bilinear upsample + per-channel min-max + argmax (csrc/post.cu)
+                seg_pred = ops.seg_postprocess(seg_logit, fh, fw, orig_hw).unsqueeze(0)
+            else:
+                seg_pred = F.interpolate(seg_logit.view(1, cv, fh, fw), size=orig_hw, mode='bilinear',
+                                         align_corners=False)
             seg_preds.append(seg_pred.detach())
 
         # one device->host copy per video; dtype promotion mirrors np.stack over the reference's per-frame arrays
