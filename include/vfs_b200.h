@@ -54,13 +54,17 @@ int vfs_split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H,
  * ResNet stem: conv 7x7/s2/p3 (3->64) + BN(eval, folded scale/shift) + ReLU + maxpool 3x3/s2/p1.
  * Replaces ResNet.forward's `self.conv1(x); self.maxpool(x)`
  * (mmaction/models/backbones/resnet.py:565-566, _make_stem_layer :422-435).
- *   in        NCHW fp32 [N,3,H,W]           weight [64,3,7,7] fp32
+ *   in        NCHW fp32 [N,3,H,W]           weight: split [2][64][192] packed by vfs_stem_pack_weight from the
+ *             OIHW fp32 [64,3,7,7] filter bank (K = 147 zero-padded to 192; the conv runs on tcgen05 with the im2col
+ *             tile built in shared memory)
  *   scale/shift [64] fp32 (gamma/sqrt(var+eps), beta - mean*scale)
  *   out_split split NHWC [N, Hp, Wp, 64], Hc = (H+6-7)/2+1, Hp = (Hc+2-3)/2+1
  *   workspace fp32 [N*Hc*Wc*64] (vfs_stem_workspace_bytes)
  * ---------------------------------------------------------------------------------------------- */
 size_t vfs_stem_workspace_bytes(int N, int H, int W);
-int vfs_stem_forward(const float* in, const float* weight, const float* scale, const float* shift, void* out_split,
+size_t vfs_stem_packed_weight_bytes(void);
+int vfs_stem_pack_weight(const float* w_oihw, void* w_split, vfs_stream_t s);
+int vfs_stem_forward(const float* in, const void* weight, const float* scale, const float* shift, void* out_split,
                      void* workspace, int N, int H, int W, vfs_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------
@@ -98,7 +102,7 @@ int vfs_conv_bn_act(const VfsConvDesc* d, const void* in_split, const void* w_sp
  * ---------------------------------------------------------------------------------------------- */
 /* stem in train mode: raw 7x7/s2 conv output (fp32 NHWC [N,Hc,Wc,64], vfs_stem_workspace_bytes) for the batch
  * statistics, then BN(scale/shift from vfs_bn_finalize)+ReLU fused into the 3x3/s2 max-pool -> split NHWC */
-int vfs_stem_conv_raw(const float* in, const float* weight, void* conv_out_f32_nhwc, int N, int H, int W,
+int vfs_stem_conv_raw(const float* in, const void* weight, void* conv_out_f32_nhwc, int N, int H, int W,
                       vfs_stream_t s);
 int vfs_stem_bn_relu_pool(const void* conv_out_f32_nhwc, const float* scale, const float* shift, void* out_split,
                           int N, int H, int W, vfs_stream_t s);

@@ -36,6 +36,8 @@ PROTOTYPES = {
     'vfs_nchw_f32_to_split_scaled': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     'vfs_split_to_nchw_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'vfs_stem_workspace_bytes': (_sz, [_i, _i, _i]),
+    'vfs_stem_packed_weight_bytes': (_sz, []),
+    'vfs_stem_pack_weight': (_i, [_vp, _vp, _vp]),
     'vfs_stem_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'vfs_conv_bn_act': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'vfs_pack_conv_weight': (_i, [_vp, _vp, _i, _i, _i, _vp]),

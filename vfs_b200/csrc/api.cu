@@ -122,10 +122,12 @@ int nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int
 int split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H, int W, cudaStream_t s);
 int pack_conv_weight(const float* w, void* w_split, int Cout, int Cin, int k, cudaStream_t s);
 size_t stem_workspace_bytes(int N, int H, int W);
-int stem_forward(const float* in, const float* weight, const float* scale, const float* shift, void* out_split,
+int stem_forward(const float* in, const void* weight, const float* scale, const float* shift, void* out_split,
                  void* workspace, int N, int H, int W, cudaStream_t s);
+size_t stem_packed_weight_bytes();
+int stem_pack_weight(const float* w, void* w_split, cudaStream_t s);
 
-int stem_conv_raw(const float* in, const float* weight, void* conv_out, int N, int H, int W, cudaStream_t s);
+int stem_conv_raw(const float* in, const void* weight, void* conv_out, int N, int H, int W, cudaStream_t s);
 int stem_bn_relu_pool(const void* conv_out, const float* scale, const float* shift, void* out_split, int N, int H,
                       int W, cudaStream_t s);
 int features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
@@ -197,11 +199,13 @@ int vfs_split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H,
   return vfs::split_to_nchw_f32(in_split, out, N, C, H, W, s);
 }
 size_t vfs_stem_workspace_bytes(int N, int H, int W) { return vfs::stem_workspace_bytes(N, H, W); }
-int vfs_stem_forward(const float* in, const float* weight, const float* scale, const float* shift, void* out_split,
+size_t vfs_stem_packed_weight_bytes(void) { return vfs::stem_packed_weight_bytes(); }
+int vfs_stem_pack_weight(const float* w_oihw, void* w_split, vfs_stream_t s) { return vfs::stem_pack_weight(w_oihw, w_split, s); }
+int vfs_stem_forward(const float* in, const void* weight, const float* scale, const float* shift, void* out_split,
                      void* workspace, int N, int H, int W, vfs_stream_t s) {
   return vfs::stem_forward(in, weight, scale, shift, out_split, workspace, N, H, W, s);
 }
-int vfs_stem_conv_raw(const float* in, const float* weight, void* conv_out_f32_nhwc, int N, int H, int W,
+int vfs_stem_conv_raw(const float* in, const void* weight, void* conv_out_f32_nhwc, int N, int H, int W,
                       vfs_stream_t s) {
   return vfs::stem_conv_raw(in, weight, conv_out_f32_nhwc, N, H, W, s);
 }

@@ -107,6 +107,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap
+  // the tail of the previous kernel in the stream; from here on its results are read and its inputs overwritten.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kchunks = p.num_taps * p.kchunks_per_tap;
@@ -389,8 +393,18 @@ int launch(const ConvKernelParams& p, int grid, cudaStream_t stream) {
                                      S::kTotal));
     configured = true;
   }
-  conv_tc_kernel<BN, STAGES><<<grid, kNumThreads, S::kTotal, stream>>>(p);
-  VFS_CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VFS_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES>, p));
   return VFS_OK;
 }
 

@@ -142,6 +142,188 @@ __global__ void stem_pool_kernel(const float* __restrict__ in, const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core stem: the same 7x7/s2 convolution as an implicit GEMM on tcgen05.
+//   M = 128 conv-output pixels (4 rows x 32 columns), N = 64 output channels, K = 147 padded to 192 (3 chunks of 64).
+// The A operand (im2col tile) cannot come from TMA (Cin = 3, stride 2), so the CTA builds it: the fp32 input patch
+// is staged in shared memory, every thread gathers 8 consecutive K values of one pixel row, splits them into hi/lo
+// halves and stores the two 16-byte chunks at the 128B-swizzled position the UMMA descriptor expects.  The split
+// weights [2][64][192] are brought once per CTA by TMA.  36 MMAs (128x64x16) per tile replace 128 x 9408 FMAs.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTcRows = 4, kTcCols = 32;                 // pixel tile
+constexpr int kTcPatchH = kTcRows * 2 + 5;               // 13 input rows
+constexpr int kTcPatchW = 72;                            // 32*2+5 = 69 -> padded
+constexpr int kTcKPad = 192;
+constexpr int kTcABytes = 3 * 2 * 128 * 128;             // 3 K-chunks x (hi, lo) x 128 rows x 128 B = 96 KB
+constexpr int kTcBBytes = 3 * 2 * 64 * 128;              // 48 KB
+constexpr int kTcPatchBytes = 3 * kTcPatchH * kTcPatchW * 4;
+constexpr int kTcSmemBytes = kTcABytes + kTcBBytes + kTcPatchBytes + 64 + 1024;
+
+struct alignas(64) StemTcParams {
+  CUtensorMap tmap_w;  // {192, 64, 2} split weights
+  const float* in;     // NCHW fp32
+  const float* scale;  // nullable: raw output
+  const float* shift;
+  float* out;          // fp32 NHWC [N, Hc, Wc, 64]
+  int N, H, W, Hc, Wc, tiles_x, tiles_y, num_tiles;
+};
+
+template <int G>
+__device__ __forceinline__ void stem_build_row(const float* __restrict__ patch, uint32_t a_base, int m, int py, int px) {
+  // chunks j = 2*i + G (16-byte chunks of 8 consecutive k); everything about k is a compile-time constant
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const int j = 2 * i + G;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = j * 8 + e;
+      if (k < 147) {
+        const int c = k / 49, r = (k / 7) % 7, s = k % 7;
+        v[e] = patch[(c * kTcPatchH + 2 * py + r) * kTcPatchW + 2 * px + s];
+      } else {
+        v[e] = 0.0f;
+      }
+    }
+    uint4 h, l;
+    split16x2(v[0], v[1], h.x, l.x);
+    split16x2(v[2], v[3], h.y, l.y);
+    split16x2(v[4], v[5], h.z, l.z);
+    split16x2(v[6], v[7], h.w, l.w);
+    const int kc = j >> 3, c16 = j & 7;
+    const uint32_t addr = a_base + kc * (2 * 128 * 128) + m * 128 + ((c16 ^ (m & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 128 * 128), "r"(l.x), "r"(l.y), "r"(l.z), "r"(l.w)
+                 : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) stem_tc_kernel(const __grid_constant__ StemTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;                        // [3][hi|lo][128 rows][128 B]
+  const uint32_t b_base = smem_base + kTcABytes;            // [3][hi|lo][64 rows][128 B]
+  const uint32_t patch_addr = b_base + kTcBBytes;
+  float* patch = reinterpret_cast<float*>(smem_raw + (patch_addr - smem_u32(smem_raw)));
+  const uint32_t bar_w = patch_addr + kTcPatchBytes;        // weights landed
+  const uint32_t bar_mma = bar_w + 8;                       // MMAs of the current tile retired
+  const uint32_t tmem_ptr_addr = bar_w + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmap_w);
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_addr, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_w, kTcBBytes);
+    for (int kc = 0; kc < 3; ++kc) tma_load_3d(b_base + kc * (2 * 64 * 128), &p.tmap_w, bar_w, kc * 64, 0, 0);
+  }
+  mbar_wait(bar_w, 0, 500);
+
+  const int m = threadIdx.x & 127, g = threadIdx.x >> 7;  // pixel row of the tile, chunk parity
+  const int py = m >> 5, px = m & 31;
+  const int q = warp & 3, half = warp >> 2;               // epilogue: TMEM lane quarter, 32-column half
+  constexpr uint32_t idesc = umma_idesc_f16_f32(128, 64);
+  uint32_t mma_phase = 0;
+
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int tx = tile % p.tiles_x;
+    const int t2 = tile / p.tiles_x;
+    const int ty = t2 % p.tiles_y;
+    const int n = t2 / p.tiles_y;
+    const int oy0 = ty * kTcRows, ox0 = tx * kTcCols;
+    const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+    const float* src = p.in + static_cast<size_t>(n) * 3 * p.H * p.W;
+    for (int i = threadIdx.x; i < 3 * kTcPatchH * kTcPatchW; i += 256) {
+      const int pc = i % kTcPatchW;
+      const int t = i / kTcPatchW;
+      const int pr = t % kTcPatchH;
+      const int c = t / kTcPatchH;
+      const int iy = iy0 + pr, ix = ix0 + pc;
+      patch[i] = (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) ? src[(static_cast<size_t>(c) * p.H + iy) * p.W + ix] : 0.0f;
+    }
+    __syncthreads();
+    if (g == 0) stem_build_row<0>(patch, a_base, m, py, px);
+    else stem_build_row<1>(patch, a_base, m, py, px);
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kc = 0; kc < 3; ++kc) {
+        const uint32_t a_hi = a_base + kc * (2 * 128 * 128), a_lo = a_hi + 128 * 128;
+        const uint32_t b_hi = b_base + kc * (2 * 64 * 128), b_lo = b_hi + 64 * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t koff = k * 32;
+          umma_f16(tmem_base, umma_desc_sw128_kmajor(a_lo + koff), umma_desc_sw128_kmajor(b_hi + koff), idesc,
+                   (kc | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_base, umma_desc_sw128_kmajor(a_hi + koff), umma_desc_sw128_kmajor(b_lo + koff), idesc, 1u);
+          umma_f16(tmem_base, umma_desc_sw128_kmajor(a_hi + koff), umma_desc_sw128_kmajor(b_hi + koff), idesc, 1u);
+        }
+      }
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, mma_phase, 600);
+    mma_phase ^= 1u;
+    tc_fence_after();
+    // epilogue: warp (q, half) reads rows 32q..32q+31, columns 32*half..+31
+    {
+      uint32_t acc[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32, acc);
+      tmem_ld_wait();
+      const int r = q * 32 + lane;
+      const int oy = oy0 + (r >> 5), ox = ox0 + (r & 31);
+      if (oy < p.Hc && ox < p.Wc) {
+        float4* dst = reinterpret_cast<float4*>(p.out + ((static_cast<size_t>(n) * p.Hc + oy) * p.Wc + ox) * 64 + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 y = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                                 __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+          if (p.scale != nullptr) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + half * 32) + j);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + half * 32) + j);
+            y.x = fmaxf(fmaf(y.x, sc.x, sh.x), 0.0f);
+            y.y = fmaxf(fmaf(y.y, sc.y, sh.y), 0.0f);
+            y.z = fmaxf(fmaf(y.z, sc.z, sh.z), 0.0f);
+            y.w = fmaxf(fmaf(y.w, sc.w, sh.w), 0.0f);
+          }
+          dst[j] = y;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // TMEM drained and the A / patch buffers free for the next tile
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// OIHW fp32 [64,3,7,7] -> split [2][64][192] (K = (c*7+r)*7+s zero-padded to 192)
+__global__ void stem_pack_weight_kernel(const float* __restrict__ w, h16* __restrict__ hi, h16* __restrict__ lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * kTcKPad) return;
+  const int k = i % kTcKPad, co = i / kTcKPad;
+  const float v = (k < 147) ? w[co * 147 + k] : 0.0f;
+  h16 h, l;
+  split16(v, h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+
 static inline void stem_dims(int H, int W, int* Hc, int* Wc, int* Hp, int* Wp) {
   *Hc = (H + 6 - 7) / 2 + 1;
   *Wc = (W + 6 - 7) / 2 + 1;
@@ -155,18 +337,41 @@ size_t stem_workspace_bytes(int N, int H, int W) {
   return static_cast<size_t>(N) * Hc * Wc * 64 * sizeof(float);
 }
 
-static int stem_conv_launch(const float* in, const float* weight, const float* scale, const float* shift,
+size_t stem_packed_weight_bytes() { return 2 * 64 * kTcKPad * sizeof(h16); }
+
+int stem_pack_weight(const float* w, void* w_split, cudaStream_t s) {
+  VFS_REQUIRE(w && w_split, VFS_EINVAL, "stem_pack_weight: null argument");
+  h16* hi = reinterpret_cast<h16*>(w_split);
+  stem_pack_weight_kernel<<<(64 * kTcKPad + 255) / 256, 256, 0, s>>>(w, hi, hi + 64 * kTcKPad);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
+// weight_split: output of stem_pack_weight (tensor-core path)
+static int stem_conv_launch(const float* in, const void* weight_split, const float* scale, const float* shift,
                             float* conv_out, int N, int H, int W, cudaStream_t s) {
   int Hc, Wc, Hp, Wp;
   stem_dims(H, W, &Hc, &Wc, &Hp, &Wp);
+  StemTcParams p;
+  memset(&p, 0, sizeof(p));
+  const uint64_t dims[3] = {kTcKPad, 64, 2};
+  const uint64_t strides[2] = {kTcKPad * 2, kTcKPad * 64 * 2};
+  const uint32_t box[3] = {64, 64, 2};
+  int rc = make_tmap_16b_sw128(&p.tmap_w, weight_split, 3, dims, strides, box);
+  if (rc != VFS_OK) return rc;
+  p.in = in; p.scale = scale; p.shift = shift; p.out = conv_out;
+  p.N = N; p.H = H; p.W = W; p.Hc = Hc; p.Wc = Wc;
+  p.tiles_x = (Wc + kTcCols - 1) / kTcCols;
+  p.tiles_y = (Hc + kTcRows - 1) / kTcRows;
+  p.num_tiles = p.tiles_x * p.tiles_y * N;
   static bool configured = false;
-  const int smem_bytes = kStemSmemFloats * static_cast<int>(sizeof(float));
   if (!configured) {
-    VFS_CUDA_OK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    VFS_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     configured = true;
   }
-  dim3 grid((Wc + kStemTileW - 1) / kStemTileW, (Hc + kStemTileH - 1) / kStemTileH, N);
-  stem_conv_kernel<<<grid, 256, smem_bytes, s>>>(in, weight, scale, shift, conv_out, H, W, Hc, Wc);
+  const int sms = device_sm_count();
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  stem_tc_kernel<<<grid, 256, kTcSmemBytes, s>>>(p);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }
@@ -184,7 +389,7 @@ static int stem_pool_launch(const float* conv_out, const float* scale, const flo
   return VFS_OK;
 }
 
-int stem_forward(const float* in, const float* weight, const float* scale, const float* shift, void* out_split,
+int stem_forward(const float* in, const void* weight, const float* scale, const float* shift, void* out_split,
                  void* workspace, int N, int H, int W, cudaStream_t s) {
   VFS_REQUIRE(in && weight && scale && shift && out_split && workspace, VFS_EINVAL, "stem_forward: null argument");
   VFS_REQUIRE(N > 0 && H >= 7 && W >= 7, VFS_ESHAPE, "stem_forward: input %dx%dx%d too small", N, H, W);
@@ -195,7 +400,7 @@ int stem_forward(const float* in, const float* weight, const float* scale, const
 }
 
 // train-mode pieces: raw conv output (statistics are computed on it), then BN+ReLU fused into the max-pool
-int stem_conv_raw(const float* in, const float* weight, void* conv_out, int N, int H, int W, cudaStream_t s) {
+int stem_conv_raw(const float* in, const void* weight, void* conv_out, int N, int H, int W, cudaStream_t s) {
   VFS_REQUIRE(in && weight && conv_out, VFS_EINVAL, "stem_conv_raw: null argument");
   VFS_REQUIRE(N > 0 && H >= 7 && W >= 7, VFS_ESHAPE, "stem_conv_raw: input %dx%dx%d too small", N, H, W);
   return stem_conv_launch(in, weight, nullptr, nullptr, reinterpret_cast<float*>(conv_out), N, H, W, s);

@@ -62,7 +62,8 @@ class BackboneEngine:
             p = _ConvPlan()
             w = cm.conv.weight.detach().to(device=device, dtype=torch.float32).contiguous()
             p.ksize = w.shape[2]
-            p.w_split = ops.pack_conv_weight(w) if w.shape[1] % 64 == 0 else w  # stem keeps OIHW fp32
+            # residual-stage convs: [2][Cout][k*k*Cin]; the 7x7 stem: [2][64][192] (K = 147 zero-padded)
+            p.w_split = ops.pack_conv_weight(w) if w.shape[1] % 64 == 0 else ops.stem_pack_weight(w)
             p.wt_split = None  # dgrad packing, built on first use by the backward pass
             p.scale, p.shift = fold_bn(cm, device)
             p.version = ver if ver is not None else self._version(cm)

@@ -110,12 +110,25 @@ def debug_conv_bn_act_simt(xs, w_split, scale, shift, ksize, stride=1, dilation=
     return out32
 
 
+def stem_pack_weight(w):
+    """OIHW fp32 [64,3,7,7] -> split [2,64,192] operand of the tensor-core stem."""
+    _require_cuda(w, 'w')
+    assert tuple(w.shape) == (64, 3, 7, 7) and w.dtype == torch.float32
+    out = torch.empty((2, 64, 192), dtype=torch.float16, device=w.device)
+    check(nat.lib().vfs_stem_pack_weight(ptr(w.contiguous()), ptr(out), current_stream()), 'stem_pack_weight')
+    return out
+
+
 def stem_forward(x, weight, scale, shift):
-    """conv7x7/s2 + BN + ReLU + maxpool3x3/s2 on NCHW fp32 input -> split NHWC [2,N,Hp,Wp,64]."""
+    """conv7x7/s2 + BN + ReLU + maxpool3x3/s2 on NCHW fp32 input -> split NHWC [2,N,Hp,Wp,64].
+    ``weight``: packed by stem_pack_weight (an OIHW fp32 tensor is packed on the fly)."""
     for t, n in ((x, 'x'), (weight, 'weight'), (scale, 'scale'), (shift, 'shift')):
         _require_cuda(t, n)
     N, C, H, W = x.shape
-    assert C == 3 and tuple(weight.shape) == (64, 3, 7, 7)
+    assert C == 3
+    if weight.dtype == torch.float32:
+        weight = stem_pack_weight(weight)
+    assert tuple(weight.shape) == (2, 64, 192)
     Hc, Wc = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
     Hp, Wp = (Hc + 2 - 3) // 2 + 1, (Wc + 2 - 3) // 2 + 1
     ws_bytes = nat.lib().vfs_stem_workspace_bytes(N, H, W)
@@ -201,6 +214,8 @@ def bn_apply(z, scale, shift, residual=None, relu=True):
 
 def stem_conv_raw(x, weight):
     N, C, H, W = x.shape
+    if weight.dtype == torch.float32:
+        weight = stem_pack_weight(weight)
     Hc, Wc = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
     z = torch.empty((N, Hc, Wc, 64), dtype=torch.float32, device=x.device)
     check(nat.lib().vfs_stem_conv_raw(ptr(x), ptr(weight), ptr(z), N, H, W, current_stream()), 'stem_conv_raw')
