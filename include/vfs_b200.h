@@ -112,6 +112,9 @@ int vfs_channel_stats_f32(const float* x, double* stats, long long M, int C, vfs
 int vfs_bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
                     float* save_invstd, int C, vfs_stream_t s);
+/* y = y*scale[c] + shift[c] (+ReLU) in place on fp32 [M,C]: the apply step of the two-phase (SyncBN) BatchNorm1d */
+int vfs_affine_act_f32(float* y, const float* scale, const float* shift, long long M, int C, int relu,
+                       vfs_stream_t s);
 int vfs_bn_apply(const float* z, const float* scale, const float* shift, const void* residual_split,
                  void* out_split, long long M, int C, int relu, vfs_stream_t s);
 
@@ -142,10 +145,11 @@ int vfs_conv_wgrad(const VfsConvDesc* d, const void* x_split, const void* dz_spl
  *   SyncBN);  dz = gamma*invstd*(g - sums0/count - xhat*sums1/count);  dgamma = param_scale*sums1, dbeta = param_scale*sums0.
  * dY comes as a split tensor or as fp32 (stem); dz goes out split (residual stages) and/or fp32 (stem); g_split
  * (optional) is the masked gradient that also flows into the block's identity branch. */
-int vfs_bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* z,
-                      const float* mean, const float* invstd, double* sums, long long M, int C, vfs_stream_t s);
-int vfs_bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
-                     const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
+int vfs_bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32,
+                      const float* z, const float* mean, const float* invstd, double* sums, long long M, int C,
+                      vfs_stream_t s);
+int vfs_bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32,
+                     const float* z, const float* mean, const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
                      float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
                      long long M, int C, vfs_stream_t s);
 int vfs_relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, long long elems, vfs_stream_t s);

@@ -49,9 +49,10 @@ PROTOTYPES = {
     'vfs_pack_conv_weight_dgrad': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'vfs_conv_wgrad_workspace_bytes': (_sz, [_i, _i, _i]),
     'vfs_conv_wgrad': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _i, _f, _vp]),
-    'vfs_bn_bwd_reduce': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
-    'vfs_bn_bwd_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _i,
-                              _f, _ll, _i, _vp]),
+    'vfs_affine_act_f32': (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
+    'vfs_bn_bwd_reduce': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
+    'vfs_bn_bwd_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _vp, _vp, _vp, _vp, _vp,
+                              _i, _f, _ll, _i, _vp]),
     'vfs_relu_bwd_split': (_i, [_vp, _vp, _vp, _ll, _vp]),
     'vfs_stem_pool_relu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'vfs_stem_wgrad': (_i, [_vp, _vp, _vp, _i, _f, _i, _i, _i, _vp]),

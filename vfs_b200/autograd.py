@@ -61,6 +61,7 @@ class LinearBnActFunction(torch.autograd.Function):
             ops.relu_(y)
         ctx.save_for_backward(x, weight, pre, y, mean, invstd, gamma)
         ctx.has_bn, ctx.relu, ctx.training, ctx.has_bias = bn is not None, relu, training, bias is not None
+        ctx.bn = bn
         ctx.need_dx = x.requires_grad
         return y
 
@@ -71,7 +72,7 @@ class LinearBnActFunction(torch.autograd.Function):
         dgamma = dbeta = None
         if ctx.has_bn:
             dpre, dgamma, dbeta = ops.bn1d_backward(dy, pre, y, gamma.detach() if gamma is not None else None, mean,
-                                                    invstd, ctx.training, ctx.relu)
+                                                    invstd, ctx.training, ctx.relu, bn=ctx.bn)
             if gamma is None:
                 dgamma = dbeta = None
         elif ctx.relu:

@@ -88,10 +88,11 @@ int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, in
 size_t wgrad_workspace_bytes(int Cout, int Cin, int ksize);
 int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_split, void* workspace, float* dw_oihw,
                   int accumulate, float out_scale, cudaStream_t stream);
-int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
-                  const float* invstd, double* sums, long long M, int C, cudaStream_t s);
-int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
-                 const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
+int affine_act_f32(float* y, const float* scale, const float* shift, long long M, int C, int relu, cudaStream_t s);
+int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32, const float* z,
+                  const float* mean, const float* invstd, double* sums, long long M, int C, cudaStream_t s);
+int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32, const float* z,
+                 const float* mean, const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
                  float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
                  long long M, int C, cudaStream_t s);
 int relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, long long elems, cudaStream_t s);
@@ -236,15 +237,20 @@ int vfs_conv_wgrad(const VfsConvDesc* d, const void* x_split, const void* dz_spl
                    int accumulate, float out_scale, vfs_stream_t s) {
   return vfs::conv_wgrad_tc(d, x_split, dz_split, workspace, dw_oihw, accumulate, out_scale, s);
 }
-int vfs_bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* z,
-                      const float* mean, const float* invstd, double* sums, long long M, int C, vfs_stream_t s) {
-  return vfs::bn_bwd_reduce(dy_split, dy_f32, y_split, z, mean, invstd, sums, M, C, s);
+int vfs_affine_act_f32(float* y, const float* scale, const float* shift, long long M, int C, int relu,
+                       vfs_stream_t s) {
+  return vfs::affine_act_f32(y, scale, shift, M, C, relu, s);
 }
-int vfs_bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
-                     const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
+int vfs_bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32,
+                      const float* z, const float* mean, const float* invstd, double* sums, long long M, int C,
+                      vfs_stream_t s) {
+  return vfs::bn_bwd_reduce(dy_split, dy_f32, y_split, y_f32, z, mean, invstd, sums, M, C, s);
+}
+int vfs_bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32,
+                     const float* z, const float* mean, const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
                      float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
                      long long M, int C, vfs_stream_t s) {
-  return vfs::bn_bwd_apply(dy_split, dy_f32, y_split, z, mean, invstd, gamma, sums, count, dz_split, dz_f32, g_split,
+  return vfs::bn_bwd_apply(dy_split, dy_f32, y_split, y_f32, z, mean, invstd, gamma, sums, count, dz_split, dz_f32, g_split,
                            dgamma, dbeta, accumulate, param_scale, M, C, s);
 }
 int vfs_relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, long long elems, vfs_stream_t s) {

@@ -8,9 +8,10 @@ namespace vfs {
 
 // x fp32 [M, C] (C multiple of 4): block = 256 threads covering C/4 float4 columns x row groups
 __global__ void channel_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, long long M, int C) {
-  const int c4 = C / 4;
-  const int col = threadIdx.x % c4;          // float4 column
-  const int rgrp = threadIdx.x / c4;         // row group inside the block
+  const int cols_here = min(1024, C - static_cast<int>(blockIdx.y) * 1024);  // this block's column range
+  const int c4 = cols_here / 4;
+  const int col = threadIdx.x % c4 + blockIdx.y * 256;  // float4 column (global)
+  const int rgrp = threadIdx.x / c4;                    // row group inside the block
   const int rows_per_block = blockDim.x / c4;
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   if (rgrp < rows_per_block) {
@@ -95,14 +96,37 @@ __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __rest
   }
 }
 
+// y = y*scale[c] + shift[c] (+ReLU) in place on fp32 [M, C] (BatchNorm1d apply of the two-phase / SyncBN path)
+__global__ void affine_act_kernel(float* __restrict__ y, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, long long total, int C, int relu) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    float v = fmaf(y[i], scale[c], shift[c]);
+    if (relu) v = fmaxf(v, 0.0f);
+    y[i] = v;
+  }
+}
+
+int affine_act_f32(float* y, const float* scale, const float* shift, long long M, int C, int relu, cudaStream_t s) {
+  VFS_REQUIRE(y && scale && shift, VFS_EINVAL, "affine_act: null argument");
+  const long long total = M * C;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  affine_act_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(y, scale, shift, total, C, relu);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
 int channel_stats_f32(const float* x, double* stats, long long M, int C, cudaStream_t s) {
   VFS_REQUIRE(x && stats, VFS_EINVAL, "channel_stats: null argument");
-  VFS_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && C / 4 <= 256, VFS_ESHAPE, "channel_stats: C=%d unsupported", C);
-  const int c4 = C / 4;
+  VFS_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && (C <= 1024 || C % 1024 == 0), VFS_ESHAPE,
+              "channel_stats: C=%d unsupported (multiple of 4, and of 1024 above 1024)", C);
+  const int c4 = (C < 1024 ? C : 1024) / 4;
   const int rows_per_block = 256 / c4;
   long long blocks = (M + rows_per_block - 1) / rows_per_block;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  channel_stats_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(x, stats, M, C);
+  channel_stats_kernel<<<dim3(static_cast<int>(blocks), (C + 1023) / 1024), 256, 0, s>>>(x, stats, M, C);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }

@@ -39,6 +39,7 @@ struct BnBwdArgs {
   const h16* dy_hi; const h16* dy_lo;  // split dY (or null when dy_f32 is used)
   const float* dy_f32;
   const h16* y_hi; const h16* y_lo;    // forward output for the ReLU mask (null: no ReLU)
+  const float* y_f32;                  // same as fp32 (SimSiam head tensors)
   const float* z;                                          // raw conv output fp32 [M, C]
   const float* mean; const float* invstd; const float* gamma;
   double* sums;                                            // [2C] (reduce: accumulated; apply: read)
@@ -59,6 +60,11 @@ __device__ __forceinline__ void bn_bwd_load_g(const BnBwdArgs& a, long long o, f
   if (a.y_hi) {
     float y[8];
     unpack8(*reinterpret_cast<const uint4*>(a.y_hi + o), *reinterpret_cast<const uint4*>(a.y_lo + o), y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.0f) ? g[e] : 0.0f;
+  } else if (a.y_f32) {
+    const float4 p = *reinterpret_cast<const float4*>(a.y_f32 + o), q = *reinterpret_cast<const float4*>(a.y_f32 + o + 4);
+    const float y[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.0f) ? g[e] : 0.0f;
   }
@@ -147,7 +153,8 @@ __global__ void bn_bwd_param_kernel(const double* __restrict__ sums, float* __re
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + db : db;
 }
 
-static int bn_bwd_fill(BnBwdArgs& a, const void* dy_split, const float* dy_f32, const void* y_split, const float* z,
+static int bn_bwd_fill(BnBwdArgs& a, const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32,
+                       const float* z,
                        const float* mean, const float* invstd, const float* gamma, double* sums, double count,
                        void* dz_split, float* dz_f32, void* g_split, long long M, int C) {
   memset(&a, 0, sizeof(a));
@@ -161,6 +168,7 @@ static int bn_bwd_fill(BnBwdArgs& a, const void* dy_split, const float* dy_f32, 
     a.y_hi = reinterpret_cast<const h16*>(y_split);
     a.y_lo = a.y_hi + plane;
   }
+  a.y_f32 = y_f32;
   a.z = z; a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.sums = sums; a.count = count;
   if (dz_split) {
     a.dz_hi = reinterpret_cast<h16*>(dz_split);
@@ -175,12 +183,13 @@ static int bn_bwd_fill(BnBwdArgs& a, const void* dy_split, const float* dy_f32, 
   return VFS_OK;
 }
 
-int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
-                  const float* invstd, double* sums, long long M, int C, cudaStream_t s) {
+int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32, const float* z,
+                  const float* mean, const float* invstd, double* sums, long long M, int C, cudaStream_t s) {
   VFS_REQUIRE((dy_split || dy_f32) && z && mean && invstd && sums, VFS_EINVAL, "bn_bwd_reduce: null argument");
   VFS_REQUIRE(M > 0 && C % 8 == 0 && C / 8 <= 256, VFS_ESHAPE, "bn_bwd_reduce: C=%d unsupported", C);
   BnBwdArgs a;
-  bn_bwd_fill(a, dy_split, dy_f32, y_split, z, mean, invstd, nullptr, sums, 1.0, nullptr, nullptr, nullptr, M, C);
+  bn_bwd_fill(a, dy_split, dy_f32, y_split, y_f32, z, mean, invstd, nullptr, sums, 1.0, nullptr, nullptr, nullptr, M,
+              C);
   const int rows_per_block = 256 / (C / 8);
   long long blocks = (M + rows_per_block - 1) / rows_per_block;
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -189,16 +198,16 @@ int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split
   return VFS_OK;
 }
 
-int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* z, const float* mean,
-                 const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
+int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32, const float* z,
+                 const float* mean, const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
                  float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
                  long long M, int C, cudaStream_t s) {
   VFS_REQUIRE((dy_split || dy_f32) && z && mean && invstd && sums && (dz_split || dz_f32), VFS_EINVAL,
               "bn_bwd_apply: null argument");
   VFS_REQUIRE(M > 0 && C % 8 == 0 && count > 0, VFS_ESHAPE, "bn_bwd_apply: bad shape");
   BnBwdArgs a;
-  bn_bwd_fill(a, dy_split, dy_f32, y_split, z, mean, invstd, gamma, const_cast<double*>(sums), count, dz_split, dz_f32,
-              g_split, M, C);
+  bn_bwd_fill(a, dy_split, dy_f32, y_split, y_f32, z, mean, invstd, gamma, const_cast<double*>(sums), count, dz_split,
+              dz_f32, g_split, M, C);
   const long long total8 = M * C / 8;
   long long blocks = (total8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;

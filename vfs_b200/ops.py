@@ -314,14 +314,24 @@ def linear_forward(x, weight, bias):
     return y
 
 
+def _is_cross_rank_syncbn(bn):
+    import torch.distributed as dist
+    return isinstance(bn, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() \
+        and dist.get_world_size() > 1
+
+
 def bn1d_forward_(y, bn, relu):
     """In-place BatchNorm1d(+ReLU) over y [M,N] with torch's running-stat bookkeeping; returns (mean, invstd,
-    training) for the backward pass.  SyncBatchNorm across ranks is not supported for the head yet."""
+    training) for the backward pass.  SyncBatchNorm in a multi-rank group takes the two-phase path: per-feature
+    sums -> all-reduce -> finalise (running stats) -> affine+ReLU."""
     M, N = y.shape
     training = bn.training or (bn.running_mean is None)
-    if training and isinstance(bn, torch.nn.SyncBatchNorm) and torch.distributed.is_available() \
-            and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-        raise NotImplementedError('vfs_b200: cross-rank SyncBN statistics are not implemented for the SimSiam head')
+    if training and _is_cross_rank_syncbn(bn):
+        stats = channel_stats(y)
+        scale, shift, mean, invstd = bn_finalize(stats, M, bn)    # all-reduces the sums, count = M * world
+        check(nat.lib().vfs_affine_act_f32(ptr(y), ptr(scale), ptr(shift), M, N, int(relu), current_stream()),
+              'affine_act')
+        return mean, invstd, True
     momentum = 0.1 if bn.momentum is None else bn.momentum
     mean = torch.empty((N, ), dtype=torch.float32, device=y.device)
     invstd = torch.empty_like(mean)
@@ -369,9 +379,24 @@ def linear_backward(dy, x, weight, need_dx=True):
     return dx, dW, db
 
 
-def bn1d_backward(dy, pre, out, gamma, mean, invstd, training, relu):
-    """Returns (dpre, dgamma, dbeta)."""
+def bn1d_backward(dy, pre, out, gamma, mean, invstd, training, relu, bn=None):
+    """Returns (dpre, dgamma, dbeta).  With a cross-rank SyncBatchNorm the two per-feature sums are all-reduced
+    (two-phase kernels shared with the backbone's BN backward)."""
     M, N = dy.shape
+    if training and bn is not None and _is_cross_rank_syncbn(bn):
+        sums = torch.zeros((2 * N, ), dtype=torch.float64, device=dy.device)
+        yf = out if relu else None
+        check(nat.lib().vfs_bn_bwd_reduce(None, ptr(dy), None, ptr(yf), ptr(pre), ptr(mean), ptr(invstd), ptr(sums), M,
+                                          N, current_stream()), 'bn_bwd_reduce')
+        count = M * _sync_sums(sums, bn)
+        dpre = torch.empty_like(dy)
+        dg = torch.empty((N, ), dtype=torch.float32, device=dy.device)
+        db = torch.empty_like(dg)
+        check(nat.lib().vfs_bn_bwd_apply(None, ptr(dy), None, ptr(yf), ptr(pre), ptr(mean), ptr(invstd), ptr(gamma),
+                                         ptr(sums), float(count), None, ptr(dpre), None, ptr(dg), ptr(db), 0, 1.0, M, N,
+                                         current_stream()), 'bn_bwd_apply')
+        LAUNCHES[0] += 1
+        return dpre, dg, db
     dpre = torch.empty_like(dy)
     dg = torch.empty((N, ), dtype=torch.float32, device=dy.device)
     db = torch.empty_like(dg)
@@ -423,15 +448,15 @@ def bn_backward(dy, y_for_relu, z, mean, invstd, bn, want_g=False, dy_is_f32=Fal
     M = N * H * W
     sums = torch.zeros((2 * C, ), dtype=torch.float64, device=z.device)
     dys, dyf = (None, dy) if dy_is_f32 else (dy, None)
-    check(nat.lib().vfs_bn_bwd_reduce(ptr(dys), ptr(dyf), ptr(y_for_relu), ptr(z), ptr(mean), ptr(invstd), ptr(sums),
-                                      M, C, current_stream()), 'bn_bwd_reduce')
+    check(nat.lib().vfs_bn_bwd_reduce(ptr(dys), ptr(dyf), ptr(y_for_relu), None, ptr(z), ptr(mean), ptr(invstd),
+                                      ptr(sums), M, C, current_stream()), 'bn_bwd_reduce')
     count = M * _sync_sums(sums, bn)
     dz = torch.empty((N, H, W, C), dtype=torch.float32, device=z.device) if want_f32 else \
         torch.empty((2, N, H, W, C), dtype=torch.float16, device=z.device)
     g = torch.empty((2, N, H, W, C), dtype=torch.float16, device=z.device) if want_g else None
     dg = torch.empty((C, ), dtype=torch.float32, device=z.device)
     db = torch.empty_like(dg)
-    check(nat.lib().vfs_bn_bwd_apply(ptr(dys), ptr(dyf), ptr(y_for_relu), ptr(z), ptr(mean), ptr(invstd),
+    check(nat.lib().vfs_bn_bwd_apply(ptr(dys), ptr(dyf), ptr(y_for_relu), None, ptr(z), ptr(mean), ptr(invstd),
                                      ptr(bn.weight.detach()) if bn.affine else None, ptr(sums), float(count),
                                      None if want_f32 else ptr(dz), ptr(dz) if want_f32 else None, ptr(g), ptr(dg),
                                      ptr(db), 0, float(param_scale), M, C, current_stream()), 'bn_bwd_apply')
