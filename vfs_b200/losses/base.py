@@ -1,19 +1,20 @@
-"""Weighted-loss base class (interface of mmaction/models/losses/base.py:6-37)."""
-from abc import ABCMeta, abstractmethod
+"""Loss base class with the reference's contract (mmaction/models/losses/base.py): subclasses provide ``_forward``;
+calling the module returns ``loss_weight * _forward(...)``."""
+import abc
 
-import torch.nn as nn
+from torch import nn
 
 
-class BaseWeightedLoss(nn.Module, metaclass=ABCMeta):
-    """Subclasses implement ``_forward``; ``forward`` multiplies by ``loss_weight``."""
+class BaseWeightedLoss(nn.Module, abc.ABC):
 
     def __init__(self, loss_weight=1.0):
-        super().__init__()
+        nn.Module.__init__(self)
         self.loss_weight = loss_weight
 
-    @abstractmethod
+    @abc.abstractmethod
     def _forward(self, *args, **kwargs):
-        pass
+        """Unweighted loss."""
 
     def forward(self, *args, **kwargs):
-        return self._forward(*args, **kwargs) * self.loss_weight
+        unweighted = self._forward(*args, **kwargs)
+        return unweighted * self.loss_weight

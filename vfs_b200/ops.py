@@ -388,12 +388,13 @@ def bn1d_backward(dy, pre, out, gamma, mean, invstd, training, relu, bn=None):
         yf = out if relu else None
         check(nat.lib().vfs_bn_bwd_reduce(None, ptr(dy), None, ptr(yf), ptr(pre), ptr(mean), ptr(invstd), ptr(sums), M,
                                           N, current_stream()), 'bn_bwd_reduce')
-        count = M * _sync_sums(sums, bn)
+        world = _sync_sums(sums, bn)
+        count = M * world
         dpre = torch.empty_like(dy)
         dg = torch.empty((N, ), dtype=torch.float32, device=dy.device)
         db = torch.empty_like(dg)
         check(nat.lib().vfs_bn_bwd_apply(None, ptr(dy), None, ptr(yf), ptr(pre), ptr(mean), ptr(invstd), ptr(gamma),
-                                         ptr(sums), float(count), None, ptr(dpre), None, ptr(dg), ptr(db), 0, 1.0, M, N,
+                                         ptr(sums), float(count), None, ptr(dpre), None, ptr(dg), ptr(db), 0, 1.0 / world, M, N,
                                          current_stream()), 'bn_bwd_apply')
         LAUNCHES[0] += 1
         return dpre, dg, db
@@ -450,7 +451,11 @@ def bn_backward(dy, y_for_relu, z, mean, invstd, bn, want_g=False, dy_is_f32=Fal
     dys, dyf = (None, dy) if dy_is_f32 else (dy, None)
     check(nat.lib().vfs_bn_bwd_reduce(ptr(dys), ptr(dyf), ptr(y_for_relu), None, ptr(z), ptr(mean), ptr(invstd),
                                       ptr(sums), M, C, current_stream()), 'bn_bwd_reduce')
-    count = M * _sync_sums(sums, bn)
+    world = _sync_sums(sums, bn)
+    count = M * world
+    # dgamma/dbeta come out of the all-reduced sums, i.e. already summed over ranks; the data-parallel gradient
+    # all-reduce averages parameter gradients afterwards, so hand it this rank's 1/world share.
+    param_scale = param_scale / world
     dz = torch.empty((N, H, W, C), dtype=torch.float32, device=z.device) if want_f32 else \
         torch.empty((2, N, H, W, C), dtype=torch.float16, device=z.device)
     g = torch.empty((2, N, H, W, C), dtype=torch.float16, device=z.device) if want_g else None

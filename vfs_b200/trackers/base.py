@@ -1,85 +1,92 @@
-"""Tracker base class -- interface of mmaction/models/trackers/base.py:12-178."""
-from abc import ABCMeta, abstractmethod
+"""Tracker base class with the reference's interface (mmaction/models/trackers/base.py:12-178): constructor
+arguments, the ``forward(imgs, return_loss=...)`` switch, and ``train_step`` / ``val_step`` returning
+``dict(loss, log_vars, num_samples)`` for mmcv's runner."""
+import abc
 from collections import OrderedDict
 
 import torch
 import torch.distributed as dist
-import torch.nn as nn
+from torch import nn
 
 from .. import builder
 
 
-class BaseTracker(nn.Module, metaclass=ABCMeta):
-    """Owns ``backbone`` (and optionally ``cls_head``); subclasses define ``forward_train`` / ``forward_test``."""
+def _batch_size(data_batch):
+    return len(next(iter(data_batch.values())))
+
+
+def _reduce_entry(name, value):
+    if torch.is_tensor(value):
+        return value.mean()
+    if isinstance(value, list):
+        return sum(item.mean() for item in value)
+    raise TypeError(f'{name} is not a tensor or list of tensors')
+
+
+class BaseTracker(nn.Module, abc.ABC):
+    """Holds ``backbone`` (built from its config) and optionally ``cls_head``; the buffer ``iteration`` counts
+    ``train_step`` calls and is part of the checkpoint, like in the reference."""
 
     def __init__(self, backbone, cls_head=None, train_cfg=None, test_cfg=None):
-        super().__init__()
+        nn.Module.__init__(self)
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.fp16_enabled = False
         self.backbone = builder.build_backbone(backbone)
         if cls_head is not None:
             self.cls_head = builder.build_head(cls_head)
-        self.train_cfg = train_cfg
-        self.test_cfg = test_cfg
         self.init_weights()
-        self.fp16_enabled = False
         self.register_buffer('iteration', torch.tensor(0, dtype=torch.float))
 
+    # -- to be provided by the concrete tracker ---------------------------------------------------------
+    @abc.abstractmethod
+    def forward_train(self, imgs, labels):
+        ...
+
+    @abc.abstractmethod
+    def forward_test(self, imgs, **kwargs):
+        ...
+
+    # -- shared behaviour -----------------------------------------------------------------------------------
     @property
     def with_cls_head(self):
-        return hasattr(self, 'cls_head') and self.cls_head is not None
+        return getattr(self, 'cls_head', None) is not None
 
     def init_weights(self):
-        self.backbone.init_weights()
-        if self.with_cls_head:
-            self.cls_head.init_weights()
+        for part in (self.backbone, self.cls_head if self.with_cls_head else None):
+            if part is not None:
+                part.init_weights()
 
     def extract_feat(self, imgs):
         return self.backbone(imgs)
 
-    @abstractmethod
-    def forward_train(self, imgs, labels):
-        pass
-
-    @abstractmethod
-    def forward_test(self, imgs, **kwargs):
-        pass
+    def forward(self, imgs, return_loss=True, **kwargs):
+        step = self.forward_train if return_loss else self.forward_test
+        return step(imgs, **kwargs)
 
     @staticmethod
     def _parse_losses(losses):
-        """mean every entry, sum the ones whose key contains 'loss', average logged scalars across ranks
-        (reference base.py:76-110).  The per-key all-reduce + ``.item()`` of the reference is batched into ONE
-        all-reduce and ONE device->host copy per step (same logged values, one host sync instead of 2+)."""
-        log_vars = OrderedDict()
-        for name, value in losses.items():
-            if isinstance(value, torch.Tensor):
-                log_vars[name] = value.mean()
-            elif isinstance(value, list):
-                log_vars[name] = sum(v.mean() for v in value)
-            else:
-                raise TypeError(f'{name} is not a tensor or list of tensors')
-        loss = sum(v for k, v in log_vars.items() if 'loss' in k)
-        log_vars['loss'] = loss
-        keys = list(log_vars)
-        packed = torch.stack([log_vars[k].detach().float().reshape(()) for k in keys])
+        """Loss dict -> (total loss tensor, OrderedDict of python floats).  Every entry is averaged; the total is the
+        sum of the entries whose key contains 'loss'; logged values are averaged over ranks (reference
+        base.py:76-110).  The reference does one all-reduce and one ``.item()`` per key; here all keys are packed
+        into one vector: ONE all-reduce and ONE device->host copy per step, same logged values."""
+        reduced = OrderedDict((name, _reduce_entry(name, value)) for name, value in losses.items())
+        total = sum(v for name, v in reduced.items() if 'loss' in name)
+        reduced['loss'] = total
+        packed = torch.stack([v.detach().float().reshape(()) for v in reduced.values()])
         if dist.is_available() and dist.is_initialized():
-            packed = packed / dist.get_world_size()
+            packed /= dist.get_world_size()
             dist.all_reduce(packed)
-        for k, v in zip(keys, packed.tolist()):
-            log_vars[k] = v
-        return loss, log_vars
+        log_vars = OrderedDict(zip(reduced.keys(), packed.tolist()))
+        return total, log_vars
 
-    def forward(self, imgs, return_loss=True, **kwargs):
-        if return_loss:
-            return self.forward_train(imgs, **kwargs)
-        return self.forward_test(imgs, **kwargs)
+    def _step_outputs(self, losses, data_batch):
+        loss, log_vars = self._parse_losses(losses)
+        return dict(loss=loss, log_vars=log_vars, num_samples=_batch_size(data_batch))
 
     def train_step(self, data_batch, optimizer, **kwargs):
-        """Returns ``dict(loss, log_vars, num_samples)`` (reference base.py:119-156)."""
         self.iteration += 1
-        losses = self(**data_batch)
-        loss, log_vars = self._parse_losses(losses)
-        return dict(loss=loss, log_vars=log_vars, num_samples=len(next(iter(data_batch.values()))))
+        return self._step_outputs(self(**data_batch), data_batch)
 
     def val_step(self, data_batch, optimizer, **kwargs):
         losses = self(data_batch['imgs'], data_batch['ref_seg_map'], data_batch['img_meta'])
-        loss, log_vars = self._parse_losses(losses)
-        return dict(loss=loss, log_vars=log_vars, num_samples=len(next(iter(data_batch.values()))))
+        return self._step_outputs(losses, data_batch)
