@@ -184,6 +184,12 @@ int vfs_debug_conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const
                                const float* shift, const void* residual_split, float* out_f32_nhwc,
                                vfs_stream_t s);
 
+/* Performance instrument: while `buffer` (device memory, 148 CTAs x 3 roles x events_per_role x 2 int64) is set,
+ * vfs_conv_bn_act / vfs_conv_stats / vfs_conv_dgrad launches record an in-kernel timeline of (event code, SM
+ * clock) pairs per CTA for the TMA warp (role 0), the MMA warp (1) and the first epilogue warp (2); see
+ * tools/conv_trace.py.  Pass NULL to switch it off (the default; the product path never enables it). */
+int vfs_debug_conv_trace(long long* buffer, int events_per_role);
+
 /* ------------------------------------------------------------------------------------------------
  * Restricted-attention label propagation (DAVIS inference).  Replaces masked_attention_efficient,
  * mmaction/models/common/local_attention.py:237-348 (F.normalize :277-279, einsum :289-291, masked_fill

@@ -1,0 +1,68 @@
+"""Runs a handful of representative conv layers of the bench workload (and the batched attention) in isolation so
+that `ncu -k regex:conv_tc_kernel` sees a short, known launch sequence.  Also prints CUDA-event timings per layer
+(L2 flushed between launches) when run without a profiler.
+
+    python tools/profile_layers.py [--iters 3] [--only NAME]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from vfs_b200 import ops  # noqa: E402
+
+# name: (N, H, W, Cin, Cout, k, stride, residual)
+LAYERS = {
+    'l1_reduce_64_64': (16, 64, 64, 64, 64, 1, 1, False),
+    'l1_3x3_64': (16, 64, 64, 64, 64, 3, 1, False),
+    'l1_expand_64_256_res': (16, 64, 64, 64, 256, 1, 1, True),
+    'l2_3x3_128': (16, 32, 32, 128, 128, 3, 1, False),
+    'l2_expand_128_512_res': (16, 32, 32, 128, 512, 1, 1, True),
+    'l3_reduce_1024_256': (16, 32, 32, 1024, 256, 1, 1, False),
+    'l3_3x3_256': (16, 32, 32, 256, 256, 3, 1, False),
+    'l3_expand_256_1024_res': (16, 32, 32, 256, 1024, 1, 1, True),
+    'l3_down_512_1024': (16, 32, 32, 512, 1024, 1, 1, False),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--iters', type=int, default=3)
+    ap.add_argument('--only', default=None)
+    a = ap.parse_args()
+    dev = torch.device('cuda', 0)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    for name, (N, H, W, Cin, Cout, k, s, res) in LAYERS.items():
+        if a.only and a.only not in name:
+            continue
+        x = ops.to_split(torch.randn(N, Cin, H, W, device=dev, generator=g))
+        w = torch.randn(Cout, Cin, k, k, device=dev, generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+        wp = ops.pack_conv_weight(w)
+        scale = torch.rand(Cout, device=dev, generator=g) + 0.5
+        shift = torch.randn(Cout, device=dev, generator=g) * 0.1
+        Ho, Wo = ops.conv_out_hw(H, W, k, s, 1)
+        r = ops.to_split(torch.randn(N, Cout, Ho, Wo, device=dev, generator=g)) if res else None
+        times = []
+        for _ in range(a.iters):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.conv_bn_act(x, wp, scale, shift, k, s, 1, True, r)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) * 1e3)
+        flops = 2.0 * N * Ho * Wo * Cout * Cin * k * k
+        bytes_ = 4.0 * N * (H * W * Cin + Ho * Wo * Cout * (2 if res else 1))
+        t = min(times)
+        print(f'{name:26s} {t:7.1f} us  {flops / t / 1e6:7.1f} TF(alg)  {bytes_ / t / 1e3:7.1f} GB/s(alg)  '
+              f'floor_hbm {bytes_ / 6.4934e6:5.1f} us  floor_mma {3 * flops / 1.4688e9:5.1f} us')
+    print('overflow', ops.overflow_count())
+
+
+if __name__ == '__main__':
+    main()

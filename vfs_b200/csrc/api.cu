@@ -82,6 +82,7 @@ int make_tmap_16b_sw128(CUtensorMap* out, const void* base, int rank, const uint
 int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
                    const float* shift, const void* residual_split, void* out_split, float* out_f32,
                    double* stats, cudaStream_t stream);
+int conv_set_trace(long long* buffer, int events_per_role);
 int conv_dgrad_tc(const VfsConvDesc* d, const void* dz_split, const void* wt_split, const float* ones,
                   const float* zeros, const void* add_split, void* dx_split, cudaStream_t stream);
 int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, int k, cudaStream_t s);
@@ -307,6 +308,10 @@ int vfs_debug_conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const
                                const float* shift, const void* residual_split, float* out_f32_nhwc,
                                vfs_stream_t s) {
   return vfs::conv_bn_act_simt(d, in_split, w_split, scale, shift, residual_split, out_f32_nhwc, s);
+}
+
+int vfs_debug_conv_trace(long long* buffer, int events_per_role) {
+  return vfs::conv_set_trace(buffer, events_per_role);
 }
 
 int vfs_features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,

@@ -58,6 +58,30 @@ struct alignas(64) ConvKernelParams {
   double* stat_sqsum;  // (train-mode BatchNorm statistics; accumulated with fp64 atomics)
 };
 
+// Optional in-kernel timeline (debug instrument, vfs_debug_conv_trace): lane 0 of the TMA warp, the MMA warp and the
+// first epilogue warp append (code, clock64) pairs to a per-CTA, per-role region of a caller-provided buffer.
+__device__ long long* g_conv_trace = nullptr;
+__device__ int g_conv_trace_cap = 0;
+
+struct TraceCursor {
+  long long* base;
+  int cap, n;
+  __device__ __forceinline__ void init(int role) {
+    long long* t = g_conv_trace;
+    cap = g_conv_trace_cap;
+    n = 0;
+    base = (t != nullptr && (threadIdx.x & 31) == 0) ? t + (static_cast<size_t>(blockIdx.x) * 3 + role) * cap * 2
+                                                     : nullptr;
+  }
+  __device__ __forceinline__ void mark(int code) {
+    if (base != nullptr && n < cap) {
+      base[2 * n] = code;
+      base[2 * n + 1] = clock64();
+      ++n;
+    }
+  }
+};
+
 template <int BN, int STAGES>
 struct ConvSmem {
   static constexpr int kTileBBytes = BN * kBlockK * 2;                    // one plane of the weight tile
@@ -119,6 +143,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     // ======================= TMA producer =======================
     int stage = 0;
     uint32_t phase = 0;
+    TraceCursor tr;
+    tr.init(0);
+    tr.mark(0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
@@ -129,6 +156,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.tn;
       for (int kc = 0; kc < num_kchunks; ++kc) {
         mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
+        tr.mark(1);
         if (lane == 0) {
           const int tap = kc / p.kchunks_per_tap;
           const int c0 = (kc - tap * p.kchunks_per_tap) * kBlockK;
@@ -153,12 +181,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
+    TraceCursor tr;
+    tr.init(1);
+    tr.mark(0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(tempty_bar(as), aphase ^ 1u, 200 + as);
+      tr.mark(8);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int kc = 0; kc < num_kchunks; ++kc) {
         mbar_wait(full_bar(stage), phase, 300 + stage);
+        tr.mark(2);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_base + stage * S::kStageBytes;
@@ -178,6 +211,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
           if (kc == num_kchunks - 1) umma_commit(tfull_bar(as));
         }
+        if (kc == num_kchunks - 1) tr.mark(3);
         __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
@@ -204,6 +238,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     auto phys_chunk = [](int r, int c) { return (c & 8) | ((c ^ (c >> 3) ^ r) & 7); };
     int as = 0;
     uint32_t aphase = 0;
+    TraceCursor tr;
+    tr.init(2);
+    if (ew != 0) tr.base = nullptr;
+    tr.mark(0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
@@ -226,7 +264,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
                        p.Cout + n_tile * BN + piece * 8;
       }
 
+      tr.mark(4);
       mbar_wait(tfull_bar(as), aphase, 400 + as);
+      tr.mark(5);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 #pragma unroll 1
@@ -267,6 +307,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // staging buffer full
+        tr.mark(6);
         float st_s[8], st_q[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) st_s[e] = st_q[e] = 0.0f;
@@ -325,6 +366,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
             }
           }
         }
+        tr.mark(7);
         if (p.stat_sum != nullptr) {
           // lanes {l, l+8, l+16, l+24} hold the same 8 channels for different rows: fold them, then one fp64
           // atomic per channel and warp
@@ -609,6 +651,12 @@ int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_spl
 // four output-parity classes (dX[2a+pa, 2b+pb] only receives the taps with matching parity), each one launch that
 // writes its strided view of dX; positions no tap reaches get the plain `add` term (or zero).
 // ------------------------------------------------------------------------------------------------
+int conv_set_trace(long long* buffer, int events_per_role) {
+  VFS_CUDA_OK(cudaMemcpyToSymbol(g_conv_trace, &buffer, sizeof(buffer)));
+  VFS_CUDA_OK(cudaMemcpyToSymbol(g_conv_trace_cap, &events_per_role, sizeof(events_per_role)));
+  return VFS_OK;
+}
+
 int conv_dgrad_tc(const VfsConvDesc* d, const void* dz_split, const void* wt_split, const float* ones,
                   const float* zeros, const void* add_split, void* dx_split, cudaStream_t stream) {
   VFS_REQUIRE(d && dz_split && wt_split && ones && zeros && dx_split, VFS_EINVAL, "conv_dgrad: null argument");
