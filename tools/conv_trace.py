@@ -52,7 +52,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     nat.check(nat.lib().vfs_debug_conv_trace(None, 0), 'trace off')
-    ghz = torch.cuda.clock_rate() / 1e6 if hasattr(torch.cuda, 'clock_rate') else 1.965
+    ghz = 1.965  # SM clock in GHz (cycles -> ns); B200 boost clock, see bench.py clocks
     t = buf.cpu().view(148, 3, CAP, 2)
     print(f'{a.layer}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us (traced), assuming {ghz:.3f} GHz')
     roles = ('tma', 'mma', 'epi')
@@ -64,7 +64,7 @@ def main():
             continue
         span = (ev[-1][1] - t0) / ghz
         print(f'-- {name}: {len(ev)} events, last at {span:.0f} ns')
-        lim = {'tma': 40, 'mma': 40, 'epi': 8 * a.tiles + 2}[name]
+        lim = {'tma': 40, 'mma': 40, 'epi': 16 * a.tiles + 2}[name]
         prev = t0
         line = []
         for c, v in ev[:lim]:

@@ -28,11 +28,25 @@ def pil_nearest_index_map(src_size, dst_size):
     return np.clip(idx, 0, src_size - 1)
 
 
+_INDEX_MAP_CACHE = {}
+
+
+def _device_index_map(src_size, dst_size, device):
+    """Index map of one axis as a device tensor, built once per (sizes, device): a pageable host->device copy per
+    call would synchronise the stream in the middle of the tracker's per-video loop."""
+    key = (int(src_size), int(dst_size), str(device))
+    t = _INDEX_MAP_CACHE.get(key)
+    if t is None:
+        t = torch.from_numpy(pil_nearest_index_map(src_size, dst_size)).to(device)
+        _INDEX_MAP_CACHE[key] = t
+    return t
+
+
 def pil_nearest_interpolate(input, size):
     """Nearest resize with Pillow semantics; ``input`` [N,1,H,W], ``size`` (h, w) -> [N,1,h,w]."""
     assert input.ndim == 4 and input.size(1) == 1
-    rows = torch.from_numpy(pil_nearest_index_map(input.size(2), size[0])).to(input.device)
-    cols = torch.from_numpy(pil_nearest_index_map(input.size(3), size[1])).to(input.device)
+    rows = _device_index_map(input.size(2), size[0], input.device)
+    cols = _device_index_map(input.size(3), size[1], input.device)
     return input.index_select(2, rows).index_select(3, cols)
 
 

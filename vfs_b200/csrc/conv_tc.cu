@@ -25,13 +25,18 @@ namespace vfs {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 B = one swizzle row
 constexpr int kTileABytes = kBlockM * kBlockK * 2;  // one plane of the activation tile (16 KB)
-constexpr int kNumThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kChunkBytes = kBlockM * 64 * 2 * 2;  // one 64-column output chunk, hi + lo planes (32 KB)
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue math (two per TMEM lane quarter), warp 10 epilogue TMA
+// (tensor stores + residual loads; idle in the legacy epilogue)
+constexpr int kNumThreads = 352;
 constexpr int kMaxTaps = 9;
 constexpr int kMaxViews = 4;
 
 struct alignas(64) ConvKernelParams {
   CUtensorMap tmap_a[kMaxViews];  // activation views (one per stride-parity), dims {C, Wv, Hv, N, 2}
   CUtensorMap tmap_b;             // weights, dims {K, Cout, 2}
+  CUtensorMap tmap_out;           // TMA epilogue: output view, dims {Cout, Wo, Ho, N, 2}, box {64, tw, th, tn, 2}
+  CUtensorMap tmap_res;           // TMA epilogue: residual through the same view
   int num_m_tiles, num_n_tiles;
   int tiles_w, tiles_h;  // m_tile = (tn_i * tiles_h + th_i) * tiles_w + tw_i
   int tw, th, tn;        // tile extent in pixels, tw*th*tn == 128
@@ -82,18 +87,24 @@ struct TraceCursor {
   }
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBUF>
 struct ConvSmem {
   static constexpr int kTileBBytes = BN * kBlockK * 2;                    // one plane of the weight tile
   static constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // hi+lo of A and B
-  static constexpr int kStagingBytes = kBlockM * 64 * 4;  // epilogue transpose buffer: 128 rows x 64 fp32 columns
-  static constexpr int kBarrierBytes = 256;
+  // epilogue staging: legacy (NBUF == 0) one 128 x 64 fp32 transpose tile; TMA epilogue NBUF output chunks
+  static constexpr int kStagingBytes = (NBUF == 0) ? kBlockM * 64 * 4 : NBUF * kChunkBytes;
+  static constexpr int kBarrierBytes = 256;  // 8 B x (2*STAGES + 4 pipeline + tmem ptr + 3 x 4 epilogue) <= 200
   static constexpr int kTotal = STAGES * kStageBytes + kStagingBytes + kBarrierBytes + 1024;  // +1024 align slack
 };
 
-template <int BN, int STAGES>
+// NBUF == 0: legacy epilogue (fp32 transpose tile, direct global stores; fp32 output and BN statistics supported).
+// NBUF  > 0: TMA epilogue (split output only): results staged as hi/lo planes in the 128B-swizzled box layout and
+//            written with one cp.async.bulk.tensor store per 64-column chunk; RES adds a residual that is brought in by
+//            TMA into the same staging buffer NBUF-1 chunks ahead.
+template <int BN, int STAGES, int NBUF, bool RES>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
-  using S = ConvSmem<BN, STAGES>;
+  using S = ConvSmem<BN, STAGES, NBUF>;
+  static_assert(!RES || NBUF >= 2, "the residual prefetch needs at least two staging buffers");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = smem_base + STAGES * S::kStageBytes;
@@ -104,6 +115,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + b); };   // residual chunk landed
+  auto staged_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 9 + b); };  // output chunk written to smem
+  auto free_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 13 + b); };   // store finished reading the buffer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,6 +133,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 8);
+    }
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(rfull_bar(b), 1);
+      mbar_init(staged_bar(b), 8);
+      mbar_init(free_bar(b), 1);
+    }
+    if (NBUF > 0) {
+      tma_prefetch_desc(&p.tmap_out);
+      if (RES) tma_prefetch_desc(&p.tmap_res);
     }
     fence_mbar_init();
   }
@@ -223,8 +246,179 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         aphase ^= 1u;
       }
     }
-  } else {
-    // ======================= epilogue (warps 2..9) =======================
+  } else if (warp == 10) {
+    // ======================= epilogue TMA warp =======================
+    // Per 64-column chunk g (staging buffer g % NBUF): wait until the eight math warps have staged it, issue the
+    // tensor store, then recycle the buffer the previous store has finished reading -- for RES by loading the
+    // residual of chunk g + NBUF - 1 into it, otherwise by signalling it free.
+    if constexpr (NBUF > 0) {
+      constexpr int kCPT = BN / 64;  // chunks per tile
+      auto chunk_coords = [&](int g, int& cc, int& w0, int& h0, int& n0) -> bool {
+        const int tile = blockIdx.x + (g / kCPT) * gridDim.x;
+        if (tile >= num_tiles) return false;
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int tw_i = m_tile % p.tiles_w;
+        const int t2 = m_tile / p.tiles_w;
+        cc = n_tile * BN + (g % kCPT) * 64;
+        w0 = tw_i * p.tw;
+        h0 = (t2 % p.tiles_h) * p.th;
+        n0 = (t2 / p.tiles_h) * p.tn;
+        return true;
+      };
+      auto issue_res = [&](int g) {
+        int cc, w0, h0, n0;
+        if (chunk_coords(g, cc, w0, h0, n0)) {
+          const int b = g % NBUF;
+          mbar_arrive_expect_tx(rfull_bar(b), kChunkBytes);
+          tma_load_5d(stg_base + b * kChunkBytes, &p.tmap_res, rfull_bar(b), cc, w0, h0, n0, 0);
+        }
+      };
+      if (lane == 0) {
+        if (RES) {
+          for (int g0 = 0; g0 < NBUF - 1; ++g0) issue_res(g0);
+        }
+        int cc, w0, h0, n0;
+        for (int g = 0; chunk_coords(g, cc, w0, h0, n0); ++g) {
+          const int b = g % NBUF;
+          mbar_wait(staged_bar(b), (g / NBUF) & 1, 600 + b);
+          tma_store_5d(&p.tmap_out, stg_base + b * kChunkBytes, cc, w0, h0, n0, 0);
+          bulk_commit_group();
+          if (RES) {
+            bulk_wait_group_read<1>();  // the previous chunk's store has released its buffer ...
+            issue_res(g + NBUF - 1);    // ... which receives the residual of chunk g + NBUF - 1
+          } else {
+            bulk_wait_group_read<NBUF - 1>();  // store g - (NBUF - 1) has released its buffer
+            if (g >= NBUF - 1) mbar_arrive(free_bar((g - (NBUF - 1)) % NBUF));
+          }
+        }
+        bulk_wait_group_all();
+      }
+    }
+  } else if constexpr (NBUF > 0) {
+    // ======================= TMA epilogue, math warps 2..9 =======================
+    // thread = accumulator row (pixel) x 32 of the chunk's 64 columns: TMEM -> registers -> scale/shift (+residual read
+    // from the staging buffer) -> ReLU -> split -> hi/lo planes of the staging buffer in the swizzled box layout.
+    // No per-pixel address arithmetic, no bounds checks (TMA clips), no block-wide barrier: each thread only touches
+    // its own 8 x 16 bytes of the buffer, hand-over to / from the TMA warp goes through mbarriers.
+    const int ew = warp - 2;
+    const int q = warp & 3;   // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+    const int ch = ew >> 2;   // which 32-column half of the 64-column chunk
+    const int row = q * 32 + lane;
+    constexpr int kCPT = BN / 64;  // chunks per tile
+    uint32_t off[4];               // byte offsets of this thread's four 16-byte pieces inside one plane
+#pragma unroll
+    for (int j = 0; j < 4; ++j) off[j] = row * 128 + (((ch * 4 + j) ^ (row & 7)) << 4);
+    const float lo_clamp = p.relu ? 0.0f : -INFINITY;
+    float amax = 0.0f;
+    TraceCursor tr;
+    tr.init(2);
+    if (ew != 0) tr.base = nullptr;
+    tr.mark(0);
+    int as = 0;
+    uint32_t aphase = 0;
+    int g = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.num_n_tiles;
+      // pull this tile's scale / shift lines into L1 while the accumulator is still being produced
+      if (lane < BN / 16) {
+        const float* base = (lane < BN / 32) ? p.scale : p.shift;
+        const int line = (lane < BN / 32) ? lane : lane - BN / 32;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(base + n_tile * BN + line * 32));
+      }
+      tr.mark(4);
+      mbar_wait(tfull_bar(as), aphase, 400 + as);
+      tr.mark(5);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < kCPT; ++c, ++g) {
+        const int b = g % NBUF;
+        const uint32_t buf = stg_base + b * kChunkBytes;
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(t_row + c * 64 + ch * 32, acc);
+        tmem_ld_wait();
+        if (c == kCPT - 1) {  // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        tr.mark(9);
+        if (RES) mbar_wait(rfull_bar(b), (g / NBUF) & 1, 500 + b);
+        tr.mark(10);
+        uint4 oh[4], ol[4];
+        uint4 rh[4], rl[4];
+        if (RES) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(rh[j].x), "=r"(rh[j].y), "=r"(rh[j].z), "=r"(rh[j].w) : "r"(buf + off[j]));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(rl[j].x), "=r"(rl[j].y), "=r"(rl[j].z), "=r"(rl[j].w)
+                         : "r"(buf + kChunkBytes / 2 + off[j]));
+          }
+        }
+        const float* sc_ptr = p.scale + n_tile * BN + c * 64 + ch * 32;
+        const float* sh_ptr = p.shift + n_tile * BN + c * 64 + ch * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 sc0 = __ldg(reinterpret_cast<const float4*>(sc_ptr + 8 * j));
+          const float4 sc1 = __ldg(reinterpret_cast<const float4*>(sc_ptr + 8 * j + 4));
+          const float4 sh0 = __ldg(reinterpret_cast<const float4*>(sh_ptr + 8 * j));
+          const float4 sh1 = __ldg(reinterpret_cast<const float4*>(sh_ptr + 8 * j + 4));
+          float2 y[4];
+          y[0] = fma2(make_float2(__uint_as_float(acc[8 * j]), __uint_as_float(acc[8 * j + 1])),
+                      make_float2(sc0.x, sc0.y), make_float2(sh0.x, sh0.y));
+          y[1] = fma2(make_float2(__uint_as_float(acc[8 * j + 2]), __uint_as_float(acc[8 * j + 3])),
+                      make_float2(sc0.z, sc0.w), make_float2(sh0.z, sh0.w));
+          y[2] = fma2(make_float2(__uint_as_float(acc[8 * j + 4]), __uint_as_float(acc[8 * j + 5])),
+                      make_float2(sc1.x, sc1.y), make_float2(sh1.x, sh1.y));
+          y[3] = fma2(make_float2(__uint_as_float(acc[8 * j + 6]), __uint_as_float(acc[8 * j + 7])),
+                      make_float2(sc1.z, sc1.w), make_float2(sh1.z, sh1.w));
+          if (RES) {
+            y[0] = add2(add2(y[0], h2_to_float2(rl[j].x)), h2_to_float2(rh[j].x));
+            y[1] = add2(add2(y[1], h2_to_float2(rl[j].y)), h2_to_float2(rh[j].y));
+            y[2] = add2(add2(y[2], h2_to_float2(rl[j].z)), h2_to_float2(rh[j].z));
+            y[3] = add2(add2(y[3], h2_to_float2(rl[j].w)), h2_to_float2(rh[j].w));
+          }
+          uint32_t h2[4], l2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            y[e].x = fmaxf(y[e].x, lo_clamp);
+            y[e].y = fmaxf(y[e].y, lo_clamp);
+            amax = fmaxf(amax, fmaxf(fabsf(y[e].x), fabsf(y[e].y)));
+            const __half2 h = __floats2half2_rn(y[e].x, y[e].y);
+            const float2 d = sub2(y[e], __half22float2(h));
+            const __half2 l = __floats2half2_rn(d.x, d.y);
+            h2[e] = *reinterpret_cast<const uint32_t*>(&h);
+            l2[e] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          oh[j] = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+          ol[j] = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+        }
+        tr.mark(11);
+        // RES: the landed residual implies the buffer was free; otherwise wait for the store NBUF chunks ago
+        if (!RES) mbar_wait(free_bar(b), ((g / NBUF) & 1) ^ 1u, 700 + b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + off[j]), "r"(oh[j].x), "r"(oh[j].y),
+                       "r"(oh[j].z), "r"(oh[j].w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + kChunkBytes / 2 + off[j]), "r"(ol[j].x),
+                       "r"(ol[j].y), "r"(ol[j].z), "r"(ol[j].w) : "memory");
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(staged_bar(b));
+        tr.mark(7);
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
+      }
+    }
+    if (!(amax <= 65504.0f)) atomicAdd(&g_split_overflow, 1u);
+  } else if (warp < 10) {
+    // ======================= legacy epilogue (warps 2..9) =======================
     // Phase A (thread = accumulator row, warp = 32 rows x 32 of the chunk's 64 columns): TMEM -> fp32 staging tile
     // in shared memory (16-byte chunks XOR-swizzled so both phases are bank-conflict free).
     // Phase B (8 threads per pixel row, 8 channels each): staging -> scale/shift (+residual) -> ReLU -> split ->
@@ -426,12 +620,13 @@ void choose_tile(int Wo, int Ho, int N, int* tw, int* th, int* tn) {
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBUF, bool RES>
 int launch(const ConvKernelParams& p, int grid, cudaStream_t stream) {
-  using S = ConvSmem<BN, STAGES>;
+  using S = ConvSmem<BN, STAGES, NBUF>;
+  static_assert(S::kTotal <= 232448, "shared memory budget (227 KB) exceeded");
   static bool configured = false;
   if (!configured) {
-    VFS_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VFS_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, NBUF, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      S::kTotal));
     configured = true;
   }
@@ -446,7 +641,7 @@ int launch(const ConvKernelParams& p, int grid, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VFS_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES>, p));
+  VFS_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, NBUF, RES>, p));
   return VFS_OK;
 }
 
@@ -577,9 +772,63 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int sms = device_sm_count();
   const int grid = num_tiles < sms ? num_tiles : sms;
-  if (BN == 256) return launch<256, 2>(p, grid, stream);
-  if (BN == 128) return launch<128, 3>(p, grid, stream);
-  return launch<64, 4>(p, grid, stream);
+  // fp32 output / BN statistics go through the legacy epilogue; the split-only contract uses the TMA epilogue
+  static int force_legacy = -1;
+  if (force_legacy < 0) {
+    const char* e = getenv("VFS_CONV_LEGACY_EPILOGUE");
+    force_legacy = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  const bool legacy = force_legacy || c.out_f32 != nullptr || c.stats != nullptr || c.out_split == nullptr;
+  if (legacy) {
+    if (BN == 256) BN = 128, p.num_n_tiles = c.Nout / 128;
+    if (BN == 128) {
+      const uint32_t box_b[3] = {64u, 128u, 2u};
+      const uint64_t dims[3] = {c.Ktot, static_cast<uint64_t>(c.Nout), 2};
+      const uint64_t strides[2] = {c.Ktot * 2, c.Ktot * c.Nout * 2};
+      int rc = make_tmap_16b_sw128(&p.tmap_b, c.b_split, 3, dims, strides, box_b);
+      if (rc != VFS_OK) return rc;
+      const int nt = p.num_m_tiles * p.num_n_tiles;
+      return launch<128, 3, 0, false>(p, nt < sms ? nt : sms, stream);
+    }
+    return launch<64, 4, 0, false>(p, grid, stream);
+  }
+  {
+    // output (and residual) through the same possibly strided pixel view the legacy epilogue addresses by hand
+    const uint32_t box_o[5] = {64u, static_cast<uint32_t>(p.tw), static_cast<uint32_t>(p.th),
+                               static_cast<uint32_t>(p.tn), 2u};
+    const uint64_t Co = static_cast<uint64_t>(c.Nout);
+    const uint64_t dims[5] = {Co, static_cast<uint64_t>(p.Wo), static_cast<uint64_t>(p.Ho),
+                              static_cast<uint64_t>(p.N), 2};
+    const uint64_t strides[4] = {static_cast<uint64_t>(p.out_sx) * Co * 2,
+                                 static_cast<uint64_t>(p.out_sy) * p.out_W * Co * 2,
+                                 static_cast<uint64_t>(p.out_H) * p.out_W * Co * 2, c.out_plane * 2};
+    const size_t view_off = (static_cast<size_t>(p.out_oy) * p.out_W + p.out_ox) * Co * 2;
+    int rc = make_tmap_16b_sw128(&p.tmap_out, reinterpret_cast<char*>(c.out_split) + view_off, 5, dims, strides, box_o);
+    if (rc != VFS_OK) return rc;
+    if (c.res_split) {
+      rc = make_tmap_16b_sw128(&p.tmap_res, reinterpret_cast<const char*>(c.res_split) + view_off, 5, dims, strides,
+                               box_o);
+      if (rc != VFS_OK) return rc;
+    }
+  }
+  if (c.res_split) {
+    if (BN == 256) {
+      BN = 128;
+      p.num_n_tiles = c.Nout / 128;
+      const uint32_t box_b[3] = {64u, 128u, 2u};
+      const uint64_t dims[3] = {c.Ktot, static_cast<uint64_t>(c.Nout), 2};
+      const uint64_t strides[2] = {c.Ktot * 2, c.Ktot * c.Nout * 2};
+      int rc = make_tmap_16b_sw128(&p.tmap_b, c.b_split, 3, dims, strides, box_b);
+      if (rc != VFS_OK) return rc;
+    }
+    const int nt = p.num_m_tiles * p.num_n_tiles;
+    const int gr = nt < sms ? nt : sms;
+    if (BN == 128) return launch<128, 2, 3, true>(p, gr, stream);
+    return launch<64, 2, 3, true>(p, gr, stream);
+  }
+  if (BN == 256) return launch<256, 2, 1, false>(p, grid, stream);
+  if (BN == 128) return launch<128, 3, 1, false>(p, grid, stream);
+  return launch<64, 4, 1, false>(p, grid, stream);
 }
 
 static int check_desc(const VfsConvDesc* d, const char* who) {

@@ -74,10 +74,24 @@ class VanillaTracker(BaseTracker):
                 xs = engine.forward_split(chunk, stage)
                 if with_norm:
                     xs = ops.normalize_split(xs)
+            if clip_len <= batch_step:
+                # single chunk: the engine's output buffer is the bank (valid until the next feature pass, i.e. for
+                # the rest of this forward_test call)
+                return xs
             if bank is None:
                 bank = torch.empty((2, clip_len) + tuple(xs.shape[2:]), dtype=torch.float16, device=xs.device)
             bank[:, ptr:ptr + xs.shape[1]].copy_(xs)
         return bank
+
+    def _feature_hw(self, img_hw):
+        """Spatial size of the selected backbone stage for an input of ``img_hw`` (stem conv 7x7/s2 p3, max-pool
+        3x3/s2 p1, then the 3x3 stride convs of the residual stages up to the output stage)."""
+        h, w = int(img_hw[0]), int(img_hw[1])
+        h, w = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
+        h, w = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        for s in tuple(self.backbone.strides)[:self._feature_stage() + 1]:
+            h, w = (h - 1) // s + 1, (w - 1) // s + 1
+        return h, w
 
     def forward_train(self, imgs, labels=None):
         raise NotImplementedError
@@ -89,10 +103,13 @@ class VanillaTracker(BaseTracker):
         imgs = imgs.reshape((-1, ) + imgs.shape[2:])
         clip_len = imgs.size(2)
         cfg = self.test_cfg
-        bank = self.get_feat_bank(imgs)                      # [2,T,h,w,C]
-        _, _, fh, fw, _ = bank.shape
+        fh, fw = self._feature_hw(imgs.shape[-2:])
         hw = fh * fw
         orig_hw = tuple(img_meta[0]['original_shape'][:2])
+        # First-frame labels before the backbone: F.one_hot sizes its output from the largest label id, which is
+        # a device->host read.  Done here it waits for two tiny kernels; done after the backbone launch (the
+        # reference's order) it would stall the host until the whole feature pass has finished and leave the GPU idle
+        # while the propagation kernels are being enqueued.
         ref_seg_map = ref_seg_map.to(imgs.device)
         input_onehot = ref_seg_map.ndim == 4
         if not input_onehot:
@@ -105,6 +122,9 @@ class VanillaTracker(BaseTracker):
         cv = first.size(1)
         seg_bank = torch.empty((clip_len, cv, hw), dtype=torch.float32, device=imgs.device)
         seg_bank[0] = first[0].reshape(cv, hw)
+
+        bank = self.get_feat_bank(imgs)                      # [2,T,h,w,C]
+        assert tuple(bank.shape[2:4]) == (fh, fw), (bank.shape, fh, fw)
 
         neighbor_range = cfg.get('neighbor_range', None)
         mask = spatial_neighbor(1, fh, fw, neighbor_range=neighbor_range, mode='circle') \
