@@ -291,6 +291,9 @@ def main():
     n_conv_launches = len(layer_list)
     marks = []
     barrier()
+    cuprof = bool(os.environ.get('VFS_BENCH_CUPROFILE'))   # ncu --profile-from-start off: only the timed steps
+    if cuprof:
+        torch.cuda.profiler.start()
     wall0 = time.perf_counter()
     for _ in range(a.steps):
         flush.fill_(1)                                        # evict L2 (512 MiB > 126 MB); outside the timed span
@@ -305,6 +308,8 @@ def main():
         marks.append(ev)
     barrier()
     wall = time.perf_counter() - wall0
+    if cuprof:
+        torch.cuda.profiler.stop()
     launches = launches_per_step * a.steps
     step_ms = [e[0].elapsed_time(e[3]) for e in marks]
     stem_ms = [e[0].elapsed_time(e[1]) for e in marks]
@@ -349,10 +354,16 @@ def main():
         pass
     peak_tf = peaks.get('bf16_tflops_sustained') or peaks.get('bf16_tflops') or 1590.0
     peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.59 PFLOP/s'
+    traffic = None
+    try:   # DRAM bytes of the 42 conv launches of one step, from the committed ncu --set full capture of this command
+        with open(os.path.join(ROOT, 'profiles', 'conv_traffic.json')) as fh_:
+            traffic = json.load(fh_).get('dram_bytes_per_step')
+    except Exception:
+        pass
     conv_med = statistics.median(conv_ms)
     achieved = conv_flops / (conv_med * 1e-3) / 1e12
     roofline = dict(bound='tensor', kernel='conv_tc_kernel', achieved=achieved, peak=peak_tf, unit='TFLOP/s',
-                    frac=achieved / peak_tf, traffic=None, peak_source=peak_src,
+                    frac=achieved / peak_tf, traffic=traffic, peak_source=peak_src,
                     note='achieved = algorithmic fp32-equivalent conv FLOPs; the kernel issues 3 bf16 MMAs per '
                          'product (split-fp16), so tensor-pipe work is 3x: frac_of_issued = %.3f' %
                          (3 * achieved / peak_tf),
