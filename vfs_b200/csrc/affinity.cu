@@ -25,7 +25,8 @@ namespace vfs {
 constexpr int kQTileW = 16, kQTileH = 8;  // 128 queries / keys per tile
 constexpr int kAttnStages = 3;
 constexpr int kAttnStageBytes = 4 * 16384;  // Q hi, Q lo, K hi, K lo (each 128 rows x 128 B)
-constexpr int kAttnSmemBytes = kAttnStages * kAttnStageBytes + 256 + 1024;
+constexpr int kAttnScratchBytes = 32 * 128 * 4;  // epilogue: one 32-column score slab per query row ([col][row] fp32)
+constexpr int kAttnSmemBytes = kAttnStages * kAttnStageBytes + 256 + kAttnScratchBytes + 1024;
 constexpr int kAttnThreads = 192;
 constexpr int kMaxKeyFrames = 32;
 constexpr int kMaxProblems = 32;   // query frames per launch
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kAttnStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kAttnStages + 2 + a); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kAttnStages + 4);
+  const uint32_t scratch_base = bar_base + 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 256;  // 2 accumulator stages x 128 key columns
 
@@ -251,7 +253,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
           uint32_t acc[32];
           tmem_ld_32x32b_x32(t_row + c0, acc);
           tmem_ld_wait();
-          // 32 columns = 2 key rows x 16 key columns
+          // 32 columns = 2 key rows x 16 key columns.  Two passes: (1) a bit mask of the columns that are inside the
+          // image / radius and beat the list's current k-th value -- a conservative filter, the k-th value only grows;
+          // (2) only those columns go through the sorted insertion, in ascending key order (identical result to
+          // testing every column, but the warp executes the ~40-instruction insertion max-over-lanes(#candidates)
+          // times instead of 32 times).  The dynamic column index of pass 2 reads the slab back from shared memory.
+          const float thr = tv[KMAX - 1];
+          uint32_t cand = 0;
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
             const int ky = ky0 + ((c0 + jj) >> 4);
@@ -261,8 +269,24 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
             if (masked) {
               ok = ok && ((p.mask_mode == 1) ? (dy * dy + dx * dx < r2) : (abs(dy) <= p.ry && abs(dx) <= p.rx));
             }
-            const float s = __uint_as_float(acc[jj]);
-            if (ok && s > tv[KMAX - 1]) topk_insert<KMAX>(tv, ti, s, u.t * HW + ky * p.W + kx);
+            if (ok && __uint_as_float(acc[jj]) > thr) cand |= (1u << jj);
+          }
+          if (__any_sync(0xffffffffu, cand != 0)) {
+            const uint32_t slab = scratch_base + static_cast<uint32_t>(row) * 4u;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(slab + jj * 512), "r"(acc[jj]) : "memory");
+            while (cand != 0) {
+              const int jj = __ffs(cand) - 1;
+              cand &= cand - 1;
+              float sc;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc) : "r"(slab + jj * 512));
+              if (sc > tv[KMAX - 1]) {
+                const int ky = ky0 + ((c0 + jj) >> 4);
+                const int kx = kx0 + ((c0 + jj) & 15);
+                topk_insert<KMAX>(tv, ti, sc, u.t * HW + ky * p.W + kx);
+              }
+            }
           }
         }
         tc_fence_before();
@@ -312,11 +336,21 @@ struct MergeParams {
   int* out_idx;    // optional [problems][topk][HW] (flat key index slot*HW + pos)
 };
 
+// Block = 32 queries x 8 sub-lanes (warp index = sub-lane, lane = query: every global access of a warp covers 32
+// consecutive queries).  Sub-lane w reduces a contiguous range of partial lists to a local top-k, warp 0 merges the
+// eight sorted lists (in slot order, so ties resolve exactly like a serial pass over the slots), computes the
+// softmax weights, and all eight warps split the value channels of the propagation.
+constexpr int kMergeSub = 8;
+
 template <int KMAX>
-__global__ void attn_merge_propagate_kernel(const MergeParams p) {
-  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * kMergeSub) attn_merge_propagate_kernel(const MergeParams p) {
+  __shared__ float sv[kMergeSub][KMAX][32];
+  __shared__ int si[kMergeSub][KMAX][32];
+  __shared__ float sw[KMAX][32];
+  const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
+  const int qi = blockIdx.x * 32 + lane;
   const int b = blockIdx.y;
-  if (qi >= p.HW) return;
+  const bool valid = qi < p.HW;
   float tv[KMAX];
   int ti[KMAX];
 #pragma unroll
@@ -324,44 +358,72 @@ __global__ void attn_merge_propagate_kernel(const MergeParams p) {
     tv[i] = -INFINITY;
     ti[i] = 0;
   }
-  for (int s = 0; s < p.slots; ++s) {
-    const size_t base = (static_cast<size_t>(b) * p.slots + s) * KMAX * p.HW + qi;
+  const int per = (p.slots + kMergeSub - 1) / kMergeSub;
+  const int s_end = min(p.slots, (sub + 1) * per);
+  if (valid) {
+    for (int s = sub * per; s < s_end; ++s) {
+      const size_t base = (static_cast<size_t>(b) * p.slots + s) * KMAX * p.HW + qi;
 #pragma unroll
-    for (int i = 0; i < KMAX; ++i) {
-      const float v = p.part_val[base + static_cast<size_t>(i) * p.HW];
-      if (v > tv[KMAX - 1]) topk_insert<KMAX>(tv, ti, v, p.part_idx[base + static_cast<size_t>(i) * p.HW]);
+      for (int i = 0; i < KMAX; ++i) {
+        const float v = p.part_val[base + static_cast<size_t>(i) * p.HW];
+        if (v > tv[KMAX - 1]) topk_insert<KMAX>(tv, ti, v, p.part_idx[base + static_cast<size_t>(i) * p.HW]);
+      }
     }
   }
-  float w[KMAX];
-  float wsum = 0.0f;
-  const float vmax = __fdiv_rn(tv[0], p.temperature);
 #pragma unroll
   for (int i = 0; i < KMAX; ++i) {
-    const float a = __fdiv_rn(tv[i], p.temperature);  // reference divides the whole affinity by temperature
-    if (i < p.topk) {
-      if (p.out_val) p.out_val[(static_cast<size_t>(b) * p.topk + i) * p.HW + qi] = a;
-      if (p.out_idx) p.out_idx[(static_cast<size_t>(b) * p.topk + i) * p.HW + qi] = ti[i];
-      if (p.mode == 0) {
-        w[i] = expf(a - vmax);
-      } else {
-        const float c = fmaxf(a, 0.0f);
-        w[i] = c * c;
+    sv[sub][i][lane] = tv[i];
+    si[sub][i][lane] = ti[i];
+  }
+  __syncthreads();
+  if (sub == 0) {
+    for (int w = 1; w < kMergeSub; ++w) {
+#pragma unroll 1
+      for (int i = 0; i < KMAX; ++i) {
+        const float v = sv[w][i][lane];
+        if (!(v > tv[KMAX - 1])) break;  // the list is sorted: nothing further can enter
+        topk_insert<KMAX>(tv, ti, v, si[w][i][lane]);
       }
-      wsum += w[i];
-    } else {
-      w[i] = 0.0f;
+    }
+    float wgt[KMAX];
+    float wsum = 0.0f;
+    const float vmax = __fdiv_rn(tv[0], p.temperature);
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      const float a = __fdiv_rn(tv[i], p.temperature);  // reference divides the whole affinity by temperature
+      if (i < p.topk) {
+        if (valid && p.out_val) p.out_val[(static_cast<size_t>(b) * p.topk + i) * p.HW + qi] = a;
+        if (valid && p.out_idx) p.out_idx[(static_cast<size_t>(b) * p.topk + i) * p.HW + qi] = ti[i];
+        if (p.mode == 0) {
+          wgt[i] = expf(a - vmax);
+        } else {
+          const float c = fmaxf(a, 0.0f);
+          wgt[i] = c * c;
+        }
+        wsum += wgt[i];
+      } else {
+        wgt[i] = 0.0f;
+      }
+    }
+    const float inv = (p.mode == 0) ? __fdiv_rn(1.0f, wsum) : 1.0f;
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+      sw[i][lane] = (p.mode == 0) ? wgt[i] * inv : wgt[i];
+      si[0][i][lane] = ti[i];
     }
   }
-  const float inv = (p.mode == 0) ? __fdiv_rn(1.0f, wsum) : 1.0f;
-  for (int c = 0; c < p.Cv; ++c) {
+  __syncthreads();
+  if (!valid) return;
+  for (int c = sub; c < p.Cv; c += kMergeSub) {
     float acc = 0.0f;
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
       if (i < p.topk) {
-        const int slot = ti[i] / p.HW, pos = ti[i] - slot * p.HW;
+        const int idx = si[0][i][lane];
+        const int slot = idx / p.HW, pos = idx - slot * p.HW;
         const float val = p.values[b * p.v_batch_stride + p.val_ids[b * p.T + slot] * p.v_frame_stride +
                                    c * p.v_chan_stride + pos];
-        acc = fmaf(val, (p.mode == 0) ? w[i] * inv : w[i], acc);
+        acc = fmaf(val, sw[i][lane], acc);
       }
     }
     p.out[(static_cast<size_t>(b) * p.Cv + c) * p.HW + qi] = acc;
@@ -591,9 +653,9 @@ int masked_attention_batched(const VfsAttnDesc* d, int B, const void* q_bank_spl
   m.v_chan_stride = v_chan_stride; m.Cv = d->Cv; m.T = d->T;
   for (int i = 0; i < B * d->T; ++i) m.val_ids[i] = static_cast<short>(val_ids[i]);
   m.out = out; m.out_val = out_topk_val; m.out_idx = out_topk_idx;
-  const dim3 mgrid((HW + 127) / 128, B);
-  if (KMAX == 10) attn_merge_propagate_kernel<10><<<mgrid, 128, 0, stream>>>(m);
-  else attn_merge_propagate_kernel<16><<<mgrid, 128, 0, stream>>>(m);
+  const dim3 mgrid((HW + 31) / 32, B);
+  if (KMAX == 10) attn_merge_propagate_kernel<10><<<mgrid, 32 * kMergeSub, 0, stream>>>(m);
+  else attn_merge_propagate_kernel<16><<<mgrid, 32 * kMergeSub, 0, stream>>>(m);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }
