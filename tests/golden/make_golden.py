@@ -20,9 +20,10 @@ from oracle import ref_shim, seeded_state_dict  # noqa: E402
 from tests.golden import cases  # noqa: E402
 
 
-def main():
+def reference_outputs():
+    """Runs every golden case through the unmodified reference and returns {key: ndarray}.  Also used by
+    tests/test_oracle_golden.py::test_oracle_bit_exact_vs_live_reference when /root/reference is present."""
     ref = ref_shim.load_reference()
-    torch.set_num_threads(8)
     out = {}
 
     # ---- backbone (eval and train-mode BN), reference ResNet.forward
@@ -102,6 +103,12 @@ def main():
             preds = tr.forward_test(imgs, seg, [dict(original_shape=(c['H'], c['W'], 3))])
         out[f'tracker_test/{name}/preds'] = np.asarray(preds[0]).astype(np.uint8)
 
+    return out
+
+
+def main():
+    torch.set_num_threads(8)
+    out = reference_outputs()
     path = os.path.join(ROOT, 'tests', 'golden', 'vfs_golden.npz')
     np.savez_compressed(path, **out)
     print(f'wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB')
