@@ -10,8 +10,10 @@ VanillaTracker.forward_test with a 2-frame video, tools/test.py:129-133 model): 
 (radius 18, top-k 10, temperature 0.07) propagating a 4-channel one-hot label map from frame 0 to frame 1.
 
   value      device-timed (CUDA events) throughput with inputs resident in HBM; L2 flushed between steps
-  e2e        the same work through the public plugin API (build_model(VanillaTracker) -> forward_test per clip) with
-             pinned HOST inputs: H2D of the frames and D2H of the predictions inside the timed region (wall clock)
+  e2e        the same work through the public plugin API (build_model(VanillaTracker) -> ONE forward_test call on the
+             batch of 8 two-frame videos) with pinned HOST inputs: H2D of the frames and D2H of the predictions inside
+             the timed region (wall clock).  `e2e.per_video_calls` is the same batch issued the way the reference
+             must issue it (one video per forward_test call, vanilla_tracker.py:56 asserts B == 1).
   roofline   tcgen05 conv kernel: algorithmic conv FLOPs of a step / CUDA-event time of the conv segment
   cpu_baseline  the CPU oracle (restatement of the reference's torch-CPU path) on a bounded sample, all host cores
 
@@ -38,7 +40,8 @@ sys.path.insert(0, ROOT)
 CLIPS, FRAMES, SIZE = 8, 2, 256
 CV = 4
 TEST_CFG = dict(precede_frames=20, topk=10, temperature=0.07, strides=(1, 2, 1, 1), out_indices=(2, ),
-                neighbor_range=36, with_first=True, with_first_neighbor=True, output_dir='eval_results')
+                neighbor_range=36, with_first=True, with_first_neighbor=True, output_dir='eval_results',
+                batch_step=CLIPS * FRAMES)   # reference key (vanilla_tracker.py:58): frames per backbone pass
 BACKBONE_CFG = dict(type='ResNet', pretrained=None, depth=50, out_indices=(2, ), strides=(1, 2, 1, 1),
                     norm_cfg=dict(type='SyncBN', requires_grad=True), norm_eval=False, zero_init_residual=True)
 WORKLOAD = 'r50_res4_feat+affinity_topk10 8clips x 2frames x 256x256 (BASELINE configs[1] shape, DAVIS test_cfg)'
@@ -321,29 +324,42 @@ def main():
     clocks = sampler.stop()
     value = world * CLIPS * a.steps / (total_ms / 1e3)
 
-    # ---------------- e2e through the public API: per clip forward_test(imgs, ref_seg_map, img_meta), host buffers
+    # ---------------- e2e through the public API: forward_test(imgs, ref_seg_map, img_meta) with host buffers
     meta = [dict(original_shape=(SIZE, SIZE, 3))]
+    seg8_host = seg_host.expand(CLIPS, SIZE, SIZE).contiguous().pin_memory()
+
     def step_e2e():
+        imgs = imgs_host.to(dev, non_blocking=True)                  # [8,1,3,2,H,W]  H2D
+        seg = seg8_host.to(dev, non_blocking=True)
+        return model.forward_test(imgs, seg, meta * CLIPS)              # 8 numpy arrays on the host (D2H inside)
+
+    def step_e2e_per_video():
         res = []
         for c in range(CLIPS):
-            imgs = imgs_host[c:c + 1].to(dev, non_blocking=True)          # [1,1,3,2,H,W]  H2D
+            imgs = imgs_host[c:c + 1].to(dev, non_blocking=True)        # [1,1,3,2,H,W]  H2D
             seg = seg_host.to(dev, non_blocking=True)
-            res.append(model.forward_test(imgs, seg, meta)[0])             # numpy on the host (D2H inside)
+            res.append(model.forward_test(imgs, seg, meta)[0])
         return res
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    e2e_steps = max(3, min(a.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        r = step_e2e()
-    torch.cuda.synchronize()
-    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * CLIPS * e2e_steps / float(e2e_dt)
-    h2d = CLIPS * (imgs_host[0].numel() * 4 + seg_host.numel() * 4)
-    d2h = CLIPS * sum(int(x.nbytes) for x in [r[0]]) if r else 0
+
+    def time_e2e(fn, steps):
+        for _ in range(3):
+            r_ = fn()
+        barrier()
+        t0_ = time.perf_counter()
+        for _ in range(steps):
+            r_ = fn()
+        torch.cuda.synchronize()
+        dt_ = torch.tensor([time.perf_counter() - t0_], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
+        return world * CLIPS * steps / float(dt_), r_
+
+    e2e_steps = max(3, min(a.steps, 20))
+    e2e_value, r = time_e2e(step_e2e, e2e_steps)
+    e2e_single, r1 = time_e2e(step_e2e_per_video, max(3, min(a.steps, 10)))
+    assert all((x == y).all() for x, y in zip(r, r1)), 'batched and per-video forward_test disagree'
+    h2d = imgs_host.numel() * 4 + seg8_host.numel() * 4
+    d2h = sum(int(x.nbytes) for x in r)
 
     # ---------------- roofline of the dominant kernel (tcgen05 conv): algorithmic FLOPs / CUDA-event time
     peaks = {}
@@ -379,8 +395,10 @@ def main():
                             parallelism=f'dp{world} (clips sharded, no collective)'),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit='frame-pairs/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         api='build_model(VanillaTracker).forward_test per 2-frame clip, pinned host inputs',
-                         steps=e2e_steps),
+                         api='build_model(VanillaTracker).forward_test, one call on the batch of 8 two-frame videos, '
+                             'pinned host inputs', steps=e2e_steps,
+                         per_video_calls=dict(value=e2e_single, unit='frame-pairs/s',
+                                              api='one forward_test call per video (reference calling convention)')),
                 gpu_launches=launches,
                 roofline=roofline,
                 breakdown_ms=dict(step_median=statistics.median(step_ms), stem_median=statistics.median(stem_ms),

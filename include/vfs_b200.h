@@ -223,6 +223,10 @@ int vfs_features_to_split_ex(const float* in_nchw, void* out_split, void* inv_no
 size_t vfs_seg_postprocess_workspace_bytes(int Cv);
 int vfs_seg_postprocess(const float* logit, unsigned char* out_labels, void* workspace, int Cv, int h, int w, int H,
                         int W, vfs_stream_t s);
+/* num_maps independent maps in the same three launches (one frame of num_maps videos): logit [num_maps][Cv][h][w] ->
+ * out_labels [num_maps][H][W]; workspace num_maps * vfs_seg_postprocess_workspace_bytes(Cv). */
+int vfs_seg_postprocess_batched(const float* logit, unsigned char* out_labels, void* workspace, int num_maps, int Cv,
+                                int h, int w, int H, int W, vfs_stream_t s);
 /* Dense helpers of common/affinity_utils.py:6-50 (compute_affinity / propagate; exported by the reference, unused by
  * its trackers).  The HW x HW GEMM itself is vfs_conv_bn_act with the dst pixels as 1x1 filters; these finish it:
  *   vfs_masked_softmax  A [B][R][ld] -> out [B][R][Cc]: mask (analytic window, mask[i,j]) to -inf, softmax over

@@ -456,6 +456,56 @@ def test_vanilla_tracker_matches_reference_golden(golden, name):
     assert agree > 0.995, f'pixel agreement {agree:.4f}'
 
 
+def test_vanilla_tracker_batched_videos_equal_single_video_calls():
+    """forward_test over B videos at once (extension of the reference, which asserts B == 1) must return exactly
+    what B separate calls return -- including videos with fewer objects than the batch's largest label id and a
+    feature pass split into several ``batch_step`` chunks."""
+    import vfs_b200
+    c = cases.TRACKER_TEST_CASES['r18_clip5']
+    test_cfg = dict(c['test_cfg'], batch_step=7)                 # 3 videos x 5 frames = 15 frames -> chunks 7+7+1
+    model = vfs_b200.build_model(dict(type='VanillaTracker', backbone=c['backbone']), train_cfg=None,
+                                 test_cfg=vfs_b200.ConfigDict(test_cfg))
+    model.backbone.load_state_dict(oracle.seeded_state_dict(model.backbone, seed=c['seed']))
+    model = model.cuda()
+    model.eval()
+    g = torch.Generator().manual_seed(77)
+    B = 3
+    imgs = torch.randn(B, 1, 3, c['T'], c['H'], c['W'], generator=g)
+    seg = torch.zeros(B, c['H'], c['W'])
+    for b in range(B):
+        for o in range(1, 2 + b):                                # video b has b+1 objects (labels 1..b+1)
+            y0, x0 = 6 * o + 3 * b, 10 * o + 5 * b
+            seg[b, y0:y0 + 20, x0:x0 + 26] = o
+    meta = [dict(original_shape=(c['H'], c['W'], 3))]
+    singles = [model.forward_test(imgs[b:b + 1].cuda(), seg[b:b + 1].cuda(), meta)[0] for b in range(B)]
+    batched = model.forward_test(imgs.cuda(), seg.cuda(), meta * B)
+    assert len(batched) == B
+    for b in range(B):
+        assert batched[b].shape == singles[b].shape == (c['T'], c['H'], c['W'])
+        assert batched[b].dtype == singles[b].dtype
+        np.testing.assert_array_equal(batched[b], singles[b])
+        assert set(np.unique(batched[b])) <= set(range(b + 2))
+
+
+@pytest.mark.parametrize('P', [1, 3])
+def test_seg_postprocess_matches_torch(P):
+    """Fused bilinear upsample + min-max + arg-max (csrc/post.cu) against the reference's torch sequence
+    (vanilla_tracker.py:162-181); one all-zero channel exercises the ``max > 0`` branch."""
+    from vfs_b200 import ops
+    g = torch.Generator().manual_seed(5 + P)
+    Cv, fh, fw, H, W = 5, 9, 13, 70, 101
+    logit = torch.rand(P, Cv, fh * fw, generator=g)
+    logit[:, 3] = 0
+    got = ops.seg_postprocess(logit.cuda() if P > 1 else logit[0].cuda(), fh, fw, (H, W)).cpu()
+    up = torch.nn.functional.interpolate(logit.view(P, Cv, fh, fw), size=(H, W), mode='bilinear', align_corners=False)
+    mn = up.flatten(2).min(-1)[0].view(P, Cv, 1, 1)
+    mx = up.flatten(2).max(-1)[0].view(P, Cv, 1, 1)
+    ref = torch.where(mx > 0, (up - mn) / (mx - mn + 1e-12), up).argmax(1).byte()
+    got = got.view(P, H, W)
+    agree = float((got == ref).float().mean())
+    assert agree > 0.999, agree                                   # fp32 interpolation order may flip exact ties
+
+
 @pytest.mark.parametrize('name', sorted(cases.TRACKER_TRAIN_CASES))
 def test_simsiam_forward_eval_mode_matches_oracle(name):
     """SimSiamBaseTracker.forward_train through build_model on the reference's model dicts, BN in eval mode

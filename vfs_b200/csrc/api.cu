@@ -135,8 +135,8 @@ int stem_bn_relu_pool(const void* conv_out, const float* scale, const float* shi
 int features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
                       int normalize, int c_stride, long long plane_stride, cudaStream_t s);
 size_t seg_postprocess_workspace_bytes(int Cv);
-int seg_postprocess(const float* logit, unsigned char* out, void* workspace, int Cv, int h, int w, int H, int W,
-                    cudaStream_t s);
+int seg_postprocess(const float* logit, unsigned char* out, void* workspace, int P, int Cv, int h, int w, int H,
+                    int W, cudaStream_t s);
 int masked_softmax(const float* A, float* out, int B, int R, int Cc, int ld, int softmax_dim, int mask_mode, int ry,
                    int rx, int W, int nan_to_zero, cudaStream_t s);
 int propagate_dense(const float* img, const float* A, float* out, int B, int Cv, int HW, int topk, cudaStream_t s);
@@ -325,7 +325,11 @@ int vfs_features_to_split_ex(const float* in_nchw, void* out_split, void* inv_no
 size_t vfs_seg_postprocess_workspace_bytes(int Cv) { return vfs::seg_postprocess_workspace_bytes(Cv); }
 int vfs_seg_postprocess(const float* logit, unsigned char* out_labels, void* workspace, int Cv, int h, int w, int H,
                         int W, vfs_stream_t s) {
-  return vfs::seg_postprocess(logit, out_labels, workspace, Cv, h, w, H, W, s);
+  return vfs::seg_postprocess(logit, out_labels, workspace, 1, Cv, h, w, H, W, s);
+}
+int vfs_seg_postprocess_batched(const float* logit, unsigned char* out_labels, void* workspace, int num_maps, int Cv,
+                                int h, int w, int H, int W, vfs_stream_t s) {
+  return vfs::seg_postprocess(logit, out_labels, workspace, num_maps, Cv, h, w, H, W, s);
 }
 int vfs_masked_softmax(const float* A, float* out, int B, int R, int Cc, int ld, int softmax_dim, int mask_mode,
                        int radius_y, int radius_x, int W, int nan_to_zero, vfs_stream_t s) {

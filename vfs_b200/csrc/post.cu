@@ -42,8 +42,10 @@ __device__ __forceinline__ float bilinear_sample(const float* __restrict__ p, in
          b.ly * (hx * p[b.y1 * w + b.x0] + b.lx * p[b.y1 * w + b.x1]);
 }
 
+// workspace layout: per problem [min[Cv], max[Cv]] as order-preserving ints
 __global__ void minmax_init_kernel(int* mm, int Cv) {
   const int c = threadIdx.x;
+  mm += static_cast<size_t>(blockIdx.x) * 2 * Cv;
   if (c < Cv) {
     mm[c] = INT_MAX;        // min
     mm[Cv + c] = INT_MIN;   // max
@@ -53,7 +55,8 @@ __global__ void minmax_init_kernel(int* mm, int Cv) {
 __global__ void upsample_minmax_kernel(const float* __restrict__ logit, int Cv, int h, int w, int H, int W, float sy,
                                        float sx, int* __restrict__ mm) {
   const int c = blockIdx.y;
-  const float* p = logit + static_cast<size_t>(c) * h * w;
+  const float* p = logit + (static_cast<size_t>(blockIdx.z) * Cv + c) * h * w;
+  mm += static_cast<size_t>(blockIdx.z) * 2 * Cv;
   float lo = INFINITY, hi = -INFINITY;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
     const Bilinear b = bilinear_setup(i / W, i % W, h, w, sy, sx);
@@ -76,6 +79,9 @@ __global__ void normalize_argmax_kernel(const float* __restrict__ logit, int Cv,
                                         float sx, const int* __restrict__ mm, unsigned char* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * W) return;
+  logit += static_cast<size_t>(blockIdx.y) * Cv * h * w;
+  mm += static_cast<size_t>(blockIdx.y) * 2 * Cv;
+  out += static_cast<size_t>(blockIdx.y) * H * W;
   const Bilinear b = bilinear_setup(i / W, i % W, h, w, sy, sx);
   float best = -INFINITY;
   int arg = 0;
@@ -93,19 +99,22 @@ __global__ void normalize_argmax_kernel(const float* __restrict__ logit, int Cv,
 
 size_t seg_postprocess_workspace_bytes(int Cv) { return 2 * static_cast<size_t>(Cv) * sizeof(int); }
 
-int seg_postprocess(const float* logit, unsigned char* out, void* workspace, int Cv, int h, int w, int H, int W,
-                    cudaStream_t s) {
+// P independent label maps (logit [P][Cv][h*w] -> out [P][H][W]) in three launches; workspace P * 2 * Cv ints.
+int seg_postprocess(const float* logit, unsigned char* out, void* workspace, int P, int Cv, int h, int w, int H,
+                    int W, cudaStream_t s) {
   VFS_REQUIRE(logit && out && workspace, VFS_EINVAL, "seg_postprocess: null argument");
-  VFS_REQUIRE(Cv >= 1 && Cv <= 256 && h > 0 && w > 0 && H > 0 && W > 0, VFS_ESHAPE, "seg_postprocess: bad shape");
+  VFS_REQUIRE(P >= 1 && P <= 65535 && Cv >= 1 && Cv <= 256 && h > 0 && w > 0 && H > 0 && W > 0, VFS_ESHAPE,
+              "seg_postprocess: bad shape");
   int* mm = reinterpret_cast<int*>(workspace);
   const float sy = static_cast<float>(h) / static_cast<float>(H), sx = static_cast<float>(w) / static_cast<float>(W);
-  minmax_init_kernel<<<1, 256, 0, s>>>(mm, Cv);
+  minmax_init_kernel<<<P, 256, 0, s>>>(mm, Cv);
   VFS_CUDA_OK(cudaGetLastError());
   int blocks = (H * W + 255) / 256;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  upsample_minmax_kernel<<<dim3(blocks, Cv), 256, 0, s>>>(logit, Cv, h, w, H, W, sy, sx, mm);
+  const int cap = (148 * 4 + P - 1) / P;
+  if (blocks > cap) blocks = cap;
+  upsample_minmax_kernel<<<dim3(blocks, Cv, P), 256, 0, s>>>(logit, Cv, h, w, H, W, sy, sx, mm);
   VFS_CUDA_OK(cudaGetLastError());
-  normalize_argmax_kernel<<<(H * W + 255) / 256, 256, 0, s>>>(logit, Cv, h, w, H, W, sy, sx, mm, out);
+  normalize_argmax_kernel<<<dim3((H * W + 255) / 256, P), 256, 0, s>>>(logit, Cv, h, w, H, W, sy, sx, mm, out);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }

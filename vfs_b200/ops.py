@@ -677,15 +677,19 @@ def masked_attention(query, key, value, mask, temperature, topk, normalize=True,
 
 
 def seg_postprocess(seg_logit, fh, fw, out_hw, out=None):
-    """Propagated logits fp32 [Cv, fh*fw] -> uint8 label map [H, W] (bilinear upsample + min-max + argmax)."""
+    """Propagated logits fp32 [Cv, fh*fw] (or a batch [P, Cv, fh*fw]) -> uint8 label map [H, W] ([P, H, W]):
+    bilinear upsample + per-channel min-max + argmax."""
     _require_cuda(seg_logit, 'seg_logit')
-    Cv = seg_logit.shape[0]
+    assert seg_logit.dtype == torch.float32 and seg_logit.is_contiguous()
+    batched = seg_logit.ndim == 3
+    P = seg_logit.shape[0] if batched else 1
+    Cv = seg_logit.shape[-2]
     H, W = out_hw
     if out is None:
-        out = torch.empty((H, W), dtype=torch.uint8, device=seg_logit.device)
-    ws = torch.empty((2 * Cv, ), dtype=torch.int32, device=seg_logit.device)
-    check(nat.lib().vfs_seg_postprocess(ptr(seg_logit), ptr(out), ptr(ws), Cv, fh, fw, H, W, current_stream()),
-          'seg_postprocess')
+        out = torch.empty((P, H, W) if batched else (H, W), dtype=torch.uint8, device=seg_logit.device)
+    ws = torch.empty((P * 2 * Cv, ), dtype=torch.int32, device=seg_logit.device)
+    check(nat.lib().vfs_seg_postprocess_batched(ptr(seg_logit), ptr(out), ptr(ws), P, Cv, fh, fw, H, W,
+                                                current_stream()), 'seg_postprocess')
     return out
 
 

@@ -55,18 +55,18 @@ class VanillaTracker(BaseTracker):
         return out_indices[0]
 
     def get_feat_bank(self, imgs):
-        """imgs [1,3,T,H,W] -> normalised split-fp16 bank [2,T,h,w,C] on the device (reference get_feats,
-        vanilla_tracker.py:55-75, chunked by ``batch_step`` frames like the reference)."""
-        assert imgs.shape[0] == 1
+        """imgs [B,3,T,H,W] -> normalised split-fp16 bank [2,B*T,h,w,C] on the device, frame (b, t) at index b*T+t
+        (reference get_feats, vanilla_tracker.py:55-75, chunked by ``batch_step`` frames like the reference; the
+        reference only accepts B == 1)."""
         batch_step = self.test_cfg.get('batch_step', 10)
         frames = video2images(imgs)
-        clip_len = frames.size(0)
+        num_frames = frames.size(0)
         stage = self._feature_stage()
         with_norm = self.test_cfg.get('with_norm', True)
         use_graph = self.test_cfg.get('cuda_graph', True)
         engine = self.backbone.engine
         bank = None
-        for ptr in range(0, clip_len, batch_step):
+        for ptr in range(0, num_frames, batch_step):
             chunk = frames[ptr:ptr + batch_step]
             if use_graph:   # one graph launch per chunk instead of ~45 kernel launches issued from Python
                 xs = engine.features_graphed(chunk, stage, normalize=with_norm)          # [2,n,h,w,C]
@@ -74,12 +74,12 @@ class VanillaTracker(BaseTracker):
                 xs = engine.forward_split(chunk, stage)
                 if with_norm:
                     xs = ops.normalize_split(xs)
-            if clip_len <= batch_step:
+            if num_frames <= batch_step:
                 # single chunk: the engine's output buffer is the bank (valid until the next feature pass, i.e. for
                 # the rest of this forward_test call)
                 return xs
             if bank is None:
-                bank = torch.empty((2, clip_len) + tuple(xs.shape[2:]), dtype=torch.float16, device=xs.device)
+                bank = torch.empty((2, num_frames) + tuple(xs.shape[2:]), dtype=torch.float16, device=xs.device)
             bank[:, ptr:ptr + xs.shape[1]].copy_(xs)
         return bank
 
@@ -97,11 +97,18 @@ class VanillaTracker(BaseTracker):
         raise NotImplementedError
 
     def forward_test(self, imgs, ref_seg_map, img_meta):
-        """imgs [1,1,3,T,H,W], ref_seg_map [1,H,W] (label ids) -> list with one uint8 array [T,H,W]."""
+        """imgs [B,1,3,T,H,W], ref_seg_map [B,H,W] (label ids) or [B,Cv,H,W] (one-hot) -> list of B arrays [T,H,W].
+
+        The reference handles one video per call (``get_feats`` asserts B == 1, vanilla_tracker.py:56).  Here B
+        videos of equal length are propagated together -- one backbone pass over the B*T frames, one attention
+        launch and one post-processing launch per frame index for all B videos -- with results identical to B
+        separate calls: label ids are one-hot encoded over the largest id of the batch, and the extra all-zero
+        channels of a video with fewer objects stay exactly zero through the propagation, keep ``max == 0`` in the
+        min-max step and lose every arg-max tie to the lower channel index."""
         if not imgs.is_cuda:
             raise RuntimeError('vfs_b200 VanillaTracker needs CUDA tensors (no CPU fallback)')
         imgs = imgs.reshape((-1, ) + imgs.shape[2:])
-        clip_len = imgs.size(2)
+        num_videos, clip_len = imgs.size(0), imgs.size(2)
         cfg = self.test_cfg
         fh, fw = self._feature_hw(imgs.shape[-2:])
         hw = fh * fw
@@ -111,19 +118,21 @@ class VanillaTracker(BaseTracker):
         # reference's order) it would stall the host until the whole feature pass has finished and leave the GPU idle
         # while the propagation kernels are being enqueued.
         ref_seg_map = ref_seg_map.to(imgs.device)
+        assert ref_seg_map.size(0) == num_videos, (ref_seg_map.shape, imgs.shape)
         input_onehot = ref_seg_map.ndim == 4
         if not input_onehot:
             resized = pil_nearest_interpolate(ref_seg_map.unsqueeze(1), size=(fh, fw)).squeeze(1).long()
-            first = F.one_hot(resized).permute(0, 3, 1, 2).float()                       # [1,Cv,h,w]
+            first = F.one_hot(resized).permute(0, 3, 1, 2).float()                       # [B,Cv,h,w]
             ref_seg_map = F.interpolate(ref_seg_map.unsqueeze(1), size=orig_hw, mode='nearest').squeeze(1)
         else:
             first = F.interpolate(ref_seg_map, size=(fh, fw), mode='bilinear', align_corners=False).float()
             ref_seg_map = F.interpolate(ref_seg_map, size=orig_hw, mode='bilinear', align_corners=False)
         cv = first.size(1)
-        seg_bank = torch.empty((clip_len, cv, hw), dtype=torch.float32, device=imgs.device)
-        seg_bank[0] = first[0].reshape(cv, hw)
+        # label bank: frame (b, t) at row b*T + t, the same numbering as the feature bank
+        seg_bank = torch.empty((num_videos, clip_len, cv, hw), dtype=torch.float32, device=imgs.device)
+        seg_bank[:, 0] = first.reshape(num_videos, cv, hw)
 
-        bank = self.get_feat_bank(imgs)                      # [2,T,h,w,C]
+        bank = self.get_feat_bank(imgs)                      # [2,B*T,h,w,C]
         assert tuple(bank.shape[2:4]) == (fh, fw), (bank.shape, fh, fw)
 
         neighbor_range = cfg.get('neighbor_range', None)
@@ -132,25 +141,33 @@ class VanillaTracker(BaseTracker):
         with_first = cfg.get('with_first', True)
         non_mask_len = 0 if cfg.get('with_first_neighbor', True) else 1
 
-        seg_preds = [ref_seg_map.detach()]
+        # predictions [B,T,H,W] assembled on the device; dtype mirrors np.stack over the reference's per-frame
+        # arrays (float32 first-frame map + uint8 arg-max maps promote to float32)
+        preds = torch.empty((num_videos, clip_len) + tuple(ref_seg_map.shape[1:]), dtype=torch.float32,
+                            device=imgs.device)
+        preds[:, 0] = ref_seg_map
         for frame_idx in range(1, clip_len):
             key_start = max(0, frame_idx - cfg.precede_frames)
             key_ids = list(range(key_start, frame_idx))
             if with_first:
                 key_ids = [0] + key_ids
-            seg_logit = ops.attention_bank(bank[:, frame_idx:frame_idx + 1], bank, key_ids, seg_bank, cv * hw, hw, cv,
-                                           mask, cfg.temperature, cfg.topk, non_mask_len=non_mask_len)
-            seg_bank[frame_idx] = seg_logit
-            if not input_onehot:
-                # fused bilinear upsample + per-channel min-max + argmax (csrc/post.cu)
-                seg_pred = ops.seg_postprocess(seg_logit, fh, fw, orig_hw).unsqueeze(0)
-            else:
-                seg_pred = F.interpolate(seg_logit.view(1, cv, fh, fw), size=orig_hw, mode='bilinear',
-                                         align_corners=False)
-            seg_preds.append(seg_pred.detach())
+            per_launch = max(1, min(32, 256 // len(key_ids)))          # problems per attention launch
+            for b0 in range(0, num_videos, per_launch):
+                vids = range(b0, min(num_videos, b0 + per_launch))
+                ids = [[b * clip_len + i for i in key_ids] for b in vids]
+                seg_logit = ops.attention_bank_batched(bank, [b * clip_len + frame_idx for b in vids], bank, ids,
+                                                       seg_bank, ids, 0, cv * hw, hw, cv, mask, cfg.temperature,
+                                                       cfg.topk, non_mask_len=non_mask_len)      # [n,Cv,hw]
+                seg_bank[b0:b0 + len(vids), frame_idx] = seg_logit
+                if not input_onehot:
+                    # fused bilinear upsample + per-channel min-max + argmax (csrc/post.cu), all videos at once
+                    preds[b0:b0 + len(vids), frame_idx] = ops.seg_postprocess(seg_logit, fh, fw, orig_hw)
+                else:
+                    preds[b0:b0 + len(vids), frame_idx] = F.interpolate(
+                        seg_logit.view(len(vids), cv, fh, fw), size=orig_hw, mode='bilinear', align_corners=False)
 
-        # one device->host copy per video; dtype promotion mirrors np.stack over the reference's per-frame arrays
-        seg_preds = np.stack([p.cpu().numpy() for p in seg_preds], axis=1)
+        # one device->host copy per call
+        seg_preds = preds.cpu().numpy()
         if self.save_np:
             assert seg_preds.shape[0] == 1
             eval_dir = '.eval'
