@@ -189,6 +189,12 @@ int vfs_debug_conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const
  * clock) pairs per CTA for the TMA warp (role 0), the MMA warp (1) and the first epilogue warp (2); see
  * tools/conv_trace.py.  Pass NULL to switch it off (the default; the product path never enables it). */
 int vfs_debug_conv_trace(long long* buffer, int events_per_role);
+/* Tile policy of vfs_conv_bn_act / vfs_conv_dgrad.  The kernel has a CTA-pair form (thread-block clusters of two,
+ * tcgen05.mma.cta_group::2, 256-pixel x 256/128-channel tiles, each CTA staging half of the weight tile) that is
+ * faster on large launches and a 1-CTA form with finer tiles for small ones.
+ *   mode 0 = never pair, 1 = pair whenever Cout % 128 == 0, 2 (default) = pair when the launch has at least
+ *   min_pair_tiles pair tiles (default 48 of the 74 TPCs).  Results are identical in every mode. */
+int vfs_conv_set_pair_policy(int mode, int min_pair_tiles);
 
 /* ------------------------------------------------------------------------------------------------
  * Restricted-attention label propagation (DAVIS inference).  Replaces masked_attention_efficient,

@@ -197,6 +197,58 @@ def test_conv_bn_act_against_fp64_and_simt(case):
     assert rel_err(out32, simt) < 5e-5
 
 
+PAIR_CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, dil, relu, residual     (split-only output = TMA epilogue; pair tiles 256 x BN)
+    (4, 16, 16, 64, 256, 1, 1, 1, 1, 0),      # flat 1x1, 8 m-tiles, BN 256
+    (3, 13, 11, 128, 256, 1, 1, 1, 1, 1),     # odd number of m-tiles (phantom tile), residual
+    (2, 24, 20, 64, 128, 3, 1, 1, 1, 0),      # 3x3, BN 128 (64 weight rows per CTA)
+    (2, 16, 16, 128, 128, 3, 1, 1, 0, 1),     # BasicBlock conv2: 3x3 + residual, BN 128
+    (2, 33, 29, 256, 256, 3, 2, 1, 1, 0),     # stride-2 parity views, ragged edges
+    (1, 30, 30, 64, 256, 3, 1, 2, 1, 0),      # dilation 2
+    (2, 32, 32, 256, 1024, 1, 1, 1, 1, 1),    # layer3 expand: 4 n-tiles x 8 pairs, residual
+    (16, 32, 32, 256, 256, 3, 1, 1, 1, 0),    # bench layer3 conv2: 64 pairs -> several tiles per cluster
+    (10, 60, 107, 512, 256, 1, 1, 1, 1, 0),   # 480p DAVIS layer3 conv1: 502 m-tiles, persistent loop
+]
+
+
+@pytest.mark.parametrize('case', PAIR_CONV_CASES)
+def test_conv_cta_pair_kernel_matches_single_cta_and_fp64(case):
+    """The cta_group::2 form of the conv kernel (clusters of two CTAs, M = 256) against the 1-CTA form (must be
+    bit-identical: same products, same accumulation order per output element) and against an fp64 convolution."""
+    import torch.nn.functional as F
+    from vfs_b200 import ops
+    N, H, W, Cin, Cout, k, stride, dil, relu, use_res = case
+    g = torch.Generator().manual_seed(sum(case) + 7)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k)**0.5
+    scale, shift = (torch.rand(Cout, generator=g) + 0.5).cuda(), (torch.randn(Cout, generator=g) * 0.1).cuda()
+    xs, wp = ops.to_split(x.cuda()), ops.pack_conv_weight(w.cuda())
+    Ho, Wo = ops.conv_out_hw(H, W, k, stride, dil)
+    rs = ops.to_split(torch.randn(N, Cout, Ho, Wo, generator=g).cuda()) if use_res else None
+    try:
+        ops.conv_set_pair_policy(0)
+        single, _ = ops.conv_bn_act(xs, wp, scale, shift, k, stride, dil, relu, rs)
+        ops.conv_set_pair_policy(1)
+        pair, _ = ops.conv_bn_act(xs, wp, scale, shift, k, stride, dil, relu, rs)
+        pair2, _ = ops.conv_bn_act(xs, wp, scale, shift, k, stride, dil, relu, rs)   # back to back (PDL overlap)
+    finally:
+        ops.conv_set_pair_policy(2, 48)
+    torch.cuda.synchronize()
+    assert torch.equal(pair, single)
+    assert torch.equal(pair2, single)
+    if N * Ho * Wo * Cout * Cin * k * k <= 2**32:
+        xr = ops.from_split(xs).cpu().double()
+        wr = (wp[0].float() + wp[1].float()).cpu().double().view(Cout, k, k, Cin).permute(0, 3, 1, 2)
+        ref = F.conv2d(xr, wr, stride=stride, padding=0 if k == 1 else dil, dilation=dil if k == 3 else 1)
+        ref = ref * scale.cpu().double().view(1, -1, 1, 1) + shift.cpu().double().view(1, -1, 1, 1)
+        if use_res:
+            ref = ref + ops.from_split(rs).cpu().double()
+        if relu:
+            ref = torch.relu(ref)
+        assert rel_err(ops.from_split(pair), ref) < 5e-5
+    assert ops.overflow_count() == 0
+
+
 DGRAD_CASES = [
     # N, H, W, Cin, Cout, k, stride, dil, with_add
     (2, 16, 16, 64, 128, 1, 1, 1, 0), (2, 16, 16, 64, 64, 3, 1, 1, 1), (1, 15, 13, 128, 64, 3, 1, 1, 0),

@@ -56,10 +56,31 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1) * 1e3)
+        # warm: 20 back-to-back launches replayed from a CUDA graph (no host issue cost; operands L2-resident like
+        # inside the bench's conv graph; PDL overlaps prologues with the previous launch's tail)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ops.conv_bn_act(x, wp, scale, shift, k, s, 1, True, r)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(20):
+                ops.conv_bn_act(x, wp, scale, shift, k, s, 1, True, r)
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        warm = e0.elapsed_time(e1) * 1e3 / 20
+        del graph
         flops = 2.0 * N * Ho * Wo * Cout * Cin * k * k
         bytes_ = 4.0 * N * (H * W * Cin + Ho * Wo * Cout * (2 if res else 1))
         t = min(times)
-        print(f'{name:26s} {t:7.1f} us  {flops / t / 1e6:7.1f} TF(alg)  {bytes_ / t / 1e3:7.1f} GB/s(alg)  '
+        print(f'{name:26s} cold {t:7.1f} us  warm {warm:6.1f} us {3 * flops / warm / 1e6:7.1f} TF(issued)  {flops / t / 1e6:7.1f} TF(alg)  {bytes_ / t / 1e3:7.1f} GB/s(alg)  '
               f'floor_hbm {bytes_ / 6.4934e6:5.1f} us  floor_mma {3 * flops / 1.4688e9:5.1f} us')
     print('overflow', ops.overflow_count())
 

@@ -83,6 +83,7 @@ int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_spl
                    const float* shift, const void* residual_split, void* out_split, float* out_f32,
                    double* stats, cudaStream_t stream);
 int conv_set_trace(long long* buffer, int events_per_role);
+int conv_set_pair_policy(int mode, int min_pair_tiles);
 int conv_dgrad_tc(const VfsConvDesc* d, const void* dz_split, const void* wt_split, const float* ones,
                   const float* zeros, const void* add_split, void* dx_split, cudaStream_t stream);
 int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, int k, cudaStream_t s);
@@ -313,6 +314,7 @@ int vfs_debug_conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const
 int vfs_debug_conv_trace(long long* buffer, int events_per_role) {
   return vfs::conv_set_trace(buffer, events_per_role);
 }
+int vfs_conv_set_pair_policy(int mode, int min_pair_tiles) { return vfs::conv_set_pair_policy(mode, min_pair_tiles); }
 
 int vfs_features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
                           int normalize, vfs_stream_t s) {

@@ -38,6 +38,7 @@ struct alignas(64) ConvKernelParams {
   CUtensorMap tmap_out;           // TMA epilogue: output view, dims {Cout, Wo, Ho, N, 2}, box {64, tw, th, tn, 2}
   CUtensorMap tmap_res;           // TMA epilogue: residual through the same view
   int num_m_tiles, num_n_tiles;
+  int num_sched_tiles;  // tiles walked by the persistent loop: m x n tiles, or (m-tile pairs) x n tiles for CTA pairs
   int tiles_w, tiles_h;  // m_tile = (tn_i * tiles_h + th_i) * tiles_w + tw_i
   int tw, th, tn;        // tile extent in pixels, tw*th*tn == 128
   int Wo, Ho, N;         // output extent
@@ -87,9 +88,10 @@ struct TraceCursor {
   }
 };
 
-template <int BN, int STAGES, int NBUF>
+template <int BN, int STAGES, int NBUF, bool PAIR = false>
 struct ConvSmem {
-  static constexpr int kTileBBytes = BN * kBlockK * 2;                    // one plane of the weight tile
+  static constexpr int kRowsB = PAIR ? BN / 2 : BN;                       // weight rows this CTA stages
+  static constexpr int kTileBBytes = kRowsB * kBlockK * 2;                // one plane of the weight tile
   static constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // hi+lo of A and B
   // epilogue staging: legacy (NBUF == 0) one 128 x 64 fp32 transpose tile; TMA epilogue NBUF output chunks
   static constexpr int kStagingBytes = (NBUF == 0) ? kBlockM * 64 * 4 : NBUF * kChunkBytes;
@@ -101,9 +103,16 @@ struct ConvSmem {
 // NBUF  > 0: TMA epilogue (split output only): results staged as hi/lo planes in the 128B-swizzled box layout and
 //            written with one cp.async.bulk.tensor store per 64-column chunk; RES adds a residual that is brought in by
 //            TMA into the same staging buffer NBUF-1 chunks ahead.
-template <int BN, int STAGES, int NBUF, bool RES>
+// PAIR: the kernel runs as clusters of two CTAs on one TPC and issues tcgen05.mma.cta_group::2 (M = 256): CTA rank r
+//       owns output pixel tile 2*pair + r (its 128 accumulator rows live in its own TMEM) and stages only HALF of the
+//       weight tile (rows r*BN/2 ...), the tensor cores of the two SMs exchange the halves.  Per SM and MMA this
+//       halves the shared-memory reads of B and the TMA fill traffic of B -- the 1-CTA kernel is bound by exactly that
+//       (profiles/r01_conv_trace_v7.log: 1093 cycles per K-chunk against an MMA floor of 768).  Only the leader CTA's
+//       warp 1 issues MMAs; its commits are multicast to the barriers of both CTAs; the peer's TMA loads signal the
+//       leader's full barriers; the peer's epilogue releases accumulator stages on the leader's barrier.
+template <int BN, int STAGES, int NBUF, bool RES, bool PAIR = false>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
-  using S = ConvSmem<BN, STAGES, NBUF>;
+  using S = ConvSmem<BN, STAGES, NBUF, PAIR>;
   static_assert(!RES || NBUF >= 2, "the residual prefetch needs at least two staging buffers");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -121,7 +130,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator stages (power of two: 128 or 256)
+  constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator stages (power of two: 128, 256 or 512)
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  // persistent schedule: this CTA (pair) walks tiles tile_first, tile_first + tile_step, ...
+  const int tile_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  auto m_tile_of = [&](int tile) {
+    const int m = tile / p.num_n_tiles;
+    return PAIR ? 2 * m + static_cast<int>(cta_rank) : m;
+  };
 
   if (warp == 0 && lane == 0) {
     for (int v = 0; v < kMaxViews; ++v) tma_prefetch_desc(&p.tmap_a[v]);
@@ -132,7 +149,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), PAIR ? 16 : 8);  // epilogue warps of both CTAs release the leader's accumulator
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(rfull_bar(b), 1);
@@ -146,11 +163,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_addr, kTmemCols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2sm(tmem_ptr_addr, kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr_addr, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything remote touches them
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
@@ -159,7 +182,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.num_sched_tiles;
   const int num_kchunks = p.num_taps * p.kchunks_per_tap;
 
   if (warp == 0) {
@@ -169,13 +192,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     TraceCursor tr;
     tr.init(0);
     tr.mark(0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+      const int m_tile = m_tile_of(tile);
+      const int n_tile = tile % p.num_n_tiles;
       const int tw_i = m_tile % p.tiles_w;
       const int t2 = m_tile / p.tiles_w;
       const int th_i = t2 % p.tiles_h;
-      const int tn_i = t2 / p.tiles_h;
+      const int tn_i = t2 / p.tiles_h;  // >= tiles_n for the phantom tile of an odd pair: every load is zero fill
       const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.tn;
       for (int kc = 0; kc < num_kchunks; ++kc) {
         mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
@@ -185,10 +208,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           const int c0 = (kc - tap * p.kchunks_per_tap) * kBlockK;
           const uint32_t sa = smem_base + stage * S::kStageBytes;
           const uint32_t sb = sa + 2 * kTileABytes;
-          mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
-          tma_load_5d(sa, &p.tmap_a[p.tap_view[tap]], full_bar(stage), c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap],
-                      n0, 0);
-          tma_load_3d(sb, &p.tmap_b, full_bar(stage), p.tap_koff[tap] + c0, n_tile * BN, 0);
+          if (PAIR) {
+            // both CTAs' bytes are counted on the leader's barrier (the MMA of the pair waits there)
+            if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * S::kStageBytes);
+            tma_load_5d_2sm(sa, &p.tmap_a[p.tap_view[tap]], full_bar(stage), c0, w0 + p.tap_dw[tap],
+                            h0 + p.tap_dh[tap], n0, 0);
+            tma_load_3d_2sm(sb, &p.tmap_b, full_bar(stage), p.tap_koff[tap] + c0,
+                            n_tile * BN + static_cast<int>(cta_rank) * S::kRowsB, 0);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
+            tma_load_5d(sa, &p.tmap_a[p.tap_view[tap]], full_bar(stage), c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap],
+                        n0, 0);
+            tma_load_3d(sb, &p.tmap_b, full_bar(stage), p.tap_koff[tap] + c0, n_tile * BN, 0);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -199,7 +231,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = umma_idesc_f16_f32(kBlockM, BN);
+    constexpr uint32_t idesc = umma_idesc_f16_f32(PAIR ? 2 * kBlockM : kBlockM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -207,7 +239,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     TraceCursor tr;
     tr.init(1);
     tr.mark(0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // PAIR: the peer CTA's warp 1 only takes part in the TMEM allocation
+    for (int tile = tile_first; tile < num_tiles && cta_rank == 0; tile += tile_step) {
       mbar_wait(tempty_bar(as), aphase ^ 1u, 200 + as);
       tr.mark(8);
       tc_fence_after();
@@ -227,12 +260,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
             const uint64_t da_lo = umma_desc_sw128_kmajor(a_lo + koff);
             const uint64_t db_hi = umma_desc_sw128_kmajor(b_hi + koff);
             const uint64_t db_lo = umma_desc_sw128_kmajor(b_lo + koff);
-            umma_f16(d_tmem, da_lo, db_hi, idesc, (kc | k) != 0 ? 1u : 0u);  // small terms first
-            umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
-            umma_f16(d_tmem, da_hi, db_hi, idesc, 1u);
+            if (PAIR) {
+              umma_f16_2sm(d_tmem, da_lo, db_hi, idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_f16_2sm(d_tmem, da_hi, db_lo, idesc, 1u);
+              umma_f16_2sm(d_tmem, da_hi, db_hi, idesc, 1u);
+            } else {
+              umma_f16(d_tmem, da_lo, db_hi, idesc, (kc | k) != 0 ? 1u : 0u);  // small terms first
+              umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+              umma_f16(d_tmem, da_hi, db_hi, idesc, 1u);
+            }
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
-          if (kc == num_kchunks - 1) umma_commit(tfull_bar(as));
+          if (PAIR) {
+            umma_commit_2sm(empty_bar(stage));  // frees the slot in BOTH CTAs when these MMAs retire
+            if (kc == num_kchunks - 1) umma_commit_2sm(tfull_bar(as));
+          } else {
+            umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+            if (kc == num_kchunks - 1) umma_commit(tfull_bar(as));
+          }
         }
         if (kc == num_kchunks - 1) tr.mark(3);
         __syncwarp();
@@ -254,10 +298,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     if constexpr (NBUF > 0) {
       constexpr int kCPT = BN / 64;  // chunks per tile
       auto chunk_coords = [&](int g, int& cc, int& w0, int& h0, int& n0) -> bool {
-        const int tile = blockIdx.x + (g / kCPT) * gridDim.x;
+        const int tile = tile_first + (g / kCPT) * tile_step;
         if (tile >= num_tiles) return false;
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m_tile = m_tile_of(tile);
+        const int n_tile = tile % p.num_n_tiles;
         const int tw_i = m_tile % p.tiles_w;
         const int t2 = m_tile / p.tiles_w;
         cc = n_tile * BN + (g % kCPT) * 64;
@@ -318,7 +362,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     int as = 0;
     uint32_t aphase = 0;
     int g = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
       const int n_tile = tile % p.num_n_tiles;
       // pull this tile's scale / shift lines into L1 while the accumulator is still being produced
       if (lane < BN / 16) {
@@ -341,7 +385,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         if (c == kCPT - 1) {  // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(as));
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(tempty_bar(as), 0);  // the pair's MMA issuer lives in the leader CTA
+            else mbar_arrive(tempty_bar(as));
+          }
         }
         tr.mark(9);
         if (RES) mbar_wait(rfull_bar(b), (g / NBUF) & 1, 500 + b);
@@ -436,7 +483,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     tr.init(2);
     if (ew != 0) tr.base = nullptr;
     tr.mark(0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    static_assert(!PAIR || NBUF > 0, "CTA pairs use the TMA epilogue");
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int tw_i = m_tile % p.tiles_w;
@@ -588,10 +636,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs are done with TMEM and with each other's barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -620,15 +670,42 @@ void choose_tile(int Wo, int Ho, int N, int* tw, int* th, int* tn) {
   }
 }
 
-template <int BN, int STAGES, int NBUF, bool RES>
-int launch(const ConvKernelParams& p, int grid, cudaStream_t stream) {
-  using S = ConvSmem<BN, STAGES, NBUF>;
+// CTA-pair policy: mode 0 = never, 1 = whenever the shape allows, 2 = when the launch has >= min_tiles pair tiles.
+// Initialised from VFS_CONV_PAIR / VFS_CONV_PAIR_MIN_TILES, changed at run time by vfs_conv_set_pair_policy (tests,
+// tuning).
+int g_pair_mode = -1, g_pair_min = 48;
+void conv_pair_policy(int* mode, int* min_tiles) {
+  if (g_pair_mode < 0) {
+    const char* e = getenv("VFS_CONV_PAIR");
+    g_pair_mode = e ? atoi(e) : 2;
+    const char* m = getenv("VFS_CONV_PAIR_MIN_TILES");
+    if (m) g_pair_min = atoi(m);
+  }
+  *mode = g_pair_mode;
+  *min_tiles = g_pair_min;
+}
+
+// Persistent launch: one CTA per SM (or one CTA pair per TPC) walking the tile list; p.num_m_tiles / num_n_tiles must
+// be final.
+template <int BN, int STAGES, int NBUF, bool RES, bool PAIR = false>
+int launch(ConvKernelParams p, cudaStream_t stream) {
+  using S = ConvSmem<BN, STAGES, NBUF, PAIR>;
   static_assert(S::kTotal <= 232448, "shared memory budget (227 KB) exceeded");
+  static_assert(2 * BN <= 512, "two accumulator stages must fit the 512 TMEM columns");
   static bool configured = false;
   if (!configured) {
-    VFS_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, NBUF, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     S::kTotal));
+    VFS_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, NBUF, RES, PAIR>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
+  }
+  const int sms = device_sm_count();
+  int grid;
+  if (PAIR) {
+    p.num_sched_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    grid = 2 * p.num_sched_tiles < (sms & ~1) ? 2 * p.num_sched_tiles : (sms & ~1);
+  } else {
+    p.num_sched_tiles = p.num_m_tiles * p.num_n_tiles;
+    grid = p.num_sched_tiles < sms ? p.num_sched_tiles : sms;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -636,12 +713,16 @@ int launch(const ConvKernelParams& p, int grid, cudaStream_t stream) {
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  VFS_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, NBUF, RES>, p));
+  cfg.numAttrs = PAIR ? 2 : 1;
+  VFS_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, NBUF, RES, PAIR>, p));
   return VFS_OK;
 }
 
@@ -769,9 +850,12 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
     int rc = make_tmap_16b_sw128(&p.tmap_b, c.b_split, 3, dims, strides, box_b);
     if (rc != VFS_OK) return rc;
   }
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int sms = device_sm_count();
-  const int grid = num_tiles < sms ? num_tiles : sms;
+  auto set_weight_map = [&](int box_rows) {
+    const uint64_t dims[3] = {c.Ktot, static_cast<uint64_t>(c.Nout), 2};
+    const uint64_t strides[2] = {c.Ktot * 2, c.Ktot * c.Nout * 2};
+    const uint32_t box_b[3] = {64u, static_cast<uint32_t>(box_rows), 2u};
+    return make_tmap_16b_sw128(&p.tmap_b, c.b_split, 3, dims, strides, box_b);
+  };
   // fp32 output / BN statistics go through the legacy epilogue; the split-only contract uses the TMA epilogue
   static int force_legacy = -1;
   if (force_legacy < 0) {
@@ -780,17 +864,14 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
   }
   const bool legacy = force_legacy || c.out_f32 != nullptr || c.stats != nullptr || c.out_split == nullptr;
   if (legacy) {
-    if (BN == 256) BN = 128, p.num_n_tiles = c.Nout / 128;
-    if (BN == 128) {
-      const uint32_t box_b[3] = {64u, 128u, 2u};
-      const uint64_t dims[3] = {c.Ktot, static_cast<uint64_t>(c.Nout), 2};
-      const uint64_t strides[2] = {c.Ktot * 2, c.Ktot * c.Nout * 2};
-      int rc = make_tmap_16b_sw128(&p.tmap_b, c.b_split, 3, dims, strides, box_b);
+    if (BN == 256) {
+      BN = 128;
+      p.num_n_tiles = c.Nout / 128;
+      int rc = set_weight_map(128);
       if (rc != VFS_OK) return rc;
-      const int nt = p.num_m_tiles * p.num_n_tiles;
-      return launch<128, 3, 0, false>(p, nt < sms ? nt : sms, stream);
     }
-    return launch<64, 4, 0, false>(p, grid, stream);
+    if (BN == 128) return launch<128, 3, 0, false>(p, stream);
+    return launch<64, 4, 0, false>(p, stream);
   }
   {
     // output (and residual) through the same possibly strided pixel view the legacy epilogue addresses by hand
@@ -811,24 +892,45 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
       if (rc != VFS_OK) return rc;
     }
   }
+  // CTA pairs (cta_group::2, 256-pixel x BNp tiles).  Policy 2 (default) uses them where they measured faster on B200
+  // (profiles/r01_layers_pair_v8.log): MMA-bound launches -- 256-wide tiles, no residual stream in the epilogue, at
+  // least 8 K-chunks -- with enough pair tiles to occupy most TPCs.  Memory-bound expand layers (short K, residual)
+  // and small launches (per-video calls, SiamFC crops) keep the finer 1-CTA tiles.  Policy 1 forces pairs wherever
+  // the shape allows (tests), 0 disables them.
+  {
+    int pair_mode, pair_min;
+    conv_pair_policy(&pair_mode, &pair_min);
+    const int BNp = (c.Nout % 256 == 0) ? 256 : ((c.Nout % 128 == 0) ? 128 : 0);
+    if (pair_mode != 0 && BNp != 0 && p.num_m_tiles >= 2) {
+      const int pair_tiles = ((p.num_m_tiles + 1) / 2) * (c.Nout / BNp);
+      const bool profitable = BNp == 256 && !c.res_split && p.num_taps * p.kchunks_per_tap >= 8 &&
+                              pair_tiles >= pair_min;
+      if (pair_mode == 1 || profitable) {
+        p.num_n_tiles = c.Nout / BNp;
+        int rc = set_weight_map(BNp / 2);
+        if (rc != VFS_OK) return rc;
+        if (c.res_split) {
+          if (BNp == 256) return launch<256, 2, 3, true, true>(p, stream);
+          return launch<128, 2, 3, true, true>(p, stream);
+        }
+        if (BNp == 256) return launch<256, 3, 1, false, true>(p, stream);
+        return launch<128, 4, 1, false, true>(p, stream);
+      }
+    }
+  }
   if (c.res_split) {
     if (BN == 256) {
       BN = 128;
       p.num_n_tiles = c.Nout / 128;
-      const uint32_t box_b[3] = {64u, 128u, 2u};
-      const uint64_t dims[3] = {c.Ktot, static_cast<uint64_t>(c.Nout), 2};
-      const uint64_t strides[2] = {c.Ktot * 2, c.Ktot * c.Nout * 2};
-      int rc = make_tmap_16b_sw128(&p.tmap_b, c.b_split, 3, dims, strides, box_b);
+      int rc = set_weight_map(128);
       if (rc != VFS_OK) return rc;
     }
-    const int nt = p.num_m_tiles * p.num_n_tiles;
-    const int gr = nt < sms ? nt : sms;
-    if (BN == 128) return launch<128, 2, 3, true>(p, gr, stream);
-    return launch<64, 2, 3, true>(p, gr, stream);
+    if (BN == 128) return launch<128, 2, 3, true>(p, stream);
+    return launch<64, 2, 3, true>(p, stream);
   }
-  if (BN == 256) return launch<256, 2, 1, false>(p, grid, stream);
-  if (BN == 128) return launch<128, 3, 1, false>(p, grid, stream);
-  return launch<64, 4, 1, false>(p, grid, stream);
+  if (BN == 256) return launch<256, 2, 1, false>(p, stream);
+  if (BN == 128) return launch<128, 3, 1, false>(p, stream);
+  return launch<64, 4, 1, false>(p, stream);
 }
 
 static int check_desc(const VfsConvDesc* d, const char* who) {
@@ -900,6 +1002,14 @@ int conv_bn_act_tc(const VfsConvDesc* d, const void* in_split, const void* w_spl
 // four output-parity classes (dX[2a+pa, 2b+pb] only receives the taps with matching parity), each one launch that
 // writes its strided view of dX; positions no tap reaches get the plain `add` term (or zero).
 // ------------------------------------------------------------------------------------------------
+int conv_set_pair_policy(int mode, int min_pair_tiles) {
+  VFS_REQUIRE(mode >= 0 && mode <= 2 && min_pair_tiles >= 1, VFS_EINVAL, "conv_set_pair_policy: mode %d min %d", mode,
+              min_pair_tiles);
+  g_pair_mode = mode;
+  g_pair_min = min_pair_tiles;
+  return VFS_OK;
+}
+
 int conv_set_trace(long long* buffer, int events_per_role) {
   VFS_CUDA_OK(cudaMemcpyToSymbol(g_conv_trace, &buffer, sizeof(buffer)));
   VFS_CUDA_OK(cudaMemcpyToSymbol(g_conv_trace_cap, &events_per_role, sizeof(events_per_role)));

@@ -98,6 +98,11 @@ def conv_bn_act(xs, w_split, scale, shift, ksize, stride=1, dilation=1, relu=Tru
     return out, out32
 
 
+def conv_set_pair_policy(mode=2, min_pair_tiles=48):
+    """0 = 1-CTA tiles only, 1 = CTA pairs whenever possible, 2 = pairs for launches with >= min_pair_tiles."""
+    check(nat.lib().vfs_conv_set_pair_policy(int(mode), int(min_pair_tiles)), 'conv_set_pair_policy')
+
+
 def debug_conv_bn_act_simt(xs, w_split, scale, shift, ksize, stride=1, dilation=1, relu=True, residual=None):
     """fp32 SIMT evaluation of the same contract (test instrument).  Returns fp32 NHWC."""
     Cout = w_split.shape[1]
