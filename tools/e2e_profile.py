@@ -1,4 +1,5 @@
-"""Where does one VanillaTracker.forward_test call (2-frame 256x256 clip, the bench's e2e unit) spend its time?
+"""Where does one VanillaTracker.forward_test call (batch of 8 two-frame 256x256 videos, the bench's e2e unit) spend
+its time?
 cProfile over 50 calls + a GPU-side view (CUDA events around the call, torch profiler kernel table)."""
 import cProfile
 import os
@@ -25,14 +26,14 @@ def main():
     model.eval()
     model.backbone.engine.check_versions = False
     g = torch.Generator().manual_seed(0)
-    imgs_host = torch.randn(1, 1, 3, bench.FRAMES, bench.SIZE, bench.SIZE, generator=g).pin_memory()
-    seg_host = bench.seg_input(g, torch).pin_memory()
+    imgs_host = torch.randn(bench.CLIPS, 1, 3, bench.FRAMES, bench.SIZE, bench.SIZE, generator=g).pin_memory()
+    seg_host = bench.seg_input(g, torch).expand(bench.CLIPS, bench.SIZE, bench.SIZE).contiguous().pin_memory()
     meta = [dict(original_shape=(bench.SIZE, bench.SIZE, 3))]
 
     def call():
         imgs = imgs_host.to(dev, non_blocking=True)
         seg = seg_host.to(dev, non_blocking=True)
-        return model.forward_test(imgs, seg, meta)[0]
+        return model.forward_test(imgs, seg, meta * bench.CLIPS)[0]
 
     for _ in range(5):
         call()

@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(160, 1) mma_rate_kernel(long long* cycles, int
   if (warp == 0) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16_f32(128, N);
+      unsigned long long g0, g1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
       const long long t0 = clock64();
       for (int it = 0; it < iters; ++it) {
         const uint32_t st = base + (it % distinct_stages) * (64 * 1024);
@@ -58,7 +60,9 @@ __global__ void __launch_bounds__(160, 1) mma_rate_kernel(long long* cycles, int
       umma_commit(bar);
       mbar_wait(bar, 0, 1);
       const long long t1 = clock64();
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
       cycles[blockIdx.x] = t1 - t0;
+      cycles[148 + blockIdx.x] = static_cast<long long>(g1 - g0);  // wall ns of the same interval
       stop = 1;
     }
   } else if (store_traffic) {
@@ -84,12 +88,12 @@ __global__ void __launch_bounds__(160, 1) mma_rate_kernel(long long* cycles, int
 template <int N>
 void run(int iters, int stages, int traffic) {
   long long* d;
-  cudaMalloc(&d, 148 * sizeof(long long));
+  cudaMalloc(&d, 2 * 148 * sizeof(long long));
   const int smem = 200 * 1024 + 1024 + 64;
   cudaFuncSetAttribute(mma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   for (int rep = 0; rep < 2; ++rep) mma_rate_kernel<N><<<148, 160, smem>>>(d, iters, stages, traffic);
   cudaError_t e = cudaDeviceSynchronize();
-  long long h[148];
+  long long h[2 * 148];
   cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
   long long mx = 0, mn = 1LL << 60;
   for (int i = 0; i < 148; ++i) {
@@ -97,9 +101,11 @@ void run(int iters, int stages, int traffic) {
     mn = h[i] < mn ? h[i] : mn;
   }
   const double per = static_cast<double>(mx) / (iters * 12.0);
-  printf("N=%3d stages=%d store_traffic=%d: %.1f cyc per MMA (K=16)  -> %.0f FLOP/cyc/SM  [min CTA %.1f]  %s\n", N,
-         stages, traffic, per, 2.0 * 128 * N * 16 / per, static_cast<double>(mn) / (iters * 12.0),
-         cudaGetErrorString(e));
+  printf("N=%3d stages=%d store_traffic=%d iters=%d: %.1f cyc per MMA (K=16)  -> %.0f FLOP/cyc/SM  [min CTA %.1f]  "
+         "SM clock during the run %.0f MHz (%.2f ms)  -> %.0f TFLOP/s chip  %s\n", N,
+         stages, traffic, iters, per, 2.0 * 128 * N * 16 / per, static_cast<double>(mn) / (iters * 12.0),
+         1e3 * static_cast<double>(h[0]) / static_cast<double>(h[148]), h[148] * 1e-6,
+         148.0 * 2.0 * 128 * N * 16 * iters * 12.0 / static_cast<double>(h[148]) * 1e-3, cudaGetErrorString(e));
   cudaFree(d);
 }
 
@@ -110,5 +116,9 @@ int main() {
     run<256>(2000, 2, traffic);
   }
   run<128>(2000, 1, 0);
+  // sustained: does the chip hold its clock under all-SM tensor load?
+  run<256>(200, 2, 0);
+  run<256>(20000, 2, 0);
+  run<256>(200000, 2, 0);
   return 0;
 }

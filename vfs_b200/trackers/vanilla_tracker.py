@@ -166,8 +166,12 @@ class VanillaTracker(BaseTracker):
                     preds[b0:b0 + len(vids), frame_idx] = F.interpolate(
                         seg_logit.view(len(vids), cv, fh, fw), size=orig_hw, mode='bilinear', align_corners=False)
 
-        # one device->host copy per call
-        seg_preds = preds.cpu().numpy()
+        # one device->host copy per call, into pinned memory from torch's caching host allocator (a pageable
+        # destination makes the copy several times slower); the returned arrays are views that keep the block alive
+        host = torch.empty(preds.shape, dtype=preds.dtype, pin_memory=True)
+        host.copy_(preds, non_blocking=True)
+        torch.cuda.current_stream(imgs.device).synchronize()
+        seg_preds = host.numpy()
         if self.save_np:
             assert seg_preds.shape[0] == 1
             eval_dir = '.eval'
