@@ -233,6 +233,15 @@ int vfs_seg_postprocess(const float* logit, unsigned char* out_labels, void* wor
  * out_labels [num_maps][H][W]; workspace num_maps * vfs_seg_postprocess_workspace_bytes(Cv). */
 int vfs_seg_postprocess_batched(const float* logit, unsigned char* out_labels, void* workspace, int num_maps, int Cv,
                                 int h, int w, int H, int W, vfs_stream_t s);
+/* SiamFC response post-processing (TrackerSiamFC.update, projects/siamfc-pytorch/siamfc/siamfc_tracker_base.py:263-291):
+ * responses fp32 [num_scales][R][R] -> cv2-compatible bicubic upsample to [U][U], scale_penalty on the non-centre
+ * scales, scale with the largest peak, (map - min) / sum blended with hann_window (fp64 [U][U], already normalised)
+ * by window_influence, first arg-max.  out_scale_row_col int32[3] = {scale id, peak row, peak column} (device memory).
+ * workspace: vfs_siamfc_peak_workspace_bytes(num_scales, U). */
+size_t vfs_siamfc_peak_workspace_bytes(int num_scales, int upscaled_size);
+int vfs_siamfc_response_peak(const float* responses, int num_scales, int response_size, int upscaled_size,
+                             const double* hann_window, float scale_penalty, float window_influence, void* workspace,
+                             int32_t* out_scale_row_col, vfs_stream_t s);
 /* Dense helpers of common/affinity_utils.py:6-50 (compute_affinity / propagate; exported by the reference, unused by
  * its trackers).  The HW x HW GEMM itself is vfs_conv_bn_act with the dst pixels as 1x1 filters; these finish it:
  *   vfs_masked_softmax  A [B][R][ld] -> out [B][R][Cc]: mask (analytic window, mask[i,j]) to -inf, softmax over

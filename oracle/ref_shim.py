@@ -160,3 +160,16 @@ def load_reference():
         compute_affinity=common.compute_affinity, propagate=common.propagate)
     _loaded = ns
     return ns
+
+
+def load_reference_siamfc_ops():
+    """projects/siamfc-pytorch/siamfc/ops.py (+ bbox_utils.py, image_utils.py: plain cv2 / numpy) imported unchanged
+    through a stub parent package, for pinning the crop helper of the SiamFC tracker."""
+    if not available():
+        raise RuntimeError(f'reference tree not found at {REF_ROOT}')
+    name = 'ref_siamfc_pkg'
+    if name not in sys.modules:
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [os.path.join(REF_ROOT, 'projects', 'siamfc-pytorch', 'siamfc')]
+        sys.modules[name] = pkg
+    return importlib.import_module(name + '.ops')

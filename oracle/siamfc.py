@@ -19,3 +19,125 @@ def siam_conv_fc(sd, z, x, out_scale=0.001, num_convs=1):
         z = F.conv2d(z, sd[f'z_convs.{i}.weight'], sd[f'z_convs.{i}.bias'])
         x = F.conv2d(x, sd[f'x_convs.{i}.weight'], sd[f'x_convs.{i}.bias'])
     return xcorr(z, x, out_scale)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# TrackerSiamFC inference (projects/siamfc-pytorch/siamfc/siamfc_tracker_base.py:200-319), restated with the same
+# cv2 / numpy calls.  The reference class derives from got10k.trackers.Tracker (not installed) and cannot be imported;
+# its crop helper (siamfc/ops.py + image_utils.py, plain cv2/numpy) CAN be, and pins ``crop_and_resize`` below
+# (tests/test_host_cpu.py::test_siamfc_crop_matches_reference).  The init/update arithmetic itself is "parity
+# unpinned": restated from the file, checked against the CUDA path only.
+# ----------------------------------------------------------------------------------------------------------------
+def crop_and_resize(img, center, size, out_size, border_value=None):
+    """ops.py:87-104 (faster=True) -> image_utils.py:7-76: crop around ``center`` (y, x), resize, pad with the mean
+    colour."""
+    import cv2
+    import numpy as np
+    size = max(2, size)
+    b = np.array([center[1], center[0], size, size]).astype(np.float32)          # bbox_utils.py:27-40 (list input)
+    x1, y1, x2, y2 = b[0] - b[2] / 2.0, b[1] - b[3] / 2.0, b[0] + b[2] / 2.0, b[1] + b[3] / 2.0
+    avg = np.mean(img, axis=(0, 1), dtype=float)
+    w, h = float(x2 - x1), float(y2 - y1)
+    xc, yc = float(x1 + x2) / 2, float(y1 + y2) / 2
+    box = np.round(np.array([xc - w / 2, yc - h / 2, xc + w / 2, yc + h / 2])).astype(int)
+    bw = np.array([box[2] - box[0], box[3] - box[1]])
+    H, W = img.shape[:2]
+    patch = img[max(box[1], 0):min(box[3], H), max(box[0], 0):min(box[2], W), :]
+    bounded = np.clip(box, 0, np.array([W, H, W, H]))
+    bwh = np.array([bounded[2] - bounded[0], bounded[3] - bounded[1]])
+    if patch.shape[0] == 0 or patch.shape[1] == 0:
+        return np.zeros((int(out_size), int(out_size), 3), dtype=patch.dtype)
+    patch = cv2.resize(patch, (max(1, int(np.round(out_size * bwh[0] / bw[0]))),
+                               max(1, int(np.round(out_size * bwh[1] / bw[1])))), interpolation=cv2.INTER_LINEAR)
+    pad = np.zeros(4, dtype=int)
+    pad[:2] = np.maximum(0, -box[:2] * out_size / bw)
+    pad[2:] = out_size - (pad[:2] + np.array(patch.shape)[[1, 0]])
+    if np.any(pad != 0):
+        if len(pad[pad < 0]) > 0:
+            return np.zeros((int(out_size), int(out_size), 3))
+        return cv2.copyMakeBorder(patch, pad[1], pad[3], pad[0], pad[2], cv2.BORDER_CONSTANT, value=avg)
+    return patch
+
+
+def response_peak(responses, hann_window, upscale_sz, scale_num, scale_penalty, window_influence):
+    """siamfc_tracker_base.py:263-291: responses float32 [S,R,R] -> (scale_id, (row, col), blended map)."""
+    import cv2
+    import numpy as np
+    responses = np.stack([cv2.resize(u, (upscale_sz, upscale_sz), interpolation=cv2.INTER_CUBIC) for u in responses])
+    responses[:scale_num // 2] *= scale_penalty
+    responses[scale_num // 2 + 1:] *= scale_penalty
+    scale_id = np.argmax(np.amax(responses, axis=(1, 2)))
+    response = responses[scale_id]
+    response -= response.min()
+    response /= response.sum() + 1e-16
+    response = (1 - window_influence) * response + window_influence * hann_window
+    loc = np.unravel_index(response.argmax(), response.shape)
+    return int(scale_id), (int(loc[0]), int(loc[1])), response
+
+
+class TrackerOracle:
+    """init / update of the reference tracker on the CPU: oracle backbone + head, cv2 crops and post-processing."""
+
+    def __init__(self, cfg, backbone_sd, head_sd, depth):
+        self.cfg, self.bsd, self.hsd, self.depth = cfg, backbone_sd, head_sd, depth
+
+    def _features(self, crops):
+        import numpy as np
+        import torch
+        from .resnet import resnet_forward
+        x = torch.from_numpy(np.ascontiguousarray(crops)).permute(0, 3, 1, 2).float()
+        mean = torch.tensor([123.675, 116.28, 103.53]).view(1, 3, 1, 1)
+        std = torch.tensor([58.395, 57.12, 57.375]).view(1, 3, 1, 1)
+        b = self.cfg['model']['backbone']
+        with torch.no_grad():
+            return resnet_forward(self.bsd, (x - mean) / std, self.depth, b['strides'], b['dilations'],
+                                  b['out_indices'])
+
+    def init(self, img, box):
+        import numpy as np
+        cfg = self.cfg
+        box = np.array([box[1] - 1 + (box[3] - 1) / 2, box[0] - 1 + (box[2] - 1) / 2, box[3], box[2]],
+                       dtype=np.float32)
+        self.center, self.target_sz = box[:2], box[2:]
+        self.upscale_sz = cfg['response_up'] * cfg['response_sz']
+        self.hann_window = np.outer(np.hanning(self.upscale_sz), np.hanning(self.upscale_sz))
+        self.hann_window /= self.hann_window.sum()
+        self.scale_factors = cfg['scale_step']**np.linspace(-(cfg['scale_num'] // 2), cfg['scale_num'] // 2,
+                                                            cfg['scale_num'])
+        context = cfg['context'] * np.sum(self.target_sz)
+        self.z_sz = np.sqrt(np.prod(self.target_sz + context))
+        self.x_sz = self.z_sz * cfg['instance_sz'] / cfg['exemplar_sz']
+        z = crop_and_resize(img, self.center, self.z_sz, cfg['exemplar_sz'])
+        self.kernel = self._features(z[None])
+
+    def responses(self, img):
+        import numpy as np
+        import torch
+        cfg = self.cfg
+        x = np.stack([crop_and_resize(img, self.center, self.x_sz * f, cfg['instance_sz'])
+                      for f in self.scale_factors], axis=0)
+        feats = self._features(x)
+        with torch.no_grad():
+            if self.hsd is not None:
+                r = siam_conv_fc(self.hsd, self.kernel, feats, cfg['out_scale'])
+            else:
+                r = xcorr(self.kernel, feats, cfg['out_scale'])
+        return r.squeeze(1).numpy()
+
+    def update(self, img, responses=None):
+        import numpy as np
+        cfg = self.cfg
+        if responses is None:
+            responses = self.responses(img)
+        scale_id, loc, _ = response_peak(responses, self.hann_window, self.upscale_sz, cfg['scale_num'],
+                                         cfg['scale_penalty'], cfg['window_influence'])
+        disp_in_response = np.array(loc) - (self.upscale_sz - 1) / 2
+        disp_in_instance = disp_in_response * cfg['total_stride'] / cfg['response_up']
+        disp_in_image = disp_in_instance * self.x_sz * self.scale_factors[scale_id] / cfg['instance_sz']
+        self.center += disp_in_image
+        scale = (1 - cfg['scale_lr']) * 1.0 + cfg['scale_lr'] * self.scale_factors[scale_id]
+        self.target_sz *= scale
+        self.z_sz *= scale
+        self.x_sz *= scale
+        return np.array([self.center[1] + 1 - (self.target_sz[1] - 1) / 2,
+                         self.center[0] + 1 - (self.target_sz[0] - 1) / 2, self.target_sz[1], self.target_sz[0]])

@@ -159,3 +159,19 @@ def tracker_test_inputs(c):
         y0, x0 = 8 * o, 12 * o
         seg[0, y0:y0 + 24, x0:x0 + 30] = o
     return imgs, seg
+
+
+# ------------------------------------------------------------------ SiamFC tracker crops (host side, cv2)
+SIAMFC_CROP_CASES = {
+    # name: (center y, center x, crop size, output size) on a seeded 180 x 240 RGB image
+    'inside_z': (90.0, 120.0, 80.3, 120),
+    'top_left_x': (10.0, 20.0, 100.7, 255),
+    'bottom_right_x': (170.0, 230.0, 150.2, 255),
+    'larger_than_image': (90.0, 120.0, 400.0, 255),
+    'tiny': (50.0, 60.0, 1.0, 120),
+}
+
+
+def siamfc_image():
+    import numpy as np
+    return np.random.RandomState(900).randint(0, 256, (180, 240, 3)).astype(np.uint8)

@@ -106,7 +106,24 @@ def reference_outputs():
     return out
 
 
+def siamfc_crop_outputs():
+    """Crops of the reference's own siamfc/ops.py::crop_and_resize (cv2) -> tests/golden/siamfc_crop_golden.npz."""
+    refops = ref_shim.load_reference_siamfc_ops()
+    img = cases.siamfc_image()
+    out = {}
+    for name, (cy, cx, size, out_size) in cases.SIAMFC_CROP_CASES.items():
+        out[name] = refops.crop_and_resize(img, np.array([cy, cx], dtype=np.float32), size, out_size=out_size,
+                                           border_value=np.mean(img, axis=(0, 1)))
+    return out
+
+
 def main():
+    crops = siamfc_crop_outputs()
+    crop_path = os.path.join(ROOT, 'tests', 'golden', 'siamfc_crop_golden.npz')
+    np.savez_compressed(crop_path, **crops)
+    print(f'wrote {crop_path}: {len(crops)} arrays')
+    if '--only-siamfc' in sys.argv:
+        return
     torch.set_num_threads(8)
     out = reference_outputs()
     path = os.path.join(ROOT, 'tests', 'golden', 'vfs_golden.npz')

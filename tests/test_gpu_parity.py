@@ -487,6 +487,84 @@ def test_xcorr_matches_reference_golden(golden, name):
     assert rel_err(got, golden[f'xcorr/{name}/siamconvfc']) < REL_TOL
 
 
+# --------------------------------------------------------------------------------------------- SiamFC tracker
+def _smooth_maps(gen, S, R):
+    """Response-like maps: a few Gaussian bumps + small noise (a pure-noise map makes the arg-max a coin toss)."""
+    ys, xs = torch.meshgrid(torch.arange(R).float(), torch.arange(R).float(), indexing='ij')
+    maps = 0.02 * torch.randn(S, R, R, generator=gen)
+    for s in range(S):
+        for _ in range(3):
+            cy, cx = (torch.rand(2, generator=gen) * (R - 1)).tolist()
+            amp, sig = float(torch.rand(1, generator=gen)) + 0.3, float(torch.rand(1, generator=gen)) * 2 + 1.0
+            maps[s] += amp * torch.exp(-((ys - cy)**2 + (xs - cx)**2) / (2 * sig * sig))
+    return maps
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_siamfc_response_peak_matches_cv2_oracle(seed):
+    """Device-side bicubic upsample + penalty + Hann blend + arg-max against the reference's cv2 / numpy sequence
+    (siamfc_tracker_base.py:263-291)."""
+    from oracle import siamfc as o_siamfc
+    from vfs_b200 import ops
+    gen = torch.Generator().manual_seed(900 + seed)
+    S, R, up = 3, 17, 16
+    U = R * up
+    maps = _smooth_maps(gen, S, R)
+    if seed % 3 == 0:
+        maps[1] *= 0.3                       # make a non-centre scale win
+    hann = np.outer(np.hanning(U), np.hanning(U))
+    hann /= hann.sum()
+    got = ops.siamfc_response_peak(maps.cuda(), torch.from_numpy(hann).cuda(), U, 0.9745, 0.176).cpu().tolist()
+    sid, loc, blended = o_siamfc.response_peak(maps.numpy().copy(), hann, U, S, 0.9745, 0.176)
+    assert got[0] == sid
+    if (got[1], got[2]) != loc:              # only an fp32-level near-tie may move the peak
+        assert abs(blended[got[1], got[2]] - blended[loc]) <= 1e-6 * abs(blended[loc])
+        assert abs(got[1] - loc[0]) <= 1 and abs(got[2] - loc[1]) <= 1
+
+
+def test_siamfc_tracker_matches_oracle():
+    """TrackerSiamFC.init / update (R18, SiamConvFC head, 127 / 255 crops) on a synthetic moving blob against the
+    CPU oracle tracker: response maps within 1e-3, boxes within a fraction of a pixel."""
+    import vfs_b200  # noqa: F401
+    from oracle import siamfc as o_siamfc
+    from vfs_b200.siamfc import TrackerSiamFC, build_cfg
+    cfg = build_cfg(dict(type='ResNet', depth=18, pretrained=None, norm_cfg=dict(type='BN', requires_grad=True)),
+                    exemplar_sz=127, out_scale=1e-3)
+    trk = TrackerSiamFC(cfg)
+    bsd = oracle.seeded_state_dict(trk.net.backbone, seed=71)
+    trk.net.backbone.load_state_dict(bsd)
+    hsd = oracle.seeded_state_dict(trk.net.head, seed=72)
+    trk.net.head.load_state_dict(hsd)
+    trk.net.to('cuda')
+    rng = np.random.RandomState(5)
+    base = (rng.rand(240, 320, 3) * 60 + 60)
+    frames = []
+    for f in range(4):
+        img = base.copy()
+        cy, cx = 120 + 6 * f, 150 + 9 * f
+        yy, xx = np.mgrid[0:240, 0:320]
+        blob = np.exp(-(((yy - cy) / 14.0)**2 + ((xx - cx) / 20.0)**2))
+        img += 150 * blob[..., None] * np.array([1.0, 0.6, 0.2])
+        frames.append(np.clip(img, 0, 255).astype(np.uint8))
+    box0 = [150 - 30 + 1, 120 - 21 + 1, 60, 42]          # 1-indexed x, y, w, h
+    ref = o_siamfc.TrackerOracle({k: cfg[k] for k in cfg}, {k: v.cpu() for k, v in bsd.items()},
+                                 {k: v.cpu() for k, v in hsd.items()}, 18)
+    trk.init(frames[0], box0)
+    ref.init(frames[0], box0)
+    assert rel_err(trk.kernel, ref.kernel) < REL_TOL
+    for img in frames[1:]:
+        r_gpu = trk.responses(img)
+        r_ref = ref.responses(img)
+        assert tuple(r_gpu.shape) == r_ref.shape == (3, 17, 17)
+        assert rel_err(r_gpu, r_ref) < REL_TOL
+        b_gpu = trk.update(img)
+        b_ref = ref.update(img, responses=r_ref)
+        assert np.abs(b_gpu - b_ref).max() < 0.75, (b_gpu, b_ref)    # <= one upsampled-response step (0.5 px)
+        # keep the two trackers on the same trajectory so that later frames compare the same crops
+        trk.center, trk.target_sz = ref.center.copy(), ref.target_sz.copy()
+        trk.z_sz, trk.x_sz = ref.z_sz, ref.x_sz
+
+
 # --------------------------------------------------------------------------------------------- trackers
 @pytest.mark.parametrize('name', sorted(cases.TRACKER_TEST_CASES))
 def test_vanilla_tracker_matches_reference_golden(golden, name):

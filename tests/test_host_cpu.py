@@ -269,3 +269,38 @@ def test_sgd_and_autograd_reject_cpu():
         build_optimizer(torch.nn.Linear(2, 2), dict(type='Adam', lr=1e-3))
     opt = build_optimizer(torch.nn.Linear(2, 2), dict(type='SGD', lr=0.05, momentum=0.9, weight_decay=1e-4))
     assert opt.param_groups[0]['momentum'] == 0.9
+
+
+# --------------------------------------------------------------------------------------------- SiamFC tracker (host)
+def test_siamfc_crop_matches_reference_golden():
+    """Product crop helper and oracle restatement == the reference's siamfc/ops.py::crop_and_resize (cv2) bit for bit:
+    committed fixtures everywhere, plus the live reference where /root/reference exists."""
+    import os
+    import numpy as np
+    from oracle import ref_shim, siamfc as o_siamfc
+    from tests.golden import cases
+    from vfs_b200.siamfc import image_ops
+    img = cases.siamfc_image()
+    with np.load(os.path.join(os.path.dirname(__file__), 'golden', 'siamfc_crop_golden.npz')) as z:
+        gold = {k: z[k] for k in z.files}
+    refops = ref_shim.load_reference_siamfc_ops() if ref_shim.available() else None
+    for name, (cy, cx, size, out_size) in cases.SIAMFC_CROP_CASES.items():
+        center = np.array([cy, cx], dtype=np.float32)
+        mine = image_ops.crop_and_resize(img, center, size, out_size)
+        orc = o_siamfc.crop_and_resize(img, center, size, out_size)
+        assert mine.dtype == gold[name].dtype and mine.shape == gold[name].shape == (out_size, out_size, 3)
+        np.testing.assert_array_equal(mine, gold[name])
+        np.testing.assert_array_equal(orc, gold[name])
+        if refops is not None:
+            live = refops.crop_and_resize(img, center, size, out_size=out_size, border_value=np.mean(img, axis=(0, 1)))
+            np.testing.assert_array_equal(live, gold[name])
+
+
+def test_siamfc_tracker_config_and_registry():
+    """default_config_base.py values and the backbone override used by TrackerSiamFC."""
+    from vfs_b200.siamfc import DEFAULT_CFG, build_cfg
+    cfg = build_cfg(dict(type='ResNet', depth=18, pretrained=None), exemplar_sz=127)
+    assert cfg.exemplar_sz == 127 and cfg.instance_sz == 255 and cfg.response_sz * cfg.response_up == 272
+    b = cfg.model.backbone
+    assert tuple(b.strides) == (1, 2, 1, 1) and tuple(b.dilations) == (1, 1, 2, 4) and b.norm_eval and b.depth == 18
+    assert DEFAULT_CFG['exemplar_sz'] == 120          # the reference default, not BASELINE's 127

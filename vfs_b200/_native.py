@@ -71,6 +71,8 @@ PROTOTYPES = {
     'vfs_features_to_split_ex': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _vp]),
     'vfs_seg_postprocess_workspace_bytes': (_sz, [_i]),
     'vfs_seg_postprocess': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'vfs_siamfc_peak_workspace_bytes': (_sz, [_i, _i]),
+    'vfs_siamfc_response_peak': (_i, [_vp, _i, _i, _i, _vp, _f, _f, _vp, _vp, _vp]),
     'vfs_seg_postprocess_batched': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'vfs_masked_softmax': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'vfs_propagate_dense': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

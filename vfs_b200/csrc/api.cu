@@ -136,6 +136,9 @@ int stem_bn_relu_pool(const void* conv_out, const float* scale, const float* shi
 int features_to_split(const float* in_nchw, void* out_split, void* inv_norm_ws, int N, int C, int H, int W,
                       int normalize, int c_stride, long long plane_stride, cudaStream_t s);
 size_t seg_postprocess_workspace_bytes(int Cv);
+size_t siamfc_peak_workspace_bytes(int S, int U);
+int siamfc_response_peak(const float* responses, int S, int R, int U, const double* hann, float scale_penalty,
+                         float window_influence, void* workspace, int* out3, cudaStream_t s);
 int seg_postprocess(const float* logit, unsigned char* out, void* workspace, int P, int Cv, int h, int w, int H,
                     int W, cudaStream_t s);
 int masked_softmax(const float* A, float* out, int B, int R, int Cc, int ld, int softmax_dim, int mask_mode, int ry,
@@ -328,6 +331,15 @@ size_t vfs_seg_postprocess_workspace_bytes(int Cv) { return vfs::seg_postprocess
 int vfs_seg_postprocess(const float* logit, unsigned char* out_labels, void* workspace, int Cv, int h, int w, int H,
                         int W, vfs_stream_t s) {
   return vfs::seg_postprocess(logit, out_labels, workspace, 1, Cv, h, w, H, W, s);
+}
+size_t vfs_siamfc_peak_workspace_bytes(int num_scales, int upscaled_size) {
+  return vfs::siamfc_peak_workspace_bytes(num_scales, upscaled_size);
+}
+int vfs_siamfc_response_peak(const float* responses, int num_scales, int response_size, int upscaled_size,
+                             const double* hann_window, float scale_penalty, float window_influence, void* workspace,
+                             int32_t* out_scale_row_col, vfs_stream_t s) {
+  return vfs::siamfc_response_peak(responses, num_scales, response_size, upscaled_size, hann_window, scale_penalty,
+                                   window_influence, workspace, out_scale_row_col, s);
 }
 int vfs_seg_postprocess_batched(const float* logit, unsigned char* out_labels, void* workspace, int num_maps, int Cv,
                                 int h, int w, int H, int W, vfs_stream_t s) {

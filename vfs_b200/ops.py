@@ -8,7 +8,7 @@ from . import _native as nat
 from ._native import VfsConvDesc, current_stream, ptr
 
 LAUNCHES = [0]  # kernels of libvfs_b200.so launched through this module (bench.py reports the count)
-_KERNELS_PER_CALL = {'stem_forward': 2, 'masked_attention': 2, 'features_to_split_norm': 2, 'conv_dgrad': 1, 'conv_wgrad': 2, 'seg_postprocess': 3}
+_KERNELS_PER_CALL = {'stem_forward': 2, 'masked_attention': 2, 'features_to_split_norm': 2, 'conv_dgrad': 1, 'conv_wgrad': 2, 'seg_postprocess': 3, 'siamfc_response_peak': 3}
 
 
 def check(rc, what=''):
@@ -695,6 +695,24 @@ def seg_postprocess(seg_logit, fh, fw, out_hw, out=None):
     ws = torch.empty((P * 2 * Cv, ), dtype=torch.int32, device=seg_logit.device)
     check(nat.lib().vfs_seg_postprocess_batched(ptr(seg_logit), ptr(out), ptr(ws), P, Cv, fh, fw, H, W,
                                                 current_stream()), 'seg_postprocess')
+    return out
+
+
+def siamfc_response_peak(responses, hann_window, upscaled_size, scale_penalty, window_influence):
+    """responses fp32 [S,R,R] (CUDA), hann_window fp64 [U,U] (CUDA, normalised) -> int32[3] device tensor
+    {scale id, peak row, peak column} of the upsampled, penalised, window-blended response (csrc/post.cu)."""
+    _require_cuda(responses, 'responses')
+    _require_cuda(hann_window, 'hann_window')
+    assert responses.dtype == torch.float32 and responses.ndim == 3 and responses.shape[1] == responses.shape[2]
+    assert hann_window.dtype == torch.float64 and tuple(hann_window.shape) == (upscaled_size, upscaled_size)
+    S, R = responses.shape[0], responses.shape[1]
+    responses, hann_window = responses.contiguous(), hann_window.contiguous()
+    ws = torch.empty((nat.lib().vfs_siamfc_peak_workspace_bytes(S, upscaled_size), ), dtype=torch.uint8,
+                     device=responses.device)
+    out = torch.empty((3, ), dtype=torch.int32, device=responses.device)
+    check(nat.lib().vfs_siamfc_response_peak(ptr(responses), S, R, int(upscaled_size), ptr(hann_window),
+                                             float(scale_penalty), float(window_influence), ptr(ws), ptr(out),
+                                             current_stream()), 'siamfc_response_peak')
     return out
 
 
