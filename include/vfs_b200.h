@@ -233,6 +233,15 @@ int vfs_seg_postprocess(const float* logit, unsigned char* out_labels, void* wor
  * out_labels [num_maps][H][W]; workspace num_maps * vfs_seg_postprocess_workspace_bytes(Cv). */
 int vfs_seg_postprocess_batched(const float* logit, unsigned char* out_labels, void* workspace, int num_maps, int Cv,
                                 int h, int w, int H, int W, vfs_stream_t s);
+/* General form of masked_attention_efficient (local_attention.py:287-342) for an arbitrary boolean mask and / or
+ * topk = None -- the cases the fused window kernel (vfs_masked_attention*) does not take.  affinity fp32
+ * [rows = T*HWk][ld >= HWq] of ONE batch item, already divided by the temperature (vfs_conv_bn_act: key pixels as the
+ * image, query pixels as 1x1 filters, scale = 1/temperature); mask uint8 [HWk][HWq] or NULL, applied to key frames
+ * t >= non_mask_len; values fp32 [Cv][rows]; topk in [1,16] or 0 = all keys; mode 0 softmax, 1 clamp(min=0)^2.
+ * out fp32 [Cv][HWq]. */
+int vfs_generic_attention(const float* affinity, int rows, int ld, int HWk, int HWq, const unsigned char* mask,
+                          int non_mask_len, const float* values, int Cv, int topk, int mode, float* out,
+                          vfs_stream_t s);
 /* SiamFC response post-processing (TrackerSiamFC.update, projects/siamfc-pytorch/siamfc/siamfc_tracker_base.py:263-291):
  * responses fp32 [num_scales][R][R] -> cv2-compatible bicubic upsample to [U][U], scale_penalty on the non-centre
  * scales, scale with the largest peak, (map - min) / sum blended with hann_window (fp64 [U][U], already normalised)

@@ -428,6 +428,50 @@ def test_attention_matches_reference_golden(golden, name):
     assert bool((tv[0][:-1] >= tv[0][1:]).all())
 
 
+GENERIC_ATTN_CASES = [
+    # name, N, C, Cv, T, (Hq, Wq), (Hk, Wk), mask kind, topk, mode, non_mask_len
+    ('bool2d_topk', 1, 64, 3, 2, (9, 11), (9, 11), 'random2d', 5, 'softmax', 0),
+    ('bool2d_first_free', 1, 64, 4, 3, (8, 8), (8, 8), 'random2d', 10, 'softmax', 1),
+    ('window_dense_softmax', 1, 32, 3, 2, (9, 11), (9, 11), 'window', None, 'softmax', 0),
+    ('nomask_dense_softmax', 2, 64, 20, 1, (7, 9), (7, 9), None, None, 'softmax', 0),
+    ('bool3d_topk', 2, 64, 3, 1, (8, 9), (8, 9), 'random3d', 4, 'softmax', 0),
+    ('dense_cosine', 1, 64, 2, 2, (6, 7), (6, 7), 'random2d', None, 'cosine', 0),
+    ('rect_query_vs_key', 1, 64, 3, 2, (6, 7), (8, 9), None, 6, 'softmax', 0),
+]
+
+
+@pytest.mark.parametrize('case', GENERIC_ATTN_CASES, ids=[c[0] for c in GENERIC_ATTN_CASES])
+def test_attention_general_masks_and_dense_softmax_match_oracle(case):
+    """Arbitrary boolean mask tensors, topk=None and query / key maps of different sizes (general kernel,
+    csrc/dense.cu) against the oracle restatement of local_attention.py:237-348."""
+    from vfs_b200.common import masked_attention_efficient, spatial_neighbor
+    _, N, C, Cv, T, (Hq, Wq), (Hk, Wk), kind, topk, mode, nml = case
+    g = torch.Generator().manual_seed(len(case[0]) * 17 + N)
+    q = torch.relu(torch.randn(N, C, Hq, Wq, generator=g))
+    k = torch.relu(torch.randn(N, C, T, Hk, Wk, generator=g))
+    v = torch.rand(N, Cv, T, Hk, Wk, generator=g)
+    hwk, hwq = Hk * Wk, Hq * Wq
+    mask = ref_mask = None
+    if kind == 'random2d':
+        ref_mask = torch.rand(hwk, hwq, generator=g) > 0.4
+        ref_mask[:16] = True                                # every query keeps at least 16 keys
+        mask = ref_mask
+    elif kind == 'random3d':
+        ref_mask = torch.rand(N, hwk, hwq, generator=g) > 0.4
+        ref_mask[:, :16] = True
+        mask = ref_mask
+    elif kind == 'window':
+        mask = spatial_neighbor(1, Hk, Wk, 8)
+        ref_mask = oracle.spatial_neighbor(Hk, Wk, 8)
+    out = masked_attention_efficient(q.cuda(), k.cuda(), v.cuda(), mask.cuda() if torch.is_tensor(mask) else mask,
+                                     temperature=0.07 if mode == 'softmax' else 1.0, topk=topk, non_mask_len=nml,
+                                     mode=mode)
+    ref = oracle.masked_attention_efficient(q, k, v, ref_mask, temperature=0.07 if mode == 'softmax' else 1.0,
+                                            topk=topk, non_mask_len=nml, mode=mode)
+    assert tuple(out.shape) == tuple(ref.shape) == (N, Cv, Hq, Wq)
+    assert rel_err(out, ref) < REL_TOL
+
+
 def test_attention_multi_batch_matches_oracle():
     """N > 1 batch items (the reference API allows it) run as problems of one launch."""
     from vfs_b200.common import masked_attention_efficient, spatial_neighbor

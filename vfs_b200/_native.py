@@ -71,6 +71,7 @@ PROTOTYPES = {
     'vfs_features_to_split_ex': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _vp]),
     'vfs_seg_postprocess_workspace_bytes': (_sz, [_i]),
     'vfs_seg_postprocess': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'vfs_generic_attention': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     'vfs_siamfc_peak_workspace_bytes': (_sz, [_i, _i]),
     'vfs_siamfc_response_peak': (_i, [_vp, _i, _i, _i, _vp, _f, _f, _vp, _vp, _vp]),
     'vfs_seg_postprocess_batched': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -8,9 +8,9 @@ from .affinity_utils import NeighborMask
 
 def masked_attention_efficient(query, key, value, mask, temperature=1, topk=None, normalize=True, step=32,
                                non_mask_len=0, mode='softmax'):
-    """query [N,C,H,W], key [N,C,T,H,W] (or [N,C,H,W]), value [N,Cv,T,H,W]; ``mask`` is None or the
-    ``NeighborMask`` returned by ``spatial_neighbor``.  ``step`` (the reference's memory chunking) is accepted and
-    ignored.  Returns [N,Cv,H,W] fp32."""
+    """query [N,C,H,W], key [N,C,T,H,W] (or [N,C,H,W]), value [N,Cv,T,H,W]; ``mask`` is None, the ``NeighborMask``
+    returned by ``spatial_neighbor`` (fused window kernel) or any boolean tensor [HWk,HWq] / [N,HWk,HWq] (general
+    kernel).  ``step`` (the reference's memory chunking) is accepted and ignored.  Returns [N,Cv,H,W] fp32."""
     assert mode in ['softmax', 'cosine']
     assert query.size(0) == key.size(0) == value.size(0)
     assert value.shape[2:] == key.shape[2:], f'{value.shape} {key.shape}'
@@ -20,16 +20,17 @@ def masked_attention_efficient(query, key, value, mask, temperature=1, topk=None
     assert value.ndim == key.ndim == 5
     clip_len = key.size(2)
     assert 0 <= non_mask_len < clip_len
+    window = mask is None or isinstance(mask, NeighborMask)
     if mask is not None:
-        if not isinstance(mask, NeighborMask):
-            raise NotImplementedError('vfs_b200.masked_attention_efficient: only masks built by spatial_neighbor() '
-                                      '(analytic circle/square windows) are supported, not arbitrary bool tensors')
         if mask.ndim == 2:
-            assert mask.shape == (key.shape[3] * key.shape[4], query.shape[2] * query.shape[3])
+            assert tuple(mask.shape) == (key.shape[3] * key.shape[4], query.shape[2] * query.shape[3])
         else:
             assert clip_len == 1
             assert non_mask_len == 0
-    if topk is None:
-        raise NotImplementedError('vfs_b200.masked_attention_efficient: topk=None (dense softmax over all keys) '
-                                  'is not used by the VFS trackers and has no native kernel')
-    return ops.masked_attention(query, key, value, mask, temperature, topk, normalize, non_mask_len, mode)
+    if window and topk is not None and query.shape[2:] == key.shape[3:]:
+        return ops.masked_attention(query, key, value, mask, temperature, topk, normalize, non_mask_len, mode)
+    # arbitrary boolean mask tensors, topk=None (softmax over every key) and query / key maps of different size:
+    # the affinity is materialised by the tcgen05 GEMM and finished by the general kernel (csrc/dense.cu)
+    if isinstance(mask, NeighborMask):
+        mask = mask.dense(device=query.device)
+    return ops.masked_attention_generic(query, key, value, mask, temperature, topk, normalize, non_mask_len, mode)

@@ -144,6 +144,8 @@ int seg_postprocess(const float* logit, unsigned char* out, void* workspace, int
 int masked_softmax(const float* A, float* out, int B, int R, int Cc, int ld, int softmax_dim, int mask_mode, int ry,
                    int rx, int W, int nan_to_zero, cudaStream_t s);
 int propagate_dense(const float* img, const float* A, float* out, int B, int Cv, int HW, int topk, cudaStream_t s);
+int generic_attention(const float* A, int rows, int ld, int HWk, int HWq, const unsigned char* mask, int non_mask_len,
+                      const float* values, int Cv, int topk, int mode, float* out, cudaStream_t s);
 int normalize_split(const void* in_split, void* out_split, long long num_pixels, int C, long long in_plane_stride,
                     long long out_plane_stride, cudaStream_t s);
 size_t attention_workspace_bytes(const VfsAttnDesc* d, int B);
@@ -351,6 +353,11 @@ int vfs_masked_softmax(const float* A, float* out, int B, int R, int Cc, int ld,
 }
 int vfs_propagate_dense(const float* img, const float* A, float* out, int B, int Cv, int HW, int topk, vfs_stream_t s) {
   return vfs::propagate_dense(img, A, out, B, Cv, HW, topk, s);
+}
+int vfs_generic_attention(const float* affinity, int rows, int ld, int HWk, int HWq, const unsigned char* mask,
+                          int non_mask_len, const float* values, int Cv, int topk, int mode, float* out,
+                          vfs_stream_t s) {
+  return vfs::generic_attention(affinity, rows, ld, HWk, HWq, mask, non_mask_len, values, Cv, topk, mode, out, s);
 }
 int vfs_normalize_split(const void* in_split, void* out_split, long long num_pixels, int C,
                         long long in_plane_stride, long long out_plane_stride, vfs_stream_t s) {

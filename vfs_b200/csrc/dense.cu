@@ -181,4 +181,160 @@ int propagate_dense(const float* img, const float* A, float* out, int B, int Cv,
   return VFS_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// General form of masked_attention_efficient (common/local_attention.py:287-342) for the cases the fused window kernel
+// (affinity.cu) does not take: an ARBITRARY boolean mask tensor and / or topk = None (softmax over every key).  The
+// affinity A [rows = T * HWk][ld >= HWq] of one batch item (already divided by the temperature) comes from the tcgen05
+// conv kernel (key pixels as the image, query pixels as the 1x1 filter bank); this kernel does, per query column,
+//   mask -> top-k (or all keys) -> softmax | clamp(min=0)^2 -> weighted sum of the value vectors.
+// mask: uint8 [HWk][HWq] (key-major like the reference asserts), applied to key frames t >= non_mask_len; NULL = none.
+// Block (32, 8): 32 consecutive queries x 8 row groups.
+// ------------------------------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void generic_attention_topk_kernel(const float* __restrict__ A, int rows, int ld, int HWk, int HWq,
+                                              const unsigned char* __restrict__ mask, int non_mask_len,
+                                              const float* __restrict__ values, int Cv, int topk, int mode,
+                                              float* __restrict__ out) {
+  __shared__ float sv[8][KMAX][33];
+  __shared__ int si[8][KMAX][33];
+  const int q = blockIdx.x * 32 + threadIdx.x;
+  const bool live = q < HWq;
+  float tv[KMAX];
+  int ti[KMAX];
+#pragma unroll
+  for (int i = 0; i < KMAX; ++i) {
+    tv[i] = -INFINITY;
+    ti[i] = -1;
+  }
+  auto insert = [&](float x, int idx) {
+#pragma unroll
+    for (int i = KMAX - 1; i >= 0; --i) {
+      if (i > 0 && x > tv[i - 1]) {
+        tv[i] = tv[i - 1];
+        ti[i] = ti[i - 1];
+      } else if (x > tv[i]) {
+        tv[i] = x;
+        ti[i] = idx;
+      }
+    }
+  };
+  // contiguous row ranges per group: ties resolve towards the lower key index like a serial scan
+  const int per = (rows + 7) / 8;
+  const int r_end = min(rows, (static_cast<int>(threadIdx.y) + 1) * per);
+  if (live)
+    for (int r = threadIdx.y * per; r < r_end; ++r) {
+      if (mask != nullptr && r / HWk >= non_mask_len && mask[static_cast<size_t>(r % HWk) * HWq + q] == 0) continue;
+      const float x = A[static_cast<size_t>(r) * ld + q];
+      if (x > tv[KMAX - 1]) insert(x, r);
+    }
+#pragma unroll
+  for (int i = 0; i < KMAX; ++i) {
+    sv[threadIdx.y][i][threadIdx.x] = tv[i];
+    si[threadIdx.y][i][threadIdx.x] = ti[i];
+  }
+  __syncthreads();
+  if (threadIdx.y != 0 || !live) return;
+  for (int g = 1; g < 8; ++g)
+#pragma unroll 1
+    for (int i = 0; i < KMAX; ++i) {
+      const float x = sv[g][i][threadIdx.x];
+      if (!(x > tv[KMAX - 1])) break;
+      insert(x, si[g][i][threadIdx.x]);
+    }
+  float w[KMAX];
+  float wsum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < KMAX; ++i) {
+    if (i < topk && ti[i] >= 0) {
+      w[i] = (mode == 0) ? expf(tv[i] - tv[0]) : fmaxf(tv[i], 0.0f) * fmaxf(tv[i], 0.0f);
+      wsum += w[i];
+    } else {
+      w[i] = 0.0f;
+    }
+  }
+  const float inv = (mode == 0) ? __fdiv_rn(1.0f, wsum) : 1.0f;
+  for (int c = 0; c < Cv; ++c) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i)
+      if (i < topk && ti[i] >= 0) acc = fmaf(values[static_cast<size_t>(c) * rows + ti[i]], w[i] * inv, acc);
+    out[static_cast<size_t>(c) * HWq + q] = acc;
+  }
+}
+
+// topk = None: softmax (or clamp^2) over ALL unmasked keys.  Two passes over the column (max, then weights), value
+// channels in groups of 8 accumulators.
+__global__ void generic_attention_dense_kernel(const float* __restrict__ A, int rows, int ld, int HWk, int HWq,
+                                               const unsigned char* __restrict__ mask, int non_mask_len,
+                                               const float* __restrict__ values, int Cv, int mode,
+                                               float* __restrict__ out) {
+  __shared__ float red[8][9][33];
+  const int q = blockIdx.x * 32 + threadIdx.x;
+  const bool live = q < HWq;
+  auto valid = [&](int r) {
+    return mask == nullptr || r / HWk < non_mask_len || mask[static_cast<size_t>(r % HWk) * HWq + q] != 0;
+  };
+  float m = -INFINITY;
+  if (live && mode == 0)
+    for (int r = threadIdx.y; r < rows; r += 8)
+      if (valid(r)) m = fmaxf(m, A[static_cast<size_t>(r) * ld + q]);
+  red[threadIdx.y][0][threadIdx.x] = m;
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < 8; ++g) m = fmaxf(m, red[g][0][threadIdx.x]);
+  __syncthreads();
+  for (int c0 = 0; c0 < Cv; c0 += 8) {
+    float acc[8], wsum = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+    if (live)
+      for (int r = threadIdx.y; r < rows; r += 8) {
+        if (!valid(r)) continue;
+        const float x = A[static_cast<size_t>(r) * ld + q];
+        const float w = (mode == 0) ? expf(x - m) : fmaxf(x, 0.0f) * fmaxf(x, 0.0f);
+        wsum += w;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (c0 + e < Cv) acc[e] = fmaf(values[static_cast<size_t>(c0 + e) * rows + r], w, acc[e]);
+      }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[threadIdx.y][e][threadIdx.x] = acc[e];
+    red[threadIdx.y][8][threadIdx.x] = wsum;
+    __syncthreads();
+    if (threadIdx.y == 0 && live) {
+      float tot[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) {
+        tot[e] = 0.0f;
+        for (int g = 0; g < 8; ++g) tot[e] += red[g][e][threadIdx.x];
+      }
+      const float inv = (mode == 0) ? __fdiv_rn(1.0f, tot[8]) : 1.0f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (c0 + e < Cv) out[static_cast<size_t>(c0 + e) * HWq + q] = tot[e] * inv;
+    }
+    __syncthreads();
+  }
+}
+
+int generic_attention(const float* A, int rows, int ld, int HWk, int HWq, const unsigned char* mask, int non_mask_len,
+                      const float* values, int Cv, int topk, int mode, float* out, cudaStream_t s) {
+  VFS_REQUIRE(A && values && out, VFS_EINVAL, "generic_attention: null argument");
+  VFS_REQUIRE(rows > 0 && HWk > 0 && rows % HWk == 0 && HWq > 0 && ld >= HWq && Cv >= 1, VFS_ESHAPE,
+              "generic_attention: bad shape (rows %d, HWk %d, HWq %d, ld %d)", rows, HWk, HWq, ld);
+  VFS_REQUIRE(topk >= 0 && topk <= 16, VFS_ESHAPE, "generic_attention: topk=%d outside [1,16] (0 = all keys)", topk);
+  VFS_REQUIRE(mode == 0 || mode == 1, VFS_EINVAL, "generic_attention: bad mode");
+  VFS_REQUIRE(non_mask_len >= 0 && non_mask_len <= rows / HWk, VFS_EINVAL, "generic_attention: bad non_mask_len");
+  const dim3 grid((HWq + 31) / 32), block(32, 8);
+  if (topk > 0)
+    generic_attention_topk_kernel<16><<<grid, block, 0, s>>>(A, rows, ld, HWk, HWq, mask, non_mask_len, values, Cv,
+                                                             topk, mode, out);
+  else
+    generic_attention_dense_kernel<<<grid, block, 0, s>>>(A, rows, ld, HWk, HWq, mask, non_mask_len, values, Cv, mode,
+                                                          out);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
 }  // namespace vfs

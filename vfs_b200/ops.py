@@ -681,6 +681,53 @@ def masked_attention(query, key, value, mask, temperature, topk, normalize=True,
     return out
 
 
+def masked_attention_generic(query, key, value, mask, temperature, topk, normalize=True, non_mask_len=0,
+                             mode='softmax'):
+    """masked_attention_efficient for an arbitrary boolean ``mask`` tensor ([HWk,HWq], or [N,HWk,HWq] with T == 1)
+    and / or ``topk=None``: the [T*HWk, HWq] affinity of each batch item is materialised by the tcgen05 conv kernel
+    (key pixels as the image, query pixels as 1x1 filters, scale = 1/temperature) and finished by
+    vfs_generic_attention (csrc/dense.cu).  O(T*HW^2) memory -- the fused window kernel is the production path."""
+    for t, n in ((query, 'query'), (key, 'key'), (value, 'value')):
+        _require_cuda(t, n)
+    N, C, Hq, Wq = query.shape
+    T, Hk, Wk = key.shape[2:]
+    Cv = value.shape[1]
+    HWq, HWk = Hq * Wq, Hk * Wk
+    rows = T * HWk
+    Cp, HWqp = -(-C // 64) * 64, -(-HWq // 64) * 64
+    if rows * HWqp * 4 > 16 * 2**30:
+        raise NotImplementedError(f'vfs_b200: the general attention path would materialise {rows}x{HWqp} affinities')
+    if topk is not None and not 1 <= topk <= 16:
+        raise NotImplementedError('vfs_b200.masked_attention_efficient: topk must be in [1, 16] or None')
+    dev = query.device
+    m8 = None
+    if mask is not None:
+        m8 = (mask != 0).to(device=dev, dtype=torch.uint8).contiguous()
+        assert m8.shape[-2:] == (HWk, HWq), (m8.shape, HWk, HWq)
+    out = torch.empty((N, Cv, HWq), dtype=torch.float32, device=dev)
+    scale = torch.full((HWqp, ), 1.0 / float(temperature), dtype=torch.float32, device=dev)
+    shift = _const_vec(0, HWqp, dev)
+    inv_ws = torch.empty((max(rows, HWq), ), dtype=torch.float32, device=dev)
+    for b in range(N):
+        a_split = torch.zeros((2, T, Hk, Wk, Cp), dtype=torch.float16, device=dev)
+        w_split = torch.zeros((2, HWqp, Cp), dtype=torch.float16, device=dev)
+        kb = key[b].float().transpose(0, 1).contiguous()                                # [T,C,Hk,Wk]
+        what = 'features_to_split_norm' if normalize else 'features_to_split'
+        check(nat.lib().vfs_features_to_split_ex(ptr(kb), ptr(a_split), ptr(inv_ws), T, C, Hk, Wk, int(normalize), Cp,
+                                                 a_split.stride(0), current_stream()), what)
+        check(nat.lib().vfs_features_to_split_ex(ptr(query[b:b + 1].float().contiguous()), ptr(w_split), ptr(inv_ws),
+                                                 1, C, Hq, Wq, int(normalize), Cp, w_split.stride(0),
+                                                 current_stream()), what)
+        _, aff = conv_bn_act(a_split, w_split, scale, shift, 1, 1, 1, relu=False, want_split=False, want_f32=True)
+        # reference quirk (local_attention.py:320-326): with top-k every batch item gathers the values of item 0
+        vals = value[0 if topk is not None else b].float().reshape(Cv, rows).contiguous()
+        mb = None if m8 is None else (m8 if m8.ndim == 2 else m8[b])
+        check(nat.lib().vfs_generic_attention(ptr(aff), rows, HWqp, HWk, HWq, ptr(mb), int(non_mask_len), ptr(vals),
+                                              Cv, int(topk or 0), 0 if mode == 'softmax' else 1, ptr(out[b]),
+                                              current_stream()), 'generic_attention')
+    return out.reshape(N, Cv, Hq, Wq)
+
+
 def seg_postprocess(seg_logit, fh, fw, out_hw, out=None):
     """Propagated logits fp32 [Cv, fh*fw] (or a batch [P, Cv, fh*fw]) -> uint8 label map [H, W] ([P, H, W]):
     bilinear upsample + per-channel min-max + argmax."""
