@@ -322,8 +322,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   } else if (warp == 10) {
     // ======================= epilogue TMA warp =======================
     // Per 64-column chunk g (staging buffer g % NBUF): wait until the eight math warps have staged it, issue the
-    // tensor store, then recycle the buffer the previous store has finished reading -- for RES by loading the
-    // residual of chunk g + NBUF - 1 into it, otherwise by signalling it free.
+    // tensor store, then recycle the buffer once the store has finished reading it -- for RES by loading the residual
+    // of chunk g + NBUF into it, otherwise by signalling it free.
     if constexpr (NBUF > 0) {
       constexpr int kCPT = BN / 64;  // chunks per tile
       auto chunk_coords = [&](int g, int& cc, int& w0, int& h0, int& n0) -> bool {
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       };
       if (lane == 0) {
         if (RES) {
-          for (int g0 = 0; g0 < NBUF - 1; ++g0) issue_res(g0);
+          for (int g0 = 0; g0 < NBUF; ++g0) issue_res(g0);
         }
         int cc, w0, h0, n0;
         for (int g = 0; chunk_coords(g, cc, w0, h0, n0); ++g) {
@@ -358,8 +358,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           tma_store_5d(&p.tmap_out, stg_base + b * kChunkBytes, cc, w0, h0, n0, 0);
           bulk_commit_group();
           if (RES) {
-            bulk_wait_group_read<1>();  // the previous chunk's store has released its buffer ...
-            issue_res(g + NBUF - 1);    // ... which receives the residual of chunk g + NBUF - 1
+            // Wait until THIS store has drained its buffer (a few hundred ns; this warp has nothing else to do until
+            // the next chunk is staged) and refill the same buffer with the residual of chunk g + NBUF: the residual
+            // ring then runs NBUF chunks ahead of the math warps instead of one (the L2 -> smem latency of a residual
+            // chunk is longer than one chunk's epilogue math).
+            bulk_wait_group_read<0>();
+            issue_res(g + NBUF);
           } else {
             bulk_wait_group_read<NBUF - 1>();  // store g - (NBUF - 1) has released its buffer
             if (g >= NBUF - 1) mbar_arrive(free_bar((g - (NBUF - 1)) % NBUF));
@@ -744,7 +748,12 @@ int launch(ConvKernelParams p, cudaStream_t stream) {
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static int pdl = -1;  // VFS_CONV_PDL=0 disables programmatic dependent launch (experiments with interleaved streams)
+  if (pdl < 0) {
+    const char* e = getenv("VFS_CONV_PDL");
+    pdl = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  attr[0].val.programmaticStreamSerializationAllowed = pdl;
   attr[1].id = cudaLaunchAttributeClusterDimension;
   attr[1].val.clusterDim.x = 2;
   attr[1].val.clusterDim.y = 1;
@@ -922,9 +931,9 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
     }
   }
   // CTA pairs (cta_group::2, 256-pixel x BNp tiles).  Policy 2 (default) uses them where they measured faster on B200
-  // (profiles/r01_layers_pair_v8.log): MMA-bound launches -- 256-wide tiles, no residual stream in the epilogue, at
-  // least 8 K-chunks -- with enough pair tiles to occupy most TPCs.  Memory-bound expand layers (short K, residual)
-  // and small launches (per-video calls, SiamFC crops) keep the finer 1-CTA tiles.  Policy 1 forces pairs wherever
+  // (profiles/r01_layers_pair_v8.log, r01_layers_pair_v9.log): 256-wide tiles with enough pair tiles to occupy most
+  // TPCs and at least 8 K-chunks, or at least 4 when a residual streams through the epilogue (layer3 expand).
+  // Shorter-K expand layers and small launches (per-video calls, SiamFC crops) keep the finer 1-CTA tiles.  Policy 1 forces pairs wherever
   // the shape allows (tests), 0 disables them.
   {
     int pair_mode, pair_min;
@@ -932,8 +941,8 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
     const int BNp = (c.Nout % 256 == 0) ? 256 : ((c.Nout % 128 == 0) ? 128 : 0);
     if (pair_mode != 0 && BNp != 0 && p.num_m_tiles >= 2) {
       const int pair_tiles = ((p.num_m_tiles + 1) / 2) * (c.Nout / BNp);
-      const bool profitable = BNp == 256 && !c.res_split && p.num_taps * p.kchunks_per_tap >= 8 &&
-                              pair_tiles >= pair_min;
+      const int kchunks = p.num_taps * p.kchunks_per_tap;
+      const bool profitable = BNp == 256 && pair_tiles >= pair_min && kchunks >= (c.res_split ? 4 : 8);
       if (pair_mode == 1 || profitable) {
         p.num_n_tiles = c.Nout / BNp;
         int rc = set_weight_map(BNp / 2);

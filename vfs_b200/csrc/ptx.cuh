@@ -39,12 +39,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `cta_rank` of this cluster
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta_rank` of this cluster.  Default semantics
+// (.release at CTA scope, like cutlass::arch::ClusterBarrier::arrive): an explicit .release.cluster measured 2-3 us
+// per arrive in the conv epilogue (profiles/r01_conv_trace_pair_v8.log, the stall before event 9 of every last chunk);
+// the TMEM reads this arrive publishes are ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta_rank) {
   asm volatile(
       "{\n\t.reg .b32 rem;\n\t"
       "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [rem];\n\t}" ::"r"(bar), "r"(cta_rank)
+      "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t}" ::"r"(bar), "r"(cta_rank)
       : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
