@@ -168,12 +168,16 @@ struct alignas(64) StemTcParams {
   int N, H, W, Hc, Wc, tiles_x, tiles_y, num_tiles;
 };
 
+constexpr int kTcThreads = 512;                          // 4 thread groups of 128 (one per pixel row of the tile)
+constexpr int kTcPatchElems = 3 * kTcPatchH * kTcPatchW;
+constexpr int kTcPatchPerThread = (kTcPatchElems + kTcThreads - 1) / kTcThreads;
+
 template <int G>
 __device__ __forceinline__ void stem_build_row(const float* __restrict__ patch, uint32_t a_base, int m, int py, int px) {
-  // chunks j = 2*i + G (16-byte chunks of 8 consecutive k); everything about k is a compile-time constant
+  // chunks j = 4*i + G (16-byte chunks of 8 consecutive k); everything about k is a compile-time constant
 #pragma unroll
-  for (int i = 0; i < 12; ++i) {
-    const int j = 2 * i + G;
+  for (int i = 0; i < 6; ++i) {
+    const int j = 4 * i + G;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -198,7 +202,7 @@ __device__ __forceinline__ void stem_build_row(const float* __restrict__ patch, 
   }
 }
 
-__global__ void __launch_bounds__(256, 1) stem_tc_kernel(const __grid_constant__ StemTcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1) stem_tc_kernel(const __grid_constant__ StemTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;                        // [3][hi|lo][128 rows][128 B]
@@ -231,11 +235,47 @@ __global__ void __launch_bounds__(256, 1) stem_tc_kernel(const __grid_constant__
   }
   mbar_wait(bar_w, 0, 500);
 
-  const int m = threadIdx.x & 127, g = threadIdx.x >> 7;  // pixel row of the tile, chunk parity
+  const int m = threadIdx.x & 127, g = threadIdx.x >> 7;  // pixel row of the tile, chunk group (j mod 4)
   const int py = m >> 5, px = m & 31;
-  const int q = warp & 3, half = warp >> 2;               // epilogue: TMEM lane quarter, 32-column half
+  const int q = warp & 3, part = warp >> 2;               // epilogue: TMEM lane quarter, 16-column quarter
   constexpr uint32_t idesc = umma_idesc_f16_f32(128, 64);
   uint32_t mma_phase = 0;
+
+  // input patch of a tile, global -> registers (the loads of tile i+1 are in flight while tile i is multiplied and
+  // written out; they reach shared memory once the im2col build of tile i no longer reads the patch buffer)
+  float pre[kTcPatchPerThread];
+  auto load_patch = [&](int tile) {
+    const int tx = tile % p.tiles_x;
+    const int t2 = tile / p.tiles_x;
+    const int ty = t2 % p.tiles_y;
+    const int n = t2 / p.tiles_y;
+    const int iy0 = ty * kTcRows * 2 - 3, ix0 = tx * kTcCols * 2 - 3;
+    const float* src = p.in + static_cast<size_t>(n) * 3 * p.H * p.W;
+#pragma unroll
+    for (int u = 0; u < kTcPatchPerThread; ++u) {
+      const int i = threadIdx.x + u * kTcThreads;
+      const int pc = i % kTcPatchW;
+      const int t = i / kTcPatchW;
+      const int pr = t % kTcPatchH;
+      const int c = t / kTcPatchH;
+      const int iy = iy0 + pr, ix = ix0 + pc;
+      pre[u] = (i < kTcPatchElems && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                   ? __ldg(src + (static_cast<size_t>(c) * p.H + iy) * p.W + ix)
+                   : 0.0f;
+    }
+  };
+  auto store_patch = [&]() {
+#pragma unroll
+    for (int u = 0; u < kTcPatchPerThread; ++u) {
+      const int i = threadIdx.x + u * kTcThreads;
+      if (i < kTcPatchElems) patch[i] = pre[u];
+    }
+  };
+  if (static_cast<int>(blockIdx.x) < p.num_tiles) {
+    load_patch(blockIdx.x);
+    store_patch();
+  }
+  __syncthreads();
 
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const int tx = tile % p.tiles_x;
@@ -243,21 +283,14 @@ __global__ void __launch_bounds__(256, 1) stem_tc_kernel(const __grid_constant__
     const int ty = t2 % p.tiles_y;
     const int n = t2 / p.tiles_y;
     const int oy0 = ty * kTcRows, ox0 = tx * kTcCols;
-    const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
-    const float* src = p.in + static_cast<size_t>(n) * 3 * p.H * p.W;
-    for (int i = threadIdx.x; i < 3 * kTcPatchH * kTcPatchW; i += 256) {
-      const int pc = i % kTcPatchW;
-      const int t = i / kTcPatchW;
-      const int pr = t % kTcPatchH;
-      const int c = t / kTcPatchH;
-      const int iy = iy0 + pr, ix = ix0 + pc;
-      patch[i] = (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) ? src[(static_cast<size_t>(c) * p.H + iy) * p.W + ix] : 0.0f;
-    }
-    __syncthreads();
     if (g == 0) stem_build_row<0>(patch, a_base, m, py, px);
-    else stem_build_row<1>(patch, a_base, m, py, px);
+    else if (g == 1) stem_build_row<1>(patch, a_base, m, py, px);
+    else if (g == 2) stem_build_row<2>(patch, a_base, m, py, px);
+    else stem_build_row<3>(patch, a_base, m, py, px);
     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
+    const int next_tile = tile + gridDim.x;
+    if (next_tile < p.num_tiles) load_patch(next_tile);   // in flight during the MMAs and the epilogue
     if (threadIdx.x == 0) {
       tc_fence_after();
 #pragma unroll
@@ -278,22 +311,22 @@ __global__ void __launch_bounds__(256, 1) stem_tc_kernel(const __grid_constant__
     mbar_wait(bar_mma, mma_phase, 600);
     mma_phase ^= 1u;
     tc_fence_after();
-    // epilogue: warp (q, half) reads rows 32q..32q+31, columns 32*half..+31
+    // epilogue: warp (q, part) reads rows 32q..32q+31, columns 16*part..+15
     {
-      uint32_t acc[32];
-      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 32, acc);
+      uint32_t acc[16];
+      tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + part * 16, acc);
       tmem_ld_wait();
       const int r = q * 32 + lane;
       const int oy = oy0 + (r >> 5), ox = ox0 + (r & 31);
       if (oy < p.Hc && ox < p.Wc) {
-        float4* dst = reinterpret_cast<float4*>(p.out + ((static_cast<size_t>(n) * p.Hc + oy) * p.Wc + ox) * 64 + half * 32);
+        float4* dst = reinterpret_cast<float4*>(p.out + ((static_cast<size_t>(n) * p.Hc + oy) * p.Wc + ox) * 64 + part * 16);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           float4 y = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
                                  __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
           if (p.scale != nullptr) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + half * 32) + j);
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + half * 32) + j);
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + part * 16) + j);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + part * 16) + j);
             y.x = fmaxf(fmaf(y.x, sc.x, sh.x), 0.0f);
             y.y = fmaxf(fmaf(y.y, sc.y, sh.y), 0.0f);
             y.z = fmaxf(fmaf(y.z, sc.z, sh.z), 0.0f);
@@ -303,8 +336,9 @@ __global__ void __launch_bounds__(256, 1) stem_tc_kernel(const __grid_constant__
         }
       }
     }
+    if (next_tile < p.num_tiles) store_patch();  // the build of this tile finished reading the patch buffer long ago
     tc_fence_before();
-    __syncthreads();  // TMEM drained and the A / patch buffers free for the next tile
+    __syncthreads();  // TMEM drained, A free and the next patch in place
   }
   if (warp == 1) {
     tc_fence_after();
@@ -371,7 +405,7 @@ static int stem_conv_launch(const float* in, const void* weight_split, const flo
   }
   const int sms = device_sm_count();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  stem_tc_kernel<<<grid, 256, kTcSmemBytes, s>>>(p);
+  stem_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(p);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }
