@@ -25,9 +25,10 @@ namespace vfs {
 constexpr int kQTileW = 16, kQTileH = 8;  // 128 queries / keys per tile
 constexpr int kAttnStages = 3;
 constexpr int kAttnStageBytes = 4 * 16384;  // Q hi, Q lo, K hi, K lo (each 128 rows x 128 B)
-constexpr int kAttnScratchBytes = 32 * 128 * 4;  // epilogue: one 32-column score slab per query row ([col][row] fp32)
+constexpr int kAttnEpiHalves = 2;                // epilogue warps per TMEM lane quarter (each owns 64 key columns)
+constexpr int kAttnScratchBytes = kAttnEpiHalves * 32 * 128 * 4;  // one 32-column score slab per row and half
 constexpr int kAttnSmemBytes = kAttnStages * kAttnStageBytes + 256 + kAttnScratchBytes + 1024;
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 64 + 128 * kAttnEpiHalves;  // TMA warp, MMA warp, 4 x kAttnEpiHalves epilogue warps
 constexpr int kMaxKeyFrames = 32;
 constexpr int kMaxProblems = 32;   // query frames per launch
 constexpr int kMaxKeySlots = 256;  // problems x key frames per launch
@@ -45,7 +46,7 @@ struct alignas(64) AttnParams {
   int non_mask_len;
   int q_tiles_x, q_tiles_y, splits;
   int num_units;
-  float* part_val;  // [problems*T*splits][KMAX][HW]
+  float* part_val;  // [problems*T*splits*kAttnEpiHalves][KMAX][HW]
   int* part_idx;
 };
 
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 4 * kAttnEpiHalves);
     }
     fence_mbar_init();
   }
@@ -223,7 +224,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
     }
   } else {
     // ======================= epilogue: per-query running top-k =======================
+    // Two warps per TMEM lane quarter: warp half h scans key columns [64h, 64h+64) of every key tile and keeps its own
+    // sorted list; the lists are merged by kernel B like the window slices.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int dqx = row % kQTileW, dqy = row / kQTileW;
     const int HW = p.H * p.W;
@@ -248,8 +252,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
         mbar_wait(tfull_bar(as), aphase, 400 + as);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 128;
+        // per key tile: squared horizontal distances and in-image flags of the 16 key columns (shared by all rows)
+        int dx2[16];
+        uint32_t xok = 0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int dx = kx0 + c - qx;
+          dx2[c] = (p.mask_mode == 2) ? abs(dx) : dx * dx;
+          if (kx0 + c < p.W) xok |= (1u << c);
+        }
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
+        for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
           uint32_t acc[32];
           tmem_ld_32x32b_x32(t_row + c0, acc);
           tmem_ld_wait();
@@ -261,18 +274,28 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
           const float thr = tv[KMAX - 1];
           uint32_t cand = 0;
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const int ky = ky0 + ((c0 + jj) >> 4);
-            const int kx = kx0 + ((c0 + jj) & 15);
-            const int dy = ky - qy, dx = kx - qx;
-            bool ok = (ky < p.H) && (kx < p.W);
+          for (int rr = 0; rr < 2; ++rr) {   // the slab's two key rows
+            const int ky = ky0 + (c0 >> 4) + rr;
+            const int dy = ky - qy;
+            // circle: dx^2 < r^2 - dy^2; square: |dx| <= rx (and |dy| <= ry); unmasked: always
+            int lim = 0x7fffffff;
+            bool rowok = ky < p.H;
             if (masked) {
-              ok = ok && ((p.mask_mode == 1) ? (dy * dy + dx * dx < r2) : (abs(dy) <= p.ry && abs(dx) <= p.rx));
+              if (p.mask_mode == 1) lim = r2 - dy * dy;
+              else {
+                lim = p.rx + 1;
+                rowok = rowok && (abs(dy) <= p.ry);
+              }
             }
-            if (ok && __uint_as_float(acc[jj]) > thr) cand |= (1u << jj);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const bool ok = rowok && ((xok >> c) & 1u) && (dx2[c] < lim);
+              if (ok && __uint_as_float(acc[rr * 16 + c]) > thr) cand |= (1u << (rr * 16 + c));
+            }
           }
           if (__any_sync(0xffffffffu, cand != 0)) {
-            const uint32_t slab = scratch_base + static_cast<uint32_t>(row) * 4u;
+            const uint32_t slab = scratch_base + static_cast<uint32_t>(half) * (32 * 128 * 4) +
+                                  static_cast<uint32_t>(row) * 4u;
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj)
               asm volatile("st.shared.b32 [%0], %1;" ::"r"(slab + jj * 512), "r"(acc[jj]) : "memory");
@@ -298,7 +321,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
         }
       }
       if (q_valid) {
-        const int slot = (u.b * p.T + u.t) * p.splits + (unit % p.splits);
+        const int slot = ((u.b * p.T + u.t) * p.splits + (unit % p.splits)) * kAttnEpiHalves + half;
         const size_t base = static_cast<size_t>(slot) * KMAX * HW + static_cast<size_t>(qy) * p.W + qx;
 #pragma unroll
         for (int i = 0; i < KMAX; ++i) {
@@ -564,7 +587,7 @@ static int attn_splits(const VfsAttnDesc* d, int B) {
 
 size_t attention_workspace_bytes(const VfsAttnDesc* d, int B) {
   if (!d || d->T <= 0 || B <= 0) return 0;
-  const size_t slots = static_cast<size_t>(B) * d->T * attn_splits(d, B);
+  const size_t slots = static_cast<size_t>(B) * d->T * attn_splits(d, B) * kAttnEpiHalves;
   return slots * attn_kmax(d->topk) * d->H * d->W * (sizeof(float) + sizeof(int));
 }
 
@@ -611,7 +634,7 @@ int masked_attention_batched(const VfsAttnDesc* d, int B, const void* q_bank_spl
   p.q_tiles_y = (d->H + kQTileH - 1) / kQTileH;
   p.splits = attn_splits(d, B);
   p.num_units = B * p.q_tiles_x * p.q_tiles_y * d->T * p.splits;
-  const size_t slots = static_cast<size_t>(B) * d->T * p.splits;
+  const size_t slots = static_cast<size_t>(B) * d->T * p.splits * kAttnEpiHalves;
   p.part_val = reinterpret_cast<float*>(workspace);
   p.part_idx = reinterpret_cast<int*>(p.part_val + slots * KMAX * HW);
   const uint32_t box[5] = {64, kQTileW, kQTileH, 1, 2};
@@ -648,7 +671,7 @@ int masked_attention_batched(const VfsAttnDesc* d, int B, const void* q_bank_spl
   MergeParams m;
   memset(&m, 0, sizeof(m));
   m.part_val = p.part_val; m.part_idx = p.part_idx;
-  m.slots = d->T * p.splits; m.HW = HW; m.topk = d->topk; m.mode = d->mode; m.temperature = d->temperature;
+  m.slots = d->T * p.splits * kAttnEpiHalves; m.HW = HW; m.topk = d->topk; m.mode = d->mode; m.temperature = d->temperature;
   m.values = values; m.v_batch_stride = v_batch_stride; m.v_frame_stride = v_frame_stride;
   m.v_chan_stride = v_chan_stride; m.Cv = d->Cv; m.T = d->T;
   for (int i = 0; i < B * d->T; ++i) m.val_ids[i] = static_cast<short>(val_ids[i]);
