@@ -242,7 +242,7 @@ def main():
     bank = torch.empty((2, CLIPS * FRAMES, fh, fw, 1024), dtype=torch.float16, device=dev)
     out = torch.empty((CLIPS, CV, hw), dtype=torch.float32, device=dev)
 
-    # The step is three CUDA graphs (stem | tcgen05 conv stages | normalise + attention) captured once over static
+    # The step is four CUDA graphs (stem | tcgen05 conv stages | normalise | attention) captured once over static
     # buffers: replaying them removes the Python/ctypes issue cost of the ~60 launches and lets CUDA events between
     # the graphs time each segment on the device.
     state = {}
@@ -253,8 +253,10 @@ def main():
     def seg_convs():
         state['feat'] = eng.run_stages(state['stem'], 2)      # 16 frames -> res4, split NHWC
 
-    def seg_attn():
+    def seg_norm():
         ops.normalize_split(state['feat'], out=bank)
+
+    def seg_attn():
         # frame 2c = key (labels known), 2c+1 = query; the 8 clips are 8 problems of ONE launch
         ids = [[2 * c] for c in range(CLIPS)]
         out.copy_(ops.attention_bank_batched(bank, [2 * c + 1 for c in range(CLIPS)], bank, ids, seg_bank, ids, 0,
@@ -270,12 +272,12 @@ def main():
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for _ in range(max(a.warmup, 3)):
-            seg_stem(); seg_convs(); seg_attn()
+            seg_stem(); seg_convs(); seg_norm(); seg_attn()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     launches0 = ops.LAUNCHES[0]
     graphs = []
-    for seg in (seg_stem, seg_convs, seg_attn):
+    for seg in (seg_stem, seg_convs, seg_norm, seg_attn):
         g_ = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_):
             seg()
@@ -300,23 +302,22 @@ def main():
     wall0 = time.perf_counter()
     for _ in range(a.steps):
         flush.fill_(1)                                        # evict L2 (512 MiB > 126 MB); outside the timed span
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record()
-        graphs[0].replay()
-        ev[1].record()
-        graphs[1].replay()
-        ev[2].record()
-        graphs[2].replay()
-        ev[3].record()
+        for gi, g_ in enumerate(graphs):
+            g_.replay()
+            ev[gi + 1].record()
         marks.append(ev)
     barrier()
     wall = time.perf_counter() - wall0
     if cuprof:
         torch.cuda.profiler.stop()
     launches = launches_per_step * a.steps
-    step_ms = [e[0].elapsed_time(e[3]) for e in marks]
+    step_ms = [e[0].elapsed_time(e[4]) for e in marks]
     stem_ms = [e[0].elapsed_time(e[1]) for e in marks]
     conv_ms = [e[1].elapsed_time(e[2]) for e in marks]
+    norm_ms = [e[2].elapsed_time(e[3]) for e in marks]
+    attn_ms = [e[3].elapsed_time(e[4]) for e in marks]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -380,18 +381,34 @@ def main():
     achieved = conv_flops / (conv_med * 1e-3) / 1e12
     roofline = dict(bound='tensor', kernel='conv_tc_kernel', achieved=achieved, peak=peak_tf, unit='TFLOP/s',
                     frac=achieved / peak_tf, traffic=traffic, peak_source=peak_src,
-                    note='achieved = algorithmic fp32-equivalent conv FLOPs; the kernel issues 3 bf16 MMAs per '
+                    note='achieved = algorithmic fp32-equivalent conv FLOPs; the kernel issues 3 fp16 MMAs per '
                          'product (split-fp16), so tensor-pipe work is 3x: frac_of_issued = %.3f' %
                          (3 * achieved / peak_tf),
                     launches_per_step=n_conv_launches, segment_ms_median=conv_med,
                     flops_per_step=conv_flops)
+
+    # second named kernel (north_star): fused affinity + top-k + softmax propagation.  Algorithmic work = the
+    # window-restricted products 2*C*sum_q |N(q)| per problem / CUDA-event time of the attention graph.
+    pairs_in_window = int(mask.dense().sum())
+    attn_flops = 2.0 * 1024 * pairs_in_window * CLIPS
+    attn_med = statistics.median(attn_ms)
+    attn_tf = attn_flops / (attn_med * 1e-3) / 1e12
+    attn_bytes = 4.0 * CLIPS * (2 * 1024 * hw + 2 * CV * hw)          # q + k features, values in, labels out
+    roofline_affinity = dict(bound='tensor', kernel='attn_scores_topk_kernel + attn_merge_propagate_kernel',
+                             achieved=attn_tf, peak=peak_tf, unit='TFLOP/s', frac=attn_tf / peak_tf, traffic=None,
+                             segment_ms_median=attn_med, flops_per_step=attn_flops,
+                             hbm_gbs_algorithmic=attn_bytes / (attn_med * 1e-3) / 1e9,
+                             note='window-restricted fp32-equivalent FLOPs (3 MMAs issued per product, and whole '
+                                  '128x128 key tiles are multiplied: the dense-tile work is larger); the fused kernel '
+                                  'is tensor/shared-memory bound, its compulsory HBM bytes would take %.1f us at the '
+                                  'measured copy bandwidth' % (attn_bytes / (peaks.get('hbm_gbs', 6650.0) * 1e3)))
 
     line = dict(metric='frame-pairs/sec (R50 res4 feat+affinity)', value=value, unit='frame-pairs/s', n_gpus=world,
                 steps=a.steps, warmup=max(a.warmup, 3), ms_per_step=total_ms / a.steps, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='fp16x3 (split-fp16 operands, fp32 accumulate)',
                 data='synthetic',
                 config=dict(workload=WORKLOAD, clips_per_gpu=CLIPS, l2='flushed (512 MiB write) between steps',
-                            timing='sum of per-step CUDA-event spans (3 CUDA graphs per step), max over ranks',
+                            timing='sum of per-step CUDA-event spans (4 CUDA graphs per step), max over ranks',
                             parallelism=f'dp{world} (clips sharded, no collective)'),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit='frame-pairs/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
@@ -401,9 +418,10 @@ def main():
                                               api='one forward_test call per video (reference calling convention)')),
                 gpu_launches=launches,
                 roofline=roofline,
+                roofline_affinity=roofline_affinity,
                 breakdown_ms=dict(step_median=statistics.median(step_ms), stem_median=statistics.median(stem_ms),
-                                  convs_median=conv_med,
-                                  normalize_attention_median=statistics.median(step_ms) - statistics.median(stem_ms) - conv_med),
+                                  convs_median=conv_med, normalize_median=statistics.median(norm_ms),
+                                  attention_median=attn_med),
                 wall_s_timed_region=wall)
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -1,11 +1,12 @@
-"""Condense an `ncu --set full` report of one bench step into profiles/<name>.json and profiles/conv_traffic.json.
+"""Condense an ncu capture of one bench step into profiles/<name>.json and profiles/conv_traffic.json.
 
-On the GPU box (one timed step only, cudaProfilerStart/Stop inside bench.py):
-    VFS_BENCH_CUPROFILE=1 ncu --set full --clock-control none --profile-from-start off -o gpurun_out/step \
-        python bench.py --steps 1 --warmup 3 --no-cpu-baseline
-Here (no GPU needed):
+On the GPU box (one timed step only, cudaProfilerStart/Stop inside bench.py); either the per-metric log
+    VFS_BENCH_CUPROFILE=1 ncu --clock-control none --profile-from-start off --metrics <METRICS> --csv \
+        --log-file gpurun_out/step_metrics.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline
+(METRICS = the keys of WANT below, comma separated) or a full report converted with
     ncu -i gpurun_out/step.ncu-rep --page raw --csv > gpurun_out/step_raw.csv
-    python tools/ncu_summary.py gpurun_out/step_raw.csv profiles/r01_ncu_step_v8.json "<source note>"
+Here (no GPU needed):
+    python tools/ncu_summary.py gpurun_out/step_metrics.csv profiles/r01_ncu_step_v10.json "<source note>"
 """
 import csv
 import json
@@ -43,11 +44,28 @@ def main():
     with open(src, newline='') as fh:
         rows = [r for r in csv.reader(fh) if r]
     start = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
-    header, units, data = rows[start], rows[start + 1], rows[start + 2:]
+    header = rows[start]
     col = {name: i for i, name in enumerate(header)}
     name_col = col['Kernel Name']
-    tensor_cols = [n for n in header if 'pipe_tensor' in n and 'pct' in n]
     kernels = []
+    if 'Metric Name' in col:   # long format of `--metrics ... --csv --log-file`: one row per (launch, metric)
+        by_id = {}
+        for r in rows[start + 1:]:
+            if len(r) != len(header):
+                continue
+            k = by_id.setdefault(r[col['ID']], {'kernel': r[name_col].replace('void vfs::', '').replace('vfs::', '')
+                                                .split('(')[0]})
+            key = WANT.get(r[col['Metric Name']])
+            v = num(r[col['Metric Value']])
+            if key is None or v is None:
+                continue
+            if key == 'time_us' or key.endswith('_bytes'):
+                v *= UNIT_SCALE.get(r[col['Metric Unit']], 1.0)
+            k[key] = v
+        kernels = [by_id[i] for i in sorted(by_id, key=int)]
+        rows = []
+    units, data = (rows[start + 1], rows[start + 2:]) if rows else ([], [])
+    tensor_cols = [n for n in header if 'pipe_tensor' in n and 'pct' in n]
     for r in data:
         if len(r) != len(header):
             continue
