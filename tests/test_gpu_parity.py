@@ -531,6 +531,57 @@ def test_xcorr_matches_reference_golden(golden, name):
     assert rel_err(got, golden[f'xcorr/{name}/siamconvfc']) < REL_TOL
 
 
+def test_graphed_train_step_equals_eager_steps():
+    """vfs_b200.GraphedTrainStep (forward + backward + SGD captured in one CUDA graph) must walk exactly the eager
+    trajectory: same losses and same parameters after three steps; building the graph must not train the model."""
+    import vfs_b200
+    from vfs_b200.optim import build_optimizer
+    c = cases.TRACKER_TRAIN_CASES['r18_intra']
+    opt_cfg = dict(type='SGD', lr=0.05, momentum=0.9, weight_decay=1e-4)
+
+    def make():
+        m = vfs_b200.build_model(c['model'], train_cfg=vfs_b200.ConfigDict(c['train_cfg']), test_cfg=None)
+        m.load_state_dict(oracle.seeded_state_dict(m, seed=c['seed']))
+        m = m.cuda()
+        m.train()
+        return m, build_optimizer(m, opt_cfg)
+
+    g = torch.Generator().manual_seed(77)
+    batches = [torch.randn(4, 2, 3, 2, 64, 64, generator=g).cuda() for _ in range(3)]
+
+    def run_eager():
+        m, opt = make()
+        losses = []
+        for b in batches:
+            out = m.train_step(dict(imgs=b), opt)
+            opt.zero_grad(set_to_none=True)
+            out['loss'].backward()
+            opt.step()
+            losses.append(out['log_vars']['loss'])
+        return m.state_dict(), losses
+
+    # Two eager runs give the run-to-run noise of the trajectory: fp32 atomics (wgrad split-K, BN sums) reorder, and
+    # tiny-batch BatchNorm amplifies that over the steps.  The graphed run must stay inside a few times that noise.
+    sd_e, losses_e = run_eager()
+    sd_e2, losses_e2 = run_eager()
+    graphed, opt_g = make()
+    before = {k: v.clone() for k, v in graphed.state_dict().items()}
+    step = vfs_b200.GraphedTrainStep(graphed, opt_g, dict(imgs=batches[0]))
+    for k, v in graphed.state_dict().items():
+        assert torch.equal(v, before[k]), f'building the graph changed {k}'
+    losses_g = [step(dict(imgs=b))['log_vars']['loss'] for b in batches]
+    torch.cuda.synchronize()
+    assert losses_g[0] == pytest.approx(losses_e[0], rel=1e-5)
+    assert losses_g == pytest.approx(losses_e, rel=1e-3)
+    sd_g = graphed.state_dict()
+    for k in sd_e:
+        if sd_e[k].dtype.is_floating_point:
+            noise = rel_err(sd_e2[k], sd_e[k])
+            assert rel_err(sd_g[k], sd_e[k]) <= 5 * noise + 1e-4, (k, noise)
+        else:
+            assert torch.equal(sd_g[k], sd_e[k]), k
+
+
 # --------------------------------------------------------------------------------------------- SiamFC tracker
 def _smooth_maps(gen, S, R):
     """Response-like maps: a few Gaussian bumps + small noise (a pure-noise map makes the arg-max a coin toss)."""

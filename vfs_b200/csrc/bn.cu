@@ -6,11 +6,15 @@
 
 namespace vfs {
 
-// x fp32 [M, C] (C multiple of 4): block = 256 threads covering C/4 float4 columns x row groups
-__global__ void channel_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, long long M, int C) {
+// x fp32 [M, C] (C multiple of 4): block = 256 threads covering C/4 float4 columns x row groups; the row groups of a
+// block are folded in shared memory so that one fp64 atomic per (block, channel, moment) reaches global memory.
+__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ x, double* __restrict__ stats,
+                                                            long long M, int C) {
+  __shared__ float red[256][9];
   const int cols_here = min(1024, C - static_cast<int>(blockIdx.y) * 1024);  // this block's column range
   const int c4 = cols_here / 4;
-  const int col = threadIdx.x % c4 + blockIdx.y * 256;  // float4 column (global)
+  const int lcol = threadIdx.x % c4;
+  const int col = lcol + blockIdx.y * 256;              // float4 column (global)
   const int rgrp = threadIdx.x / c4;                    // row group inside the block
   const int rows_per_block = blockDim.x / c4;
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
@@ -22,10 +26,23 @@ __global__ void channel_stats_kernel(const float* __restrict__ x, double* __rest
       q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]);
       q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
     }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    red[threadIdx.x][e] = s[e];
+    red[threadIdx.x][4 + e] = q[e];
+  }
+  __syncthreads();
+  if (rgrp == 0) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      atomicAdd(stats + col * 4 + e, static_cast<double>(s[e]));
-      atomicAdd(stats + C + col * 4 + e, static_cast<double>(q[e]));
+      double ts = 0.0, tq = 0.0;
+      for (int r = 0; r < rows_per_block; ++r) {
+        ts += static_cast<double>(red[r * c4 + lcol][e]);
+        tq += static_cast<double>(red[r * c4 + lcol][4 + e]);
+      }
+      atomicAdd(stats + col * 4 + e, ts);
+      atomicAdd(stats + C + col * 4 + e, tq);
     }
   }
 }
@@ -125,7 +142,7 @@ int channel_stats_f32(const float* x, double* stats, long long M, int C, cudaStr
   const int c4 = (C < 1024 ? C : 1024) / 4;
   const int rows_per_block = 256 / c4;
   long long blocks = (M + rows_per_block - 1) / rows_per_block;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   channel_stats_kernel<<<dim3(static_cast<int>(blocks), (C + 1023) / 1024), 256, 0, s>>>(x, stats, M, C);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;

@@ -70,11 +70,16 @@ __device__ __forceinline__ void bn_bwd_load_g(const BnBwdArgs& a, long long o, f
   }
 }
 
-__global__ void bn_bwd_reduce_kernel(const BnBwdArgs a) {
+// Per-channel sums of g and g * xhat over all M pixels.  256 threads = (C/8 eight-channel pieces) x row groups; every
+// thread walks rows grid-stride, the row groups of a block are folded in shared memory and ONE fp64 atomic per
+// (block, channel, sum) reaches global memory -- the first version issued 16 fp64 atomics per THREAD on 2C addresses
+// and spent 310 us per call on atomic contention (profiles/r01_train_profile_v11.log).
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
+  __shared__ float red[256][17];
   const int pieces = a.C / 8;
   const int piece = threadIdx.x % pieces, rgrp = threadIdx.x / pieces;
   const int rows_per_block = blockDim.x / pieces;
-  if (rgrp >= rows_per_block) return;
+  const bool active = rgrp < rows_per_block;
   const int c = piece * 8;
   float sg[8], sx[8], mu[8], is[8];
 #pragma unroll
@@ -83,23 +88,37 @@ __global__ void bn_bwd_reduce_kernel(const BnBwdArgs a) {
     mu[e] = a.mean[c + e];
     is[e] = a.invstd[c + e];
   }
-  for (long long r = static_cast<long long>(blockIdx.x) * rows_per_block + rgrp; r < a.M;
-       r += static_cast<long long>(gridDim.x) * rows_per_block) {
-    const long long o = r * a.C + c;
-    float g[8];
-    bn_bwd_load_g(a, o, g);
-    const float4 z0 = *reinterpret_cast<const float4*>(a.z + o), z1 = *reinterpret_cast<const float4*>(a.z + o + 4);
-    const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+  if (active)
+    for (long long r = static_cast<long long>(blockIdx.x) * rows_per_block + rgrp; r < a.M;
+         r += static_cast<long long>(gridDim.x) * rows_per_block) {
+      const long long o = r * a.C + c;
+      float g[8];
+      bn_bwd_load_g(a, o, g);
+      const float4 z0 = *reinterpret_cast<const float4*>(a.z + o), z1 = *reinterpret_cast<const float4*>(a.z + o + 4);
+      const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      sg[e] += g[e];
-      sx[e] = fmaf(g[e], (zz[e] - mu[e]) * is[e], sx[e]);
+      for (int e = 0; e < 8; ++e) {
+        sg[e] += g[e];
+        sx[e] = fmaf(g[e], (zz[e] - mu[e]) * is[e], sx[e]);
+      }
     }
-  }
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    atomicAdd(a.sums + c + e, static_cast<double>(sg[e]));
-    atomicAdd(a.sums + a.C + c + e, static_cast<double>(sx[e]));
+    red[threadIdx.x][e] = sg[e];
+    red[threadIdx.x][8 + e] = sx[e];
+  }
+  __syncthreads();
+  if (rgrp == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      double tg = 0.0, tx = 0.0;
+      for (int r = 0; r < rows_per_block; ++r) {
+        tg += static_cast<double>(red[r * pieces + piece][e]);
+        tx += static_cast<double>(red[r * pieces + piece][8 + e]);
+      }
+      atomicAdd(a.sums + c + e, tg);
+      atomicAdd(a.sums + a.C + c + e, tx);
+    }
   }
 }
 
@@ -192,7 +211,7 @@ int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split
               C);
   const int rows_per_block = 256 / (C / 8);
   long long blocks = (M + rows_per_block - 1) / rows_per_block;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   bn_bwd_reduce_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(a);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
@@ -387,7 +406,9 @@ int stem_wgrad(const float* x, const float* dz, float* dw, int accumulate, float
 // ------------------------------------------------------------------------------------------------
 // SimSiam head backward
 // ------------------------------------------------------------------------------------------------
-// dX[m, k] = sum_n dY[m, n] W[n, k]; block = 256 consecutive k, rows tiled by 16
+// dX[m, k] = sum_n dY[m, n] W[n, k]; block = 256 consecutive k, rows tiled by 16, the n range split over blockIdx.z
+// in slices of 128 (the weight matrix is the whole traffic: 8 blocks cannot pull it through; dX is zeroed by the caller
+// and the slices are combined with fp32 atomics).
 __global__ void __launch_bounds__(256) linear_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ W,
                                                               float* __restrict__ dx, int M, int N, int K) {
   __shared__ float dys[16][128];
@@ -396,7 +417,8 @@ __global__ void __launch_bounds__(256) linear_bwd_data_kernel(const float* __res
   float acc[16];
 #pragma unroll
   for (int m = 0; m < 16; ++m) acc[m] = 0.0f;
-  for (int n0 = 0; n0 < N; n0 += 128) {
+  {
+    const int n0 = blockIdx.z * 128;
     __syncthreads();
     for (int i = threadIdx.x; i < 16 * 128; i += 256) {
       const int m = i >> 7, nn = i & 127;
@@ -415,7 +437,7 @@ __global__ void __launch_bounds__(256) linear_bwd_data_kernel(const float* __res
   if (k < K) {
 #pragma unroll
     for (int m = 0; m < 16; ++m)
-      if (m0 + m < M) dx[static_cast<size_t>(m0 + m) * K + k] = acc[m];
+      if (m0 + m < M) atomicAdd(dx + static_cast<size_t>(m0 + m) * K + k, acc[m]);
   }
 }
 
@@ -609,7 +631,8 @@ int linear_backward(const float* dy, const float* x, const float* W, float* dx, 
   VFS_REQUIRE(dy && x && W, VFS_EINVAL, "linear_backward: null argument");
   VFS_REQUIRE(M > 0 && N > 0 && K > 0, VFS_ESHAPE, "linear_backward: bad shape");
   if (dx) {
-    linear_bwd_data_kernel<<<dim3((K + 255) / 256, (M + 15) / 16), 256, 0, s>>>(dy, W, dx, M, N, K);
+    VFS_CUDA_OK(cudaMemsetAsync(dx, 0, static_cast<size_t>(M) * K * sizeof(float), s));
+    linear_bwd_data_kernel<<<dim3((K + 255) / 256, (M + 15) / 16, (N + 127) / 128), 256, 0, s>>>(dy, W, dx, M, N, K);
     VFS_CUDA_OK(cudaGetLastError());
   }
   if (dW) {
