@@ -30,6 +30,12 @@ class GraphedTrainStep:
         self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in data_batch.items()}
         self.num_samples = _batch_size(data_batch)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1:
+            # measured on 2 x B200 (round 1): capturing the ~330 SyncBN / gradient NCCL collectives of the step
+            # dead-locks inside the capture; multi-rank training runs the eager step until the collectives are fused
+            # into the BN kernels
+            raise NotImplementedError('vfs_b200.GraphedTrainStep: multi-rank capture is not supported yet, '
+                                      'use model.train_step eagerly')
         self._keys = None
         self._capture(warmup)
 
