@@ -58,14 +58,17 @@ class BackboneEngine:
     def plan(self, cm, device):
         p = self._plans.get(id(cm))
         ver = self._version(cm) if (self.check_versions or p is None) else None
-        if p is None or (ver is not None and p.version != ver) or p.scale.device != device:
+        if p is None or (ver is not None and p.version != ver) or p.w_split.device != device:
             p = _ConvPlan()
             w = cm.conv.weight.detach().to(device=device, dtype=torch.float32).contiguous()
             p.ksize = w.shape[2]
             # residual-stage convs: [2][Cout][k*k*Cin]; the 7x7 stem: [2][64][192] (K = 147 zero-padded)
             p.w_split = ops.pack_conv_weight(w) if w.shape[1] % 64 == 0 else ops.stem_pack_weight(w)
             p.wt_split = None  # dgrad packing, built on first use by the backward pass
-            p.scale, p.shift = fold_bn(cm, device)
+            # the eval-mode fold (~12 tiny fp64 kernels) is only needed when the BN runs on running statistics; a
+            # train-mode step re-plans every layer after each optimizer step and must not pay for it
+            train_bn = cm.with_norm and cm.norm.training
+            p.scale, p.shift = (None, None) if train_bn else fold_bn(cm, device)
             p.version = ver if ver is not None else self._version(cm)
             self._plans[id(cm)] = p
         return p
@@ -101,6 +104,8 @@ class BackboneEngine:
                 self.tape.append(dict(cm=cm, xs=xs, z=z, mean=mean, invstd=invstd, y=y, relu=relu,
                                       residual=residual, k=k, stride=stride, dil=dil))
             return y
+        if p.scale is None:   # planned while the BN was in train mode
+            p.scale, p.shift = fold_bn(cm, xs.device)
         out, out32 = ops.conv_bn_act(xs, p.w_split, p.scale, p.shift, k, stride, dil, relu, residual,
                                      want_split=not want_f32, want_f32=want_f32)
         return out32 if want_f32 else out
@@ -118,6 +123,8 @@ class BackboneEngine:
                 self.tape.append(dict(cm=cm, stem=True, x=x, z=z, mean=mean, invstd=invstd, scale=scale,
                                       shift=shift, y=y))
             return y
+        if p.scale is None:
+            p.scale, p.shift = fold_bn(cm, x.device)
         return ops.stem_forward(x, p.w_split, p.scale, p.shift)
 
     # -------------------------------------------------------------- whole backbone
