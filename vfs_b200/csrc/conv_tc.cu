@@ -95,7 +95,9 @@ struct ConvSmem {
   static constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // hi+lo of A and B
   // epilogue staging: legacy (NBUF == 0) one 128 x 64 fp32 transpose tile; TMA epilogue NBUF output chunks
   static constexpr int kStagingBytes = (NBUF == 0) ? kBlockM * 64 * 4 : NBUF * kChunkBytes;
-  static constexpr int kBarrierBytes = 256;  // 8 B x (2*STAGES + 4 pipeline + tmem ptr + 3 x 4 epilogue) <= 200
+  // 8 B x (2*STAGES + 4 pipeline + tmem ptr + 3 x 4 epilogue) <= 200, then (legacy epilogue) 2 x BN fp32 per-tile
+  // partial sums of the BatchNorm statistics
+  static constexpr int kBarrierBytes = 256 + (NBUF == 0 ? 2 * BN * 4 : 0);
   static constexpr int kTotal = STAGES * kStageBytes + kStagingBytes + kBarrierBytes + 1024;  // +1024 align slack
 };
 
@@ -509,6 +511,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;         // 0..255 over the epilogue threads
     const int piece = et & 7, rr = et >> 3;  // phase B: 8-channel piece of the chunk, first of 4 rows (stride 32)
+    // per-tile partial sums of the BN statistics: [sum[BN], sum of squares[BN]] fp32 in shared memory, flushed with
+    // ONE fp64 atomic per channel and tile (the first version sent 2 x 8 fp64 atomics per warp and chunk to global)
+    float* s_stat = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
+    if (p.stat_sum != nullptr) {
+      for (int i = et; i < 2 * BN; i += 256) s_stat[i] = 0.0f;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+    }
     auto phys_chunk = [](int r, int c) { return (c & 8) | ((c ^ (c >> 3) ^ r) & 7); };
     int as = 0;
     uint32_t aphase = 0;
@@ -655,11 +664,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           if (lane < 8) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              atomicAdd(p.stat_sum + cg + e, static_cast<double>(st_s[e]));
-              atomicAdd(p.stat_sqsum + cg + e, static_cast<double>(st_q[e]));
+              atomicAdd(s_stat + c0 + piece * 8 + e, st_s[e]);
+              atomicAdd(s_stat + BN + c0 + piece * 8 + e, st_q[e]);
             }
           }
         }
+      }
+      if (p.stat_sum != nullptr) {
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // every warp's partial sums of this tile are in
+        if (et < BN) {
+          atomicAdd(p.stat_sum + n_tile * BN + et, static_cast<double>(s_stat[et]));
+          atomicAdd(p.stat_sqsum + n_tile * BN + et, static_cast<double>(s_stat[BN + et]));
+          s_stat[et] = 0.0f;
+          s_stat[BN + et] = 0.0f;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // zeroed before the next tile accumulates
       }
       if (++as == 2) {
         as = 0;
