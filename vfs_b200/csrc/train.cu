@@ -134,14 +134,31 @@ __global__ void bn_bwd_apply_kernel(const BnBwdArgs a) {
     const float4 z0 = *reinterpret_cast<const float4*>(a.z + o), z1 = *reinterpret_cast<const float4*>(a.z + o + 4);
     const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
     float dz[8];
+    float isv[8], muv[8], gav[8];
+    double s0[8], s1[8];
+    *reinterpret_cast<float4*>(isv) = __ldg(reinterpret_cast<const float4*>(a.invstd + c));
+    *reinterpret_cast<float4*>(isv + 4) = __ldg(reinterpret_cast<const float4*>(a.invstd + c + 4));
+    *reinterpret_cast<float4*>(muv) = __ldg(reinterpret_cast<const float4*>(a.mean + c));
+    *reinterpret_cast<float4*>(muv + 4) = __ldg(reinterpret_cast<const float4*>(a.mean + c + 4));
+    if (a.gamma) {
+      *reinterpret_cast<float4*>(gav) = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+      *reinterpret_cast<float4*>(gav + 4) = __ldg(reinterpret_cast<const float4*>(a.gamma + c + 4));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gav[e] = 1.0f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      *reinterpret_cast<double2*>(s0 + e) = *reinterpret_cast<const double2*>(a.sums + c + e);
+      *reinterpret_cast<double2*>(s1 + e) = *reinterpret_cast<const double2*>(a.sums + a.C + c + e);
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float is = a.invstd[c + e];
-      const float xhat = (zz[e] - a.mean[c + e]) * is;
-      const float sgm = static_cast<float>(a.sums[c + e]) * inv_count;
-      const float sxm = static_cast<float>(a.sums[a.C + c + e]) * inv_count;
-      const float gam = a.gamma ? a.gamma[c + e] : 1.0f;
-      dz[e] = gam * is * (g[e] - sgm - xhat * sxm);
+      const float is = isv[e];
+      const float xhat = (zz[e] - muv[e]) * is;
+      const float sgm = static_cast<float>(s0[e]) * inv_count;
+      const float sxm = static_cast<float>(s1[e]) * inv_count;
+      dz[e] = gav[e] * is * (g[e] - sgm - xhat * sxm);
     }
     if (a.dz_hi) {
       uint4 h, l;
@@ -209,9 +226,11 @@ int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split
   BnBwdArgs a;
   bn_bwd_fill(a, dy_split, dy_f32, y_split, y_f32, z, mean, invstd, nullptr, sums, 1.0, nullptr, nullptr, nullptr, M,
               C);
+  // every block ends with 2C fp64 atomics: give each thread at least ~8 rows before adding blocks
   const int rows_per_block = 256 / (C / 8);
-  long long blocks = (M + rows_per_block - 1) / rows_per_block;
+  long long blocks = (M + 8LL * rows_per_block - 1) / (8LL * rows_per_block);
   if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
   bn_bwd_reduce_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(a);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
