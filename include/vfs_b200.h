@@ -263,6 +263,9 @@ int vfs_propagate_dense(const float* img, const float* A, float* out, int B, int
 int vfs_normalize_split(const void* in_split, void* out_split, long long num_pixels, int C,
                         long long in_plane_stride, long long out_plane_stride, vfs_stream_t s);
 
+/* Form of the scores kernel: 1 (default) = two 128-key tiles per step (N = 256 MMAs, the query tile is staged once per
+ * two key tiles), 0 = one key tile per step.  Identical results. */
+int vfs_attention_set_wide(int mode);
 size_t vfs_attention_workspace_bytes(const VfsAttnDesc* d, int num_problems);
 /*   q_split        hi plane of the query frame [H][W][C]; lo plane at +q_plane_stride elements
  *   k_bank_split   hi plane of a bank of frames [k_bank_frames][H][W][C]; lo plane at +k_plane_stride elements

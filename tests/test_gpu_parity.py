@@ -472,6 +472,42 @@ def test_attention_general_masks_and_dense_softmax_match_oracle(case):
     assert rel_err(out, ref) < REL_TOL
 
 
+ATTN_FORM_CASES = [
+    # C, Cv, T, H, W, range, non_mask_len
+    (64, 3, 1, 9, 21, 8, 0),        # ragged right edge
+    (128, 4, 3, 17, 40, 12, 0),     # odd number of key tiles in some windows (phantom second tile)
+    (64, 2, 2, 16, 32, None, 0),    # no mask: the window is the whole map
+    (64, 4, 3, 12, 35, 10, 1),      # first key frame exempt from the mask
+    (64, 2, 1, 7, 9, 6, 0),         # a single key tile: every step has a phantom partner
+    (1024, 4, 1, 32, 32, 36, 0),    # bench shape (256x256 input, stride 8)
+    (256, 5, 2, 60, 107, 36, 0),    # 480p DAVIS map
+]
+
+
+@pytest.mark.parametrize('case', ATTN_FORM_CASES)
+def test_attention_wide_form_matches_narrow_form(case):
+    """Two key tiles per step (N = 256 MMAs) select exactly the keys, values and outputs of one key tile per step."""
+    from vfs_b200 import ops
+    from vfs_b200.common import spatial_neighbor
+    C, Cv, T, H, W, rng, nml = case
+    g = torch.Generator().manual_seed(sum(x or 0 for x in case))
+    q = torch.relu(torch.randn(1, C, H, W, generator=g)).cuda()
+    k = torch.relu(torch.randn(1, C, T, H, W, generator=g)).cuda()
+    v = torch.rand(1, Cv, T, H, W, generator=g).cuda()
+    mask = spatial_neighbor(1, H, W, rng) if rng else None
+    try:
+        ops.attention_set_wide(0)
+        o0, tv0, ti0 = ops.masked_attention(q, k, v, mask, 0.07, 10, True, nml, 'softmax', return_topk=True)
+        ops.attention_set_wide(1)
+        o1, tv1, ti1 = ops.masked_attention(q, k, v, mask, 0.07, 10, True, nml, 'softmax', return_topk=True)
+    finally:
+        ops.attention_set_wide(1)
+    torch.cuda.synchronize()
+    assert torch.equal(tv0, tv1)
+    assert torch.equal(ti0, ti1)
+    assert torch.equal(o0, o1)
+
+
 def test_attention_multi_batch_matches_oracle():
     """N > 1 batch items (the reference API allows it) run as problems of one launch."""
     from vfs_b200.common import masked_attention_efficient, spatial_neighbor

@@ -43,6 +43,7 @@ PROTOTYPES = {
     'vfs_pack_conv_weight': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'vfs_debug_conv_trace': (_i, [_vp, _i]),
     'vfs_conv_set_pair_policy': (_i, [_i, _i]),
+    'vfs_attention_set_wide': (_i, [_i]),
     'vfs_debug_conv_bn_act_simt': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'vfs_stem_conv_raw': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'vfs_stem_bn_relu_pool': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -23,11 +23,19 @@
 namespace vfs {
 
 constexpr int kQTileW = 16, kQTileH = 8;  // 128 queries / keys per tile
-constexpr int kAttnStages = 3;
-constexpr int kAttnStageBytes = 4 * 16384;  // Q hi, Q lo, K hi, K lo (each 128 rows x 128 B)
+// Two forms of the scores kernel.  Narrow: one 128-key tile per step (N = 128 MMAs), 3 stages of 64 KB.  WIDE: two key
+// tiles per step (N = 256 MMAs: the query tile is staged once per two key tiles and read from shared memory once per
+// 256 key columns), 2 stages of 96 KB, 2 x 256 TMEM columns.
+template <bool WIDE>
+struct AttnCfg {
+  static constexpr int kStages = WIDE ? 2 : 3;
+  static constexpr int kKeyBytes = (WIDE ? 2 : 1) * 2 * 16384;  // K hi + K lo planes of the step's key tile(s)
+  static constexpr int kStageBytes = 2 * 16384 + kKeyBytes;     // Q hi, Q lo, then K hi, K lo
+  static constexpr int kNC = WIDE ? 256 : 128;                  // key columns per accumulator stage
+};
 constexpr int kAttnEpiHalves = 2;                // epilogue warps per TMEM lane quarter (each owns 64 key columns)
 constexpr int kAttnScratchBytes = kAttnEpiHalves * 32 * 128 * 4;  // one 32-column score slab per row and half
-constexpr int kAttnSmemBytes = kAttnStages * kAttnStageBytes + 256 + kAttnScratchBytes + 1024;
+constexpr int kAttnSmemBytes = 3 * 65536 + 256 + kAttnScratchBytes + 1024;  // both forms: 192 KB of stages
 constexpr int kAttnThreads = 64 + 128 * kAttnEpiHalves;  // TMA warp, MMA warp, 4 x kAttnEpiHalves epilogue warps
 constexpr int kMaxKeyFrames = 32;
 constexpr int kMaxProblems = 32;   // query frames per launch
@@ -36,6 +44,7 @@ constexpr int kMaxKeySlots = 256;  // problems x key frames per launch
 struct alignas(64) AttnParams {
   CUtensorMap tmap_q;  // {C, W, H, q frames, 2}
   CUtensorMap tmap_k;  // {C, W, H, k frames, 2}
+  CUtensorMap tmap_k1; // same tensor, box of ONE plane (WIDE: the two key tiles interleave per plane in smem)
   int H, W, kchunks;
   int T;  // number of key frame slots per problem
   int num_problems;
@@ -78,10 +87,12 @@ __device__ __forceinline__ KeyWindow key_window(const AttnParams& p, int qy0, in
 }
 
 struct UnitInfo {
-  int b, qy0, qx0, t, j_begin, j_end;
+  int b, qy0, qx0, t, j_begin, j_end;  // j_*: steps (WIDE: pairs of key tiles)
+  int n;                               // key tiles in the window
   KeyWindow w;
 };
 
+template <bool WIDE>
 __device__ __forceinline__ UnitInfo decode_unit(const AttnParams& p, int unit) {
   UnitInfo u;
   const int s = unit % p.splits;
@@ -94,11 +105,23 @@ __device__ __forceinline__ UnitInfo decode_unit(const AttnParams& p, int unit) {
   u.qx0 = (qt % p.q_tiles_x) * kQTileW;
   u.qy0 = (qt / p.q_tiles_x) * kQTileH;
   u.w = key_window(p, u.qy0, u.qx0, u.t);
-  const int n = u.w.ny * u.w.nx;
-  const int per = (n + p.splits - 1) / p.splits;
-  u.j_begin = min(n, s * per);
-  u.j_end = min(n, u.j_begin + per);
+  u.n = u.w.ny * u.w.nx;
+  const int steps = WIDE ? (u.n + 1) / 2 : u.n;
+  const int per = (steps + p.splits - 1) / p.splits;
+  u.j_begin = min(steps, s * per);
+  u.j_end = min(steps, u.j_begin + per);
   return u;
+}
+// origin of key tile j of the unit's window; a tile past the end (odd window in the WIDE form) lies outside the image:
+// its TMA load is pure zero fill and the epilogue skips its columns
+__device__ __forceinline__ void key_tile_origin(const AttnParams& p, const UnitInfo& u, int j, int& ky0, int& kx0) {
+  if (j < u.n) {
+    ky0 = u.w.wy0 + (j / u.w.nx) * kQTileH;
+    kx0 = u.w.wx0 + (j % u.w.nx) * kQTileW;
+  } else {
+    ky0 = p.H;
+    kx0 = 0;
+  }
 }
 
 template <int KMAX>
@@ -115,8 +138,12 @@ __device__ __forceinline__ void topk_insert(float (&v)[KMAX], int (&id)[KMAX], f
   }
 }
 
-template <int KMAX>
+template <int KMAX, bool WIDE>
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const __grid_constant__ AttnParams p) {
+  using A = AttnCfg<WIDE>;
+  constexpr int kAttnStages = A::kStages;
+  constexpr int kAttnStageBytes = A::kStageBytes;
+  constexpr int kNC = A::kNC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + kAttnStages * kAttnStageBytes;
@@ -127,11 +154,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * kAttnStages + 4);
   const uint32_t scratch_base = bar_base + 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t kTmemCols = 256;  // 2 accumulator stages x 128 key columns
+  constexpr uint32_t kTmemCols = 2 * kNC;  // 2 accumulator stages
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_q);
     tma_prefetch_desc(&p.tmap_k);
+    if (WIDE) tma_prefetch_desc(&p.tmap_k1);
     for (int s = 0; s < kAttnStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -157,19 +185,29 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
     int stage = 0;
     uint32_t phase = 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-      const UnitInfo u = decode_unit(p, unit);
+      const UnitInfo u = decode_unit<WIDE>(p, unit);
       const int frame = p.frame_ids[u.b * p.T + u.t];
       const int qframe = p.q_ids[u.b];
       for (int j = u.j_begin; j < u.j_end; ++j) {
-        const int ky0 = u.w.wy0 + (j / u.w.nx) * kQTileH;
-        const int kx0 = u.w.wx0 + (j % u.w.nx) * kQTileW;
+        int ky0, kx0, ky1 = 0, kx1 = 0;
+        key_tile_origin(p, u, WIDE ? 2 * j : j, ky0, kx0);
+        if (WIDE) key_tile_origin(p, u, 2 * j + 1, ky1, kx1);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
           if (lane == 0) {
             const uint32_t sq = smem_base + stage * kAttnStageBytes;
             mbar_arrive_expect_tx(full_bar(stage), kAttnStageBytes);
             tma_load_5d(sq, &p.tmap_q, full_bar(stage), kc * 64, u.qx0, u.qy0, qframe, 0);
-            tma_load_5d(sq + 32768, &p.tmap_k, full_bar(stage), kc * 64, kx0, ky0, frame, 0);
+            if (WIDE) {
+              // K hi = [tile 2j rows 0..127 | tile 2j+1 rows 128..255], then K lo likewise: one plane per load
+              const uint32_t sk = sq + 32768;
+              tma_load_5d(sk, &p.tmap_k1, full_bar(stage), kc * 64, kx0, ky0, frame, 0);
+              tma_load_5d(sk + 16384, &p.tmap_k1, full_bar(stage), kc * 64, kx1, ky1, frame, 0);
+              tma_load_5d(sk + 32768, &p.tmap_k1, full_bar(stage), kc * 64, kx0, ky0, frame, 1);
+              tma_load_5d(sk + 49152, &p.tmap_k1, full_bar(stage), kc * 64, kx1, ky1, frame, 1);
+            } else {
+              tma_load_5d(sq + 32768, &p.tmap_k, full_bar(stage), kc * 64, kx0, ky0, frame, 0);
+            }
           }
           __syncwarp();
           if (++stage == kAttnStages) {
@@ -181,23 +219,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = umma_idesc_f16_f32(128, 128);
+    constexpr uint32_t idesc = umma_idesc_f16_f32(128, kNC);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-      const UnitInfo u = decode_unit(p, unit);
+      const UnitInfo u = decode_unit<WIDE>(p, unit);
       for (int j = u.j_begin; j < u.j_end; ++j) {
         mbar_wait(tempty_bar(as), aphase ^ 1u, 200 + as);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * 128;
+        const uint32_t d_tmem = tmem_base + as * kNC;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(full_bar(stage), phase, 300 + stage);
           tc_fence_after();
           if (lane == 0) {
             const uint32_t q_hi = smem_base + stage * kAttnStageBytes, q_lo = q_hi + 16384;
-            const uint32_t k_hi = q_hi + 32768, k_lo = k_hi + 16384;
+            const uint32_t k_hi = q_hi + 32768, k_lo = k_hi + A::kKeyBytes / 2;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t koff = k * 32;
@@ -234,7 +272,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
     int as = 0;
     uint32_t aphase = 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-      const UnitInfo u = decode_unit(p, unit);
+      const UnitInfo u = decode_unit<WIDE>(p, unit);
       const int qy = u.qy0 + dqy, qx = u.qx0 + dqx;
       const bool q_valid = (qy < p.H) && (qx < p.W);
       const bool masked = (p.mask_mode != 0) && (u.t >= p.non_mask_len);
@@ -247,11 +285,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
         ti[i] = 0;
       }
       for (int j = u.j_begin; j < u.j_end; ++j) {
-        const int ky0 = u.w.wy0 + (j / u.w.nx) * kQTileH;
-        const int kx0 = u.w.wx0 + (j % u.w.nx) * kQTileW;
+        // narrow: this warp half scans columns [64h, 64h+64) of the step's key tile; WIDE: half h owns key tile 2j+h
+        // (accumulator columns [128h, 128h+128))
+        const int jt = WIDE ? 2 * j + half : j;
+        int ky0, kx0;
+        key_tile_origin(p, u, jt, ky0, kx0);
         mbar_wait(tfull_bar(as), aphase, 400 + as);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 128;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kNC + (WIDE ? 128 * half : 0);
         // per key tile: squared horizontal distances and in-image flags of the 16 key columns (shared by all rows)
         int dx2[16];
         uint32_t xok = 0;
@@ -261,8 +302,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
           dx2[c] = (p.mask_mode == 2) ? abs(dx) : dx * dx;
           if (kx0 + c < p.W) xok |= (1u << c);
         }
+        const int c_begin = WIDE ? 0 : 64 * half;
+        const int c_end = (jt < u.n) ? (WIDE ? 128 : 64 * half + 64) : c_begin;   // phantom tile: nothing to scan
 #pragma unroll 1
-        for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t acc[32];
           tmem_ld_32x32b_x32(t_row + c0, acc);
           tmem_ld_wait();
@@ -575,6 +618,22 @@ int normalize_split(const void* in_split, void* out_split, long long num_pixels,
 
 static int attn_kmax(int topk) { return topk <= 10 ? 10 : 16; }
 
+// 1 (default) = WIDE form (two key tiles per step), 0 = one key tile per step.  VFS_ATTN_WIDE sets the default,
+// vfs_attention_set_wide changes it at run time (tests, tuning).  Results are identical.
+static int g_attn_wide = -1;
+static bool attn_use_wide() {
+  if (g_attn_wide < 0) {
+    const char* e = getenv("VFS_ATTN_WIDE");
+    g_attn_wide = e ? (atoi(e) != 0) : 1;
+  }
+  return g_attn_wide != 0;
+}
+int attention_set_wide(int mode) {
+  VFS_REQUIRE(mode == 0 || mode == 1, VFS_EINVAL, "attention_set_wide: mode %d", mode);
+  g_attn_wide = mode;
+  return VFS_OK;
+}
+
 static int attn_splits(const VfsAttnDesc* d, int B) {
   const int q_tiles = ((d->W + kQTileW - 1) / kQTileW) * ((d->H + kQTileH - 1) / kQTileH);
   const int target = 2 * device_sm_count();
@@ -654,18 +713,37 @@ int masked_attention_batched(const VfsAttnDesc* d, int B, const void* q_bank_spl
     int rc = make_tmap_16b_sw128(&p.tmap_k, k_bank_split, 5, dims, strides, box);
     if (rc != VFS_OK) return rc;
   }
+  const bool wide = attn_use_wide();
+  if (wide) {
+    const uint32_t box1[5] = {64, kQTileW, kQTileH, 1, 1};
+    const uint64_t dims[5] = {static_cast<uint64_t>(d->C), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+                              static_cast<uint64_t>(k_bank_frames), 2};
+    const uint64_t strides[4] = {static_cast<uint64_t>(d->C) * 2, static_cast<uint64_t>(d->W) * d->C * 2,
+                                 static_cast<uint64_t>(HW) * d->C * 2, static_cast<uint64_t>(k_plane_stride) * 2};
+    int rc = make_tmap_16b_sw128(&p.tmap_k1, k_bank_split, 5, dims, strides, box1);
+    if (rc != VFS_OK) return rc;
+  }
   const int sms = device_sm_count();
   const int grid = p.num_units < sms ? p.num_units : sms;
   static bool configured = false;
   if (!configured) {
-    VFS_CUDA_OK(cudaFuncSetAttribute(attn_scores_topk_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VFS_CUDA_OK(cudaFuncSetAttribute(attn_scores_topk_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kAttnSmemBytes));
-    VFS_CUDA_OK(cudaFuncSetAttribute(attn_scores_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VFS_CUDA_OK(cudaFuncSetAttribute(attn_scores_topk_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kAttnSmemBytes));
+    VFS_CUDA_OK(cudaFuncSetAttribute(attn_scores_topk_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kAttnSmemBytes));
+    VFS_CUDA_OK(cudaFuncSetAttribute(attn_scores_topk_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kAttnSmemBytes));
     configured = true;
   }
-  if (KMAX == 10) attn_scores_topk_kernel<10><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
-  else attn_scores_topk_kernel<16><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
+  if (wide) {
+    if (KMAX == 10) attn_scores_topk_kernel<10, true><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
+    else attn_scores_topk_kernel<16, true><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
+  } else {
+    if (KMAX == 10) attn_scores_topk_kernel<10, false><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
+    else attn_scores_topk_kernel<16, false><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
+  }
   VFS_CUDA_OK(cudaGetLastError());
 
   MergeParams m;

@@ -149,6 +149,7 @@ int generic_attention(const float* A, int rows, int ld, int HWk, int HWq, const 
 int normalize_split(const void* in_split, void* out_split, long long num_pixels, int C, long long in_plane_stride,
                     long long out_plane_stride, cudaStream_t s);
 size_t attention_workspace_bytes(const VfsAttnDesc* d, int B);
+int attention_set_wide(int mode);
 int masked_attention_batched(const VfsAttnDesc* d, int B, const void* q_bank_split, long long q_plane_stride,
                              int q_bank_frames, const int* q_ids, const void* k_bank_split, long long k_plane_stride,
                              int k_bank_frames, const int* key_ids, const float* values, const int* val_ids,
@@ -363,6 +364,7 @@ int vfs_normalize_split(const void* in_split, void* out_split, long long num_pix
                         long long in_plane_stride, long long out_plane_stride, vfs_stream_t s) {
   return vfs::normalize_split(in_split, out_split, num_pixels, C, in_plane_stride, out_plane_stride, s);
 }
+int vfs_attention_set_wide(int mode) { return vfs::attention_set_wide(mode); }
 size_t vfs_attention_workspace_bytes(const VfsAttnDesc* d, int num_problems) {
   return vfs::attention_workspace_bytes(d, num_problems);
 }

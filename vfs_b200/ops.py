@@ -597,6 +597,11 @@ def normalize_split(xs, out=None):
 _MASK_MODES = {None: 0, 'circle': 1, 'square': 2}
 
 
+def attention_set_wide(mode=1):
+    """1 = two key tiles per step in the scores kernel (default), 0 = one."""
+    check(nat.lib().vfs_attention_set_wide(int(mode)), 'attention_set_wide')
+
+
 def attention_bank_batched(q_bank, q_ids, k_bank, key_ids, values, val_ids, v_batch_stride, v_frame_stride,
                            v_chan_stride, Cv, mask, temperature, topk, non_mask_len=0, mode='softmax',
                            return_topk=False):
