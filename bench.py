@@ -331,8 +331,9 @@ def main():
 
     def step_e2e():
         imgs = imgs_host.to(dev, non_blocking=True)                  # [8,1,3,2,H,W]  H2D
-        seg = seg8_host.to(dev, non_blocking=True)
-        return model.forward_test(imgs, seg, meta * CLIPS)              # 8 numpy arrays on the host (D2H inside)
+        # the label maps go in as the pinned host tensor: forward_test copies them itself and reads the class count
+        # on the host instead of synchronising on the device maximum
+        return model.forward_test(imgs, seg8_host, meta * CLIPS)        # 8 numpy arrays on the host (D2H inside)
 
     def step_e2e_per_video():
         res = []

@@ -740,7 +740,10 @@ def test_vanilla_tracker_batched_videos_equal_single_video_calls():
     meta = [dict(original_shape=(c['H'], c['W'], 3))]
     singles = [model.forward_test(imgs[b:b + 1].cuda(), seg[b:b + 1].cuda(), meta)[0] for b in range(B)]
     batched = model.forward_test(imgs.cuda(), seg.cuda(), meta * B)
+    from_host_labels = model.forward_test(imgs.cuda(), seg.pin_memory(), meta * B)    # class count read on the host
     assert len(batched) == B
+    for b in range(B):
+        np.testing.assert_array_equal(from_host_labels[b], batched[b])
     for b in range(B):
         assert batched[b].shape == singles[b].shape == (c['T'], c['H'], c['W'])
         assert batched[b].dtype == singles[b].dtype

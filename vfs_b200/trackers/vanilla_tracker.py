@@ -117,12 +117,19 @@ class VanillaTracker(BaseTracker):
         # a device->host read.  Done here it waits for two tiny kernels; done after the backbone launch (the
         # reference's order) it would stall the host until the whole feature pass has finished and leave the GPU idle
         # while the propagation kernels are being enqueued.
-        ref_seg_map = ref_seg_map.to(imgs.device)
+        # A label map that is still on the host tells the number of classes for free; from a device map F.one_hot
+        # has to read the maximum back (a stream synchronisation in the middle of the call).
+        num_classes = -1
+        if not ref_seg_map.is_cuda and ref_seg_map.ndim == 3 and ref_seg_map.numel() > 0:
+            num_classes = int(ref_seg_map.max()) + 1
+        ref_seg_map = ref_seg_map.to(imgs.device, non_blocking=True)
         assert ref_seg_map.size(0) == num_videos, (ref_seg_map.shape, imgs.shape)
         input_onehot = ref_seg_map.ndim == 4
         if not input_onehot:
             resized = pil_nearest_interpolate(ref_seg_map.unsqueeze(1), size=(fh, fw)).squeeze(1).long()
-            first = F.one_hot(resized).permute(0, 3, 1, 2).float()                       # [B,Cv,h,w]
+            # (the nearest resize may drop the largest id; sizing by the full-resolution maximum only adds all-zero
+            # channels, which cannot win the arg-max -- see the docstring)
+            first = F.one_hot(resized, num_classes).permute(0, 3, 1, 2).float()          # [B,Cv,h,w]
             ref_seg_map = F.interpolate(ref_seg_map.unsqueeze(1), size=orig_hw, mode='nearest').squeeze(1)
         else:
             first = F.interpolate(ref_seg_map, size=(fh, fw), mode='bilinear', align_corners=False).float()
