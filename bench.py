@@ -213,14 +213,14 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    import oracle
     import vfs_b200
     from vfs_b200 import ops
     from vfs_b200.common import spatial_neighbor
+    from vfs_b200.synthetic import seeded_state_dict
 
     model = vfs_b200.build_model(dict(type='VanillaTracker', backbone=BACKBONE_CFG), train_cfg=None,
                                  test_cfg=vfs_b200.ConfigDict(TEST_CFG))
-    model.backbone.load_state_dict(oracle.seeded_state_dict(model.backbone, seed=0))
+    model.backbone.load_state_dict(seeded_state_dict(model.backbone, seed=0))
     model = model.to(dev)
     model.eval()
     eng = model.backbone.engine

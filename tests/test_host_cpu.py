@@ -304,3 +304,15 @@ def test_siamfc_tracker_config_and_registry():
     b = cfg.model.backbone
     assert tuple(b.strides) == (1, 2, 1, 1) and tuple(b.dilations) == (1, 1, 2, 4) and b.norm_eval and b.depth == 18
     assert DEFAULT_CFG['exemplar_sz'] == 120          # the reference default, not BASELINE's 127
+
+
+def test_synthetic_weights_match_oracle_seeding():
+    """vfs_b200.synthetic (bench / tools) and oracle.seeded_state_dict (tests) implement the same name-keyed fill."""
+    import oracle
+    from vfs_b200.backbones import ResNet
+    from vfs_b200.synthetic import seeded_state_dict
+    net = ResNet(18)
+    a, b = seeded_state_dict(net, seed=5), oracle.seeded_state_dict(net, seed=5)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k

@@ -17,8 +17,8 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-import oracle  # noqa: E402  (seeded weights only)
 import vfs_b200  # noqa: E402
+from vfs_b200.synthetic import seeded_state_dict  # noqa: E402
 from vfs_b200 import ops  # noqa: E402
 from vfs_b200.optim import allreduce_grads, build_optimizer  # noqa: E402
 
@@ -48,7 +48,7 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     model = vfs_b200.build_model(MODEL, train_cfg=vfs_b200.ConfigDict(dict(intra_video=False)), test_cfg=None)
-    model.load_state_dict(oracle.seeded_state_dict(model, seed=0))
+    model.load_state_dict(seeded_state_dict(model, seed=0))
     model = model.to(dev)
     model.train()
     opt = build_optimizer(model, dict(type='SGD', lr=0.05, momentum=0.9, weight_decay=1e-4))

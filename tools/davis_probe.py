@@ -13,8 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import bench  # noqa: E402
-import oracle  # noqa: E402
 import vfs_b200  # noqa: E402
+from vfs_b200.synthetic import seeded_state_dict  # noqa: E402
 
 
 def main():
@@ -24,7 +24,7 @@ def main():
     test_cfg = dict(bench.TEST_CFG, batch_step=10)
     model = vfs_b200.build_model(dict(type='VanillaTracker', backbone=bench.BACKBONE_CFG), train_cfg=None,
                                  test_cfg=vfs_b200.ConfigDict(test_cfg))
-    model.backbone.load_state_dict(oracle.seeded_state_dict(model.backbone, seed=0))
+    model.backbone.load_state_dict(seeded_state_dict(model.backbone, seed=0))
     model = model.to(dev).eval()
     model.backbone.engine.check_versions = False
     g = torch.Generator().manual_seed(0)

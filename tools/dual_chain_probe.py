@@ -10,8 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import bench  # noqa: E402
-import oracle  # noqa: E402
 import vfs_b200  # noqa: E402
+from vfs_b200.synthetic import seeded_state_dict  # noqa: E402
 
 
 def main():
@@ -19,7 +19,7 @@ def main():
     dev = torch.device('cuda', 0)
     model = vfs_b200.build_model(dict(type='VanillaTracker', backbone=bench.BACKBONE_CFG), train_cfg=None,
                                  test_cfg=vfs_b200.ConfigDict(bench.TEST_CFG))
-    model.backbone.load_state_dict(oracle.seeded_state_dict(model.backbone, seed=0))
+    model.backbone.load_state_dict(seeded_state_dict(model.backbone, seed=0))
     model = model.to(dev).eval()
     eng = model.backbone.engine
     eng.check_versions = False
