@@ -132,7 +132,7 @@ int vfs_conv_dgrad(const VfsConvDesc* d, const void* dz_split, const void* wt_sp
 int vfs_pack_conv_weight_dgrad(const float* w_oihw, void* wt_split, int Cout, int Cin, int ksize, vfs_stream_t s);
 
 /* Backward of the convolution w.r.t. its weight: dW[co,ci,r,q] = sum_pixels dZ[pix,co] * X[pix + off(r,q), ci] as a
- * tcgen05 GEMM over the pixel axis with MN-major split-bf16 operands (csrc/wgrad_tc.cu).  Replaces torch autograd's
+ * tcgen05 GEMM over the pixel axis with MN-major split-fp16 operands (csrc/wgrad_tc.cu).  Replaces torch autograd's
  * cudnn_convolution_backward_weight.  `d` is the FORWARD descriptor.
  *   x_split split NHWC [N,H,W,Cin]; dz_split split NHWC [N,Ho,Wo,Cout]; workspace vfs_conv_wgrad_workspace_bytes;
  *   dw_oihw fp32 [Cout,Cin,k,k]: overwritten, or accumulated into when accumulate != 0 (second SimSiam view). */

@@ -3,7 +3,7 @@
 // Replaces the reference's per-32-query chunk loop  einsum -> /T -> masked_fill(-inf) -> topk -> index_select ->
 // softmax -> einsum  (mmaction/models/common/local_attention.py:287-342) by two kernels:
 //
-//  A  attn_scores_topk_kernel : S = Q K^T on tcgen05 (split-bf16 operands, 3 products per K-chunk, fp32 TMEM
+//  A  attn_scores_topk_kernel : S = Q K^T on tcgen05 (split-fp16 operands, 3 products per K-chunk, fp32 TMEM
 //     accumulators), for one tile of 128 queries (8 rows x 16 cols of the feature map) against 128-key tiles
 //     (8 x 16) that intersect the query tile's neighbour window -- key tiles outside the window are never loaded.
 //     Each epilogue thread owns one query row of the accumulator and keeps a sorted top-k (value, key index) list

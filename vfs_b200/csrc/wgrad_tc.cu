@@ -5,7 +5,7 @@
 // GEMM view: M = Cout (128 per tile), N = Cin (128 or 64 per tile), K = output pixels walked in chunks of 64.
 // Both operands are pixel-major in memory (NHWC: channels contiguous), i.e. *MN-major* for this GEMM, so the very
 // same TMA boxes the forward kernel uses ({64 channels, pixel tile}, 128B swizzle) are consumed by the tensor core
-// through MN-major shared-memory descriptors -- no transposition pass.  Operands are split-bf16 (3 MMAs per
+// through MN-major shared-memory descriptors -- no transposition pass.  Operands are split-fp16 (3 MMAs per
 // product).  Work is split over (Cout block, Cin block, filter tap, pixel range); every unit reduces its fp32
 // partial into dW with vector atomics (red.global.add.v4.f32).  Same warp roles as conv_tc.cu.
 #include "host_common.h"

@@ -1,4 +1,4 @@
-"""Host-side executor of the backbone: owns the device-side plan of a ``ResNet`` module (packed split-bf16
+"""Host-side executor of the backbone: owns the device-side plan of a ``ResNet`` module (packed split-fp16
 weights, folded BN scale/shift) and walks the block list issuing one fused kernel per ConvModule through the
 C ABI.  It never computes anything in torch: tensors here are only device buffers handed to libvfs_b200.so.
 

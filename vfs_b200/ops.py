@@ -1,5 +1,5 @@
 """torch-tensor front end of the C ABI (device memory + stream plumbing only; all arithmetic is in
-libvfs_b200.so).  "split" tensors are bf16 [2, N, H, W, C] (hi/lo planes, NHWC) -- see include/vfs_b200.h."""
+libvfs_b200.so).  "split" tensors are fp16 [2, N, H, W, C] (hi/lo planes, NHWC) -- see include/vfs_b200.h."""
 import ctypes
 
 import torch
@@ -33,7 +33,7 @@ def conv_out_hw(H, W, ksize, stride, dilation):
 
 
 def to_split(x):
-    """NCHW fp32 -> split NHWC bf16 [2,N,H,W,C]."""
+    """NCHW fp32 -> split NHWC fp16 [2,N,H,W,C]."""
     _require_cuda(x, 'x')
     assert x.dtype == torch.float32 and x.ndim == 4
     N, C, H, W = x.shape
