@@ -813,24 +813,9 @@ def test_simsiam_forward_eval_mode_matches_oracle(name):
 def _oracle_train_reference(c, sd, imgs):
     """Loss and parameter gradients of SimSiamBaseTracker.forward_train by torch autograd through the oracle
     (CPU fp32; the oracle functions are plain differentiable torch code)."""
-    from vfs_b200.common import images2video, video2images
     params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in sd.items()}
-    depth = c['model']['backbone']['depth']
-    bsd = {k[len('backbone.'):]: v for k, v in params.items() if k.startswith('backbone.')}
-    hsd = {k[len('img_head.'):]: v for k, v in params.items() if k.startswith('img_head.')}
-    clip_len = imgs.size(3)
-    i1 = video2images(imgs[:, 0].contiguous().reshape(-1, *imgs.shape[2:]))
-    i2 = video2images(imgs[:, 1].contiguous().reshape(-1, *imgs.shape[2:]))
-    z1, p1 = oracle.simsiam_head_forward(hsd, oracle.resnet_forward(bsd, i1, depth, bn_training=True), bn_training=True)
-    z2, p2 = oracle.simsiam_head_forward(hsd, oracle.resnet_forward(bsd, i2, depth, bn_training=True), bn_training=True)
-    intra = c['train_cfg'].get('intra_video', False)
-    w = 1. / clip_len if intra else 1.
-    losses = [oracle.simsiam_loss(p1, z1, p2, z2, weight=w)]
-    if intra:
-        z2v, p2v = images2video(z2, clip_len), images2video(p2, clip_len)
-        for i in range(1, clip_len):
-            losses.append(oracle.simsiam_loss(p1, z1, video2images(p2v.roll(i, dims=2)),
-                                              video2images(z2v.roll(i, dims=2)), weight=w))
+    losses = oracle.simsiam_forward_train(params, imgs, c['model']['backbone']['depth'],
+                                          intra_video=c['train_cfg'].get('intra_video', False)).values()
     loss = sum(l.mean() for l in losses)
     loss.backward()
     return float(loss), {k: v.grad for k, v in params.items() if v.requires_grad and v.grad is not None}

@@ -111,6 +111,39 @@ def test_xcorr_matches_reference(golden, name):
     _pinned(got, golden[f'xcorr/{name}/siamconvfc'])
 
 
+@pytest.mark.parametrize('name', sorted(cases.TRACKER_TRAIN_CASES))
+def test_simsiam_forward_train_matches_reference(golden, name):
+    import vfs_b200
+    c = cases.TRACKER_TRAIN_CASES[name]
+    model = vfs_b200.build_model(c['model'], train_cfg=vfs_b200.ConfigDict(c['train_cfg']), test_cfg=None)
+    sd = oracle.seeded_state_dict(model, seed=c['seed'])
+    with torch.no_grad():
+        losses = oracle.simsiam_forward_train(sd, cases.tracker_train_input(c), c['model']['backbone']['depth'],
+                                              intra_video=c['train_cfg'].get('intra_video', False))
+    keys = sorted(k for k in golden if k.startswith(f'tracker_train/{name}/'))
+    assert sorted(f'tracker_train/{name}/{k}' for k in losses) == keys
+    for k, v in losses.items():
+        _pinned(v.numpy(), golden[f'tracker_train/{name}/{k}'])
+
+
+@pytest.mark.parametrize('name', sorted(cases.TRACKER_TEST_CASES))
+def test_vanilla_forward_test_matches_reference(golden, name):
+    """Label maps are arg-maxes: identical up to isolated pixels whose two best logits differ by host-ISA rounding."""
+    from vfs_b200.backbones import ResNet
+    c = cases.TRACKER_TEST_CASES[name]
+    b = c['backbone']
+    net = ResNet(b['depth'], norm_cfg=b['norm_cfg'], strides=b['strides'], out_indices=b['out_indices'])
+    bsd = oracle.seeded_state_dict(net, seed=c['seed'])
+    imgs, seg = cases.tracker_test_inputs(c)
+    # make_golden.py calls tr.eval(): BatchNorm runs on the running statistics
+    preds = oracle.vanilla_forward_test(bsd, imgs, seg, (c['H'], c['W'], 3), b['depth'], b['strides'], b['out_indices'],
+                                        c['test_cfg'])
+    got = np.asarray(preds[0]).astype(np.uint8)
+    ref = golden[f'tracker_test/{name}/preds']
+    assert got.shape == ref.shape
+    assert float((got == ref).mean()) > 0.999
+
+
 # ------------------------------------------------------------------ live pin (authoring container only)
 def _oracle_outputs():
     """Every array of make_golden.reference_outputs() that the oracle restates, computed by the oracle."""
@@ -159,6 +192,22 @@ def _oracle_outputs():
             out[f'xcorr/{name}/siamfc'] = oracle.xcorr(z, x, c['out_scale']).numpy()
             sd = oracle.seeded_state_dict(SiamConvFC(c['C'], c['C'], out_scale=c['out_scale']), seed=c['seed'])
             out[f'xcorr/{name}/siamconvfc'] = oracle.siam_conv_fc(sd, z, x, c['out_scale']).numpy()
+        import vfs_b200
+        for name, c in cases.TRACKER_TRAIN_CASES.items():
+            model = vfs_b200.build_model(c['model'], train_cfg=vfs_b200.ConfigDict(c['train_cfg']), test_cfg=None)
+            sd = oracle.seeded_state_dict(model, seed=c['seed'])
+            losses = oracle.simsiam_forward_train(sd, cases.tracker_train_input(c), c['model']['backbone']['depth'],
+                                                  intra_video=c['train_cfg'].get('intra_video', False))
+            for k, v in losses.items():
+                out[f'tracker_train/{name}/{k}'] = v.numpy()
+        for name, c in cases.TRACKER_TEST_CASES.items():
+            b = c['backbone']
+            net = ResNet(b['depth'], norm_cfg=b['norm_cfg'], strides=b['strides'], out_indices=b['out_indices'])
+            bsd = oracle.seeded_state_dict(net, seed=c['seed'])
+            imgs, seg = cases.tracker_test_inputs(c)
+            preds = oracle.vanilla_forward_test(bsd, imgs, seg, (c['H'], c['W'], 3), b['depth'], b['strides'],
+                                                b['out_indices'], c['test_cfg'])
+            out[f'tracker_test/{name}/preds'] = np.asarray(preds[0]).astype(np.uint8)
     return out
 
 
@@ -172,7 +221,7 @@ def test_oracle_bit_exact_vs_live_reference(golden):
     for key, arr in ref.items():
         _pinned(arr, golden[key])
     mine = _oracle_outputs()
-    missing = [k for k in ref if k not in mine and not k.startswith('tracker_')]
+    missing = [k for k in ref if k not in mine]
     assert not missing, missing
     for key, arr in mine.items():
         _pinned(arr, ref[key], exact=True)
