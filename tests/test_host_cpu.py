@@ -316,3 +316,14 @@ def test_synthetic_weights_match_oracle_seeding():
     assert a.keys() == b.keys()
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
+def test_gpu_only_entry_points_fail_loudly_without_cuda():
+    """No silent CPU path: the graphed training step and the SiamFC tracker refuse to run without a CUDA device."""
+    import vfs_b200
+    from vfs_b200.siamfc import TrackerSiamFC, build_cfg
+    with pytest.raises(RuntimeError):
+        vfs_b200.GraphedTrainStep(torch.nn.Linear(2, 2), None, dict(imgs=torch.zeros(1)))
+    with pytest.raises(RuntimeError):
+        TrackerSiamFC(build_cfg(dict(type='ResNet', depth=18, pretrained=None)))
