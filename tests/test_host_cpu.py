@@ -327,3 +327,26 @@ def test_gpu_only_entry_points_fail_loudly_without_cuda():
         vfs_b200.GraphedTrainStep(torch.nn.Linear(2, 2), None, dict(imgs=torch.zeros(1)))
     with pytest.raises(RuntimeError):
         TrackerSiamFC(build_cfg(dict(type='ResNet', depth=18, pretrained=None)))
+
+
+def test_masked_attention_argument_checks_mirror_the_reference():
+    """local_attention.py:263-272, 294: mode, batch equality, value/key shapes, non_mask_len range and mask shape are
+    asserted before anything is computed (here: before the CUDA-only path is even reached)."""
+    from vfs_b200.common import masked_attention_efficient, spatial_neighbor
+    q = torch.zeros(1, 64, 4, 5)
+    k = torch.zeros(1, 64, 2, 4, 5)
+    v = torch.zeros(1, 3, 2, 4, 5)
+    with pytest.raises(AssertionError):
+        masked_attention_efficient(q, k, v, None, topk=5, mode='dot')
+    with pytest.raises(AssertionError):
+        masked_attention_efficient(torch.zeros(2, 64, 4, 5), k, v, None, topk=5)
+    with pytest.raises(AssertionError):
+        masked_attention_efficient(q, k, torch.zeros(1, 3, 1, 4, 5), None, topk=5)
+    with pytest.raises(AssertionError):
+        masked_attention_efficient(q, k, v, None, topk=5, non_mask_len=2)
+    with pytest.raises(AssertionError):
+        masked_attention_efficient(q, k, v, torch.ones(19, 20, dtype=torch.bool), topk=5)       # mask must be [HWk, HWq]
+    with pytest.raises(AssertionError):
+        masked_attention_efficient(q, k, v, spatial_neighbor(1, 4, 5, 4, mode='square'), topk=5)  # 3-D mask needs T == 1
+    with pytest.raises(RuntimeError):                                                           # valid call, CPU tensors
+        masked_attention_efficient(q, k, v, spatial_neighbor(1, 4, 5, 4), topk=5)
