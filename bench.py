@@ -356,8 +356,18 @@ def main():
             dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
         return world * CLIPS * steps / float(dt_), r_
 
+    # the same call fed the way the reference's loader would feed it if Normalize + FormatShape ran on the device:
+    # uint8 HWC frames cross PCIe (a quarter of the bytes), vfs_b200.DeviceNormalizeFormat builds the fp32 clip tensor
+    u8_host = torch.randint(0, 256, (CLIPS, FRAMES, SIZE, SIZE, 3), dtype=torch.uint8, generator=g).pin_memory()
+    feed = vfs_b200.DeviceNormalizeFormat(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_bgr=False)
+
+    def step_e2e_u8():
+        imgs = feed(u8_host).unsqueeze(1)                               # H2D of uint8 frames, [8,1,3,2,H,W] fp32 in HBM
+        return model.forward_test(imgs, seg8_host, meta * CLIPS)
+
     e2e_steps = max(3, min(a.steps, 20))
     e2e_value, r = time_e2e(step_e2e, e2e_steps)
+    e2e_u8, _ = time_e2e(step_e2e_u8, e2e_steps)
     e2e_single, r1 = time_e2e(step_e2e_per_video, max(3, min(a.steps, 10)))
     assert all((x == y).all() for x, y in zip(r, r1)), 'batched and per-video forward_test disagree'
     h2d = imgs_host.numel() * 4 + seg8_host.numel() * 4
@@ -416,7 +426,10 @@ def main():
                          api='build_model(VanillaTracker).forward_test, one call on the batch of 8 two-frame videos, '
                              'pinned host inputs', steps=e2e_steps,
                          per_video_calls=dict(value=e2e_single, unit='frame-pairs/s',
-                                              api='one forward_test call per video (reference calling convention)')),
+                                              api='one forward_test call per video (reference calling convention)'),
+                         from_uint8_frames=dict(value=e2e_u8, unit='frame-pairs/s', h2d_bytes_per_step=int(u8_host.numel()),
+                                                api='uint8 HWC host frames -> DeviceNormalizeFormat (Normalize + '
+                                                    'FormatShape on the device) -> forward_test')),
                 gpu_launches=launches,
                 roofline=roofline,
                 roofline_affinity=roofline_affinity,

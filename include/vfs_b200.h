@@ -311,6 +311,14 @@ int vfs_relu(float* y, size_t n, vfs_stream_t s);
 int vfs_cosine_sim_loss(const float* p, const float* z, float* loss, int B, int D, int with_norm, int negative,
                         vfs_stream_t s);
 
+/* Data feed: ``Normalize`` (mmaction/datasets/pipelines/augmentations.py:711-757 -> mmcv.imnormalize_)
+ * + ``FormatShape('NCTHW')`` (formating.py:248-258) on the device.  frames uint8 [clips][T][H][W][3] (device memory,
+ * H*W % 4 == 0) -> out fp32 [clips][3][T][H][W] = fp32(fp64(fp32(x - mean)) * stdinv) per channel, which is what
+ * cv2.subtract / cv2.multiply produce for mmcv's float64 mean and 1/std vectors; swap_rb != 0 swaps channels 0 and 2
+ * first (the pipeline's ``to_bgr``).  mean3 (three floats) and stdinv3 (three doubles = 1 / double(std)) are HOST
+ * pointers. */
+int vfs_frames_u8_to_ncthw_f32(const unsigned char* frames, float* out, long long clips, int T, int H, int W,
+                               const float* mean3, const double* stdinv3, int swap_rb, vfs_stream_t s);
 /* ------------------------------------------------------------------------------------------------
  * SiamFC cross-correlation.  Replaces SiamFC._fast_xcorr (projects/siamfc-pytorch/siamfc/heads.py:16-23).
  *   z fp32 NHWC [nz,hz,wz,C], x fp32 NHWC [nx,h,w,C] -> out fp32 [nx,1,h-hz+1,w-wz+1], x[i] pairs with z[i % nz]

@@ -618,6 +618,23 @@ def test_graphed_train_step_equals_eager_steps():
     assert losses_g == pytest.approx(losses_e, rel=2e-3)
 
 
+# --------------------------------------------------------------------------------------------- data feed
+@pytest.mark.parametrize('to_bgr', [False, True])
+def test_device_normalize_format_matches_pipeline_oracle(to_bgr):
+    """uint8 HWC frames -> fp32 NCTHW on the device == Normalize + FormatShape('NCTHW') of the reference pipeline
+    (cv2 arithmetic), bit for bit."""
+    import vfs_b200
+    rng = np.random.RandomState(3 + int(to_bgr))
+    B, T, H, W = 3, 2, 22, 34
+    frames = rng.randint(0, 256, (B, T, H, W, 3)).astype(np.uint8)
+    cfg = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_bgr=to_bgr)   # configs/*:85-86
+    feed = vfs_b200.DeviceNormalizeFormat(**cfg)
+    got = feed(torch.from_numpy(frames).pin_memory()).cpu().numpy()
+    ref = np.concatenate([oracle.normalize_format_ncthw(frames[b], num_clips=1, **cfg) for b in range(B)], axis=0)
+    assert got.shape == ref.shape == (B, 3, T, H, W) and got.dtype == np.float32
+    np.testing.assert_array_equal(got, ref)
+
+
 # --------------------------------------------------------------------------------------------- SiamFC tracker
 def _smooth_maps(gen, S, R):
     """Response-like maps: a few Gaussian bumps + small noise (a pure-noise map makes the arg-max a coin toss)."""

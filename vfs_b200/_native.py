@@ -91,6 +91,8 @@ PROTOTYPES = {
     'vfs_relu': (_i, [_vp, _sz, _vp]),
     'vfs_cosine_sim_loss': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'vfs_nchw_to_nhwc_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'vfs_frames_u8_to_ncthw_f32': (_i, [_vp, _vp, _ll, _i, _i, _i, ctypes.POINTER(ctypes.c_float),
+                                        ctypes.POINTER(ctypes.c_double), _i, _vp]),
     'vfs_xcorr_nhwc': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
 }
 

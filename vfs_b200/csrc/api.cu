@@ -168,6 +168,8 @@ int relu_inplace(float* y, size_t n, cudaStream_t s);
 int cosine_sim_loss(const float* p, const float* z, float* loss, int B, int D, int with_norm, int negative,
                     cudaStream_t s);
 int nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, cudaStream_t s);
+int frames_u8_to_ncthw_f32(const unsigned char* in, float* out, long long clips, int T, int H, int W, const float* mean3,
+                           const double* stdinv3, int swap_rb, cudaStream_t s);
 int xcorr_nhwc(const float* z, const float* x, float* out, int nz, int nx, int C, int hz, int wz, int h, int w,
                float out_scale, cudaStream_t s);
 
@@ -405,6 +407,10 @@ int vfs_relu(float* y, size_t n, vfs_stream_t s) { return vfs::relu_inplace(y, n
 int vfs_cosine_sim_loss(const float* p, const float* z, float* loss, int B, int D, int with_norm, int negative,
                         vfs_stream_t s) {
   return vfs::cosine_sim_loss(p, z, loss, B, D, with_norm, negative, s);
+}
+int vfs_frames_u8_to_ncthw_f32(const unsigned char* frames, float* out, long long clips, int T, int H, int W,
+                               const float* mean3, const double* stdinv3, int swap_rb, vfs_stream_t s) {
+  return vfs::frames_u8_to_ncthw_f32(frames, out, clips, T, H, W, mean3, stdinv3, swap_rb, s);
 }
 int vfs_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, vfs_stream_t s) {
   return vfs::nchw_to_nhwc_f32(in, out, N, C, H, W, s);

@@ -203,6 +203,67 @@ int conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const void* w_s
   return VFS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Data feed: the reference's CPU pipeline steps ``Normalize`` (mmaction/datasets/pipelines/
+// augmentations.py:711-757 -> mmcv.imnormalize_: optional channel swap, (x - mean) * (1/std) in fp32) and
+// ``FormatShape('NCTHW')`` (formating.py:248-258: [M,H,W,C] -> [M/T, C, T, H, W]) on the device, so that frames cross
+// PCIe as uint8 HWC (a quarter of the fp32 NCTHW bytes).
+//   in  uint8 [clips][T][H][W][3]      out fp32 [clips][3][T][H][W]
+// One thread = 4 consecutive pixels: three 4-byte loads (12 bytes), three float4 stores (one per channel plane).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void frames_u8_to_ncthw_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, long long clips,
+                                          int T, long long HW, float m0, float m1, float m2, double s0, double s1, double s2,
+                                          int swap_rb) {
+  const long long quads = HW / 4;  // HW % 4 == 0 is required by the caller
+  const long long total = clips * T * quads;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long qd = i % quads;
+    const long long ft = i / quads;  // clip * T + t
+    const long long t = ft % T, clip = ft / T;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (ft * HW + qd * 4) * 3);
+    const uint32_t w0 = src[0], w1 = src[1], w2 = src[2];
+    // bytes: p0 = (b0 b1 b2) p1 = (b3 b4 b5) p2 = (b6 b7 b8) p3 = (b9 b10 b11)
+    float c0[4], c1[4], c2[4];
+    c0[0] = static_cast<float>(w0 & 0xff);         c1[0] = static_cast<float>((w0 >> 8) & 0xff);
+    c2[0] = static_cast<float>((w0 >> 16) & 0xff); c0[1] = static_cast<float>(w0 >> 24);
+    c1[1] = static_cast<float>(w1 & 0xff);         c2[1] = static_cast<float>((w1 >> 8) & 0xff);
+    c0[2] = static_cast<float>((w1 >> 16) & 0xff); c1[2] = static_cast<float>(w1 >> 24);
+    c2[2] = static_cast<float>(w2 & 0xff);         c0[3] = static_cast<float>((w2 >> 8) & 0xff);
+    c1[3] = static_cast<float>((w2 >> 16) & 0xff); c2[3] = static_cast<float>(w2 >> 24);
+    const float* first = swap_rb ? c2 : c0;   // channel written to output plane 0
+    const float* third = swap_rb ? c0 : c2;
+    const long long plane = T * HW;
+    float* dst = out + (clip * 3 * T + t) * HW + qd * 4;
+    // cv2.subtract on a CV_32F image rounds to fp32; cv2.multiply by the float64 1/std scalar multiplies in fp64 and
+    // rounds once to fp32 (checked against cv2 bit for bit by the parity test)
+    auto norm = [](float x, float m, double sinv) {
+      return __double2float_rn(static_cast<double>(__fsub_rn(x, m)) * sinv);
+    };
+    *reinterpret_cast<float4*>(dst) =
+        make_float4(norm(first[0], m0, s0), norm(first[1], m0, s0), norm(first[2], m0, s0), norm(first[3], m0, s0));
+    *reinterpret_cast<float4*>(dst + plane) =
+        make_float4(norm(c1[0], m1, s1), norm(c1[1], m1, s1), norm(c1[2], m1, s1), norm(c1[3], m1, s1));
+    *reinterpret_cast<float4*>(dst + 2 * plane) =
+        make_float4(norm(third[0], m2, s2), norm(third[1], m2, s2), norm(third[2], m2, s2), norm(third[3], m2, s2));
+  }
+}
+
+int frames_u8_to_ncthw_f32(const unsigned char* in, float* out, long long clips, int T, int H, int W, const float* mean3,
+                           const double* stdinv3, int swap_rb, cudaStream_t s) {
+  VFS_REQUIRE(in && out && mean3 && stdinv3, VFS_EINVAL, "frames_u8_to_ncthw_f32: null argument");
+  VFS_REQUIRE(clips > 0 && T > 0 && H > 0 && W > 0, VFS_ESHAPE, "frames_u8_to_ncthw_f32: empty input");
+  const long long HW = static_cast<long long>(H) * W;
+  VFS_REQUIRE(HW % 4 == 0, VFS_ESHAPE, "frames_u8_to_ncthw_f32: H*W = %lld must be a multiple of 4", HW);
+  const long long total = clips * T * (HW / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  frames_u8_to_ncthw_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(in, out, clips, T, HW, mean3[0], mean3[1], mean3[2],
+                                                                    stdinv3[0], stdinv3[1], stdinv3[2], swap_rb);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
 VFS_DEFINE_OVERFLOW_ACCESSOR(overflow_layout)
 
 }  // namespace vfs
