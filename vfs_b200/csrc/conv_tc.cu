@@ -185,28 +185,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   const int num_tiles = p.num_sched_tiles;
   const int num_kchunks = p.num_taps * p.kchunks_per_tap;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap
-  // the tail of the previous kernel in the stream.  So may the WEIGHT tiles of this CTA's first pipeline fill -- they
-  // do not depend on the previous layer: the producer issues them before the dependency wait, which takes half of
-  // the start-up burst (all CTAs filling STAGES slots at once) out of the critical path.  From the wait on, the
-  // previous kernel's results are read and its inputs overwritten.
-  int pre_b = 0;  // stages whose weight half is already in flight (producer lane only)
-  if (warp == 0 && lane == 0 && tile_first < num_tiles) {
-    const int n_tile = tile_first % p.num_n_tiles;
-    pre_b = num_kchunks < STAGES ? num_kchunks : STAGES;
-    for (int kc = 0; kc < pre_b; ++kc) {
-      const int tap = kc / p.kchunks_per_tap;
-      const int c0 = (kc - tap * p.kchunks_per_tap) * kBlockK;
-      const uint32_t sb = smem_base + kc * S::kStageBytes + 2 * kTileABytes;
-      if (PAIR) {
-        if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(kc), 2 * S::kStageBytes);
-        tma_load_3d_2sm(sb, &p.tmap_b, full_bar(kc), p.tap_koff[tap] + c0,
-                        n_tile * BN + static_cast<int>(cta_rank) * S::kRowsB, 0);
-      } else {
-        mbar_arrive_expect_tx(full_bar(kc), S::kStageBytes);
-        tma_load_3d(sb, &p.tmap_b, full_bar(kc), p.tap_koff[tap] + c0, n_tile * BN, 0);
-      }
-    }
-  }
+  // the tail of the previous kernel in the stream; from the wait on, its results are read and its inputs overwritten.
+  // NOTHING that reads global memory may move above the wait -- not even the weight tiles: callers do produce weights
+  // with the immediately preceding launch (pack -> conv in training, features -> conv in the dense affinity paths),
+  // and a kernel that never triggers early only guarantees visibility of its stores at griddepcontrol.wait.  (Round 1
+  // tried issuing the first weight tiles before the wait: -1 % on the bench, one flaky parity failure.)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
@@ -233,16 +216,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           const int c0 = (kc - tap * p.kchunks_per_tap) * kBlockK;
           const uint32_t sa = smem_base + stage * S::kStageBytes;
           const uint32_t sb = sa + 2 * kTileABytes;
-          if (pre_b > 0) {
-            // first fill: the weight half and the expected byte count were issued before the dependency wait
-            --pre_b;
-            if (PAIR)
-              tma_load_5d_2sm(sa, &p.tmap_a[p.tap_view[tap]], full_bar(stage), c0, w0 + p.tap_dw[tap],
-                              h0 + p.tap_dh[tap], n0, 0);
-            else
-              tma_load_5d(sa, &p.tmap_a[p.tap_view[tap]], full_bar(stage), c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap],
-                          n0, 0);
-          } else if (PAIR) {
+          if (PAIR) {
             // both CTAs' bytes are counted on the leader's barrier (the MMA of the pair waits there)
             if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * S::kStageBytes);
             tma_load_5d_2sm(sa, &p.tmap_a[p.tap_view[tap]], full_bar(stage), c0, w0 + p.tap_dw[tap],
