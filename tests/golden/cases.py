@@ -175,3 +175,42 @@ SIAMFC_CROP_CASES = {
 def siamfc_image():
     import numpy as np
     return np.random.RandomState(900).randint(0, 256, (180, 240, 3)).astype(np.uint8)
+
+
+# ------------------------------------------------------------------ attention, general forms (bool masks, topk=None)
+ATTENTION_EXTRA_CASES = {
+    # name: N, C, Cv, T, (Hq, Wq), (Hk, Wk), mask kind, topk, mode, non_mask_len, temperature
+    'bool2d_topk': dict(seed=71, N=1, C=64, Cv=3, T=2, q=(9, 11), k=(9, 11), mask='random2d', topk=5, mode='softmax',
+                        non_mask_len=0, temperature=0.07),
+    'bool2d_first_free': dict(seed=72, N=1, C=64, Cv=4, T=3, q=(8, 8), k=(8, 8), mask='random2d', topk=10,
+                              mode='softmax', non_mask_len=1, temperature=0.07),
+    'window_dense_softmax': dict(seed=73, N=1, C=32, Cv=3, T=2, q=(9, 11), k=(9, 11), mask='window', topk=None,
+                                 mode='softmax', non_mask_len=0, temperature=0.07),
+    'nomask_dense_softmax': dict(seed=74, N=2, C=64, Cv=20, T=1, q=(7, 9), k=(7, 9), mask=None, topk=None,
+                                 mode='softmax', non_mask_len=0, temperature=0.07),
+    'bool3d_topk': dict(seed=75, N=2, C=64, Cv=3, T=1, q=(8, 9), k=(8, 9), mask='random3d', topk=4, mode='softmax',
+                        non_mask_len=0, temperature=0.07),
+    'dense_cosine': dict(seed=76, N=1, C=64, Cv=2, T=2, q=(6, 7), k=(6, 7), mask='random2d', topk=None, mode='cosine',
+                         non_mask_len=0, temperature=1.0),
+    'rect_query_vs_key': dict(seed=77, N=1, C=64, Cv=3, T=2, q=(6, 7), k=(8, 9), mask=None, topk=6, mode='softmax',
+                              non_mask_len=0, temperature=0.07),
+}
+
+
+def attention_extra_inputs(c):
+    """-> (query, key, value, mask tensor | ('window', range) | None)."""
+    g = _gen(900 + c['seed'])
+    (hq, wq), (hk, wk) = c['q'], c['k']
+    q = torch.relu(torch.randn(c['N'], c['C'], hq, wq, generator=g))
+    k = torch.relu(torch.randn(c['N'], c['C'], c['T'], hk, wk, generator=g))
+    v = torch.rand(c['N'], c['Cv'], c['T'], hk, wk, generator=g)
+    mask = None
+    if c['mask'] == 'random2d':
+        mask = torch.rand(hk * wk, hq * wq, generator=g) > 0.4
+        mask[:16] = True                                    # every query keeps at least 16 keys
+    elif c['mask'] == 'random3d':
+        mask = torch.rand(c['N'], hk * wk, hq * wq, generator=g) > 0.4
+        mask[:, :16] = True
+    elif c['mask'] == 'window':
+        mask = ('window', 8)
+    return q, k, v, mask

@@ -117,12 +117,32 @@ def siamfc_crop_outputs():
     return out
 
 
+def attention_extra_outputs():
+    """masked_attention_efficient of the unmodified reference for arbitrary bool masks / topk=None / rectangular maps
+    -> tests/golden/attention_extra_golden.npz."""
+    ref = ref_shim.load_reference()
+    out = {}
+    for name, c in cases.ATTENTION_EXTRA_CASES.items():
+        q, k, v, mask = cases.attention_extra_inputs(c)
+        if isinstance(mask, tuple):
+            mask = ref.spatial_neighbor(1, c['k'][0], c['k'][1], neighbor_range=mask[1], device='cpu',
+                                        dtype=torch.float32, mode='circle')
+        with torch.no_grad():
+            out[name] = ref.masked_attention_efficient(q, k, v, mask, temperature=c['temperature'], topk=c['topk'],
+                                                       non_mask_len=c['non_mask_len'], mode=c['mode']).numpy()
+    return out
+
+
 def main():
+    extra = attention_extra_outputs()
+    extra_path = os.path.join(ROOT, 'tests', 'golden', 'attention_extra_golden.npz')
+    np.savez_compressed(extra_path, **extra)
+    print(f'wrote {extra_path}: {len(extra)} arrays')
     crops = siamfc_crop_outputs()
     crop_path = os.path.join(ROOT, 'tests', 'golden', 'siamfc_crop_golden.npz')
     np.savez_compressed(crop_path, **crops)
     print(f'wrote {crop_path}: {len(crops)} arrays')
-    if '--only-siamfc' in sys.argv:
+    if '--only-siamfc' in sys.argv or '--only-small' in sys.argv:
         return
     torch.set_num_threads(8)
     out = reference_outputs()

@@ -144,6 +144,30 @@ def test_vanilla_forward_test_matches_reference(golden, name):
     assert float((got == ref).mean()) > 0.999
 
 
+def _attention_extra_oracle(c):
+    q, k, v, mask = cases.attention_extra_inputs(c)
+    if isinstance(mask, tuple):
+        mask = oracle.spatial_neighbor(c['k'][0], c['k'][1], mask[1], mode='circle')
+    return oracle.masked_attention_efficient(q, k, v, mask, temperature=c['temperature'], topk=c['topk'],
+                                             non_mask_len=c['non_mask_len'], mode=c['mode']).numpy()
+
+
+@pytest.mark.parametrize('name', sorted(cases.ATTENTION_EXTRA_CASES))
+def test_attention_general_forms_match_reference(name):
+    """Arbitrary boolean masks, topk=None (dense softmax / cosine) and rectangular query/key maps: the oracle against
+    outputs of the unmodified reference (tests/golden/attention_extra_golden.npz), live bit-exact where available."""
+    import os
+    with np.load(os.path.join(os.path.dirname(__file__), 'golden', 'attention_extra_golden.npz')) as z:
+        ref = z[name]
+    got = _attention_extra_oracle(cases.ATTENTION_EXTRA_CASES[name])
+    _pinned(got, ref)
+    if ref_shim.available():
+        from tests.golden import make_golden
+        live = make_golden.attention_extra_outputs()[name]
+        _pinned(live, ref)
+        _pinned(got, live, exact=True)
+
+
 # ------------------------------------------------------------------ live pin (authoring container only)
 def _oracle_outputs():
     """Every array of make_golden.reference_outputs() that the oracle restates, computed by the oracle."""
