@@ -13,8 +13,11 @@ VanillaTracker.forward_test with a 2-frame video, tools/test.py:129-133 model): 
   e2e        the same work through the public plugin API (build_model(VanillaTracker) -> ONE forward_test call on the
              batch of 8 two-frame videos) with pinned HOST inputs: H2D of the frames and D2H of the predictions inside
              the timed region (wall clock).  `e2e.per_video_calls` is the same batch issued the way the reference
-             must issue it (one video per forward_test call, vanilla_tracker.py:56 asserts B == 1).
+             must issue it (one video per forward_test call, vanilla_tracker.py:56 asserts B == 1);
+             `e2e.from_uint8_frames` feeds uint8 HWC frames through vfs_b200.DeviceNormalizeFormat (Normalize +
+             FormatShape on the device) instead of fp32 clips.
   roofline   tcgen05 conv kernel: algorithmic conv FLOPs of a step / CUDA-event time of the conv segment
+  roofline_affinity  the fused affinity / top-k / propagation kernels the same way (window-restricted FLOPs)
   cpu_baseline  the CPU oracle (restatement of the reference's torch-CPU path) on a bounded sample, all host cores
 
 `--impl reference` times the reference's CPU implementation of the same step (the oracle port: /root/reference is a
