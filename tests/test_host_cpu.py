@@ -350,3 +350,30 @@ def test_masked_attention_argument_checks_mirror_the_reference():
         masked_attention_efficient(q, k, v, spatial_neighbor(1, 4, 5, 4, mode='square'), topk=5)  # 3-D mask needs T == 1
     with pytest.raises(RuntimeError):                                                           # valid call, CPU tensors
         masked_attention_efficient(q, k, v, spatial_neighbor(1, 4, 5, 4), topk=5)
+
+
+def test_checkpoint_conversion_roundtrips_through_torchvision_names(tmp_path):
+    """tools/convert_weights/convert_to_pretrained.py equivalent: tracker checkpoint -> torchvision-style backbone
+    checkpoint that torchvision itself accepts and that ``ResNet(pretrained=...)`` loads back unchanged."""
+    import torchvision
+    import vfs_b200
+    from tests.golden import cases
+    from vfs_b200.backbones import ResNet
+    from vfs_b200.convert import backbone_to_torchvision, convert
+    from vfs_b200.synthetic import seeded_state_dict
+    c = cases.TRACKER_TRAIN_CASES['r50']
+    model = vfs_b200.build_model(c['model'], train_cfg=vfs_b200.ConfigDict(c['train_cfg']), test_cfg=None)
+    model.load_state_dict(seeded_state_dict(model, seed=3))
+    tv_sd = backbone_to_torchvision(model.state_dict())
+    tv = torchvision.models.resnet50(weights=None)
+    missing, unexpected = tv.load_state_dict(tv_sd, strict=False)
+    assert sorted(missing) == ['fc.bias', 'fc.weight'] and not unexpected
+    src, dst = tmp_path / 'latest.pth', tmp_path / 'backbone_tv.pth'
+    torch.save(dict(state_dict=model.state_dict(), meta=dict(epoch=1)), src)
+    convert(str(src), str(dst))
+    net = ResNet(50, pretrained=str(dst), torchvision_pretrain=True)
+    net.init_weights()
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, model.state_dict()['backbone.' + k]), k
+    with pytest.raises(RuntimeError):
+        backbone_to_torchvision({'backbone.layer1.0.mystery.weight': torch.zeros(1)})
