@@ -377,3 +377,48 @@ def test_checkpoint_conversion_roundtrips_through_torchvision_names(tmp_path):
         assert torch.equal(v, model.state_dict()['backbone.' + k]), k
     with pytest.raises(RuntimeError):
         backbone_to_torchvision({'backbone.layer1.0.mystery.weight': torch.zeros(1)})
+
+
+class _EchoModel(torch.nn.Module):
+    """forward(return_loss=False, idx=...) -> one result per sample (stands in for a tracker's forward_test)."""
+
+    def forward(self, return_loss=True, idx=None):
+        assert not return_loss
+        return [dict(sample=int(i), doubled=int(i) * 2) for i in idx]
+
+
+def _multi_gpu_test_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from torch.utils.data import DataLoader, Dataset
+    from torch.utils.data.distributed import DistributedSampler
+    from vfs_b200.apis import multi_gpu_test
+
+    class Videos(Dataset):
+        def __len__(self):
+            return 7                      # odd: the sampler pads one sample
+
+        def __getitem__(self, i):
+            return dict(idx=i)
+
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    ds = Videos()
+    loader = DataLoader(ds, batch_size=2, sampler=DistributedSampler(ds, world, rank, shuffle=False))
+    q.put((rank, multi_gpu_test(_EchoModel(), loader)))
+    dist.destroy_process_group()
+
+
+def test_multi_gpu_test_orders_results_like_the_reference_gloo_world2():
+    """mmaction/apis/test.py:47-194 on two gloo ranks: rank 0 gets the 7 results in dataset order, rank 1 gets None."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_multi_gpu_test_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res[1] is None
+    assert [r['sample'] for r in res[0]] == list(range(7))
+    assert all(r['doubled'] == 2 * r['sample'] for r in res[0])
