@@ -57,6 +57,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='vfs_b200', choices=['vfs_b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the train / affinity_480p sub-benches')
     return ap.parse_args()
 
 
@@ -195,6 +196,207 @@ def run_reference_arm(a):
                 e2e=dict(value=value, unit='frame-pairs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------- train step
+TRAIN_MODEL = dict(
+    type='SimSiamBaseTracker',                       # model dict of configs/r50_nc_sgd_cos_100e_r5_1xNx2_k400.py:2-24
+    backbone=dict(type='ResNet', pretrained=None, depth=50, out_indices=(3, ),
+                  norm_cfg=dict(type='SyncBN', requires_grad=True), norm_eval=False, zero_init_residual=True),
+    img_head=dict(type='SimSiamHead', in_channels=2048, norm_cfg=dict(type='SyncBN'), num_projection_fcs=3,
+                  projection_mid_channels=2048, projection_out_channels=2048, num_predictor_fcs=2,
+                  predictor_mid_channels=512, predictor_out_channels=2048, with_norm=True,
+                  loss_feat=dict(type='CosineSimLoss', negative=False), spatial_type='avg'))
+
+
+def bench_train(torch, dist, dev, rank, world, clips, size, steps, peak_tf, label):
+    """SimSiam pre-training step of the r50_nc config (SURVEY cfg-2 / cfg-4): imgs [clips,2,3,1,size,size] per rank,
+    forward (2 backbone + 2 head passes, cosine loss) + native backward + gradient all-reduce (world > 1) + SGD, SyncBN
+    in backbone and head, replayed from ONE CUDA graph per step (vfs_b200.GraphedTrainStep).  Multi-rank: every
+    collective is a peer-memory kernel inside the graph.  Returns the sub-object for the JSON line."""
+    import vfs_b200
+    from vfs_b200 import ops
+    from vfs_b200.optim import build_optimizer
+    from vfs_b200.synthetic import seeded_state_dict
+    model = vfs_b200.build_model(TRAIN_MODEL, train_cfg=vfs_b200.ConfigDict(dict(intra_video=False)), test_cfg=None)
+    model.load_state_dict(seeded_state_dict(model, seed=0))
+    model = model.to(dev)
+    model.train()
+    opt = build_optimizer(model, dict(type='SGD', lr=0.05, momentum=0.9, weight_decay=1e-4))   # configs/*:134
+    g = torch.Generator().manual_seed(4321 + rank)
+    host = torch.randn(clips, 2, 3, 1, size, size, generator=g).pin_memory()
+    imgs = host.to(dev)
+    l0 = ops.LAUNCHES[0]
+    step = vfs_b200.GraphedTrainStep(model, opt, dict(imgs=imgs), warmup=2)
+    launches_per_step = (ops.LAUNCHES[0] - l0) // 3          # 2 warm-up steps + the captured one
+    for _ in range(3):
+        step(dict(imgs=imgs), log=False)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step(dict(imgs=imgs), log=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    # e2e: the batch comes from pinned host memory every step and the logged loss is read back (runner contract)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = step(dict(imgs=host), log=True)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    loss = float(out['log_vars']['loss'])
+    layers = model.backbone.engine.conv_layer_list((2 * clips, 3, size, size), 3)
+    fwd = sum(l['flops'] for l in layers) + 2.0 * 2 * clips * (size // 2)**2 * 64 * 147
+    achieved = 3 * fwd / (ms * 1e-3) / 1e12
+    res = dict(workload=label, clips_per_gpu=clips, size=size, ms_per_step=ms,
+               pairs_per_s=world * clips / (ms * 1e-3), unit='frame-pairs/s',
+               e2e=dict(pairs_per_s=world * clips * steps / float(dt), h2d_bytes_per_step=int(host.numel() * 4),
+                        d2h_bytes_per_step=8, api='GraphedTrainStep(model, optimizer)(data_batch) with a pinned host '
+                                                  'batch; logged loss read back every step'),
+               steps=steps, loss=loss, mode='one CUDA graph per step', launches_per_step=int(launches_per_step),
+               collectives=('none (1 rank)' if world == 1 else
+                            'peer-memory kernels over NVLink inside the graph: SyncBN statistics per layer (fwd+bwd), '
+                            'two-shot gradient all-reduce of %.1f MB, logged scalars' % (step.flat.numel * 4 / 1e6)),
+               roofline=dict(bound='tensor', achieved=achieved, peak=peak_tf, unit='TFLOP/s', frac=achieved / peak_tf,
+                             flops_per_step=3 * fwd,
+                             note='algorithmic fp32-equivalent conv FLOPs of fwd + dgrad + wgrad (3 x forward) / '
+                                  'device step time; 3 fp16 MMAs are issued per product'),
+               overflow=ops.overflow_count())
+    step.flat.close()
+    del step, model, opt
+    torch.cuda.empty_cache()
+    return res
+
+
+def dp_rank_check(torch, dist, dev, rank, world):
+    """Cross-rank correctness of the data-parallel step on the box the bench runs on (world > 1): every rank runs the
+    SimSiam step of a small R18 model on ITS shard with SyncBN statistics exchanged and gradients averaged over the
+    peer-memory communicator; rank 0 also runs the whole batch alone (cross-rank exchange switched off).  Both must
+    give the same loss and gradients (the definition of SyncBN + DDP)."""
+    import vfs_b200
+    from vfs_b200 import ops, peer
+    from vfs_b200.synthetic import seeded_state_dict
+    cfg = dict(type='SimSiamBaseTracker',
+               backbone=dict(type='ResNet', pretrained=None, depth=18, out_indices=(3, ),
+                             norm_cfg=dict(type='SyncBN', requires_grad=True), norm_eval=False,
+                             zero_init_residual=True),
+               img_head=dict(type='SimSiamHead', in_channels=512, norm_cfg=dict(type='SyncBN'), num_projection_fcs=3,
+                             projection_mid_channels=512, projection_out_channels=512, num_predictor_fcs=2,
+                             predictor_mid_channels=128, predictor_out_channels=512, with_norm=True,
+                             loss_feat=dict(type='CosineSimLoss', negative=False), spatial_type='avg'))
+    per = 4
+    g = torch.Generator().manual_seed(99)
+    full = torch.randn(per * world, 2, 3, 1, 64, 64, generator=g)
+
+    def grads_of(imgs, cross):
+        m = vfs_b200.build_model(cfg, train_cfg=vfs_b200.ConfigDict(dict(intra_video=False)), test_cfg=None)
+        m.load_state_dict(seeded_state_dict(m, seed=1))
+        m = m.to(dev)
+        m.train()
+        ops.CROSS_RANK_SYNCBN[0] = cross
+        try:
+            losses = m(imgs=imgs.to(dev))
+            loss = sum(v.mean() for k, v in losses.items() if 'loss' in k)
+            loss.backward()
+        finally:
+            ops.CROSS_RANK_SYNCBN[0] = True
+        return loss.detach(), [p.grad.reshape(-1) for p in m.parameters() if p.grad is not None]
+
+    loss, grads = grads_of(full[rank * per:(rank + 1) * per], True)
+    flat = torch.cat(grads)
+    n = flat.numel() // 4 * 4
+    comm = peer.active()
+    buf = comm.data()[:n * 4].view(torch.float32)
+    buf.copy_(flat[:n])
+    comm.allreduce_(buf, 1.0 / world)
+    packed = torch.stack([loss.float() / world])
+    ops.cross_rank_sum_(packed)
+    comm.check()
+    res = None
+    if rank == 0:
+        ref_loss, ref_grads = grads_of(full, False)
+        ref = torch.cat(ref_grads)[:n]
+        err = float((buf - ref).norm() / ref.norm())
+        res = dict(model='R18 SimSiam, %d clips x 2 views x 64^2 per rank' % per, grad_rel_l2_err=err,
+                   loss_abs_err=abs(float(packed[0]) - float(ref_loss)), ok=bool(err < 1e-3))
+    dist.barrier()
+    return res
+
+
+def bench_affinity_480p(torch, dev, T, peaks, peak_tf, flush):
+    """SURVEY cfg-3: DAVIS-style propagation of one 480p query frame (R50 res4 map 60x107, C = 1024, Cv = 4, radius 18,
+    top-k 10) against T key frames; T = 21 is the steady state of VanillaTracker.forward_test with frame 0 in the key
+    set twice (vanilla_tracker.py:133-149).  The fused kernels run from a CUDA graph; L2 is flushed between
+    iterations."""
+    from vfs_b200 import ops
+    from vfs_b200.common import spatial_neighbor
+    H, W, C, Cv = 60, 107, 1024, 4
+    hw = H * W
+    gen = torch.Generator(device='cuda').manual_seed(T)
+    F = T + 1
+    bank = torch.empty((2, F, H, W, C), dtype=torch.float16, device=dev)
+    for f in range(F):      # frame by frame: the fp32 NCHW staging copy of 21 frames would be 550 MB
+        bank[:, f:f + 1] = ops.features_to_split(torch.relu(torch.randn(1, C, H, W, device=dev, generator=gen)), True)
+    vals = torch.rand(F, Cv, hw, device=dev, generator=gen)
+    mask = spatial_neighbor(1, H, W, 36)
+    keys = list(range(T)) if T < 21 else [0] + list(range(T - 1))      # frame 0 twice, like the tracker's key set
+    ids = [keys]
+    out = torch.empty((1, Cv, hw), dtype=torch.float32, device=dev)
+
+    def call():
+        out.copy_(ops.attention_bank_batched(bank, [T], bank, ids, vals, ids, 0, Cv * hw, hw, Cv, mask, 0.07, 10))
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            call()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        call()
+    times = []
+    for _ in range(12):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = statistics.median(times[2:])
+    alg_bytes = 4.0 * ((1 + T) * C * hw + T * Cv * hw + Cv * hw)                # SURVEY 8d compulsory bytes
+    alg_flops = 2.0 * C * T * float(mask.dense().sum())                          # window-restricted products
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'affinity_traffic.json')) as fh_:
+            traffic = json.load(fh_).get(f'T{T}_dram_bytes')
+    except Exception:
+        pass
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    tf = alg_flops / (ms * 1e-3) / 1e12
+    return dict(workload=f'480p 60x107 C=1024 Cv=4 radius 18 top-k 10, T={T} key frames', T=T, us_per_frame=ms * 1e3,
+                key_frames_per_s=T / (ms * 1e-3),
+                roofline=dict(bound='hbm', achieved=gbs, peak=hbm_peak, unit='GB/s', frac=gbs / hbm_peak,
+                              traffic=traffic, bytes_per_launch=alg_bytes,
+                              note='compulsory bytes 4*[(1+T)*C*HW + T*Cv*HW + Cv*HW] / CUDA-event time of the fused '
+                                   'kernels (scores+top-k, merge+propagate); L2 flushed'),
+                roofline_tensor=dict(bound='tensor', achieved=tf, peak=peak_tf, unit='TFLOP/s', frac=tf / peak_tf,
+                                     flops_per_launch=alg_flops,
+                                     note='window-restricted fp32-equivalent FLOPs 2*C*T*sum_q|N(q)|'))
 
 
 # ----------------------------------------------------------------------------------------------------- main arm
@@ -383,8 +585,9 @@ def main():
             peaks = json.load(fh_)
     except Exception:
         pass
-    peak_tf = peaks.get('bf16_tflops_sustained') or peaks.get('bf16_tflops') or 1590.0
-    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.59 PFLOP/s'
+    # the timed region is tens of milliseconds at full clocks -> the BURST peak is the fair denominator
+    peak_tf = peaks.get('bf16_tflops') or 1590.0
+    peak_src = 'measured burst (MEASURED_PEAKS.json bf16_tflops)' if peaks else 'fallback 1.59 PFLOP/s'
     traffic = None
     try:   # DRAM bytes of the 42 conv launches of one step, from the committed ncu --set full capture of this command
         with open(os.path.join(ROOT, 'profiles', 'conv_traffic.json')) as fh_:
@@ -440,6 +643,21 @@ def main():
                                   convs_median=conv_med, normalize_median=statistics.median(norm_ms),
                                   attention_median=attn_med),
                 wall_s_timed_region=wall)
+
+    # ---------------- the north_star's own configs as sub-objects (each with its roofline)
+    if not a.no_extra:
+        if world == 1:
+            line['affinity_480p'] = dict(T1=bench_affinity_480p(torch, dev, 1, peaks, peak_tf, flush),
+                                         T21=bench_affinity_480p(torch, dev, 21, peaks, peak_tf, flush))
+            line['train_cfg2'] = bench_train(torch, dist, dev, rank, world, 8, 256, max(3, min(a.steps, 10)), peak_tf,
+                                             'SURVEY cfg-2: R50 SimSiam train step, 8 clips x 2 views x 256^2, 1 GPU')
+        if world > 1:
+            from vfs_b200 import peer
+            peer.install(peer.PeerComm(data_bytes=160 * 1024 * 1024))      # flat R50 SimSiam gradients: 152.8 MB
+            line['dp_rank_check'] = dp_rank_check(torch, dist, dev, rank, world)
+        line['train'] = bench_train(torch, dist, dev, rank, world, 32, 224, max(3, min(a.steps, 10)), peak_tf,
+                                    'SURVEY cfg-4: r50_nc_sgd_cos_100e_r5_1xNx2_k400 train step, 32 clips x 2 views x '
+                                    '224^2 per GPU, SyncBN + gradient all-reduce, data-parallel over %d GPU(s)' % world)
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         o, sd, frames, seg_onehot, m = cpu_reference_setup(torch)

@@ -174,6 +174,41 @@ int vfs_cosine_loss_backward(const float* p, const float* z, const float* gout, 
 int vfs_sgd_momentum_step(float* p, const float* g, float* buf, size_t n, float lr, float momentum, float wd,
                           int first, float grad_scale, vfs_stream_t s);
 
+/* The same update with {lr, momentum, weight_decay, grad_scale} read from DEVICE memory (hyper fp32[4]): a captured
+ * CUDA graph follows the per-iteration LR schedule of the configs (lr_config CosineAnnealing by_epoch=False,
+ * configs/*:136) by copying four floats.  Momentum buffers must start zeroed (== torch's first-step rule). */
+int vfs_sgd_momentum_step_dev(float* p, const float* g, float* buf, size_t n, const float* hyper, vfs_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Peer-memory communicator: the collectives of the data-parallel training step as kernels over NVLink peer memory
+ * (one process per GPU of one box).  Replaces, for this path, the NCCL calls torch issues for
+ *   - torch.nn.SyncBatchNorm (norm_cfg=dict(type='SyncBN'), configs/*:9,15): per-layer statistics exchange, fwd + bwd
+ *   - MMDistributedDataParallel's gradient all-reduce (mmaction/apis/train.py:58-66)
+ *   - BaseTracker._parse_losses' all-reduce of the logged scalars (mmaction/models/trackers/base.py:103-108)
+ * Every rank allocates a symmetric segment (control words + small-exchange slots + a caller-visible data region) and
+ * exports a CUDA IPC handle; the caller moves the handles between the processes (torch.distributed here) and
+ * connects.  After that nothing involves the host: every call below only enqueues kernels on `s`, so the whole
+ * multi-rank step can live in one CUDA graph.  All ranks must issue the same sequence of calls.
+ *   vfs_comm_allreduce_small_*  in-place sum over ranks of up to 4096 fp64 / 8192 fp32 values (device pointer
+ *                               anywhere); summed in rank order -> bit-identical on all ranks
+ *   vfs_comm_allreduce_f32      in-place sum (times `scale`) of n floats at byte `offset` of the DATA region of
+ *                               every rank (16-byte aligned, n % 4 == 0): barrier, two-shot reduce/broadcast, barrier
+ *   vfs_comm_error              1 if a spin-wait's watchdog expired since creation (VFS_COMM_TIMEOUT_MS, default
+ *                               20000; synchronous read)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct VfsComm VfsComm;
+size_t vfs_comm_handle_bytes(void);
+int vfs_comm_create(int rank, int world, size_t data_bytes, VfsComm** out, void* handle_out);
+int vfs_comm_connect(VfsComm* c, const void* all_handles /* [world][vfs_comm_handle_bytes()] in rank order */);
+int vfs_comm_destroy(VfsComm* c);
+void* vfs_comm_data_ptr(VfsComm* c);
+size_t vfs_comm_data_bytes(VfsComm* c);
+int vfs_comm_error(VfsComm* c);
+int vfs_comm_allreduce_small_f64(VfsComm* c, double* data, int n, vfs_stream_t s);
+int vfs_comm_allreduce_small_f32(VfsComm* c, float* data, int n, vfs_stream_t s);
+int vfs_comm_barrier(VfsComm* c, vfs_stream_t s);
+int vfs_comm_allreduce_f32(VfsComm* c, size_t offset_bytes, size_t n, float scale, vfs_stream_t s);
+
 /* OIHW fp32 [Cout,Cin,k,k] -> split [2][Cout][k*k*Cin] (device to device). */
 int vfs_pack_conv_weight(const float* w_oihw, void* w_split, int Cout, int Cin, int ksize, vfs_stream_t s);
 

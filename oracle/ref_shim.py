@@ -173,3 +173,37 @@ def load_reference_siamfc_ops():
         pkg.__path__ = [os.path.join(REF_ROOT, 'projects', 'siamfc-pytorch', 'siamfc')]
         sys.modules[name] = pkg
     return importlib.import_module(name + '.ops')
+
+
+def load_reference_siamfc_tracker():
+    """projects/siamfc-pytorch/siamfc/siamfc_tracker_base.py imported UNCHANGED (TrackerSiamFC.init / update / track,
+    Net, _convert_batchnorm).  Its only missing imports are ``got10k.trackers.Tracker`` (a trivial base class holding
+    ``name`` / ``is_deterministic``), a few mmcv helpers the inference path never calls, and sibling modules of the
+    project (datasets / transforms / losses: plain torch / cv2 / numpy, loaded from the reference tree as they are)."""
+    ref = load_reference()
+    if 'got10k' not in sys.modules:
+        got10k = types.ModuleType('got10k')
+        got10k.__path__ = []
+        trackers = types.ModuleType('got10k.trackers')
+
+        class Tracker:                                   # got10k/trackers/__init__.py: name + determinism flag
+            def __init__(self, name, is_deterministic=False):
+                self.name, self.is_deterministic = name, is_deterministic
+
+        trackers.Tracker = Tracker
+        got10k.trackers = trackers
+        sys.modules['got10k'], sys.modules['got10k.trackers'] = got10k, trackers
+    mmcv = sys.modules['mmcv']
+    mmcv.parallel.is_module_wrapper = lambda m: False
+    mmcv.runner.save_checkpoint = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError())
+    if not hasattr(mmcv, 'ProgressBar'):
+        mmcv.ProgressBar = type('ProgressBar', (), {'__init__': lambda self, n: None, 'update': lambda self: None})
+    models = sys.modules['mmaction.models']
+    models.ResNet = ref.ResNet
+    models.build_backbone = sys.modules['mmaction.models.builder'].build_backbone
+    name = 'ref_siamfc_pkg'
+    if name not in sys.modules:
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [os.path.join(REF_ROOT, 'projects', 'siamfc-pytorch', 'siamfc')]
+        sys.modules[name] = pkg
+    return importlib.import_module(name + '.siamfc_tracker_base')

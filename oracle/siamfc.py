@@ -23,10 +23,10 @@ def siam_conv_fc(sd, z, x, out_scale=0.001, num_convs=1):
 
 # ----------------------------------------------------------------------------------------------------------------
 # TrackerSiamFC inference (projects/siamfc-pytorch/siamfc/siamfc_tracker_base.py:200-319), restated with the same
-# cv2 / numpy calls.  The reference class derives from got10k.trackers.Tracker (not installed) and cannot be imported;
-# its crop helper (siamfc/ops.py + image_utils.py, plain cv2/numpy) CAN be, and pins ``crop_and_resize`` below
-# (tests/test_host_cpu.py::test_siamfc_crop_matches_reference).  The init/update arithmetic itself is "parity
-# unpinned": restated from the file, checked against the CUDA path only.
+# cv2 / numpy calls.  PINNED: oracle/ref_shim.py::load_reference_siamfc_tracker imports the unmodified reference file
+# (its base class got10k.trackers.Tracker is a trivial stub); tests/golden/siamfc_tracker_golden.npz holds its kernel /
+# responses / boxes on a synthetic sequence and tests/test_oracle_golden.py checks this restatement against it -- bit
+# for bit where the reference tree is present.
 # ----------------------------------------------------------------------------------------------------------------
 def crop_and_resize(img, center, size, out_size, border_value=None):
     """ops.py:87-104 (faster=True) -> image_utils.py:7-76: crop around ``center`` (y, x), resize, pad with the mean
@@ -81,11 +81,17 @@ class TrackerOracle:
     def __init__(self, cfg, backbone_sd, head_sd, depth):
         self.cfg, self.bsd, self.hsd, self.depth = cfg, backbone_sd, head_sd, depth
 
-    def _features(self, crops):
+    def _features(self, crops, exemplar=False):
         import numpy as np
         import torch
         from .resnet import resnet_forward
-        x = torch.from_numpy(np.ascontiguousarray(crops)).permute(0, 3, 1, 2).float()
+        if exemplar:
+            # siamfc_tracker_base.py:239-241 builds the exemplar batch with permute(2,0,1).unsqueeze(0): the size-1
+            # batch stride makes ATen treat it as NCHW, the stacked search batch (:258-260) is genuinely channels-last
+            # -- different conv kernels, different fp32 summation order; restated exactly for bit parity
+            x = torch.from_numpy(np.ascontiguousarray(crops)).permute(2, 0, 1).unsqueeze(0).float()
+        else:
+            x = torch.from_numpy(np.ascontiguousarray(crops)).permute(0, 3, 1, 2).float()
         mean = torch.tensor([123.675, 116.28, 103.53]).view(1, 3, 1, 1)
         std = torch.tensor([58.395, 57.12, 57.375]).view(1, 3, 1, 1)
         b = self.cfg['model']['backbone']
@@ -108,7 +114,7 @@ class TrackerOracle:
         self.z_sz = np.sqrt(np.prod(self.target_sz + context))
         self.x_sz = self.z_sz * cfg['instance_sz'] / cfg['exemplar_sz']
         z = crop_and_resize(img, self.center, self.z_sz, cfg['exemplar_sz'])
-        self.kernel = self._features(z[None])
+        self.kernel = self._features(z, exemplar=True)
 
     def responses(self, img):
         import numpy as np

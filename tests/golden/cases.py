@@ -172,6 +172,46 @@ SIAMFC_CROP_CASES = {
 }
 
 
+# ------------------------------------------------------------------ SiamFC tracker (init + updates on a moving blob)
+SIAMFC_TRACKER_CASES = {
+    # reference default exemplar size (default_config_base.py:6) and the 127 px of BASELINE cfg-5
+    'r18_convfc_120': dict(depth=18, exemplar_sz=120, extra_conv=True, out_scale=1e-3, seed=71),
+    'r18_convfc_127': dict(depth=18, exemplar_sz=127, extra_conv=True, out_scale=1e-3, seed=73),
+    'r18_fc_127': dict(depth=18, exemplar_sz=127, extra_conv=False, out_scale=1e-3, seed=75),
+}
+
+
+def siamfc_tracker_frames(num=4):
+    """RGB uint8 frames [240,320,3] with a bright blob drifting down-right, and its 1-indexed (x, y, w, h) box."""
+    import numpy as np
+    rng = np.random.RandomState(5)
+    base = (rng.rand(240, 320, 3) * 60 + 60)
+    frames = []
+    for f in range(num):
+        img = base.copy()
+        cy, cx = 120 + 6 * f, 150 + 9 * f
+        yy, xx = np.mgrid[0:240, 0:320]
+        blob = np.exp(-(((yy - cy) / 14.0)**2 + ((xx - cx) / 20.0)**2))
+        img += 150 * blob[..., None] * np.array([1.0, 0.6, 0.2])
+        frames.append(np.clip(img, 0, 255).astype(np.uint8))
+    return frames, [150 - 30 + 1, 120 - 21 + 1, 60, 42]
+
+
+def siamfc_tracker_cfg(c):
+    """default_config_base.py:2-51 with the case's overrides, as a plain nested dict."""
+    cfg = dict(out_scale=c['out_scale'], exemplar_sz=c['exemplar_sz'], instance_sz=255, context=0.5, scale_num=3,
+               scale_step=1.0375, scale_lr=0.59, scale_penalty=0.9745, window_influence=0.176, response_sz=17,
+               response_up=16, total_stride=8, epoch_num=50, batch_size=8, num_workers=8, initial_lr=1e-3,
+               ultimate_lr=1e-5, weight_decay=5e-4, momentum=0.9, r_pos=16, r_neg=0, pairs_per_seq=1, optimizer='Adam',
+               loss='focal', lr_schedule='exp', lr_step_size=10, extra_conv=c['extra_conv'], out_channels=512,
+               reduction=1, auto_resume=False, force_wd=False, out_block_index=None, checkpoint=None,
+               work_dir='/tmp', suffix='vfs_golden',
+               model=dict(backbone=dict(type='ResNet', depth=c['depth'], pretrained=None, frozen_stages=4,
+                                        dilations=(1, 1, 2, 4), strides=(1, 2, 1, 1), out_indices=(3, ), with_cp=False,
+                                        norm_eval=True, norm_cfg=dict(type='SyncBN', requires_grad=True))))
+    return cfg
+
+
 def siamfc_image():
     import numpy as np
     return np.random.RandomState(900).randint(0, 256, (180, 240, 3)).astype(np.uint8)

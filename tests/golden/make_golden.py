@@ -117,6 +117,39 @@ def siamfc_crop_outputs():
     return out
 
 
+def siamfc_tracker_outputs():
+    """The UNMODIFIED reference TrackerSiamFC (siamfc_tracker_base.py:88-319, got10k base class stubbed) run on the
+    synthetic sequence: exemplar kernel, per-frame raw responses and boxes -> tests/golden/siamfc_tracker_golden.npz."""
+    import logging
+    import oracle
+    from vfs_b200.mmcv_lite import ConfigDict
+    mod = ref_shim.load_reference_siamfc_tracker()
+    frames, box0 = cases.siamfc_tracker_frames()
+    out = {}
+    for name, c in cases.SIAMFC_TRACKER_CASES.items():
+        trk = mod.TrackerSiamFC(ConfigDict(cases.siamfc_tracker_cfg(c)), logging.getLogger('ref_siamfc'))
+        trk.net.backbone.load_state_dict(oracle.seeded_state_dict(trk.net.backbone, seed=c['seed']))
+        if c['extra_conv']:
+            trk.net.head.load_state_dict(oracle.seeded_state_dict(trk.net.head, seed=c['seed'] + 1))
+        trk.net.cpu()
+        trk.device = torch.device('cpu')
+        # record the raw responses the reference computes inside update(): same net, same crops, no state change
+        trk.init(frames[0], box0)
+        out[f'{name}/kernel'] = trk.kernel.numpy().copy()
+        boxes, responses = [], []
+        for img in frames[1:]:
+            x = np.stack([mod.ops.crop_and_resize(img, trk.center, trk.x_sz * f, out_size=trk.cfg.instance_sz,
+                                                  border_value=trk.avg_color) for f in trk.scale_factors], axis=0)
+            with torch.no_grad():
+                xt = trk.normalize(torch.from_numpy(x).permute(0, 3, 1, 2).float())
+                responses.append(trk.net.head(trk.kernel, trk.net.backbone(xt)).squeeze(1).numpy().copy())
+            boxes.append(trk.update(img).copy())
+        out[f'{name}/responses'] = np.stack(responses)
+        out[f'{name}/boxes'] = np.stack(boxes)
+        out[f'{name}/state'] = np.concatenate([trk.center, trk.target_sz, [trk.z_sz, trk.x_sz]]).astype(np.float64)
+    return out
+
+
 def attention_extra_outputs():
     """masked_attention_efficient of the unmodified reference for arbitrary bool masks / topk=None / rectangular maps
     -> tests/golden/attention_extra_golden.npz."""
@@ -142,6 +175,10 @@ def main():
     crop_path = os.path.join(ROOT, 'tests', 'golden', 'siamfc_crop_golden.npz')
     np.savez_compressed(crop_path, **crops)
     print(f'wrote {crop_path}: {len(crops)} arrays')
+    trk = siamfc_tracker_outputs()
+    trk_path = os.path.join(ROOT, 'tests', 'golden', 'siamfc_tracker_golden.npz')
+    np.savez_compressed(trk_path, **trk)
+    print(f'wrote {trk_path}: {len(trk)} arrays')
     if '--only-siamfc' in sys.argv or '--only-small' in sys.argv:
         return
     torch.set_num_threads(8)

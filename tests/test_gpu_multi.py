@@ -12,14 +12,16 @@ from tests.golden import cases
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, name, q):
+def _worker(rank, world, port, name, q, use_peer=False):
     import torch.distributed as dist
     import vfs_b200
-    from vfs_b200 import ops
+    from vfs_b200 import ops, peer
     from vfs_b200.optim import allreduce_grads
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world,
                             device_id=torch.device('cuda', rank))
+    if use_peer:     # SyncBN exchanges + logged scalars through the peer-memory communicator instead of NCCL
+        peer.install(peer.PeerComm(data_bytes=64 * 1024 * 1024))
     c = cases.TRACKER_TRAIN_CASES[name]
     model = vfs_b200.build_model(c['model'], train_cfg=vfs_b200.ConfigDict(c['train_cfg']), test_cfg=None)
     model.load_state_dict(oracle.seeded_state_dict(model, seed=c['seed']))
@@ -32,7 +34,26 @@ def _worker(rank, world, port, name, q):
     out = model.train_step(dict(imgs=mine), None)
     out['loss'].backward()
     params = [p for p in model.parameters() if p.grad is not None]
-    allreduce_grads(params, average=True)
+    if use_peer:
+        comm = peer.active()
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        n = flat.numel() // 4 * 4
+        buf = comm.data()[:n * 4].view(torch.float32)
+        buf.copy_(flat[:n])
+        comm.allreduce_(buf, 1.0 / world)
+        comm.check()
+        off = 0
+        for p in params:
+            k = min(p.numel(), n - off)
+            p.grad.reshape(-1)[:k].copy_(buf[off:off + k])
+            off += p.numel()
+        # the last (< 4) elements fall outside the 16-byte granularity of the flat all-reduce: reduce them with NCCL
+        if n < flat.numel():
+            tail = flat[n:].clone()
+            dist.all_reduce(tail)
+            params[-1].grad.reshape(-1)[-(flat.numel() - n):].copy_(tail / world)
+    else:
+        allreduce_grads(params, average=True)
     overflow = ops.overflow_count()
     if rank == 0:
         q.put((out['log_vars']['loss'], {k: p.grad.cpu() for k, p in model.named_parameters() if p.grad is not None},
@@ -41,8 +62,9 @@ def _worker(rank, world, port, name, q):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('use_peer', [False, True], ids=['nccl', 'peer_memory'])
 @pytest.mark.parametrize('name', ['r18_intra'])
-def test_two_rank_syncbn_training_step_equals_single_process(name):
+def test_two_rank_syncbn_training_step_equals_single_process(name, use_peer):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     import torch.multiprocessing as mp
@@ -60,7 +82,7 @@ def test_two_rank_syncbn_training_step_equals_single_process(name):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = 33500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port + int(use_peer), name, q, use_peer)) for r in range(2)]
     for p in procs:
         p.start()
     loss, grads, running, overflow = q.get(timeout=600)
@@ -75,6 +97,76 @@ def test_two_rank_syncbn_training_step_equals_single_process(name):
         denom = max(float(r64.norm()), 1e-6 * gnorm)
         mine = float((g.double() - r64).norm()) / denom
         base = float((ref[k].double() - r64).norm()) / denom
-        if mine > max(20 * base, 3e-3):
+        if mine > max(5 * base, 3e-3):
             failures.append((k, mine, base))
     assert not failures, failures[:8]
+
+
+def _graph_worker(rank, world, port, q):
+    """world == 2: each rank captures the SimSiam step on its half of the batch (peer-memory SyncBN + gradient
+    all-reduce inside the CUDA graph); world == 1: the same model on the whole batch.  Returns loss + parameters
+    after two steps."""
+    import torch.distributed as dist
+    import vfs_b200
+    from vfs_b200.optim import build_optimizer
+    torch.cuda.set_device(rank)
+    if world > 1:
+        dist.init_process_group('nccl', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world,
+                                device_id=torch.device('cuda', rank))
+    c = cases.TRACKER_TRAIN_CASES['r18_intra']
+    model = vfs_b200.build_model(c['model'], train_cfg=vfs_b200.ConfigDict(c['train_cfg']), test_cfg=None)
+    model.load_state_dict(oracle.seeded_state_dict(model, seed=c['seed']))
+    model = model.cuda()
+    model.train()
+    opt = build_optimizer(model, dict(type='SGD', lr=0.05, momentum=0.9, weight_decay=1e-4))
+    g = torch.Generator().manual_seed(4242)
+    batches = [torch.randn((8, ) + tuple(c['shape'][1:]), generator=g) for _ in range(2)]
+    per = 8 // world
+    mine = [b[rank * per:(rank + 1) * per].cuda() for b in batches]
+    step = vfs_b200.GraphedTrainStep(model, opt, dict(imgs=mine[0]))
+    losses = []
+    sd_after_first = None
+    for i, b in enumerate(mine):
+        opt.param_groups[0]['lr'] = 0.05 if i == 0 else 0.02      # an LR schedule must be followed without re-capture
+        losses.append(step(dict(imgs=b))['log_vars']['loss'])
+        if i == 0:
+            torch.cuda.synchronize()
+            sd_after_first = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    torch.cuda.synchronize()
+    if rank == 0:
+        q.put((losses, sd_after_first))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_two_rank_graphed_step_equals_single_rank_graphed_step():
+    """GraphedTrainStep at world 2 (every collective a peer-memory kernel inside the captured graph) walks the same
+    trajectory as one process on the whole batch: same logged losses over two steps with a changing learning rate, same
+    parameters / BN running statistics after the first (tiny-batch BN amplifies fp32 summation-order noise chaotically
+    over further steps, so later parameters are only held through the loss)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    results = []
+    for world in (1, 2):
+        q = ctx.Queue()
+        port = 35500 + os.getpid() % 2000 + world
+        procs = [ctx.Process(target=_graph_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        results.append(q.get(timeout=600))
+        for p in procs:
+            p.join(timeout=120)
+    (l1, sd1), (l2, sd2) = results
+    assert l2[0] == pytest.approx(l1[0], rel=1e-4)
+    assert l2 == pytest.approx(l1, rel=2e-3)
+    worst = 0.0
+    for k in sd1:
+        if sd1[k].dtype.is_floating_point and sd1[k].numel() > 0:
+            denom = float(sd1[k].abs().max()) + 1e-12
+            worst = max(worst, float((sd1[k] - sd2[k]).abs().max()) / denom)
+        else:
+            assert torch.equal(sd1[k], sd2[k]), k
+    assert worst < 2e-3, worst

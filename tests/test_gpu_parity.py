@@ -45,6 +45,28 @@ def test_backbone_eval_matches_reference_golden(golden, name):
     assert rel_err(y, ref) < REL_TOL
 
 
+@pytest.mark.parametrize('depth', [18, 50])
+def test_backbone_480x854_davis_features_match_oracle(depth):
+    """DAVIS inference geometry of the configs (480x854 frame, strides (1,2,1,1), out index 2 -> [1,C,60,107]; W = 107
+    is prime, HW = 6420 is not a multiple of the 128-pixel tile) against the CPU oracle."""
+    from vfs_b200.backbones import ResNet
+    net = ResNet(depth, norm_cfg=dict(type='SyncBN', requires_grad=True), strides=(1, 2, 1, 1), out_indices=(2, ))
+    sd = oracle.seeded_state_dict(net, seed=40 + depth)
+    net = _load(net, sd)
+    net.train(False)
+    x = torch.randn(1, 3, 480, 854, generator=torch.Generator().manual_seed(depth))
+    y = net(x.cuda())
+    with torch.no_grad():
+        ref = oracle.resnet_forward(sd, x, depth, strides=(1, 2, 1, 1), out_indices=(2, ))
+    assert tuple(y.shape) == tuple(ref.shape) == (1, 1024 if depth == 50 else 256, 60, 107)
+    assert rel_err(y, ref) < REL_TOL
+    # elementwise view of the same bar: 99.9 % of the activations within 1e-3 of their own magnitude (+ 1e-3 of the
+    # mean magnitude for values near zero)
+    yc, rf = y.cpu().double(), ref.double()
+    ok = (yc - rf).abs() <= REL_TOL * (rf.abs() + rf.abs().mean())
+    assert float(ok.double().mean()) > 0.999
+
+
 @pytest.mark.parametrize('name', sorted(cases.BACKBONE_CASES))
 def test_backbone_train_mode_bn_matches_reference_golden(golden, name):
     """Batch-statistics BatchNorm (train mode): outputs and the running-statistics update."""
@@ -365,6 +387,13 @@ def test_cosine_loss_matches_reference_golden(golden):
 
 
 # --------------------------------------------------------------------------------------------- attention
+# A disagreement with the fp64 top-k set is only accepted when every disputed key's fp64 affinity lies within
+# TIE_TOL * max(1, |k-th affinity|) of the selection boundary: 5e-6 relative is ~3 fp32 ulps of a 1024-term dot product
+# (the reference's own fp32 einsum cannot resolve it either).  TIE_EXCUSES counts how often that was needed.
+TIE_TOL = 5e-6
+TIE_EXCUSES = [0]
+
+
 def _check_topk_modulo_ties(q, k, c, mask_dense, tv, ti, topk, non_mask_len):
     """Index parity: the selected key set must equal the fp64 top-k set, except where the k-th / (k+1)-th fp64
     affinities are closer than the fp32 noise floor (a tie for any fp32 implementation, including the reference)."""
@@ -391,8 +420,10 @@ def _check_topk_modulo_ties(q, k, c, mask_dense, tv, ti, topk, non_mask_len):
         kth = srt[topk - 1, qi]
         diff = (exact ^ got)
         vals = aff[list(diff), qi]
-        if not bool(((vals - kth).abs() <= 2e-5 * max(1.0, float(kth.abs()))).all()):
+        if not bool(((vals - kth).abs() <= TIE_TOL * max(1.0, float(kth.abs()))).all()):
             bad += 1
+        else:
+            TIE_EXCUSES[0] += 1
     return bad, n_q
 
 
@@ -422,8 +453,11 @@ def test_attention_matches_reference_golden(golden, name):
     if mask is not None:
         dense = mask.dense()
         dense = dense[0] if dense.ndim == 3 else dense
+    TIE_EXCUSES[0] = 0
     bad, n_q = _check_topk_modulo_ties(q, k, c, dense, tv[0], ti[0], c['topk'], c.get('non_mask_len', 0))
+    print(f'[top-k parity] {name}: {TIE_EXCUSES[0]}/{n_q} queries needed the near-tie window ({TIE_TOL:g} rel)')
     assert bad == 0, f'{bad}/{n_q} queries selected a different key set outside the near-tie tolerance'
+    assert TIE_EXCUSES[0] <= max(2, n_q // 200), f'{TIE_EXCUSES[0]}/{n_q} queries hid behind the near-tie window'
     # selected affinities are sorted and finite
     assert bool((tv[0][:-1] >= tv[0][1:]).all())
 
@@ -521,6 +555,81 @@ def test_attention_multi_batch_matches_oracle():
     ref = oracle.masked_attention_efficient(q, k, v, oracle.spatial_neighbor(H, W, 12), temperature=0.07, topk=10)
     err = rel_err(out, ref)
     assert err < REL_TOL, (err, int(torch.isnan(out).sum()), [float(rel_err(out[i:i + 1], ref[i:i + 1])) for i in range(N)])
+
+
+def _fullsize_attention_inputs(T, dup_first):
+    H, W, C, Cv = 60, 107, 1024, 4
+    g = torch.Generator().manual_seed(1000 + T)
+    q = torch.relu(torch.randn(1, C, H, W, generator=g))
+    k = torch.relu(torch.randn(1, C, T, H, W, generator=g))
+    v = torch.rand(1, Cv, T, H, W, generator=g)
+    if dup_first:      # VanillaTracker's key set while frame_idx <= 20: frame 0 twice (vanilla_tracker.py:133-149)
+        k[:, :, 1] = k[:, :, 0]
+        v[:, :, 1] = v[:, :, 0]
+    return q, k, v
+
+
+def _fp64_topk_parity_on_device(q, k, ti, topk, radius, temperature, chunk=1070):
+    """Index parity at sizes whose [T*HW, HW] fp64 affinity (6.9 GB at T = 21) does not fit a host test: the fp64
+    affinities are formed on the device, a chunk of queries at a time (torch fp64 matmul as the yardstick).  Returns
+    (#queries whose key set differs beyond the near-tie window, #queries that needed the window, #queries)."""
+    import torch.nn.functional as F
+    _, C, T, H, W = k.shape
+    HW = H * W
+    dev = torch.device('cuda')
+    qn = F.normalize(q.to(dev).double(), dim=1).reshape(C, HW)
+    kn = F.normalize(k.to(dev).double(), dim=1).reshape(C, T * HW)
+    ky = (torch.arange(T * HW, device=dev) % HW) // W
+    kx = (torch.arange(T * HW, device=dev) % HW) % W
+    ti = ti.to(dev).long()                                                   # [topk, HW]
+    bad = excused = 0
+    for q0 in range(0, HW, chunk):
+        q1 = min(HW, q0 + chunk)
+        aff = (kn.t() @ qn[:, q0:q1]) / temperature                          # [T*HW, n]
+        qy = (torch.arange(q0, q1, device=dev) // W)[None]
+        qx = (torch.arange(q0, q1, device=dev) % W)[None]
+        inside = ((ky[:, None] - qy)**2 + (kx[:, None] - qx)**2).double().sqrt() < radius   # affinity_utils.py:150
+        aff = aff.masked_fill(~inside, float('-inf'))
+        top = aff.topk(topk, dim=0)
+        kth = top.values[topk - 1]                                           # [n]
+        got = ti[:, q0:q1]
+        got_vals = aff.gather(0, got)
+        same = (got.sort(dim=0).values == top.indices.sort(dim=0).values).all(dim=0)
+        tol = TIE_TOL * kth.abs().clamp_min(1.0)
+        # a differing set is excused iff every selected key and every exact key is within tol of the boundary or in both
+        # sets; equivalently: all selected values >= kth - tol (nothing clearly worse was picked)
+        ok_vals = (got_vals >= (kth - tol)[None]).all(dim=0) & torch.isfinite(got_vals).all(dim=0)
+        bad += int((~same & ~ok_vals).sum())
+        excused += int((~same & ok_vals).sum())
+        del aff, inside, top
+    return bad, excused, HW
+
+
+@pytest.mark.parametrize('T,dup_first', [(1, False), (21, True)], ids=['T1', 'T21_first_frame_twice'])
+def test_attention_full_size_matches_oracle(T, dup_first):
+    """BASELINE cfg-3 at its real size (480p: 60x107 map, C = 1024, radius 18, top-k 10, temperature 0.07), one key
+    frame and the 21-frame steady state with frame 0 in the key set twice: VALUES against the CPU oracle
+    (masked_attention_efficient, local_attention.py:237-348) and INDEX sets against fp64 affinities."""
+    from vfs_b200 import ops
+    from vfs_b200.common import spatial_neighbor
+    q, k, v = _fullsize_attention_inputs(T, dup_first)
+    H, W = q.shape[2:]
+    mask = spatial_neighbor(1, H, W, 36, mode='circle')
+    out, tv, ti = ops.masked_attention(q.cuda(), k.cuda(), v.cuda(), mask, 0.07, 10, True, 0, 'softmax',
+                                       return_topk=True)
+    assert ops.overflow_count() == 0
+    torch.set_num_threads(max(1, min(16, len(__import__('os').sched_getaffinity(0)))))
+    with torch.no_grad():
+        ref = oracle.masked_attention_efficient(q, k, v, oracle.spatial_neighbor(H, W, 36), temperature=0.07, topk=10)
+    bad, excused, n_q = _fp64_topk_parity_on_device(q, k, ti[0], 10, 18, 0.07)
+    print(f'[top-k parity] 480p T={T}: {excused}/{n_q} queries needed the near-tie window ({TIE_TOL:g} rel), {bad} bad')
+    assert bad == 0
+    assert excused <= max(2, n_q // 200)
+    # values: a query whose 10th/11th keys are an fp32 tie may legitimately propagate a different value vector, so
+    # at most `excused` queries may exceed the tolerance (the reference's own fp32 einsum decides those by rounding)
+    err = ((out.cpu() - ref).abs().amax(dim=1) / ref.abs().max()).reshape(-1)          # per query
+    assert int((err > REL_TOL).sum()) <= 2 * max(excused, 1) + 2, float(err.max())
+    assert float(err.median()) < 1e-5
 
 
 def test_attention_full_size_properties():
@@ -713,6 +822,39 @@ def test_siamfc_tracker_matches_oracle():
         trk.z_sz, trk.x_sz = ref.z_sz, ref.x_sz
 
 
+@pytest.mark.parametrize('name', sorted(cases.SIAMFC_TRACKER_CASES))
+def test_siamfc_tracker_matches_reference_golden(name):
+    """TrackerSiamFC.init / update against the fixture written by the UNMODIFIED reference tracker
+    (siamfc_tracker_base.py:200-319 via oracle/ref_shim.py::load_reference_siamfc_tracker): exemplar kernel and raw
+    responses within 1e-3, boxes within one upsampled-response step, for the reference-default 120 px exemplar, the
+    127 px of BASELINE cfg-5 and the head without adapters."""
+    import os
+    import vfs_b200  # noqa: F401
+    from vfs_b200.siamfc import TrackerSiamFC, build_cfg
+    with np.load(os.path.join(os.path.dirname(__file__), 'golden', 'siamfc_tracker_golden.npz')) as z:
+        gold = {k: z[k] for k in z.files}
+    c = cases.SIAMFC_TRACKER_CASES[name]
+    full = cases.siamfc_tracker_cfg(c)
+    backbone = dict(full['model']['backbone'])
+    backbone['norm_cfg'] = dict(type='BN', requires_grad=True)
+    cfg = build_cfg(backbone, exemplar_sz=c['exemplar_sz'], out_scale=c['out_scale'], extra_conv=c['extra_conv'])
+    trk = TrackerSiamFC(cfg)
+    trk.net.backbone.load_state_dict(oracle.seeded_state_dict(trk.net.backbone, seed=c['seed']))
+    if c['extra_conv']:
+        trk.net.head.load_state_dict(oracle.seeded_state_dict(trk.net.head, seed=c['seed'] + 1))
+    trk.net.to('cuda')
+    frames, box0 = cases.siamfc_tracker_frames()
+    trk.init(frames[0], box0)
+    assert rel_err(trk.kernel, gold[f'{name}/kernel']) < REL_TOL
+    for i, img in enumerate(frames[1:]):
+        r_gpu = trk.responses(img)
+        assert rel_err(r_gpu, gold[f'{name}/responses'][i]) < REL_TOL
+        b_gpu = trk.update(img)
+        assert np.abs(b_gpu - gold[f'{name}/boxes'][i]).max() < 0.75, (b_gpu, gold[f'{name}/boxes'][i])
+    state = np.concatenate([trk.center, trk.target_sz, [trk.z_sz, trk.x_sz]])
+    assert np.abs(state - gold[f'{name}/state']).max() < 0.75
+
+
 # --------------------------------------------------------------------------------------------- trackers
 @pytest.mark.parametrize('name', sorted(cases.TRACKER_TEST_CASES))
 def test_vanilla_tracker_matches_reference_golden(golden, name):
@@ -858,7 +1000,7 @@ def test_train_step_gradients_match_oracle_autograd(name):
     ref_loss, ref_grads = _oracle_train_reference(c, sd, imgs)
     # fp64 run of the same oracle: the yardstick.  ReLU / max-pool make the gradient discontinuous, so single
     # elements flip under ANY rounding change (the fp32 oracle itself is up to 1e-1 away from fp64 on some tensors);
-    # a tensor passes if its relative L2 error against fp64 is within 20x the fp32 oracle's own error (floor 3e-3):
+    # a tensor passes if its relative L2 error against fp64 is within 5x the fp32 oracle's own error (floor 3e-3):
     # split-fp16 operands carry 22 significant bits against fp32's 24, i.e. a few times fp32's rounding per op.
     sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
     _, ref64 = _oracle_train_reference(c, sd64, imgs.double())
@@ -879,9 +1021,14 @@ def test_train_step_gradients_match_oracle_autograd(name):
         mine = float((g.cpu().double() - r64).norm()) / denom
         base = float((ref_grads[k].double() - r64).norm()) / denom
         ratios.append(mine / max(base, 1e-7))
-        if mine > max(20 * base, 3e-3):
+        if mine > max(5 * base, 3e-3):
             failures.append((k, mine, base))
+    ratios = sorted(ratios)
+    print(f'[grad parity] {name}: error vs fp64 relative to the fp32 oracle\'s own error: median '
+          f'{ratios[len(ratios) // 2]:.2f}x, p90 {ratios[int(len(ratios) * 0.9)]:.2f}x, max {ratios[-1]:.2f}x '
+          f'over {len(ratios)} tensors')
     assert not failures, failures[:8]
+    assert ratios[len(ratios) // 2] < 3.0, 'median gradient error is more than 3x the fp32 oracle\'s own'
 
     # one SGD step (first step: momentum buffer = g + wd*p)
     before = {k: p.detach().clone() for k, p in model.named_parameters()}

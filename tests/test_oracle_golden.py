@@ -249,3 +249,73 @@ def test_oracle_bit_exact_vs_live_reference(golden):
     assert not missing, missing
     for key, arr in mine.items():
         _pinned(arr, ref[key], exact=True)
+
+
+# --------------------------------------------------------------------------------------------- SiamFC tracker
+def _oracle_siamfc_tracker(name):
+    """oracle.siamfc.TrackerOracle on the synthetic sequence -> the arrays of tests/golden/siamfc_tracker_golden.npz."""
+    from oracle import siamfc as o_siamfc
+    from vfs_b200.siamfc import SiamConvFC
+    from vfs_b200.backbones import ResNet
+    c = cases.SIAMFC_TRACKER_CASES[name]
+    cfg = cases.siamfc_tracker_cfg(c)
+    b = cfg['model']['backbone']
+    net = ResNet(c['depth'], norm_cfg=dict(type='BN', requires_grad=True), strides=b['strides'],
+                 dilations=b['dilations'], out_indices=b['out_indices'])
+    bsd = oracle.seeded_state_dict(net, seed=c['seed'])
+    hsd = oracle.seeded_state_dict(SiamConvFC(512, 512, out_scale=c['out_scale']), seed=c['seed'] + 1) \
+        if c['extra_conv'] else None
+    trk = o_siamfc.TrackerOracle(cfg, bsd, hsd, c['depth'])
+    frames, box0 = cases.siamfc_tracker_frames()
+    trk.init(frames[0], box0)
+    out = {f'{name}/kernel': trk.kernel.numpy()}
+    boxes, responses = [], []
+    for img in frames[1:]:
+        r = trk.responses(img)
+        responses.append(r.copy())
+        boxes.append(trk.update(img, responses=r))
+    out[f'{name}/responses'] = np.stack(responses)
+    out[f'{name}/boxes'] = np.stack(boxes)
+    out[f'{name}/state'] = np.concatenate([trk.center, trk.target_sz, [trk.z_sz, trk.x_sz]]).astype(np.float64)
+    return out
+
+
+@pytest.fixture(scope='module')
+def siamfc_tracker_golden():
+    import os
+    path = os.path.join(os.path.dirname(__file__), 'golden', 'siamfc_tracker_golden.npz')
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize('name', sorted(cases.SIAMFC_TRACKER_CASES))
+def test_siamfc_tracker_oracle_matches_reference_golden(siamfc_tracker_golden, name):
+    """TrackerSiamFC.init / update (siamfc_tracker_base.py:200-319): the oracle restatement against the fixture written
+    by the UNMODIFIED reference class -- exemplar kernel and raw responses to GOLDEN_TOL (host-ISA fp32 re-association),
+    boxes / tracker state to 1e-6 relative (float64 host arithmetic on the same peak)."""
+    mine = _oracle_siamfc_tracker(name)
+    for key, arr in mine.items():
+        ref = siamfc_tracker_golden[key]
+        assert arr.shape == ref.shape, key
+        if key.endswith('boxes') or key.endswith('state'):
+            np.testing.assert_allclose(arr, ref, rtol=1e-6, atol=1e-6, err_msg=key)
+        else:
+            _pinned(arr.astype(ref.dtype), ref)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference tree not present (GPU box)')
+def test_siamfc_tracker_oracle_bit_exact_vs_live_reference(siamfc_tracker_golden):
+    """Same process, same cores: oracle.siamfc.TrackerOracle must reproduce the unmodified reference tracker bit for
+    bit, and the live reference must agree with the committed fixture."""
+    from tests.golden import make_golden
+    ref = make_golden.siamfc_tracker_outputs()
+    assert set(ref) == set(siamfc_tracker_golden), 'fixture out of date: re-run tests/golden/make_golden.py'
+    for key, arr in ref.items():
+        g = siamfc_tracker_golden[key]
+        if key.endswith('boxes') or key.endswith('state'):
+            np.testing.assert_allclose(arr, g, rtol=1e-6, atol=1e-6, err_msg=key)
+        else:
+            _pinned(arr, g)
+    for name in cases.SIAMFC_TRACKER_CASES:
+        for key, arr in _oracle_siamfc_tracker(name).items():
+            np.testing.assert_array_equal(np.asarray(arr, dtype=ref[key].dtype), ref[key], err_msg=key)

@@ -65,6 +65,18 @@ PROTOTYPES = {
     'vfs_avgpool_backward': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'vfs_cosine_loss_backward': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'vfs_sgd_momentum_step': (_i, [_vp, _vp, _vp, _sz, _f, _f, _f, _i, _f, _vp]),
+    'vfs_sgd_momentum_step_dev': (_i, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    'vfs_comm_handle_bytes': (_sz, []),
+    'vfs_comm_create': (_i, [_i, _i, _sz, ctypes.POINTER(ctypes.c_void_p), _vp]),
+    'vfs_comm_connect': (_i, [_vp, _vp]),
+    'vfs_comm_destroy': (_i, [_vp]),
+    'vfs_comm_data_ptr': (_vp, [_vp]),
+    'vfs_comm_data_bytes': (_sz, [_vp]),
+    'vfs_comm_error': (_i, [_vp]),
+    'vfs_comm_allreduce_small_f64': (_i, [_vp, _vp, _i, _vp]),
+    'vfs_comm_allreduce_small_f32': (_i, [_vp, _vp, _i, _vp]),
+    'vfs_comm_barrier': (_i, [_vp, _vp]),
+    'vfs_comm_allreduce_f32': (_i, [_vp, _sz, _sz, _f, _vp]),
     'vfs_channel_stats_f32': (_i, [_vp, _vp, _ll, _i, _vp]),
     'vfs_bn_finalize': (_i, [_vp, ctypes.c_double, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     'vfs_bn_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),

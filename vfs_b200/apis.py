@@ -23,7 +23,11 @@ def single_gpu_test(model, data_loader):
     results = []
     for data in data_loader:
         with torch.no_grad():
-            results.extend(model(return_loss=False, **data))
+            result = model(return_loss=False, **data)
+        if isinstance(result, list):        # reference test.py:36-39: lists are flattened, anything else is one result
+            results.extend(result)
+        else:
+            results.append(result)
     return results
 
 

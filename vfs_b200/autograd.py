@@ -62,7 +62,8 @@ class LinearBnActFunction(torch.autograd.Function):
         ctx.save_for_backward(x, weight, pre, y, mean, invstd, gamma)
         ctx.has_bn, ctx.relu, ctx.training, ctx.has_bias = bn is not None, relu, training, bias is not None
         ctx.bn = bn
-        ctx.need_dx = x.requires_grad
+        ctx.bias = bias
+        ctx.need_dx = ctx.needs_input_grad[0]   # (x.requires_grad is False inside forward for a .contiguous() copy)
         return y
 
     @staticmethod
@@ -79,6 +80,12 @@ class LinearBnActFunction(torch.autograd.Function):
             dpre = ops.relu_backward(dy, y)
         else:
             dpre = dy
+        dW_sink = ops.grad_sink(weight)
+        db_sink = ops.grad_sink(ctx.bias) if ctx.has_bias else None
+        if dW_sink is not None and (db_sink is not None or not ctx.has_bias):
+            dx, _, _ = ops.linear_backward(dpre, x, weight.detach(), need_dx=ctx.need_dx, dW_out=dW_sink,
+                                           db_out=db_sink)
+            return dx, None, None, dgamma, dbeta, None, None
         dx, dW, db = ops.linear_backward(dpre, x, weight.detach(), need_dx=ctx.need_dx)
         return dx, dW, (db if ctx.has_bias else None), dgamma, dbeta, None, None
 

@@ -113,6 +113,18 @@ int cosine_loss_backward(const float* p, const float* z, const float* gout, floa
                          int negative, cudaStream_t s);
 int sgd_momentum_step(float* p, const float* g, float* buf, size_t n, float lr, float momentum, float wd, int first,
                       float grad_scale, cudaStream_t s);
+int sgd_momentum_step_dev(float* p, const float* g, float* buf, size_t n, const float* hyper, cudaStream_t s);
+struct Comm;
+size_t comm_handle_bytes();
+int comm_create(int rank, int world, size_t data_bytes, Comm** out, void* handle_out);
+int comm_connect(Comm* c, const void* all_handles);
+int comm_destroy(Comm* c);
+void* comm_data_ptr(Comm* c);
+size_t comm_data_bytes(Comm* c);
+int comm_error(Comm* c);
+int comm_allreduce_small(Comm* c, void* data, int n, int is_f64, cudaStream_t s);
+int comm_barrier(Comm* c, cudaStream_t s);
+int comm_allreduce_f32(Comm* c, size_t offset_bytes, size_t n, float scale, cudaStream_t s);
 int channel_stats_f32(const float* x, double* stats, long long M, int C, cudaStream_t s);
 int bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean,
                 float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
@@ -296,6 +308,30 @@ int vfs_cosine_loss_backward(const float* p, const float* z, const float* gout, 
 int vfs_sgd_momentum_step(float* p, const float* g, float* buf, size_t n, float lr, float momentum, float wd,
                           int first, float grad_scale, vfs_stream_t s) {
   return vfs::sgd_momentum_step(p, g, buf, n, lr, momentum, wd, first, grad_scale, s);
+}
+int vfs_sgd_momentum_step_dev(float* p, const float* g, float* buf, size_t n, const float* hyper, vfs_stream_t s) {
+  return vfs::sgd_momentum_step_dev(p, g, buf, n, hyper, s);
+}
+size_t vfs_comm_handle_bytes(void) { return vfs::comm_handle_bytes(); }
+int vfs_comm_create(int rank, int world, size_t data_bytes, VfsComm** out, void* handle_out) {
+  return vfs::comm_create(rank, world, data_bytes, reinterpret_cast<vfs::Comm**>(out), handle_out);
+}
+int vfs_comm_connect(VfsComm* c, const void* all_handles) {
+  return vfs::comm_connect(reinterpret_cast<vfs::Comm*>(c), all_handles);
+}
+int vfs_comm_destroy(VfsComm* c) { return vfs::comm_destroy(reinterpret_cast<vfs::Comm*>(c)); }
+void* vfs_comm_data_ptr(VfsComm* c) { return vfs::comm_data_ptr(reinterpret_cast<vfs::Comm*>(c)); }
+size_t vfs_comm_data_bytes(VfsComm* c) { return vfs::comm_data_bytes(reinterpret_cast<vfs::Comm*>(c)); }
+int vfs_comm_error(VfsComm* c) { return vfs::comm_error(reinterpret_cast<vfs::Comm*>(c)); }
+int vfs_comm_allreduce_small_f64(VfsComm* c, double* data, int n, vfs_stream_t s) {
+  return vfs::comm_allreduce_small(reinterpret_cast<vfs::Comm*>(c), data, n, 1, s);
+}
+int vfs_comm_allreduce_small_f32(VfsComm* c, float* data, int n, vfs_stream_t s) {
+  return vfs::comm_allreduce_small(reinterpret_cast<vfs::Comm*>(c), data, n, 0, s);
+}
+int vfs_comm_barrier(VfsComm* c, vfs_stream_t s) { return vfs::comm_barrier(reinterpret_cast<vfs::Comm*>(c), s); }
+int vfs_comm_allreduce_f32(VfsComm* c, size_t offset_bytes, size_t n, float scale, vfs_stream_t s) {
+  return vfs::comm_allreduce_f32(reinterpret_cast<vfs::Comm*>(c), offset_bytes, n, scale, s);
 }
 int vfs_channel_stats_f32(const float* x, double* stats, long long M, int C, vfs_stream_t s) {
   return vfs::channel_stats_f32(x, stats, M, C, s);

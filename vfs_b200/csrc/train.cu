@@ -633,6 +633,52 @@ __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restri
   }
 }
 
+// Same update with the hyper-parameters read from device memory ({lr, momentum, weight_decay, grad_scale}): a CUDA
+// graph that captured the launch follows an LR schedule by copying four floats, no re-capture.  Momentum buffers start
+// zeroed (momentum * 0 + g' = g' is torch's first-step rule).  float4-vectorised (n % 4 == 0 and 16-byte alignment
+// checked by the host); the tail runs scalar.
+__global__ void sgd_momentum_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                                        size_t n, const float* __restrict__ hyper, int vec) {
+  const float lr = hyper[0], momentum = hyper[1], wd = hyper[2], grad_scale = hyper[3];
+  if (vec) {
+    const size_t n4 = n / 4;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      float4 pv = reinterpret_cast<float4*>(p)[i];
+      const float4 gv = reinterpret_cast<const float4*>(g)[i];
+      float4 bv = reinterpret_cast<float4*>(buf)[i];
+      bv.x = fmaf(momentum, bv.x, fmaf(wd, pv.x, gv.x * grad_scale));
+      bv.y = fmaf(momentum, bv.y, fmaf(wd, pv.y, gv.y * grad_scale));
+      bv.z = fmaf(momentum, bv.z, fmaf(wd, pv.z, gv.z * grad_scale));
+      bv.w = fmaf(momentum, bv.w, fmaf(wd, pv.w, gv.w * grad_scale));
+      pv.x -= lr * bv.x; pv.y -= lr * bv.y; pv.z -= lr * bv.z; pv.w -= lr * bv.w;
+      reinterpret_cast<float4*>(buf)[i] = bv;
+      reinterpret_cast<float4*>(p)[i] = pv;
+    }
+    return;
+  }
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float gg = fmaf(wd, p[i], g[i] * grad_scale);
+    const float b = fmaf(momentum, buf[i], gg);
+    buf[i] = b;
+    p[i] = p[i] - lr * b;
+  }
+}
+
+int sgd_momentum_step_dev(float* p, const float* g, float* buf, size_t n, const float* hyper, cudaStream_t s) {
+  VFS_REQUIRE(p && g && buf && hyper, VFS_EINVAL, "sgd_momentum_step_dev: null argument");
+  if (n == 0) return VFS_OK;
+  const bool vec = n % 4 == 0 && (reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                                  reinterpret_cast<uintptr_t>(buf)) % 16 == 0;
+  const size_t work = vec ? n / 4 : n;
+  size_t blocks = (work + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sgd_momentum_dev_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(p, g, buf, n, hyper, vec ? 1 : 0);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
 int relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, long long elems, cudaStream_t s) {
   VFS_REQUIRE(dy_split && y_split && g_split && elems % 8 == 0, VFS_EINVAL, "relu_bwd_split: bad argument");
   const h16* dh = reinterpret_cast<const h16*>(dy_split);

@@ -41,13 +41,15 @@ class BackboneEngine:
         self.check_versions = True  # re-pack when parameters were modified in place / reloaded
         self.events = None          # bench instrumentation: list collecting (tag, cuda event) at phase boundaries
         self.tape = None            # training: list recording what backward needs (set by the autograd wrapper)
-        self._graphs = {}           # (input shape, stage, normalize) -> captured CUDA graph over static buffers
+        self._graphs = {}           # (input shape, stage, normalize, geometry) -> captured CUDA graph (LRU order)
+        self.max_graphs = 8
+        self._convs = None
         self._tensors = None
 
     # -------------------------------------------------------------- plans
     @staticmethod
     def _version(cm):
-        v = cm.conv.weight._version + cm.conv.weight.data_ptr()
+        v = cm.conv.weight._version + cm.conv.weight.data_ptr() + (ops.WEIGHT_EPOCH[0] << 20)
         if cm.with_norm:
             bn = cm.norm
             for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked):
@@ -81,7 +83,7 @@ class BackboneEngine:
         """Cheap global version stamp of every parameter/buffer (in-place updates and reloads bump it)."""
         if self._tensors is None:
             self._tensors = list(self.net.parameters()) + list(self.net.buffers())
-        return sum(t._version for t in self._tensors)
+        return sum(t._version for t in self._tensors) + (ops.WEIGHT_EPOCH[0] << 20)
 
     # -------------------------------------------------------------- single fused layer
     def conv(self, cm, xs, relu, residual=None, want_f32=False):
@@ -198,8 +200,11 @@ class BackboneEngine:
                 dz32, _, dgam, dbet = ops.bn_backward(g32, None, op['z'], op['mean'], op['invstd'], bn, dy_is_f32=True,
                                                       want_f32=True, param_scale=inv)
                 if cm.conv.weight.requires_grad:
-                    pgrads[id(cm.conv.weight)] = ops.stem_wgrad(op['x'], dz32, out_scale=inv)
-                if bn.affine and bn.weight.requires_grad:
+                    sink = ops.grad_sink(cm.conv.weight)
+                    dw = ops.stem_wgrad(op['x'], dz32, out_scale=inv, out=sink)
+                    if sink is None:
+                        pgrads[id(cm.conv.weight)] = dw
+                if bn.affine and bn.weight.requires_grad and dgam is not None:
                     pgrads[id(bn.weight)], pgrads[id(bn.bias)] = dgam, dbet
                 continue
             want_g = op['residual'] is not None
@@ -209,11 +214,14 @@ class BackboneEngine:
                 if id(op['residual']) in grad:
                     raise NotImplementedError('vfs_b200: unexpected second gradient for a residual input')
                 grad[id(op['residual'])] = g
-            if bn.affine and bn.weight.requires_grad:
+            if bn.affine and bn.weight.requires_grad and dgam is not None:
                 pgrads[id(bn.weight)], pgrads[id(bn.bias)] = dgam, dbet
             if cm.conv.weight.requires_grad:
-                pgrads[id(cm.conv.weight)] = ops.conv_wgrad(op['xs'], dz, op['k'], op['stride'], op['dil'],
-                                                            out_scale=inv)
+                sink = ops.grad_sink(cm.conv.weight)   # flat gradient view: accumulate in place (dp.FlatTrainState)
+                dw = ops.conv_wgrad(op['xs'], dz, op['k'], op['stride'], op['dil'], out=sink,
+                                    accumulate=sink is not None, out_scale=inv)
+                if sink is None:
+                    pgrads[id(cm.conv.weight)] = dw
             plan = self.plan(cm, dz.device)
             if plan.wt_split is None:
                 plan.wt_split = ops.pack_conv_weight_dgrad(
@@ -253,7 +261,13 @@ class BackboneEngine:
         """forward_split (+ optional L2 normalisation over channels) replayed from a CUDA graph captured once per
         input shape over static buffers: one graph launch instead of ~45 Python/ctypes kernel launches.  The
         returned split tensor is the graph's static output (valid until the next call with the same shape)."""
-        key = (tuple(x.shape), int(stage), bool(normalize), x.device.index)
+        # geometry (switch_strides / StrideContext / change_stride rewrite conv.stride without touching any tensor)
+        # is part of the key; parameter / buffer updates are caught by the stamp (tensor versions + ops.WEIGHT_EPOCH,
+        # which native optimiser steps and training-graph replays bump)
+        if self._convs is None:
+            self._convs = [m for m in self.net.modules() if isinstance(m, torch.nn.Conv2d)]
+        geom = tuple((m.stride[0], m.dilation[0], m.padding[0]) for m in self._convs)
+        key = (tuple(x.shape), int(stage), bool(normalize), x.device.index, geom)
         stamp = self._stamp()
         ent = self._graphs.get(key)
         if ent is not None and ent[3] != stamp:
@@ -279,6 +293,10 @@ class BackboneEngine:
             self.events = saved_events
             ent = (graph, static_in, xs, stamp)
             self._graphs[key] = ent
+            while len(self._graphs) > self.max_graphs:          # LRU bound: each entry pins its activation pool
+                self._graphs.pop(next(iter(self._graphs)))
+        else:
+            self._graphs[key] = self._graphs.pop(key)           # mark as most recently used
         graph, static_in, xs, _ = ent
         static_in.copy_(x, non_blocking=True)
         graph.replay()

@@ -8,7 +8,18 @@ from . import _native as nat
 from ._native import VfsConvDesc, current_stream, ptr
 
 LAUNCHES = [0]  # kernels of libvfs_b200.so launched through this module (bench.py reports the count)
-_KERNELS_PER_CALL = {'stem_forward': 2, 'masked_attention': 2, 'features_to_split_norm': 2, 'conv_dgrad': 1, 'conv_wgrad': 2, 'seg_postprocess': 3, 'siamfc_response_peak': 3}
+# parameter data_ptr -> gradient tensor the native backward kernels ACCUMULATE into (dp.FlatTrainState registers the
+# views of its flat gradient buffer here; autograd then receives None for those parameters)
+GRAD_SINKS = {}
+GRAD_SINK_OWNER = {}   # parameter data_ptr -> the dp.FlatTrainState owning its gradient view
+# bumped whenever native kernels rewrote parameters / BN buffers without touching tensor versions (flat SGD step,
+# CUDA-graph replays of a training step): part of every engine's plan / graph validity stamp
+WEIGHT_EPOCH = [0]
+
+
+def grad_sink(p):
+    return GRAD_SINKS.get(p.data_ptr()) if (p is not None and GRAD_SINKS) else None
+_KERNELS_PER_CALL = {'comm_allreduce_f32': 3, 'stem_forward': 2, 'masked_attention': 2, 'features_to_split_norm': 2, 'conv_dgrad': 1, 'conv_wgrad': 2, 'seg_postprocess': 3, 'siamfc_response_peak': 3}
 
 
 def check(rc, what=''):
@@ -181,16 +192,27 @@ def channel_stats(z):
     return stats
 
 
+def cross_rank_sum_(t):
+    """In-place sum of a small CUDA statistics tensor over the ranks of the default group.  With a peer communicator
+    installed (vfs_b200.peer) this is one kernel over NVLink peer memory on the current stream (no NCCL call, no host
+    round trip, graph-capturable); otherwise torch.distributed.all_reduce.  Returns the world size."""
+    import torch.distributed as dist
+    from . import peer
+    comm = peer.active()
+    if comm is not None and comm.world > 1:
+        comm.allreduce_small_(t)
+        return comm.world
+    dist.all_reduce(t)
+    return dist.get_world_size()
+
+
 def bn_finalize(stats, count, bn):
     """Batch statistics -> (scale, shift, save_mean, save_invstd); updates bn.running_* like torch.  With
     SyncBatchNorm in an initialised multi-rank process group the statistics are all-reduced first (that IS the
     SyncBN exchange: [sum, sum of squares] is equivalent to torch's gather of mean/invstd/count)."""
     C = stats.numel() // 2
-    import torch.distributed as dist
-    if isinstance(bn, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() \
-            and dist.get_world_size() > 1:
-        dist.all_reduce(stats)
-        count = count * dist.get_world_size()
+    if _is_cross_rank_syncbn(bn):
+        count = count * cross_rank_sum_(stats)
     dev = stats.device
     scale = torch.empty((C, ), dtype=torch.float32, device=dev)
     shift = torch.empty_like(scale)
@@ -319,9 +341,12 @@ def linear_forward(x, weight, bias):
     return y
 
 
+CROSS_RANK_SYNCBN = [True]   # test switch: False makes SyncBatchNorm use this rank's statistics only
+
+
 def _is_cross_rank_syncbn(bn):
     import torch.distributed as dist
-    return isinstance(bn, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() \
+    return CROSS_RANK_SYNCBN[0] and isinstance(bn, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() \
         and dist.get_world_size() > 1
 
 
@@ -371,17 +396,27 @@ def linear_bn_act(x, lin, bn=None, relu=False):
 
 
 # ---- backward pieces of the head -------------------------------------------------------------------------
-def linear_backward(dy, x, weight, need_dx=True):
-    """Returns (dx | None, dW, db) for y = x W^T + b."""
+def linear_backward(dy, x, weight, need_dx=True, dW_out=None, db_out=None):
+    """Returns (dx | None, dW, db) for y = x W^T + b.  ``dW_out`` / ``db_out``: existing gradient tensors to
+    ACCUMULATE into (flat gradient views); dW / db are then returned as None."""
     M, N = dy.shape
     K = x.shape[1]
     dx = torch.empty((M, K), dtype=torch.float32, device=dy.device) if need_dx else None
-    dW = torch.empty((N, K), dtype=torch.float32, device=dy.device)
-    db = torch.empty((N, ), dtype=torch.float32, device=dy.device)
-    check(nat.lib().vfs_linear_backward(ptr(dy), ptr(x), ptr(weight), ptr(dx), ptr(dW), ptr(db), M, N, K, 0,
+    sunk = dW_out is not None
+    dW = dW_out if sunk else torch.empty((N, K), dtype=torch.float32, device=dy.device)
+    db = db_out if sunk else torch.empty((N, ), dtype=torch.float32, device=dy.device)
+    check(nat.lib().vfs_linear_backward(ptr(dy), ptr(x), ptr(weight), ptr(dx), ptr(dW), ptr(db), M, N, K, int(sunk),
                                         current_stream()), 'linear_backward')
     LAUNCHES[0] += 1 if need_dx else 0
-    return dx, dW, db
+    return (dx, None, None) if sunk else (dx, dW, db)
+
+
+def _bn_param_sinks(bn):
+    """(dgamma, dbeta) accumulation targets registered for an affine norm layer, or (None, None)."""
+    if bn is None or not getattr(bn, 'affine', False):
+        return None, None
+    dg, db = grad_sink(bn.weight), grad_sink(bn.bias)
+    return (dg, db) if (dg is not None and db is not None) else (None, None)
 
 
 def bn1d_backward(dy, pre, out, gamma, mean, invstd, training, relu, bn=None):
@@ -396,20 +431,26 @@ def bn1d_backward(dy, pre, out, gamma, mean, invstd, training, relu, bn=None):
         world = _sync_sums(sums, bn)
         count = M * world
         dpre = torch.empty_like(dy)
+        dg, db = _bn_param_sinks(bn)
+        sunk = dg is not None
+        if not sunk:
+            dg = torch.empty((N, ), dtype=torch.float32, device=dy.device)
+            db = torch.empty_like(dg)
+        check(nat.lib().vfs_bn_bwd_apply(None, ptr(dy), None, ptr(yf), ptr(pre), ptr(mean), ptr(invstd), ptr(gamma),
+                                         ptr(sums), float(count), None, ptr(dpre), None, ptr(dg), ptr(db), int(sunk),
+                                         1.0 / world, M, N, current_stream()), 'bn_bwd_apply')
+        LAUNCHES[0] += 1
+        return (dpre, None, None) if sunk else (dpre, dg, db)
+    dpre = torch.empty_like(dy)
+    dg, db = _bn_param_sinks(bn)
+    sunk = dg is not None
+    if not sunk:
         dg = torch.empty((N, ), dtype=torch.float32, device=dy.device)
         db = torch.empty_like(dg)
-        check(nat.lib().vfs_bn_bwd_apply(None, ptr(dy), None, ptr(yf), ptr(pre), ptr(mean), ptr(invstd), ptr(gamma),
-                                         ptr(sums), float(count), None, ptr(dpre), None, ptr(dg), ptr(db), 0, 1.0 / world, M, N,
-                                         current_stream()), 'bn_bwd_apply')
-        LAUNCHES[0] += 1
-        return dpre, dg, db
-    dpre = torch.empty_like(dy)
-    dg = torch.empty((N, ), dtype=torch.float32, device=dy.device)
-    db = torch.empty_like(dg)
     check(nat.lib().vfs_bn1d_backward(ptr(dy), ptr(pre), ptr(out), ptr(dpre), M, N, ptr(gamma), ptr(mean),
-                                      ptr(invstd), int(training), int(relu), ptr(dg), ptr(db), 0, current_stream()),
-          'bn1d_backward')
-    return dpre, dg, db
+                                      ptr(invstd), int(training), int(relu), ptr(dg), ptr(db), int(sunk),
+                                      current_stream()), 'bn1d_backward')
+    return (dpre, None, None) if sunk else (dpre, dg, db)
 
 
 def relu_backward(dy, out):
@@ -437,11 +478,8 @@ def cosine_loss_backward(p, z, gout, with_norm=True, negative=False):
 
 # ---- backward pieces of the backbone ---------------------------------------------------------------------
 def _sync_sums(sums, bn):
-    import torch.distributed as dist
-    if isinstance(bn, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() \
-            and dist.get_world_size() > 1:
-        dist.all_reduce(sums)
-        return dist.get_world_size()
+    if _is_cross_rank_syncbn(bn):
+        return cross_rank_sum_(sums)
     return 1
 
 
@@ -464,13 +502,19 @@ def bn_backward(dy, y_for_relu, z, mean, invstd, bn, want_g=False, dy_is_f32=Fal
     dz = torch.empty((N, H, W, C), dtype=torch.float32, device=z.device) if want_f32 else \
         torch.empty((2, N, H, W, C), dtype=torch.float16, device=z.device)
     g = torch.empty((2, N, H, W, C), dtype=torch.float16, device=z.device) if want_g else None
-    dg = torch.empty((C, ), dtype=torch.float32, device=z.device)
-    db = torch.empty_like(dg)
+    dg, db, acc = (grad_sink(bn.weight), grad_sink(bn.bias), 1) if bn.affine else (None, None, 0)
+    sunk = dg is not None and db is not None
+    if not sunk:
+        dg = torch.empty((C, ), dtype=torch.float32, device=z.device)
+        db = torch.empty_like(dg)
+        acc = 0
     check(nat.lib().vfs_bn_bwd_apply(ptr(dys), ptr(dyf), ptr(y_for_relu), None, ptr(z), ptr(mean), ptr(invstd),
                                      ptr(bn.weight.detach()) if bn.affine else None, ptr(sums), float(count),
                                      None if want_f32 else ptr(dz), ptr(dz) if want_f32 else None, ptr(g), ptr(dg),
-                                     ptr(db), 0, float(param_scale), M, C, current_stream()), 'bn_bwd_apply')
+                                     ptr(db), acc, float(param_scale), M, C, current_stream()), 'bn_bwd_apply')
     LAUNCHES[0] += 1
+    if sunk:
+        return dz, g, None, None     # accumulated into the registered gradient views
     return dz, g, dg, db
 
 
@@ -483,11 +527,12 @@ def stem_pool_relu_backward(dpool, z, scale, shift, in_hw):
     return g
 
 
-def stem_wgrad(x, dz, out_scale=1.0):
+def stem_wgrad(x, dz, out_scale=1.0, out=None):
+    """7x7 stem weight gradient; ``out``: existing gradient tensor to ACCUMULATE into."""
     N, _, H, W = x.shape
-    dw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=x.device)
-    check(nat.lib().vfs_stem_wgrad(ptr(x), ptr(dz), ptr(dw), 0, float(out_scale), N, H, W, current_stream()),
-          'stem_wgrad')
+    dw = torch.empty((64, 3, 7, 7), dtype=torch.float32, device=x.device) if out is None else out
+    check(nat.lib().vfs_stem_wgrad(ptr(x), ptr(dz), ptr(dw), int(out is not None), float(out_scale), N, H, W,
+                                   current_stream()), 'stem_wgrad')
     return dw
 
 

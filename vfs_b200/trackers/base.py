@@ -73,9 +73,10 @@ class BaseTracker(nn.Module, abc.ABC):
         total = sum(v for name, v in reduced.items() if 'loss' in name)
         reduced['loss'] = total
         packed = torch.stack([v.detach().float().reshape(()) for v in reduced.values()])
-        if dist.is_available() and dist.is_initialized():
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from .. import ops
             packed /= dist.get_world_size()
-            dist.all_reduce(packed)
+            ops.cross_rank_sum_(packed)     # peer-memory kernel when a communicator is installed, else all_reduce
         log_vars = OrderedDict(zip(reduced.keys(), packed.tolist()))
         return total, log_vars
 

@@ -122,7 +122,10 @@ class VanillaTracker(BaseTracker):
         num_classes = -1
         if not ref_seg_map.is_cuda and ref_seg_map.ndim == 3 and ref_seg_map.numel() > 0:
             num_classes = int(ref_seg_map.max()) + 1
-        ref_seg_map = ref_seg_map.to(imgs.device, non_blocking=True)
+        # the reference stacks the (loader dtype) first-frame map with uint8 arg-max maps (vanilla_tracker.py:196-203):
+        # a uint8 label map gives uint8 predictions, a float map promotes everything to float32
+        label_dtype = ref_seg_map.dtype
+        ref_seg_map = ref_seg_map.to(imgs.device, non_blocking=True).float()
         assert ref_seg_map.size(0) == num_videos, (ref_seg_map.shape, imgs.shape)
         input_onehot = ref_seg_map.ndim == 4
         if not input_onehot:
@@ -150,7 +153,8 @@ class VanillaTracker(BaseTracker):
 
         # predictions [B,T,H,W] assembled on the device; dtype mirrors np.stack over the reference's per-frame
         # arrays (float32 first-frame map + uint8 arg-max maps promote to float32)
-        preds = torch.empty((num_videos, clip_len) + tuple(ref_seg_map.shape[1:]), dtype=torch.float32,
+        pred_dtype = torch.uint8 if (label_dtype == torch.uint8 and not input_onehot) else torch.float32
+        preds = torch.empty((num_videos, clip_len) + tuple(ref_seg_map.shape[1:]), dtype=pred_dtype,
                             device=imgs.device)
         preds[:, 0] = ref_seg_map
         for frame_idx in range(1, clip_len):
