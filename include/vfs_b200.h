@@ -212,6 +212,19 @@ int vfs_comm_allreduce_f32(VfsComm* c, size_t offset_bytes, size_t n, float scal
 /* OIHW fp32 [Cout,Cin,k,k] -> split [2][Cout][k*k*Cin] (device to device). */
 int vfs_pack_conv_weight(const float* w_oihw, void* w_split, int Cout, int Cin, int ksize, vfs_stream_t s);
 
+/* All conv weights of a network in one launch (training re-packs them after every optimiser step).  items: DEVICE
+ * array of n entries sorted by first_block; entry i owns blocks [first_block_i, first_block_{i+1}) of a launch of
+ * total_blocks blocks, vfs_pack_blocks(Cout, Cin, ksize) blocks each.  mode 0 = vfs_pack_conv_weight layout,
+ * 1 = vfs_pack_conv_weight_dgrad layout. */
+typedef struct VfsPackItem {
+  const float* w;   /* OIHW fp32 [Cout,Cin,k,k] */
+  void* dst_split;  /* split [2][...] */
+  int32_t Cout, Cin, ksize, mode;
+  int32_t first_block, reserved;
+} VfsPackItem;
+int vfs_pack_blocks(int Cout, int Cin, int ksize);
+int vfs_pack_conv_weights_multi(const VfsPackItem* items_dev, int n, int total_blocks, vfs_stream_t s);
+
 /* Test instrument: the same contract as vfs_conv_bn_act computed with plain fp32 FMAs (one thread per
  * output element, fixed summation order).  Exists so the tensor-core path can be checked on the device
  * at sizes the CPU oracle cannot reach; never called by the product path. */

@@ -95,13 +95,13 @@ def main():
                 loss=float(out['loss']), mode='cuda-graph' if a.graph else 'eager', native_launches_per_step=(ops.LAUNCHES[0] - launches0) / a.steps,
                 conv_gflop_fwd=fwd / 1e9, conv_tflops_algorithmic_fwd_bwd=3 * fwd / (ms * 1e-3) / 1e12,
                 overflow=ops.overflow_count(), timing='CUDA events over the timed steps, max over ranks')
-    if a.profile and rank == 0 and not a.graph:
+    if a.profile and rank == 0:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             for _ in range(2):
                 step()
             torch.cuda.synchronize()
-        print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=40, max_name_column_width=70))
+        print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=70))
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -17,6 +17,11 @@ class VfsConvDesc(ctypes.Structure):
                 for n in ('N', 'H', 'W', 'Cin', 'Cout', 'ksize', 'stride', 'dilation', 'relu')]
 
 
+class VfsPackItem(ctypes.Structure):
+    _fields_ = [('w', ctypes.c_void_p), ('dst_split', ctypes.c_void_p)] + \
+        [(n, ctypes.c_int32) for n in ('Cout', 'Cin', 'ksize', 'mode', 'first_block', 'reserved')]
+
+
 class VfsAttnDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ('H', 'W', 'C', 'Cv', 'T', 'topk', 'mask_mode', 'radius_y', 'radius_x',
                                               'non_mask_len', 'mode')] + [('temperature', ctypes.c_float)]
@@ -41,6 +46,8 @@ PROTOTYPES = {
     'vfs_stem_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'vfs_conv_bn_act': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'vfs_pack_conv_weight': (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    'vfs_pack_blocks': (_i, [_i, _i, _i]),
+    'vfs_pack_conv_weights_multi': (_i, [_vp, _i, _i, _vp]),
     'vfs_debug_conv_trace': (_i, [_vp, _i]),
     'vfs_conv_set_pair_policy': (_i, [_i, _i]),
     'vfs_attention_set_wide': (_i, [_i]),

@@ -136,6 +136,7 @@ int conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const void* w_s
 int nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, float scale, cudaStream_t s);
 int split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H, int W, cudaStream_t s);
 int pack_conv_weight(const float* w, void* w_split, int Cout, int Cin, int k, cudaStream_t s);
+int pack_conv_weights_multi(const VfsPackItem* items_dev, int n, int total_blocks, cudaStream_t s);
 size_t stem_workspace_bytes(int N, int H, int W);
 int stem_forward(const float* in, const void* weight, const float* scale, const float* shift, void* out_split,
                  void* workspace, int N, int H, int W, cudaStream_t s);
@@ -345,6 +346,13 @@ int vfs_bn_finalize(double* stats, double count, const float* gamma, const float
 int vfs_bn_apply(const float* z, const float* scale, const float* shift, const void* residual_split,
                  void* out_split, long long M, int C, int relu, vfs_stream_t s) {
   return vfs::bn_apply(z, scale, shift, residual_split, out_split, M, C, relu, s);
+}
+int vfs_pack_blocks(int Cout, int Cin, int ksize) {
+  const long long total = static_cast<long long>(Cout) * Cin * ksize * ksize;
+  return static_cast<int>((total + 2047) / 2048);
+}
+int vfs_pack_conv_weights_multi(const VfsPackItem* items_dev, int n, int total_blocks, vfs_stream_t s) {
+  return vfs::pack_conv_weights_multi(items_dev, n, total_blocks, s);
 }
 int vfs_pack_conv_weight(const float* w_oihw, void* w_split, int Cout, int Cin, int ksize, vfs_stream_t s) {
   return vfs::pack_conv_weight(w_oihw, w_split, Cout, Cin, ksize, s);

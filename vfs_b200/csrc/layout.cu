@@ -118,6 +118,54 @@ __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, h16* __res
   }
 }
 
+// Multi-tensor form: every conv of the network (forward and / or data-gradient layout) in ONE launch.  A training step
+// re-packs all weights after each optimiser update; per-tensor launches were 208 of its ~1200 kernels
+// (profiles/r02_train_profile_cfg4_v1.log).  Block b serves the item whose [first_block, next first_block) contains it.
+constexpr int kPackPerBlock = 2048;
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const VfsPackItem* __restrict__ items, int n) {
+  int lo_i = 0, hi_i = n - 1;
+  while (lo_i < hi_i) {   // last item with first_block <= blockIdx.x
+    const int mid = (lo_i + hi_i + 1) >> 1;
+    if (items[mid].first_block <= static_cast<int>(blockIdx.x)) lo_i = mid;
+    else hi_i = mid - 1;
+  }
+  const VfsPackItem it = items[lo_i];
+  const int Cout = it.Cout, Cin = it.Cin, kk = it.ksize * it.ksize;
+  const size_t total = static_cast<size_t>(Cout) * Cin * kk;
+  h16* hi = reinterpret_cast<h16*>(it.dst_split);
+  h16* lo = hi + total;
+  const size_t begin = static_cast<size_t>(blockIdx.x - it.first_block) * kPackPerBlock;
+  size_t end = begin + kPackPerBlock;
+  if (end > total) end = total;
+  for (size_t i = begin + threadIdx.x; i < end; i += 256) {
+    float v;
+    if (it.mode == 0) {   // forward operand: i = (co * k*k + tap) * Cin + ci
+      const int ci = static_cast<int>(i % Cin);
+      const size_t t = i / Cin;
+      const int tap = static_cast<int>(t % kk);
+      const int co = static_cast<int>(t / kk);
+      v = it.w[(static_cast<size_t>(co) * Cin + ci) * kk + tap];
+    } else {              // data-gradient operand: i = (ci * k*k + tap') * Cout + co, kernel flipped
+      const int co = static_cast<int>(i % Cout);
+      const size_t t = i / Cout;
+      const int tap = static_cast<int>(t % kk);
+      const int ci = static_cast<int>(t / kk);
+      v = it.w[(static_cast<size_t>(co) * Cin + ci) * kk + (kk - 1 - tap)];
+    }
+    h16 h, l;
+    split16(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+int pack_conv_weights_multi(const VfsPackItem* items_dev, int n, int total_blocks, cudaStream_t s) {
+  VFS_REQUIRE(items_dev && n > 0 && total_blocks > 0, VFS_EINVAL, "pack_conv_weights_multi: bad argument");
+  pack_weights_multi_kernel<<<total_blocks, 256, 0, s>>>(items_dev, n);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
 int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, int k, cudaStream_t s) {
   VFS_REQUIRE(w && wt_split, VFS_EINVAL, "pack_conv_weight_dgrad: null argument");
   VFS_REQUIRE(Cout > 0 && Cin > 0 && k > 0, VFS_ESHAPE, "pack_conv_weight_dgrad: bad shape");

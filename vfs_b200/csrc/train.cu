@@ -3,6 +3,7 @@
 // and the fused SGD-momentum update.  All exact fp32 (fp64 for cross-pixel reductions), fixed formulas of
 // torch.nn.functional.batch_norm / max_pool2d / linear backward.
 #include <math.h>
+#include <stdlib.h>
 
 #include "host_common.h"
 #include "ptx.cuh"
@@ -40,15 +41,27 @@ struct BnBwdArgs {
   const float* dy_f32;
   const h16* y_hi; const h16* y_lo;    // forward output for the ReLU mask (null: no ReLU)
   const float* y_f32;                  // same as fp32 (SimSiam head tensors)
-  const float* z;                                          // raw conv output fp32 [M, C]
+  const float* z;                                          // raw conv output fp32 [M, C] (or null when z_hi is set)
+  const h16* z_hi; const h16* z_lo;                        // raw conv output as a split tensor
   const float* mean; const float* invstd; const float* gamma;
   double* sums;                                            // [2C] (reduce: accumulated; apply: read)
   double count;
   h16* dz_hi; h16* dz_lo;              // split dz (or null)
   float* dz_f32;                                           // fp32 dz (stem)
   h16* g_hi; h16* g_lo;                // optional: masked gradient for the residual branch
+  float* dgamma; float* dbeta;         // optional (apply): parameter gradients = param_scale * sums, written by block row 0
+  int accumulate; float param_scale;
   long long M; int C;
 };
+
+__device__ __forceinline__ void load_z8(const BnBwdArgs& a, long long o, float (&zz)[8]) {
+  if (a.z) {
+    const float4 z0 = *reinterpret_cast<const float4*>(a.z + o), z1 = *reinterpret_cast<const float4*>(a.z + o + 4);
+    zz[0] = z0.x; zz[1] = z0.y; zz[2] = z0.z; zz[3] = z0.w; zz[4] = z1.x; zz[5] = z1.y; zz[6] = z1.z; zz[7] = z1.w;
+  } else {
+    unpack8(*reinterpret_cast<const uint4*>(a.z_hi + o), *reinterpret_cast<const uint4*>(a.z_lo + o), zz);
+  }
+}
 
 __device__ __forceinline__ void bn_bwd_load_g(const BnBwdArgs& a, long long o, float (&g)[8]) {
   if (a.dy_f32) {
@@ -70,17 +83,45 @@ __device__ __forceinline__ void bn_bwd_load_g(const BnBwdArgs& a, long long o, f
   }
 }
 
-// Per-channel sums of g and g * xhat over all M pixels.  256 threads = (C/8 eight-channel pieces) x row groups; every
-// thread walks rows grid-stride, the row groups of a block are folded in shared memory and ONE fp64 atomic per
-// (block, channel, sum) reaches global memory -- the first version issued 16 fp64 atomics per THREAD on 2C addresses
-// and spent 310 us per call on atomic contention (profiles/r01_train_profile_v11.log).
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
-  __shared__ float red[256][17];
-  const int pieces = a.C / 8;
+// ReLU mask from the forward output: y = hi + lo with hi = half(y) >= 0, so y > 0 <=> hi > 0 except for 0 < y < 2^-25
+// (hi rounds to zero; such a pixel's gradient is dropped -- immeasurable, and it saves the lo plane's 2 bytes/element).
+__device__ __forceinline__ void bn_bwd_load_g2(const BnBwdArgs& a, long long o, float (&g)[8]) {
+  if (a.dy_f32) {
+    const float4 p = *reinterpret_cast<const float4*>(a.dy_f32 + o), q = *reinterpret_cast<const float4*>(a.dy_f32 + o + 4);
+    g[0] = p.x; g[1] = p.y; g[2] = p.z; g[3] = p.w; g[4] = q.x; g[5] = q.y; g[6] = q.z; g[7] = q.w;
+  } else {
+    unpack8(*reinterpret_cast<const uint4*>(a.dy_hi + o), *reinterpret_cast<const uint4*>(a.dy_lo + o), g);
+  }
+  if (a.y_hi) {
+    const uint4 h = *reinterpret_cast<const uint4*>(a.y_hi + o);
+    const float y[8] = {lo16_to_float(h.x), hi16_to_float(h.x), lo16_to_float(h.y), hi16_to_float(h.y),
+                        lo16_to_float(h.z), hi16_to_float(h.z), lo16_to_float(h.w), hi16_to_float(h.w)};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.0f) ? g[e] : 0.0f;
+  } else if (a.y_f32) {
+    const float4 p = *reinterpret_cast<const float4*>(a.y_f32 + o), q = *reinterpret_cast<const float4*>(a.y_f32 + o + 4);
+    const float y[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = (y[e] > 0.0f) ? g[e] : 0.0f;
+  }
+}
+
+// Channel-slab layout shared by the reduce and apply kernels: a block of kBnThreads threads covers a slab of
+// `slab` <= 512 channels (blockIdx.y) as slab/8 eight-channel pieces x row groups; every thread keeps ITS eight channels
+// for the whole kernel (row stride = whole rows), so the per-channel constants live in registers and every warp access
+// is a run of whole 128-byte lines.  Two rows per loop iteration keep ~12 16-byte loads in flight per thread.
+constexpr int kBnThreads = 512;
+
+// Per-channel sums of g and g * xhat over all M pixels: row groups of a block are folded in shared memory, one fp64
+// atomic per (block, channel, sum) reaches global memory.  (History: 16 fp64 atomics per THREAD = 310 us per call;
+// 256-thread blocks without unrolling and a serial 8-thread fold = 2.4 TB/s, profiles/r02_bn_bench_v1.log.)
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const BnBwdArgs a, int slab) {
+  __shared__ float red[kBnThreads][17];
+  const int pieces = slab / 8;
   const int piece = threadIdx.x % pieces, rgrp = threadIdx.x / pieces;
-  const int rows_per_block = blockDim.x / pieces;
+  const int rows_per_block = kBnThreads / pieces;
   const bool active = rgrp < rows_per_block;
-  const int c = piece * 8;
+  const int c = blockIdx.y * slab + piece * 8;
   float sg[8], sx[8], mu[8], is[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -88,77 +129,89 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
     mu[e] = a.mean[c + e];
     is[e] = a.invstd[c + e];
   }
-  if (active)
-    for (long long r = static_cast<long long>(blockIdx.x) * rows_per_block + rgrp; r < a.M;
-         r += static_cast<long long>(gridDim.x) * rows_per_block) {
-      const long long o = r * a.C + c;
-      float g[8];
-      bn_bwd_load_g(a, o, g);
-      const float4 z0 = *reinterpret_cast<const float4*>(a.z + o), z1 = *reinterpret_cast<const float4*>(a.z + o + 4);
-      const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+  if (active) {
+    const long long stride = static_cast<long long>(gridDim.x) * rows_per_block;
+    long long r = static_cast<long long>(blockIdx.x) * rows_per_block + rgrp;
+    for (; r + stride < a.M; r += 2 * stride) {
+      const long long o0 = r * a.C + c, o1 = (r + stride) * a.C + c;
+      float g0[8], g1[8];
+      bn_bwd_load_g2(a, o0, g0);
+      bn_bwd_load_g2(a, o1, g1);
+      float z0[8], z1[8];
+      load_z8(a, o0, z0);
+      load_z8(a, o1, z1);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        sg[e] += g[e];
-        sx[e] = fmaf(g[e], (zz[e] - mu[e]) * is[e], sx[e]);
+        sg[e] += g0[e];
+        sx[e] = fmaf(g0[e], (z0[e] - mu[e]) * is[e], sx[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sg[e] += g1[e];
+        sx[e] = fmaf(g1[e], (z1[e] - mu[e]) * is[e], sx[e]);
       }
     }
+    if (r < a.M) {
+      const long long o0 = r * a.C + c;
+      float g0[8], z0[8];
+      bn_bwd_load_g2(a, o0, g0);
+      load_z8(a, o0, z0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sg[e] += g0[e];
+        sx[e] = fmaf(g0[e], (z0[e] - mu[e]) * is[e], sx[e]);
+      }
+    }
+  }
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     red[threadIdx.x][e] = sg[e];
     red[threadIdx.x][8 + e] = sx[e];
   }
   __syncthreads();
-  if (rgrp == 0) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      double tg = 0.0, tx = 0.0;
-      for (int r = 0; r < rows_per_block; ++r) {
-        tg += static_cast<double>(red[r * pieces + piece][e]);
-        tx += static_cast<double>(red[r * pieces + piece][8 + e]);
-      }
-      atomicAdd(a.sums + c + e, tg);
-      atomicAdd(a.sums + a.C + c + e, tx);
-    }
+  // value v of the block's 2 * slab outputs: which = v / slab (0: sum g, 1: sum g xhat), channel cc = v % slab
+  for (int v = threadIdx.x; v < 2 * slab; v += kBnThreads) {
+    const int which = v / slab, cc = v - which * slab;
+    const int pc = cc >> 3, e = (cc & 7) + 8 * which;
+    double t = 0.0;
+    for (int rg = 0; rg < rows_per_block; ++rg) t += static_cast<double>(red[rg * pieces + pc][e]);
+    atomicAdd(a.sums + which * a.C + blockIdx.y * slab + cc, t);
   }
 }
 
-__global__ void bn_bwd_apply_kernel(const BnBwdArgs a) {
-  const long long total8 = a.M * a.C / 8;
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const BnBwdArgs a, int slab) {
+  const int pieces = slab / 8;
+  const int piece = threadIdx.x % pieces, rgrp = threadIdx.x / pieces;
+  const int rows_per_block = kBnThreads / pieces;
+  if (rgrp >= rows_per_block) return;
+  const int c = blockIdx.y * slab + piece * 8;
   const float inv_count = static_cast<float>(1.0 / a.count);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long o = i * 8;
-    const int c = static_cast<int>(o % a.C);
-    float g[8];
-    bn_bwd_load_g(a, o, g);
-    const float4 z0 = *reinterpret_cast<const float4*>(a.z + o), z1 = *reinterpret_cast<const float4*>(a.z + o + 4);
-    const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-    float dz[8];
-    float isv[8], muv[8], gav[8];
-    double s0[8], s1[8];
-    *reinterpret_cast<float4*>(isv) = __ldg(reinterpret_cast<const float4*>(a.invstd + c));
-    *reinterpret_cast<float4*>(isv + 4) = __ldg(reinterpret_cast<const float4*>(a.invstd + c + 4));
-    *reinterpret_cast<float4*>(muv) = __ldg(reinterpret_cast<const float4*>(a.mean + c));
-    *reinterpret_cast<float4*>(muv + 4) = __ldg(reinterpret_cast<const float4*>(a.mean + c + 4));
-    if (a.gamma) {
-      *reinterpret_cast<float4*>(gav) = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
-      *reinterpret_cast<float4*>(gav + 4) = __ldg(reinterpret_cast<const float4*>(a.gamma + c + 4));
-    } else {
+  float mu[8], is[8], ga[8], sgm[8], sxm[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) gav[e] = 1.0f;
-    }
-#pragma unroll
-    for (int e = 0; e < 8; e += 2) {
-      *reinterpret_cast<double2*>(s0 + e) = *reinterpret_cast<const double2*>(a.sums + c + e);
-      *reinterpret_cast<double2*>(s1 + e) = *reinterpret_cast<const double2*>(a.sums + a.C + c + e);
-    }
+  for (int e = 0; e < 8; ++e) {
+    mu[e] = a.mean[c + e];
+    is[e] = a.invstd[c + e];
+    ga[e] = (a.gamma ? a.gamma[c + e] : 1.0f) * is[e];
+    sgm[e] = static_cast<float>(a.sums[c + e]) * inv_count;
+    sxm[e] = static_cast<float>(a.sums[a.C + c + e]) * inv_count;
+  }
+  if (blockIdx.x == 0 && rgrp == 0 && (a.dgamma || a.dbeta)) {
+    // dgamma = param_scale * sum g xhat, dbeta = param_scale * sum g (one writer per channel; formerly a third launch)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float is = isv[e];
-      const float xhat = (zz[e] - muv[e]) * is;
-      const float sgm = static_cast<float>(s0[e]) * inv_count;
-      const float sxm = static_cast<float>(s1[e]) * inv_count;
-      dz[e] = gav[e] * is * (g[e] - sgm - xhat * sxm);
+      const float dg = static_cast<float>(a.sums[a.C + c + e]) * a.param_scale;
+      const float db = static_cast<float>(a.sums[c + e]) * a.param_scale;
+      if (a.dgamma) a.dgamma[c + e] = a.accumulate ? a.dgamma[c + e] + dg : dg;
+      if (a.dbeta) a.dbeta[c + e] = a.accumulate ? a.dbeta[c + e] + db : db;
+    }
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * rows_per_block;
+  auto emit = [&](long long o, const float (&g)[8], const float (&zz)[8]) {
+    float dz[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xhat = (zz[e] - mu[e]) * is[e];
+      dz[e] = ga[e] * (g[e] - sgm[e] - xhat * sxm[e]);
     }
     if (a.dz_hi) {
       uint4 h, l;
@@ -176,6 +229,24 @@ __global__ void bn_bwd_apply_kernel(const BnBwdArgs a) {
       *reinterpret_cast<uint4*>(a.g_hi + o) = h;
       *reinterpret_cast<uint4*>(a.g_lo + o) = l;
     }
+  };
+  long long r = static_cast<long long>(blockIdx.x) * rows_per_block + rgrp;
+  for (; r + stride < a.M; r += 2 * stride) {
+    const long long o0 = r * a.C + c, o1 = (r + stride) * a.C + c;
+    float g0[8], g1[8], z0[8], z1[8];
+    bn_bwd_load_g2(a, o0, g0);
+    bn_bwd_load_g2(a, o1, g1);
+    load_z8(a, o0, z0);
+    load_z8(a, o1, z1);
+    emit(o0, g0, z0);
+    emit(o1, g1, z1);
+  }
+  if (r < a.M) {
+    const long long o0 = r * a.C + c;
+    float g0[8], z0[8];
+    bn_bwd_load_g2(a, o0, g0);
+    load_z8(a, o0, z0);
+    emit(o0, g0, z0);
   }
 }
 
@@ -219,19 +290,39 @@ static int bn_bwd_fill(BnBwdArgs& a, const void* dy_split, const float* dy_f32, 
   return VFS_OK;
 }
 
+// channel slab of a block: the whole C when C <= 512 (C/8 must divide kBnThreads), else 512-channel slabs
+static bool bn_slab(int C, int* slab) {
+  if (C <= 0 || C % 8 != 0) return false;
+  if (C <= 512) {
+    if (kBnThreads % (C / 8) != 0) return false;
+    *slab = C;
+    return true;
+  }
+  if (C % 512 != 0) return false;
+  *slab = 512;
+  return true;
+}
+// grid.x blocks walk the rows (each thread at least ~4 rows, at most 2 blocks per SM in total), grid.y the channel slabs
+static dim3 bn_grid(long long M, int C, int slab) {
+  const int rows_per_block = kBnThreads / (slab / 8);
+  const int slabs = C / slab;
+  long long bx = (M + 4LL * rows_per_block - 1) / (4LL * rows_per_block);
+  const long long cap = (2LL * 148 + slabs - 1) / slabs;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  return dim3(static_cast<unsigned>(bx), static_cast<unsigned>(slabs));
+}
+
 int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32, const float* z,
                   const float* mean, const float* invstd, double* sums, long long M, int C, cudaStream_t s) {
   VFS_REQUIRE((dy_split || dy_f32) && z && mean && invstd && sums, VFS_EINVAL, "bn_bwd_reduce: null argument");
-  VFS_REQUIRE(M > 0 && C % 8 == 0 && C / 8 <= 256, VFS_ESHAPE, "bn_bwd_reduce: C=%d unsupported", C);
+  int slab = 0;
+  VFS_REQUIRE(M > 0 && bn_slab(C, &slab), VFS_ESHAPE, "bn_bwd_reduce: C=%d unsupported", C);
   BnBwdArgs a;
   bn_bwd_fill(a, dy_split, dy_f32, y_split, y_f32, z, mean, invstd, nullptr, sums, 1.0, nullptr, nullptr, nullptr, M,
               C);
-  // every block ends with 2C fp64 atomics: give each thread at least ~8 rows before adding blocks
-  const int rows_per_block = 256 / (C / 8);
-  long long blocks = (M + 8LL * rows_per_block - 1) / (8LL * rows_per_block);
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  if (blocks < 1) blocks = 1;
-  bn_bwd_reduce_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(a);
+  const dim3 grid = bn_grid(M, C, slab);
+  bn_bwd_reduce_kernel<<<grid, kBnThreads, 0, s>>>(a, slab);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }
@@ -242,19 +333,18 @@ int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split,
                  long long M, int C, cudaStream_t s) {
   VFS_REQUIRE((dy_split || dy_f32) && z && mean && invstd && sums && (dz_split || dz_f32), VFS_EINVAL,
               "bn_bwd_apply: null argument");
-  VFS_REQUIRE(M > 0 && C % 8 == 0 && count > 0, VFS_ESHAPE, "bn_bwd_apply: bad shape");
+  int slab = 0;
+  VFS_REQUIRE(M > 0 && count > 0 && bn_slab(C, &slab), VFS_ESHAPE, "bn_bwd_apply: C=%d unsupported", C);
   BnBwdArgs a;
   bn_bwd_fill(a, dy_split, dy_f32, y_split, y_f32, z, mean, invstd, gamma, const_cast<double*>(sums), count, dz_split,
               dz_f32, g_split, M, C);
-  const long long total8 = M * C / 8;
-  long long blocks = (total8 + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  bn_bwd_apply_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(a);
+  a.dgamma = dgamma;
+  a.dbeta = dbeta;
+  a.accumulate = accumulate;
+  a.param_scale = param_scale;
+  const dim3 grid = bn_grid(M, C, slab);
+  bn_bwd_apply_kernel<<<grid, kBnThreads, 0, s>>>(a, slab);
   VFS_CUDA_OK(cudaGetLastError());
-  if (dgamma || dbeta) {
-    bn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, dgamma, dbeta, C, accumulate, param_scale);
-    VFS_CUDA_OK(cudaGetLastError());
-  }
   return VFS_OK;
 }
 
@@ -349,52 +439,141 @@ __global__ void stem_pool_relu_bwd_kernel(const h16* __restrict__ dp_hi, const h
   }
 }
 
-// dW[co][c][r][s] += sum_{n,oy,ox} dz[n,oy,ox,co] * x[n,c,2oy+r-3,2ox+s-3]; block = strip of conv pixels,
-// thread = (co, 37 k values); partial sums reduced with fp32 atomics.
+// dW[co][c][r][s] += sum_{n,oy,ox} dz[n,oy,ox,co] * x[n,c,2oy+r-3,2ox+s-3].
+// Block = one segment of <= 32 conv pixels of one output row per iteration (grid-stride); the 7 input rows the segment
+// touches and its dz vectors are staged in shared memory.  Thread = 4 output channels x 10 filter taps (k = kg + 16 j),
+// i.e. 40 accumulators: per pixel one 16-byte load of dz and 10 broadcast loads of the input patch feed 40 FMAs -- the
+// first version held 1 x 37 accumulators and issued two shared-memory loads per FMA (1.1 ms per call at 64 x 224^2,
+// profiles/r02_train_profile_cfg4_v1.log).  Partial sums are combined with fp32 atomics.
+constexpr int kStemSegMax = 32;
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
                                                          float* __restrict__ dw, int N, int H, int W, int Hc, int Wc,
-                                                         float out_scale) {
-  __shared__ float patch[3][7][70];   // input rows needed by one output row segment of 32 pixels
-  __shared__ float dzs[32][64];
-  const int co = threadIdx.x & 63, kq = threadIdx.x >> 6;  // kq in 0..3 -> k = kq, kq+4, ...
-  float acc[37];
+                                                         int seg_w, float out_scale) {
+  __shared__ float patch[3 * 7 * 72];              // [c][r][pc], pc < 2*seg_w + 5 <= 69 (row pitch 72)
+  __shared__ __align__(16) float dzs[kStemSegMax][64];
+  const int cg = threadIdx.x & 15, kg = threadIdx.x >> 4;   // co = 4 cg .. 4 cg + 3 ; k = kg + 16 j
+  int poff[10];                                             // patch offset of tap j (without the 2*px term)
+  bool kok[10];
 #pragma unroll
-  for (int j = 0; j < 37; ++j) acc[j] = 0.0f;
-  const int segs_per_row = (Wc + 31) / 32;
+  for (int j = 0; j < 10; ++j) {
+    const int k = kg + 16 * j;
+    kok[j] = k < 147;
+    const int kk = kok[j] ? k : 0;
+    const int c = kk / 49, r = (kk / 7) % 7, sx = kk % 7;
+    poff[j] = (c * 7 + r) * 72 + sx;
+  }
+  float acc[10][4];
+#pragma unroll
+  for (int j = 0; j < 10; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.0f;
+  const int segs_per_row = (Wc + seg_w - 1) / seg_w;
+  const int pw = 2 * seg_w + 5;
   const long long total_segs = static_cast<long long>(N) * Hc * segs_per_row;
   for (long long sidx = blockIdx.x; sidx < total_segs; sidx += gridDim.x) {
     const int seg = static_cast<int>(sidx % segs_per_row);
-    long long t = sidx / segs_per_row;
+    const long long t = sidx / segs_per_row;
     const int oy = static_cast<int>(t % Hc);
     const int n = static_cast<int>(t / Hc);
-    const int ox0 = seg * 32;
+    const int ox0 = seg * seg_w;
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * 7 * 70; i += 256) {
-      const int pc = i % 70, r = (i / 70) % 7, c = i / 490;
+    for (int i = threadIdx.x; i < 21 * pw; i += 256) {
+      const int pc = i % pw, cr = i / pw;            // cr = c * 7 + r
+      const int c = cr / 7, r = cr - 7 * c;
       const int iy = 2 * oy + r - 3, ix = 2 * ox0 + pc - 3;
-      patch[c][r][pc] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[(static_cast<size_t>(n) * 3 + c) * H * W + static_cast<size_t>(iy) * W + ix] : 0.0f;
+      patch[cr * 72 + pc] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                                ? __ldg(x + (static_cast<size_t>(n) * 3 + c) * H * W + static_cast<size_t>(iy) * W + ix)
+                                : 0.0f;
     }
-    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
-      const int px = i >> 6, c = i & 63;
-      dzs[px][c] = (ox0 + px < Wc) ? dz[((static_cast<size_t>(n) * Hc + oy) * Wc + ox0 + px) * 64 + c] : 0.0f;
+    const float4* dz4 = reinterpret_cast<const float4*>(dz + ((static_cast<size_t>(n) * Hc + oy) * Wc + ox0) * 64);
+    for (int i = threadIdx.x; i < seg_w * 16; i += 256) {
+      const int px = i >> 4;
+      reinterpret_cast<float4*>(&dzs[0][0])[i] = (ox0 + px < Wc) ? __ldg(dz4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
+#pragma unroll 2
+    for (int px = 0; px < seg_w; ++px) {
+      const float4 d = *reinterpret_cast<const float4*>(&dzs[px][4 * cg]);
 #pragma unroll
-    for (int j = 0; j < 37; ++j) {
-      const int k = kq + 4 * j;
-      if (k < 147) {
-        const int c = k / 49, r = (k / 7) % 7, s = k % 7;
-        float a = acc[j];
-#pragma unroll 8
-        for (int px = 0; px < 32; ++px) a = fmaf(dzs[px][co], patch[c][r][2 * px + s], a);
-        acc[j] = a;
+      for (int j = 0; j < 10; ++j) {
+        const float pv = patch[poff[j] + 2 * px];
+        acc[j][0] = fmaf(d.x, pv, acc[j][0]);
+        acc[j][1] = fmaf(d.y, pv, acc[j][1]);
+        acc[j][2] = fmaf(d.z, pv, acc[j][2]);
+        acc[j][3] = fmaf(d.w, pv, acc[j][3]);
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 37; ++j) {
-    const int k = kq + 4 * j;
-    if (k < 147) atomicAdd(dw + co * 147 + k, acc[j] * out_scale);
+  for (int j = 0; j < 10; ++j) {
+    if (!kok[j]) continue;
+    const int k = kg + 16 * j;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) atomicAdd(dw + (4 * cg + e) * 147 + k, acc[j][e] * out_scale);
+  }
+}
+
+// Max-pool(3,2,1) + ReLU backward as a SCATTER over the pooled grid: thread = (pool position, 8 channels) finds the
+// first maximum of its 3x3 window of a = relu(z*scale + shift) in row-major scan order (torch's arg-max rule) and adds
+// its gradient there when a > 0 (the ReLU mask).  g must be zero-filled by the caller.  The gather form above visits up
+// to 36 activations per conv pixel; this one reads 9 per pool position (a quarter as many positions).
+__global__ void stem_pool_relu_bwd_scatter_kernel(const h16* __restrict__ dp_hi, const h16* __restrict__ dp_lo,
+                                                  const float* __restrict__ z, const float* __restrict__ scale,
+                                                  const float* __restrict__ shift, float* __restrict__ g, int N, int Hc,
+                                                  int Wc, int Hp, int Wp) {
+  const size_t total = static_cast<size_t>(N) * Hp * Wp * 8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int grp = static_cast<int>(i & 7);
+    size_t t = i >> 3;
+    const int px = static_cast<int>(t % Wp);
+    t /= Wp;
+    const int py = static_cast<int>(t % Hp);
+    const int n = static_cast<int>(t / Hp);
+    float sc[8], sh[8], best[8];
+    int arg[8];
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + grp * 8));
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + grp * 8 + 4));
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + grp * 8));
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + grp * 8 + 4));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      best[e] = -1.0f;     // activations are >= 0: the first visited position always wins over the sentinel
+      arg[e] = 0;
+    }
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = 2 * py + dy;
+      if (yy < 0 || yy >= Hc) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = 2 * px + dx;
+        if (xx < 0 || xx >= Wc) continue;
+        const float4* src =
+            reinterpret_cast<const float4*>(z + ((static_cast<size_t>(n) * Hc + yy) * Wc + xx) * 64 + grp * 8);
+        const float4 p = src[0], q = src[1];
+        const float v[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
+        const int code = (dy + 1) * 3 + (dx + 1);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float a = fmaxf(fmaf(v[e], sc[e], sh[e]), 0.0f);
+          if (a > best[e]) {
+            best[e] = a;
+            arg[e] = code;
+          }
+        }
+      }
+    }
+    float d[8];
+    const size_t po = ((static_cast<size_t>(n) * Hp + py) * Wp + px) * 64 + grp * 8;
+    unpack8(*reinterpret_cast<const uint4*>(dp_hi + po), *reinterpret_cast<const uint4*>(dp_lo + po), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (best[e] > 0.0f && d[e] != 0.0f) {
+        const int yy = 2 * py + arg[e] / 3 - 1, xx = 2 * px + arg[e] % 3 - 1;
+        atomicAdd(g + ((static_cast<size_t>(n) * Hc + yy) * Wc + xx) * 64 + grp * 8 + e, d[e]);
+      }
+    }
   }
 }
 
@@ -404,10 +583,23 @@ int stem_pool_relu_bwd(const void* dpool_split, const float* z, const float* sca
   const int Hc = (H + 6 - 7) / 2 + 1, Wc = (W + 6 - 7) / 2 + 1;
   const int Hp = (Hc + 2 - 3) / 2 + 1, Wp = (Wc + 2 - 3) / 2 + 1;
   const h16* hi = reinterpret_cast<const h16*>(dpool_split);
-  const size_t total = static_cast<size_t>(N) * Hc * Wc * 8;
-  const int blocks = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  stem_pool_relu_bwd_kernel<<<blocks, 256, 0, s>>>(hi, hi + static_cast<size_t>(N) * Hp * Wp * 64, z, scale, shift, g, N,
-                                                   Hc, Wc, Hp, Wp);
+  static int gather = -1;   // VFS_STEM_POOL_BWD_GATHER=1 selects the deterministic gather form (debug / comparison)
+  if (gather < 0) {
+    const char* e = getenv("VFS_STEM_POOL_BWD_GATHER");
+    gather = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  if (gather) {
+    const size_t total = static_cast<size_t>(N) * Hc * Wc * 8;
+    const int blocks = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    stem_pool_relu_bwd_kernel<<<blocks, 256, 0, s>>>(hi, hi + static_cast<size_t>(N) * Hp * Wp * 64, z, scale, shift, g,
+                                                     N, Hc, Wc, Hp, Wp);
+  } else {
+    VFS_CUDA_OK(cudaMemsetAsync(g, 0, static_cast<size_t>(N) * Hc * Wc * 64 * sizeof(float), s));
+    const size_t total = static_cast<size_t>(N) * Hp * Wp * 8;
+    const int blocks = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    stem_pool_relu_bwd_scatter_kernel<<<blocks, 256, 0, s>>>(hi, hi + static_cast<size_t>(N) * Hp * Wp * 64, z, scale,
+                                                             shift, g, N, Hc, Wc, Hp, Wp);
+  }
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }
@@ -417,7 +609,9 @@ int stem_wgrad(const float* x, const float* dz, float* dw, int accumulate, float
   VFS_REQUIRE(x && dz && dw, VFS_EINVAL, "stem_wgrad: null argument");
   const int Hc = (H + 6 - 7) / 2 + 1, Wc = (W + 6 - 7) / 2 + 1;
   if (!accumulate) VFS_CUDA_OK(cudaMemsetAsync(dw, 0, 64 * 147 * sizeof(float), s));
-  stem_wgrad_kernel<<<148 * 2, 256, 0, s>>>(x, dz, dw, N, H, W, Hc, Wc, out_scale);
+  const int segs = (Wc + kStemSegMax - 1) / kStemSegMax;
+  const int seg_w = (Wc + segs - 1) / segs;          // e.g. Wc = 112 -> 4 segments of 28 pixels
+  stem_wgrad_kernel<<<148 * 3, 256, 0, s>>>(x, dz, dw, N, H, W, Hc, Wc, seg_w, out_scale);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }

@@ -41,10 +41,15 @@ class BackboneEngine:
         self.check_versions = True  # re-pack when parameters were modified in place / reloaded
         self.events = None          # bench instrumentation: list collecting (tag, cuda event) at phase boundaries
         self.tape = None            # training: list recording what backward needs (set by the autograd wrapper)
+        self._train_pack = None     # persistent packed weights + descriptor table of the multi-tensor pack
         self._graphs = {}           # (input shape, stage, normalize, geometry) -> captured CUDA graph (LRU order)
         self.max_graphs = 8
         self._convs = None
         self._tensors = None
+        self._arena = None          # fp64 statistics arena of the running training pass (forward or backward)
+        self._arena_off = 0
+        self._arena_size = None
+        self._nbt = None            # num_batches_tracked tensors to bump at the end of the pass
 
     # -------------------------------------------------------------- plans
     @staticmethod
@@ -78,6 +83,58 @@ class BackboneEngine:
     def invalidate(self):
         self._plans.clear()
         self._graphs.clear()
+        if self._train_pack is not None:
+            self._train_pack['stamp'] = None     # buffers and descriptor table stay (no H2D copy inside a capture)
+
+    def _refresh_train_weights(self, device):
+        """Training entry: (re)pack the weights of EVERY residual-stage conv -- forward and data-gradient operand
+        layouts -- with ONE launch into persistent buffers (vfs_pack_conv_weights_multi) when any parameter changed
+        since the last pack; ``plan()`` then finds every plan current.  Replaces ~210 per-tensor pack launches per
+        training step."""
+        import ctypes
+        from . import _native as nat
+        tp = self._train_pack
+        # conv weights only: BN running statistics change between the two views of a step without touching the operands
+        stamp = (ops.WEIGHT_EPOCH[0] << 20) + (sum(cm.conv.weight._version for cm in tp['cms']) if tp else 0)
+        if tp is not None and tp['stamp'] == stamp and tp['device'] == device:
+            return
+        if tp is None or tp['device'] != device or tp['ptrs'] != [cm.conv.weight.data_ptr() for cm in tp['cms']]:
+            cms = [m for m in self.net.modules() if isinstance(m, ConvModule) and m.conv.in_channels % 64 == 0]
+            items, bufs, first = [], [], 0
+            for cm in cms:
+                w = cm.conv.weight
+                if w.device != device or w.dtype != torch.float32 or not w.is_contiguous():
+                    raise RuntimeError('vfs_b200 training needs contiguous float32 CUDA conv weights')
+                cout, cin, k, _ = w.shape
+                ws = torch.empty((2, cout, k * k * cin), dtype=torch.float16, device=device)
+                wt = torch.empty((2, cin, k * k * cout), dtype=torch.float16, device=device)
+                bufs.append((ws, wt))
+                nb = int(nat.lib().vfs_pack_blocks(cout, cin, k))
+                for mode, dst in ((0, ws), (1, wt)):
+                    items.append(nat.VfsPackItem(w=w.data_ptr(), dst_split=dst.data_ptr(), Cout=cout, Cin=cin, ksize=k,
+                                                 mode=mode, first_block=first, reserved=0))
+                    first += nb
+            arr = (nat.VfsPackItem * len(items))(*items)
+            table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+            tp = dict(cms=cms, bufs=bufs, table=table, n=len(items), blocks=first, device=device,
+                      ptrs=[cm.conv.weight.data_ptr() for cm in cms], stamp=None)
+            self._train_pack = tp
+        ops.check(nat.lib().vfs_pack_conv_weights_multi(nat.ptr(tp['table']), tp['n'], tp['blocks'],
+                                                         nat.current_stream()), 'pack_conv_weights_multi')
+        for cm, (ws, wt) in zip(tp['cms'], tp['bufs']):
+            p = self._plans.get(id(cm))
+            if p is None:
+                p = _ConvPlan()
+                p.scale = p.shift = None
+                self._plans[id(cm)] = p
+            p.ksize = cm.conv.kernel_size[0]
+            p.w_split, p.wt_split = ws, wt
+            if not (cm.with_norm and cm.norm.training):
+                p.scale, p.shift = fold_bn(cm, device)
+            else:
+                p.scale = p.shift = None
+            p.version = self._version(cm)
+        tp['stamp'] = (ops.WEIGHT_EPOCH[0] << 20) + sum(cm.conv.weight._version for cm in tp['cms'])
 
     def _stamp(self):
         """Cheap global version stamp of every parameter/buffer (in-place updates and reloads bump it)."""
@@ -99,8 +156,9 @@ class BackboneEngine:
             # batch statistics: conv (+ per-channel sums in the epilogue) -> finalise (+ SyncBN all-reduce,
             # running-stat update) -> normalise + residual + ReLU
             assert not want_f32
-            z, stats = ops.conv_stats(xs, p.w_split, k, stride, dil)
-            scale, shift, mean, invstd = ops.bn_finalize(stats, z.numel() // z.shape[-1], cm.norm)
+            z, stats = ops.conv_stats(xs, p.w_split, k, stride, dil,
+                                      stats=self.stats_vec(2 * cm.conv.out_channels, xs.device))
+            scale, shift, mean, invstd = ops.bn_finalize(stats, z.numel() // z.shape[-1], cm.norm, nbt_list=self._nbt)
             y = ops.bn_apply(z, scale, shift, residual, relu)
             if self.tape is not None:
                 self.tape.append(dict(cm=cm, xs=xs, z=z, mean=mean, invstd=invstd, y=y, relu=relu,
@@ -118,8 +176,8 @@ class BackboneEngine:
         p = self.plan(cm, x.device)
         if cm.with_norm and cm.norm.training:
             z = ops.stem_conv_raw(x, p.w_split)
-            stats = ops.channel_stats(z)
-            scale, shift, mean, invstd = ops.bn_finalize(stats, z.numel() // 64, cm.norm)
+            stats = ops.channel_stats(z, stats=self.stats_vec(128, x.device))
+            scale, shift, mean, invstd = ops.bn_finalize(stats, z.numel() // 64, cm.norm, nbt_list=self._nbt)
             y = ops.stem_bn_relu_pool(z, scale, shift, x.shape[2:])
             if self.tape is not None:
                 self.tape.append(dict(cm=cm, stem=True, x=x, z=z, mean=mean, invstd=invstd, scale=scale,
@@ -164,15 +222,45 @@ class BackboneEngine:
         bookkeeping).  ``self.tape`` must be a list; train-mode ConvModules append what their backward needs."""
         assert self.tape is not None
         x = x.contiguous().float()
-        xs = self.stem(x)
-        outs, out_splits = [], []
-        for i, name in enumerate(self.net.res_layers):
-            for block in getattr(self.net, name):
-                xs = block.native_forward(self, xs)
-            if i in out_indices:
-                outs.append(ops.from_split(xs))
-                out_splits.append(xs)
+        self._refresh_train_weights(x.device)
+        self._begin_stats_arena(x.device)
+        try:
+            xs = self.stem(x)
+            outs, out_splits = [], []
+            for i, name in enumerate(self.net.res_layers):
+                for block in getattr(self.net, name):
+                    xs = block.native_forward(self, xs)
+                if i in out_indices:
+                    outs.append(ops.from_split(xs))
+                    out_splits.append(xs)
+        finally:
+            self._end_stats_arena()
         return outs, out_splits
+
+    # -- per-pass arena of zero-initialised fp64 statistics vectors: one fill per pass instead of one per BN layer
+    def _arena_total(self):
+        if self._arena_size is None:
+            self._arena_size = sum(2 * m.num_features for m in self.net.modules() if isinstance(m, _BatchNorm))
+        return self._arena_size
+
+    def _begin_stats_arena(self, device):
+        self._arena = torch.zeros((self._arena_total(), ), dtype=torch.float64, device=device)
+        self._arena_off = 0
+        self._nbt = []
+
+    def _end_stats_arena(self):
+        self._arena = None
+        if self._nbt:
+            torch._foreach_add_(self._nbt, 1)      # one launch for every num_batches_tracked of the pass
+        self._nbt = None
+
+    def stats_vec(self, n, device):
+        """Zeroed fp64 [n] for per-channel sums: a slice of the pass's arena when one is open."""
+        if self._arena is not None and self._arena_off + n <= self._arena.numel():
+            v = self._arena[self._arena_off:self._arena_off + n]
+            self._arena_off += n
+            return v
+        return torch.zeros((n, ), dtype=torch.float64, device=device)
 
     def backward(self, tape, out_splits, grad_outs):
         """Reverse walk over the tape.  Gradients of activations are split tensors scaled by autograd.GRAD_SCALE;
@@ -189,6 +277,14 @@ class BackboneEngine:
             grad[id(xs)] = gs
         pgrads = {}
         inv = 1.0 / S
+        if tape:
+            self._begin_stats_arena(tape[0]['z'].device)
+        try:
+            return self._backward_walk(tape, grad, pgrads, inv)
+        finally:
+            self._end_stats_arena()
+
+    def _backward_walk(self, tape, grad, pgrads, inv):
         for op in reversed(tape):
             dy = grad.pop(id(op['y']), None)
             if dy is None:
@@ -198,7 +294,8 @@ class BackboneEngine:
             if op.get('stem'):
                 g32 = ops.stem_pool_relu_backward(dy, op['z'], op['scale'], op['shift'], op['x'].shape[2:])
                 dz32, _, dgam, dbet = ops.bn_backward(g32, None, op['z'], op['mean'], op['invstd'], bn, dy_is_f32=True,
-                                                      want_f32=True, param_scale=inv)
+                                                      want_f32=True, param_scale=inv,
+                                                      sums=self.stats_vec(128, g32.device))
                 if cm.conv.weight.requires_grad:
                     sink = ops.grad_sink(cm.conv.weight)
                     dw = ops.stem_wgrad(op['x'], dz32, out_scale=inv, out=sink)
@@ -209,7 +306,8 @@ class BackboneEngine:
                 continue
             want_g = op['residual'] is not None
             dz, g, dgam, dbet = ops.bn_backward(dy, op['y'] if op['relu'] else None, op['z'], op['mean'], op['invstd'],
-                                                bn, want_g=want_g, param_scale=inv)
+                                                bn, want_g=want_g, param_scale=inv,
+                                                sums=self.stats_vec(2 * op['z'].shape[-1], dy.device))
             if want_g:
                 if id(op['residual']) in grad:
                     raise NotImplementedError('vfs_b200: unexpected second gradient for a residual input')

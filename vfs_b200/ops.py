@@ -170,13 +170,15 @@ def _const_vec(value, n, device):
     return t
 
 
-def conv_stats(xs, w_split, ksize, stride=1, dilation=1):
-    """Raw conv output (fp32 NHWC) + per-channel [sum | sum of squares] (fp64 [2*Cout]) in one kernel."""
+def conv_stats(xs, w_split, ksize, stride=1, dilation=1, stats=None):
+    """Raw conv output (fp32 NHWC) + per-channel [sum | sum of squares] (fp64 [2*Cout]) in one kernel.  ``stats``: a
+    ZEROED fp64 [2*Cout] vector to accumulate into (the engine hands out slices of one arena per pass)."""
     Cout = w_split.shape[1]
     _, N, H, W, Cin = xs.shape
     Ho, Wo = conv_out_hw(H, W, ksize, stride, dilation)
     z = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=xs.device)
-    stats = torch.zeros((2 * Cout, ), dtype=torch.float64, device=xs.device)
+    if stats is None:
+        stats = torch.zeros((2 * Cout, ), dtype=torch.float64, device=xs.device)
     d = _desc(xs, Cout, ksize, stride, dilation, False)
     check(nat.lib().vfs_conv_stats(ctypes.byref(d), ptr(xs), ptr(w_split), ptr(_const_vec(1, Cout, xs.device)),
                                    ptr(_const_vec(0, Cout, xs.device)), ptr(z), ptr(stats), current_stream()),
@@ -184,10 +186,11 @@ def conv_stats(xs, w_split, ksize, stride=1, dilation=1):
     return z, stats
 
 
-def channel_stats(z):
-    """fp32 [..., C] -> fp64 [2*C] per-channel sum | sum of squares."""
+def channel_stats(z, stats=None):
+    """fp32 [..., C] -> fp64 [2*C] per-channel sum | sum of squares (``stats``: zeroed vector to accumulate into)."""
     C = z.shape[-1]
-    stats = torch.zeros((2 * C, ), dtype=torch.float64, device=z.device)
+    if stats is None:
+        stats = torch.zeros((2 * C, ), dtype=torch.float64, device=z.device)
     check(nat.lib().vfs_channel_stats_f32(ptr(z), ptr(stats), z.numel() // C, C, current_stream()), 'channel_stats')
     return stats
 
@@ -206,7 +209,7 @@ def cross_rank_sum_(t):
     return dist.get_world_size()
 
 
-def bn_finalize(stats, count, bn):
+def bn_finalize(stats, count, bn, nbt_list=None):
     """Batch statistics -> (scale, shift, save_mean, save_invstd); updates bn.running_* like torch.  With
     SyncBatchNorm in an initialised multi-rank process group the statistics are all-reduced first (that IS the
     SyncBN exchange: [sum, sum of squares] is equivalent to torch's gather of mean/invstd/count)."""
@@ -226,7 +229,10 @@ def bn_finalize(stats, count, bn):
                                     float(momentum), float(bn.eps), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), C,
                                     current_stream()), 'bn_finalize')
     if track and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1   # also bumps a tensor version so cached eval-mode folds are refreshed
+        if nbt_list is not None:
+            nbt_list.append(bn.num_batches_tracked)   # bumped by ONE multi-tensor launch at the end of the pass
+        else:
+            bn.num_batches_tracked += 1   # also bumps a tensor version so cached eval-mode folds are refreshed
     return scale, shift, mean, invstd
 
 
@@ -439,7 +445,6 @@ def bn1d_backward(dy, pre, out, gamma, mean, invstd, training, relu, bn=None):
         check(nat.lib().vfs_bn_bwd_apply(None, ptr(dy), None, ptr(yf), ptr(pre), ptr(mean), ptr(invstd), ptr(gamma),
                                          ptr(sums), float(count), None, ptr(dpre), None, ptr(dg), ptr(db), int(sunk),
                                          1.0 / world, M, N, current_stream()), 'bn_bwd_apply')
-        LAUNCHES[0] += 1
         return (dpre, None, None) if sunk else (dpre, dg, db)
     dpre = torch.empty_like(dy)
     dg, db = _bn_param_sinks(bn)
@@ -484,13 +489,14 @@ def _sync_sums(sums, bn):
 
 
 def bn_backward(dy, y_for_relu, z, mean, invstd, bn, want_g=False, dy_is_f32=False, want_f32=False,
-                param_scale=1.0):
+                param_scale=1.0, sums=None):
     """BatchNorm(+ReLU) backward.  ``dy``: split [2,N,H,W,C] (or fp32 NHWC when dy_is_f32), ``y_for_relu``: forward
     output (split) or None, ``z`` raw conv output fp32 NHWC.  Returns (dz, g|None, dgamma, dbeta); dz is split (or
     fp32 when want_f32).  SyncBN: the two per-channel sums are all-reduced across ranks."""
     N, H, W, C = z.shape
     M = N * H * W
-    sums = torch.zeros((2 * C, ), dtype=torch.float64, device=z.device)
+    if sums is None:
+        sums = torch.zeros((2 * C, ), dtype=torch.float64, device=z.device)
     dys, dyf = (None, dy) if dy_is_f32 else (dy, None)
     check(nat.lib().vfs_bn_bwd_reduce(ptr(dys), ptr(dyf), ptr(y_for_relu), None, ptr(z), ptr(mean), ptr(invstd),
                                       ptr(sums), M, C, current_stream()), 'bn_bwd_reduce')
@@ -512,7 +518,6 @@ def bn_backward(dy, y_for_relu, z, mean, invstd, bn, want_g=False, dy_is_f32=Fal
                                      ptr(bn.weight.detach()) if bn.affine else None, ptr(sums), float(count),
                                      None if want_f32 else ptr(dz), ptr(dz) if want_f32 else None, ptr(g), ptr(dg),
                                      ptr(db), acc, float(param_scale), M, C, current_stream()), 'bn_bwd_apply')
-    LAUNCHES[0] += 1
     if sunk:
         return dz, g, None, None     # accumulated into the registered gradient views
     return dz, g, dg, db
