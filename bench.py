@@ -283,8 +283,8 @@ def dp_rank_check(torch, dist, dev, rank, world):
     """Cross-rank correctness of the data-parallel step on the box the bench runs on (world > 1): every rank runs the
     SimSiam step of a small R18 model on ITS shard with SyncBN statistics exchanged and gradients averaged over the
     peer-memory communicator; rank 0 also runs the whole batch alone (cross-rank exchange switched off).  Both must
-    give the same loss and gradients (the definition of SyncBN + DDP).  Criterion: the MEDIAN per-tensor relative error
-    (and a loose bound on the global one): the forward pass differs run to run by fp32 summation order (~2e-6), which
+    give the same loss and gradients (the definition of SyncBN + DDP).  Criterion: loss to 1e-5, global relative L2 error
+    of the gradients < 3e-2 and every tensor < 0.1 (a wrong rank scaling or a missing shard is O(1)): the forward pass differs run to run by fp32 summation order (~2e-6), which
     occasionally flips the ReLU mask of an activation sitting at zero -- on this small model one flipped element moves
     every upstream gradient by ~5e-3 even between two single-process runs (tools/repeat_check.py), so the global L2
     error is bimodal by construction."""
@@ -346,7 +346,8 @@ def dp_rank_check(torch, dist, dev, rank, world):
         loss_err = abs(float(packed[0]) - float(ref_loss))
         res = dict(model='R18 SimSiam, %d clips x 2 views x 96^2 per rank' % per, grad_rel_l2_err=err,
                    median_tensor_rel_err=med, loss_abs_err=loss_err,
-                   ok=bool(loss_err < 1e-5 and err < 3e-2 and (med < 1e-3 or err < 1e-3)))
+                   max_tensor_rel_err=per_tensor[-1],
+                   ok=bool(loss_err < 1e-5 and err < 3e-2 and per_tensor[-1] < 0.1))
     dist.barrier()
     return res
 

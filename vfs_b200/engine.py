@@ -12,7 +12,7 @@ from .mmcv_lite import ConvModule
 
 
 class _ConvPlan:
-    __slots__ = ('w_split', 'wt_split', 'scale', 'shift', 'ksize', 'version')
+    __slots__ = ('w_split', 'wt_split', 'scale', 'shift', 'ksize', 'w_version', 'bn_version')
 
 
 def fold_bn(conv_module, device):
@@ -53,8 +53,16 @@ class BackboneEngine:
 
     # -------------------------------------------------------------- plans
     @staticmethod
-    def _version(cm):
-        v = cm.conv.weight._version + cm.conv.weight.data_ptr() + (ops.WEIGHT_EPOCH[0] << 20)
+    def _w_version(cm):
+        """Validity stamp of the packed weight operands (conv weight only)."""
+        return cm.conv.weight._version + cm.conv.weight.data_ptr() + (ops.WEIGHT_EPOCH[0] << 20)
+
+    @staticmethod
+    def _bn_version(cm):
+        """Validity stamp of the folded eval-mode scale / shift (BN parameters and running statistics, conv bias)."""
+        v = ops.WEIGHT_EPOCH[0] << 20
+        if cm.conv.bias is not None:
+            v += cm.conv.bias._version
         if cm.with_norm:
             bn = cm.norm
             for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked):
@@ -62,22 +70,35 @@ class BackboneEngine:
                     v += t._version + t.data_ptr()
         return v
 
+    @classmethod
+    def _version(cls, cm):
+        return cls._w_version(cm) + cls._bn_version(cm)
+
     def plan(self, cm, device):
+        """Device-side plan of one ConvModule: packed split-fp16 weights (re-packed when the conv weight changed) and
+        the folded eval-mode BN (re-folded when BN tensors changed; skipped while the BN is in batch-statistics mode,
+        whose running-stat updates must not invalidate the weight pack between the two views of a training step)."""
         p = self._plans.get(id(cm))
-        ver = self._version(cm) if (self.check_versions or p is None) else None
-        if p is None or (ver is not None and p.version != ver) or p.w_split.device != device:
+        check = self.check_versions or p is None
+        wv = self._w_version(cm) if check else None
+        if p is None or (wv is not None and p.w_version != wv) or p.w_split.device != device:
             p = _ConvPlan()
             w = cm.conv.weight.detach().to(device=device, dtype=torch.float32).contiguous()
             p.ksize = w.shape[2]
             # residual-stage convs: [2][Cout][k*k*Cin]; the 7x7 stem: [2][64][192] (K = 147 zero-padded)
             p.w_split = ops.pack_conv_weight(w) if w.shape[1] % 64 == 0 else ops.stem_pack_weight(w)
             p.wt_split = None  # dgrad packing, built on first use by the backward pass
-            # the eval-mode fold (~12 tiny fp64 kernels) is only needed when the BN runs on running statistics; a
-            # train-mode step re-plans every layer after each optimizer step and must not pay for it
-            train_bn = cm.with_norm and cm.norm.training
-            p.scale, p.shift = (None, None) if train_bn else fold_bn(cm, device)
-            p.version = ver if ver is not None else self._version(cm)
+            p.scale = p.shift = None
+            p.w_version = wv if wv is not None else self._w_version(cm)
+            p.bn_version = None
             self._plans[id(cm)] = p
+        train_bn = cm.with_norm and cm.norm.training
+        if not train_bn:
+            bv = self._bn_version(cm) if (check or p.bn_version is None) else p.bn_version
+            if p.scale is None or p.bn_version != bv:
+                # (~12 tiny fp64 kernels; a train-mode step never pays for it)
+                p.scale, p.shift = fold_bn(cm, device)
+                p.bn_version = bv
         return p
 
     def invalidate(self):
@@ -127,13 +148,10 @@ class BackboneEngine:
                 p = _ConvPlan()
                 p.scale = p.shift = None
                 self._plans[id(cm)] = p
+                p.bn_version = None
             p.ksize = cm.conv.kernel_size[0]
             p.w_split, p.wt_split = ws, wt
-            if not (cm.with_norm and cm.norm.training):
-                p.scale, p.shift = fold_bn(cm, device)
-            else:
-                p.scale = p.shift = None
-            p.version = self._version(cm)
+            p.w_version = self._w_version(cm)
         tp['stamp'] = (ops.WEIGHT_EPOCH[0] << 20) + sum(cm.conv.weight._version for cm in tp['cms'])
 
     def _stamp(self):
