@@ -108,6 +108,11 @@ int vfs_stem_bn_relu_pool(const void* conv_out_f32_nhwc, const float* scale, con
                           int N, int H, int W, vfs_stream_t s);
 int vfs_conv_stats(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
                    const float* shift, float* out_f32_nhwc, double* stats, vfs_stream_t s);
+/* same with the raw conv output kept as a SPLIT tensor (z_split, split NHWC [N,Ho,Wo,Cout]) written by the TMA
+ * epilogue, the statistics accumulated by its math warps (column sums by warp shuffles): the fast train-mode forward.
+ * ones / zeros: fp32 [Cout] constant vectors. */
+int vfs_conv_stats_split(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* ones,
+                         const float* zeros, void* z_split, double* stats, vfs_stream_t s);
 int vfs_channel_stats_f32(const float* x, double* stats, long long M, int C, vfs_stream_t s);
 int vfs_bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
@@ -115,8 +120,9 @@ int vfs_bn_finalize(double* stats, double count, const float* gamma, const float
 /* y = y*scale[c] + shift[c] (+ReLU) in place on fp32 [M,C]: the apply step of the two-phase (SyncBN) BatchNorm1d */
 int vfs_affine_act_f32(float* y, const float* scale, const float* shift, long long M, int C, int relu,
                        vfs_stream_t s);
-int vfs_bn_apply(const float* z, const float* scale, const float* shift, const void* residual_split,
-                 void* out_split, long long M, int C, int relu, vfs_stream_t s);
+/* z (fp32 [M,C]) or, when z is NULL, z_split (split [2][M][C]) is the raw conv output */
+int vfs_bn_apply(const float* z, const void* z_split, const float* scale, const float* shift,
+                 const void* residual_split, void* out_split, long long M, int C, int relu, vfs_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------
  * Backward of the convolution w.r.t. its input (training): dX = conv_transpose(dZ, W) (+ add), the same tcgen05
@@ -146,12 +152,12 @@ int vfs_conv_wgrad(const VfsConvDesc* d, const void* x_split, const void* dz_spl
  * dY comes as a split tensor or as fp32 (stem); dz goes out split (residual stages) and/or fp32 (stem); g_split
  * (optional) is the masked gradient that also flows into the block's identity branch. */
 int vfs_bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32,
-                      const float* z, const float* mean, const float* invstd, double* sums, long long M, int C,
-                      vfs_stream_t s);
+                      const float* z, const void* z_split, const float* mean, const float* invstd, double* sums,
+                      long long M, int C, vfs_stream_t s);
 int vfs_bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32,
-                     const float* z, const float* mean, const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
-                     float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
-                     long long M, int C, vfs_stream_t s);
+                     const float* z, const void* z_split, const float* mean, const float* invstd, const float* gamma,
+                     const double* sums, double count, void* dz_split, float* dz_f32, void* g_split, float* dgamma,
+                     float* dbeta, int accumulate, float param_scale, long long M, int C, vfs_stream_t s);
 int vfs_relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, long long elems, vfs_stream_t s);
 /* stem backward: max-pool(3,2,1)+ReLU backward onto the raw conv output grid (g fp32 [N,Hc,Wc,64]), and the 7x7
  * weight gradient dw[64,3,7,7] (+)= out_scale * sum dz * x */
@@ -367,6 +373,19 @@ int vfs_cosine_sim_loss(const float* p, const float* z, float* loss, int B, int 
  * pointers. */
 int vfs_frames_u8_to_ncthw_f32(const unsigned char* frames, float* out, long long clips, int T, int H, int W,
                                const float* mean3, const double* stdinv3, int swap_rb, vfs_stream_t s);
+/* Training data feed: RandomResizedCrop's crop (box drawn on the host, augmentations.py:214-262) ->
+ * Resize(scale, keep_ratio=False) = cv2.resize INTER_LINEAR on uint8, bit for bit (:487-597 -> mmcv.imresize) ->
+ * Flip horizontal (:600-711) -> Normalize -> FormatShape('NCTHW'), one kernel per batch.  items: DEVICE array of
+ * clips*T entries (frame f = clip*T + t); frames may differ in size.  out fp32 [clips][3][T][dst_h][dst_w]. */
+typedef struct VfsAugItem {
+  const unsigned char* src; /* uint8 HWC frame [H][W][3] in device memory */
+  int32_t H, W;
+  int32_t crop_x0, crop_y0, crop_w, crop_h; /* crop box inside the frame */
+  int32_t flip;                             /* mirror horizontally after the resize */
+  int32_t reserved;
+} VfsAugItem;
+int vfs_augment_u8_to_ncthw_f32(const VfsAugItem* items_dev, float* out, long long clips, int T, int dst_h, int dst_w,
+                                const float* mean3, const double* stdinv3, int swap_rb, vfs_stream_t s);
 /* ------------------------------------------------------------------------------------------------
  * SiamFC cross-correlation.  Replaces SiamFC._fast_xcorr (projects/siamfc-pytorch/siamfc/heads.py:16-23).
  *   z fp32 NHWC [nz,hz,wz,C], x fp32 NHWC [nx,h,w,C] -> out fp32 [nx,1,h-hz+1,w-wz+1], x[i] pairs with z[i % nz]

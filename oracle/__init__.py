@@ -15,5 +15,5 @@ from .attention import (compute_affinity, masked_attention_efficient, propagate,
 from .head import cosine_sim_loss, simsiam_head_forward, simsiam_loss  # noqa: F401
 from .resnet import resnet_forward, seeded_state_dict  # noqa: F401
 from .siamfc import siam_conv_fc, xcorr  # noqa: F401
-from .pipeline import normalize_format_ncthw  # noqa: F401
+from .pipeline import normalize_format_ncthw, sample_train_augment, train_augment_ncthw  # noqa: F401
 from .tracker import simsiam_forward_train, vanilla_forward_test  # noqa: F401

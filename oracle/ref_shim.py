@@ -207,3 +207,64 @@ def load_reference_siamfc_tracker():
         pkg.__path__ = [os.path.join(REF_ROOT, 'projects', 'siamfc-pytorch', 'siamfc')]
         sys.modules[name] = pkg
     return importlib.import_module(name + '.siamfc_tracker_base')
+
+
+def load_reference_pipelines():
+    """mmaction/datasets/pipelines/{augmentations,formating}.py imported UNCHANGED (RandomResizedCrop, Resize, Flip,
+    Normalize, FormatShape ...).  The three mmcv image helpers they call are restated with the cv2 calls mmcv-full 1.2.1
+    makes (mmcv/image/geometric.py: imresize -> cv2.resize, imflip_ -> cv2.flip in place; photometric.py: imnormalize_
+    -> cv2.subtract / cv2.multiply with float64 row vectors); skimage (absent, used only by an unrelated transform) is
+    stubbed."""
+    import cv2
+    import numpy as np
+    load_reference()
+    mmcv = sys.modules['mmcv']
+    codes = {'nearest': cv2.INTER_NEAREST, 'bilinear': cv2.INTER_LINEAR, 'bicubic': cv2.INTER_CUBIC,
+             'area': cv2.INTER_AREA, 'lanczos': cv2.INTER_LANCZOS4}
+    pillow_imresize = mmcv.imresize
+
+    def imresize(img, size, return_scale=False, interpolation='bilinear', out=None, backend=None):
+        if backend == 'pillow':
+            return pillow_imresize(img, size, interpolation=interpolation, backend='pillow')
+        h, w = img.shape[:2]
+        resized = cv2.resize(img, size, dst=out, interpolation=codes[interpolation])
+        if not return_scale:
+            return resized
+        return resized, size[0] / w, size[1] / h
+
+    def imflip_(img, direction='horizontal'):
+        assert direction in ['horizontal', 'vertical']
+        return cv2.flip(img, 1 if direction == 'horizontal' else 0, img)
+
+    def imnormalize_(img, mean, std, to_rgb=True):
+        assert img.dtype != np.uint8
+        mean = np.float64(mean.reshape(1, -1))
+        stdinv = 1 / np.float64(std.reshape(1, -1))
+        if to_rgb:
+            cv2.cvtColor(img, cv2.COLOR_BGR2RGB, img)
+        cv2.subtract(img, mean, img)
+        cv2.multiply(img, stdinv, img)
+        return img
+
+    def is_tuple_of(seq, expected_type):
+        return isinstance(seq, tuple) and all(isinstance(x, expected_type) for x in seq)
+
+    mmcv.imresize, mmcv.imflip_, mmcv.imnormalize_, mmcv.is_tuple_of = imresize, imflip_, imnormalize_, is_tuple_of
+    mmcv.imflip = lambda img, direction='horizontal': np.flip(img, axis=1 if direction == 'horizontal' else 0)
+    mmcv.rescale_size = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError())
+    mmcv.parallel.DataContainer = type('DataContainer', (), {'__init__': lambda self, data, **k: setattr(self, 'data', data)})
+    mmcv.is_str = lambda x: isinstance(x, str)
+    if 'skimage' not in sys.modules:
+        sk = types.ModuleType('skimage')
+        sk.__path__ = []
+        sku = types.ModuleType('skimage.util')
+        sku.view_as_windows = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError())
+        sk.util = sku
+        sys.modules['skimage'], sys.modules['skimage.util'] = sk, sku
+    ds = os.path.join(REF_ROOT, 'mmaction', 'datasets')
+    _stub_pkg('mmaction.datasets', ds)
+    importlib.import_module('mmaction.datasets.registry')
+    _stub_pkg('mmaction.datasets.pipelines', os.path.join(ds, 'pipelines'))
+    aug = importlib.import_module('mmaction.datasets.pipelines.augmentations')
+    fmt = importlib.import_module('mmaction.datasets.pipelines.formating')
+    return types.SimpleNamespace(augmentations=aug, formating=fmt)

@@ -172,6 +172,31 @@ SIAMFC_CROP_CASES = {
 }
 
 
+# ------------------------------------------------------------------ training data pipeline (crop / resize / flip / normalise)
+NORM_CFG = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375])      # configs/*:46-47
+TRAIN_PIPELINE_CASES = {
+    # the configs' setting: 2 clips of 1 frame, every frame its own crop and flip, 224 x 224
+    'k400_2x1': dict(seed=11, H=180, W=240, num_clips=2, clip_len=1, scale=(224, 224), area_range=(0.2, 1.),
+                     flip_ratio=0.5, same_on_clip=False, same_across_clip=False, to_bgr=False),
+    'clips_2x2_shared': dict(seed=12, H=97, W=131, num_clips=2, clip_len=2, scale=(64, 48), area_range=(0.08, 1.),
+                             flip_ratio=0.5, same_on_clip=True, same_across_clip=False, to_bgr=False),
+    'upscale_bgr': dict(seed=13, H=40, W=56, num_clips=3, clip_len=1, scale=(96, 96), area_range=(0.2, 1.),
+                        flip_ratio=0.7, same_on_clip=False, same_across_clip=False, to_bgr=True),
+}
+
+
+def train_pipeline_frames(c):
+    import numpy as np
+    rng = np.random.RandomState(1000 + c['seed'])
+    n = c['num_clips'] * c['clip_len']
+    yy, xx = np.mgrid[0:c['H'], 0:c['W']]
+    frames = []
+    for i in range(n):
+        smooth = 127 + 90 * np.sin(yy[..., None] / (7.0 + i) + np.arange(3)) * np.cos(xx[..., None] / (11.0 + 2 * i))
+        frames.append(np.clip(smooth + rng.randint(-30, 31, (c['H'], c['W'], 3)), 0, 255).astype(np.uint8))
+    return frames
+
+
 # ------------------------------------------------------------------ SiamFC tracker (init + updates on a moving blob)
 SIAMFC_TRACKER_CASES = {
     # reference default exemplar size (default_config_base.py:6) and the 127 px of BASELINE cfg-5

@@ -150,6 +150,32 @@ def siamfc_tracker_outputs():
     return out
 
 
+def train_pipeline_outputs():
+    """The UNMODIFIED reference pipeline classes RandomResizedCrop -> Resize -> Flip -> Normalize -> FormatShape
+    (configs/*:48-92) on seeded synthetic frames -> tests/golden/train_pipeline_golden.npz."""
+    import random
+    ns = ref_shim.load_reference_pipelines()
+    A, F = ns.augmentations, ns.formating
+    out = {}
+    for name, c in cases.TRAIN_PIPELINE_CASES.items():
+        frames = cases.train_pipeline_frames(c)
+        np.random.seed(c['seed'])
+        random.seed(c['seed'])
+        results = dict(imgs=[f.copy() for f in frames], img_shape=(c['H'], c['W']), original_shape=(c['H'], c['W']),
+                       clip_len=c['clip_len'], num_clips=c['num_clips'], modality='RGB')
+        steps = [A.RandomResizedCrop(area_range=c['area_range'], same_across_clip=c['same_across_clip'],
+                                     same_on_clip=c['same_on_clip']),
+                 A.Resize(scale=c['scale'], keep_ratio=False),
+                 A.Flip(flip_ratio=c['flip_ratio'], same_across_clip=c['same_across_clip'],
+                        same_on_clip=c['same_on_clip']),
+                 A.Normalize(to_bgr=c['to_bgr'], **cases.NORM_CFG),
+                 F.FormatShape(input_format='NCTHW')]
+        for step in steps:
+            results = step(results)
+        out[name] = np.ascontiguousarray(results['imgs'])
+    return out
+
+
 def attention_extra_outputs():
     """masked_attention_efficient of the unmodified reference for arbitrary bool masks / topk=None / rectangular maps
     -> tests/golden/attention_extra_golden.npz."""
@@ -175,6 +201,10 @@ def main():
     crop_path = os.path.join(ROOT, 'tests', 'golden', 'siamfc_crop_golden.npz')
     np.savez_compressed(crop_path, **crops)
     print(f'wrote {crop_path}: {len(crops)} arrays')
+    tp = train_pipeline_outputs()
+    tp_path = os.path.join(ROOT, 'tests', 'golden', 'train_pipeline_golden.npz')
+    np.savez_compressed(tp_path, **tp)
+    print(f'wrote {tp_path}: {len(tp)} arrays', {k: v.shape for k, v in tp.items()})
     trk = siamfc_tracker_outputs()
     trk_path = os.path.join(ROOT, 'tests', 'golden', 'siamfc_tracker_golden.npz')
     np.savez_compressed(trk_path, **trk)

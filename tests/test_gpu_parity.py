@@ -746,6 +746,49 @@ def test_device_normalize_format_matches_pipeline_oracle(to_bgr):
     np.testing.assert_array_equal(got, ref)
 
 
+@pytest.mark.parametrize('name', sorted(cases.TRAIN_PIPELINE_CASES))
+def test_device_train_augment_matches_reference_golden(name):
+    """RandomResizedCrop -> Resize -> Flip -> Normalize -> FormatShape on the device (one kernel) == the output of the
+    unmodified reference pipeline classes for the same seeds, bit for bit (cv2-exact fixed-point bilinear resize)."""
+    import os
+    import random
+    import vfs_b200
+    c = cases.TRAIN_PIPELINE_CASES[name]
+    with np.load(os.path.join(os.path.dirname(__file__), 'golden', 'train_pipeline_golden.npz')) as z:
+        ref = z[name]
+    frames = cases.train_pipeline_frames(c)
+    aug = vfs_b200.DeviceTrainAugment(scale=c['scale'], area_range=c['area_range'], flip_ratio=c['flip_ratio'],
+                                      same_on_clip=c['same_on_clip'], same_across_clip=c['same_across_clip'],
+                                      to_bgr=c['to_bgr'], **cases.NORM_CFG)
+    np.random.seed(c['seed'])
+    random.seed(c['seed'])
+    boxes, flips = aug.sample((c['H'], c['W']), len(frames), c['clip_len'])
+    got = aug(torch.from_numpy(np.stack(frames)).pin_memory(), boxes, flips, clip_len=c['clip_len']).cpu().numpy()
+    assert got.shape == ref.shape and got.dtype == np.float32
+    np.testing.assert_array_equal(got, ref)
+    # frames of different sizes in one launch (K400 videos are not uniform): each against the oracle
+    big = [np.ascontiguousarray(np.pad(f, ((0, 7 * i), (0, 5 * i), (0, 0)), mode='edge')) for i, f in enumerate(frames)]
+    boxes2 = [(1, 2, f.shape[1] - 3, f.shape[0] - 1) for f in big]
+    got2 = aug([torch.from_numpy(f) for f in big], boxes2, flips, clip_len=c['clip_len']).cpu().numpy()
+    exp2 = oracle.train_augment_ncthw(big, boxes2, flips, c['scale'], to_bgr=c['to_bgr'], num_clips=c['num_clips'],
+                                      **cases.NORM_CFG)
+    np.testing.assert_array_equal(got2, exp2)
+
+
+def test_pinned_ring_overlapped_feed_returns_batches_in_order():
+    import vfs_b200
+    ring = vfs_b200.PinnedRing(slots=2)
+    batches = [torch.full((3, 1000), float(i)) for i in range(5)]
+    ring.put(batches[0])
+    for i in range(5):
+        if i + 1 < 5:
+            ring.put(batches[i + 1])            # next batch's H2D overlaps this batch's consumer
+        dev = ring.get()
+        assert dev.is_cuda and float(dev.sum()) == 3000.0 * i
+    with pytest.raises(RuntimeError):
+        ring.get()
+
+
 # --------------------------------------------------------------------------------------------- SiamFC tracker
 def _smooth_maps(gen, S, R):
     """Response-like maps: a few Gaussian bumps + small noise (a pure-noise map makes the arg-max a coin toss)."""
@@ -968,6 +1011,33 @@ def test_simsiam_forward_eval_mode_matches_oracle(name):
     out = model.train_step(dict(imgs=imgs.cuda()), None)
     assert set(out) == {'loss', 'log_vars', 'num_samples'} and out['num_samples'] == imgs.shape[0]
     assert abs(out['log_vars']['loss'] - float(sum(v.mean() for v in exp.values()))) < 1e-3
+
+
+@pytest.mark.parametrize('pair_mode', [0, 1], ids=['one_cta', 'cta_pair'])
+@pytest.mark.parametrize('shape', [(3, 7, 9, 64, 64, 3, 1), (2, 14, 14, 128, 256, 1, 1), (5, 6, 6, 64, 128, 3, 2),
+                                   (4, 8, 8, 256, 512, 1, 1), (9, 5, 5, 64, 256, 3, 1)])
+def test_conv_stats_tma_epilogue_matches_legacy_epilogue(shape, pair_mode):
+    """Train-mode forward conv through the TMA epilogue (split z + statistics from warp-shuffle column sums) against
+    the fp32-output epilogue: same raw conv output (to split precision), same per-channel sum / sum of squares --
+    ragged tiles, stride 2, several N tiles, the CTA-pair form with its phantom tile."""
+    from vfs_b200 import ops
+    N, H, W, Cin, Cout, k, stride = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    xs = ops.to_split(torch.randn(N, Cin, H, W, generator=g).cuda())
+    w = ops.pack_conv_weight((torch.randn(Cout, Cin, k, k, generator=g) * 0.1).cuda())
+    try:
+        ops.conv_set_pair_policy(pair_mode, 1)
+        z_ref, st_ref = ops.conv_stats(xs, w, k, stride, 1)
+        z_new, st_new = ops.conv_stats_split(xs, w, k, stride, 1)
+    finally:
+        ops.conv_set_pair_policy(2, 48)
+    zn = (z_new[0].float() + z_new[1].float())
+    assert tuple(zn.shape) == tuple(z_ref.shape)
+    assert rel_err(zn, z_ref) < 2e-6
+    assert float((st_new - st_ref).abs().max() / st_ref.abs().max()) < 1e-6
+    # and against the values themselves (fp64 sums of the fp32 output)
+    exp = torch.cat([z_ref.double().sum(dim=(0, 1, 2)), (z_ref.double()**2).sum(dim=(0, 1, 2))])
+    assert float((st_new - exp).abs().max() / exp.abs().max()) < 1e-5
 
 
 # --------------------------------------------------------------------------------------------- training step

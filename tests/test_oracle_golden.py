@@ -319,3 +319,56 @@ def test_siamfc_tracker_oracle_bit_exact_vs_live_reference(siamfc_tracker_golden
     for name in cases.SIAMFC_TRACKER_CASES:
         for key, arr in _oracle_siamfc_tracker(name).items():
             np.testing.assert_array_equal(np.asarray(arr, dtype=ref[key].dtype), ref[key], err_msg=key)
+
+
+# --------------------------------------------------------------------------------------------- training data pipeline
+def _oracle_train_pipeline(name):
+    import random
+    c = cases.TRAIN_PIPELINE_CASES[name]
+    frames = cases.train_pipeline_frames(c)
+    np.random.seed(c['seed'])
+    random.seed(c['seed'])
+    boxes, flips = oracle.sample_train_augment((c['H'], c['W']), len(frames), c['clip_len'], c['area_range'],
+                                               (3 / 4, 4 / 3), c['flip_ratio'], c['same_on_clip'],
+                                               c['same_across_clip'])
+    return oracle.train_augment_ncthw(frames, boxes, flips, c['scale'], to_bgr=c['to_bgr'], num_clips=c['num_clips'],
+                                      **cases.NORM_CFG), boxes, flips
+
+
+@pytest.fixture(scope='module')
+def train_pipeline_golden():
+    import os
+    with np.load(os.path.join(os.path.dirname(__file__), 'golden', 'train_pipeline_golden.npz')) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize('name', sorted(cases.TRAIN_PIPELINE_CASES))
+def test_train_pipeline_oracle_matches_reference_golden(train_pipeline_golden, name):
+    """RandomResizedCrop -> Resize -> Flip -> Normalize -> FormatShape: the oracle (same RNG draws, cv2 calls) against
+    the output of the unmodified reference pipeline classes, bit for bit (integer / cv2 arithmetic: no host-ISA
+    dependence)."""
+    got, boxes, flips = _oracle_train_pipeline(name)
+    ref = train_pipeline_golden[name]
+    assert got.shape == ref.shape and got.dtype == ref.dtype == np.float32
+    np.testing.assert_array_equal(got, ref)
+    # the package's own sampler (vfs_b200.pipelines) consumes the generators identically
+    import random
+    from vfs_b200.pipelines import DeviceTrainAugment
+    c = cases.TRAIN_PIPELINE_CASES[name]
+    np.random.seed(c['seed'])
+    random.seed(c['seed'])
+    aug = DeviceTrainAugment(scale=c['scale'], area_range=c['area_range'], flip_ratio=c['flip_ratio'],
+                             same_on_clip=c['same_on_clip'], same_across_clip=c['same_across_clip'],
+                             to_bgr=c['to_bgr'], device='cpu', **cases.NORM_CFG)
+    b2, f2 = aug.sample((c['H'], c['W']), c['num_clips'] * c['clip_len'], c['clip_len'])
+    assert [tuple(int(v) for v in b) for b in b2] == [tuple(b) for b in boxes]
+    assert list(f2) == list(flips)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference tree not present (GPU box)')
+def test_train_pipeline_golden_is_current_vs_live_reference(train_pipeline_golden):
+    from tests.golden import make_golden
+    ref = make_golden.train_pipeline_outputs()
+    assert set(ref) == set(train_pipeline_golden)
+    for k in ref:
+        np.testing.assert_array_equal(ref[k], train_pipeline_golden[k])

@@ -53,7 +53,7 @@ def main():
         sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
 
         def red():
-            nat.lib().vfs_bn_bwd_reduce(ptr(dy), None, ptr(y), None, ptr(z), ptr(mean), ptr(invstd), ptr(sums), M, C,
+            nat.lib().vfs_bn_bwd_reduce(ptr(dy), None, ptr(y), None, ptr(z), None, ptr(mean), ptr(invstd), ptr(sums), M, C,
                                         current_stream())
 
         dz = torch.empty_like(dy)
@@ -62,7 +62,7 @@ def main():
         db = torch.empty(C, device=dev)
 
         def app():
-            nat.lib().vfs_bn_bwd_apply(ptr(dy), None, ptr(y), None, ptr(z), ptr(mean), ptr(invstd), ptr(bn.weight),
+            nat.lib().vfs_bn_bwd_apply(ptr(dy), None, ptr(y), None, ptr(z), None, ptr(mean), ptr(invstd), ptr(bn.weight),
                                        ptr(sums), float(M), ptr(dz), None, ptr(g), ptr(dg), ptr(db), 0, 1.0, M, C,
                                        current_stream())
 

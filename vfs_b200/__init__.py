@@ -4,7 +4,7 @@ mmaction2/mmcv registry + config API.  Importing the package registers ``ResNet`
 (``vfs_b200.registry``) so the reference's ``configs/*.py`` build unchanged through ``build_model``."""
 from . import backbones, heads, losses, trackers  # noqa: F401  (registration side effects)
 from .graphs import GraphedTrainStep  # noqa: F401
-from .pipelines import DeviceNormalizeFormat  # noqa: F401
+from .pipelines import DeviceNormalizeFormat, DeviceTrainAugment, PinnedRing  # noqa: F401
 from .builder import (build_backbone, build_head, build_loss, build_model, build_tracker)  # noqa: F401
 from .mmcv_lite import Config, ConfigDict  # noqa: F401
 from .registry import BACKBONES, HEADS, LOSSES, TRACKERS  # noqa: F401

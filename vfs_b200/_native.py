@@ -22,6 +22,11 @@ class VfsPackItem(ctypes.Structure):
         [(n, ctypes.c_int32) for n in ('Cout', 'Cin', 'ksize', 'mode', 'first_block', 'reserved')]
 
 
+class VfsAugItem(ctypes.Structure):
+    _fields_ = [('src', ctypes.c_void_p)] + \
+        [(n, ctypes.c_int32) for n in ('H', 'W', 'crop_x0', 'crop_y0', 'crop_w', 'crop_h', 'flip', 'reserved')]
+
+
 class VfsAttnDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ('H', 'W', 'C', 'Cv', 'T', 'topk', 'mask_mode', 'radius_y', 'radius_x',
                                               'non_mask_len', 'mode')] + [('temperature', ctypes.c_float)]
@@ -60,9 +65,10 @@ PROTOTYPES = {
     'vfs_conv_wgrad_workspace_bytes': (_sz, [_i, _i, _i]),
     'vfs_conv_wgrad': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _i, _f, _vp]),
     'vfs_affine_act_f32': (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
-    'vfs_bn_bwd_reduce': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
-    'vfs_bn_bwd_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _vp, _vp, _vp, _vp, _vp,
-                              _i, _f, _ll, _i, _vp]),
+    'vfs_bn_bwd_reduce': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
+    'vfs_bn_bwd_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _vp, _vp, _vp, _vp,
+                              _vp, _i, _f, _ll, _i, _vp]),
+    'vfs_conv_stats_split': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'vfs_relu_bwd_split': (_i, [_vp, _vp, _vp, _ll, _vp]),
     'vfs_stem_pool_relu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'vfs_stem_wgrad': (_i, [_vp, _vp, _vp, _i, _f, _i, _i, _i, _vp]),
@@ -86,7 +92,7 @@ PROTOTYPES = {
     'vfs_comm_allreduce_f32': (_i, [_vp, _sz, _sz, _f, _vp]),
     'vfs_channel_stats_f32': (_i, [_vp, _vp, _ll, _i, _vp]),
     'vfs_bn_finalize': (_i, [_vp, ctypes.c_double, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
-    'vfs_bn_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
+    'vfs_bn_apply': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     'vfs_features_to_split': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'vfs_features_to_split_ex': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _vp]),
     'vfs_seg_postprocess_workspace_bytes': (_sz, [_i]),
@@ -112,6 +118,8 @@ PROTOTYPES = {
     'vfs_nchw_to_nhwc_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'vfs_frames_u8_to_ncthw_f32': (_i, [_vp, _vp, _ll, _i, _i, _i, ctypes.POINTER(ctypes.c_float),
                                         ctypes.POINTER(ctypes.c_double), _i, _vp]),
+    'vfs_augment_u8_to_ncthw_f32': (_i, [_vp, _vp, _ll, _i, _i, _i, ctypes.POINTER(ctypes.c_float),
+                                         ctypes.POINTER(ctypes.c_double), _i, _vp]),
     'vfs_xcorr_nhwc': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
 }
 

@@ -92,9 +92,11 @@ int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_spli
                   int accumulate, float out_scale, cudaStream_t stream);
 int affine_act_f32(float* y, const float* scale, const float* shift, long long M, int C, int relu, cudaStream_t s);
 int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32, const float* z,
-                  const float* mean, const float* invstd, double* sums, long long M, int C, cudaStream_t s);
+                  const void* z_split, const float* mean, const float* invstd, double* sums, long long M, int C,
+                  cudaStream_t s);
 int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32, const float* z,
-                 const float* mean, const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
+                 const void* z_split, const float* mean, const float* invstd, const float* gamma, const double* sums,
+                 double count, void* dz_split,
                  float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
                  long long M, int C, cudaStream_t s);
 int relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, long long elems, cudaStream_t s);
@@ -129,8 +131,8 @@ int channel_stats_f32(const float* x, double* stats, long long M, int C, cudaStr
 int bn_finalize(double* stats, double count, const float* gamma, const float* beta, float* running_mean,
                 float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
                 float* save_invstd, int C, cudaStream_t s);
-int bn_apply(const float* z, const float* scale, const float* shift, const void* residual_split, void* out_split,
-             long long M, int C, int relu, cudaStream_t s);
+int bn_apply(const float* z, const void* z_split, const float* scale, const float* shift, const void* residual_split,
+             void* out_split, long long M, int C, int relu, cudaStream_t s);
 int conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
                      const float* shift, const void* residual_split, float* out_f32, cudaStream_t stream);
 int nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, float scale, cudaStream_t s);
@@ -183,6 +185,8 @@ int cosine_sim_loss(const float* p, const float* z, float* loss, int B, int D, i
 int nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W, cudaStream_t s);
 int frames_u8_to_ncthw_f32(const unsigned char* in, float* out, long long clips, int T, int H, int W, const float* mean3,
                            const double* stdinv3, int swap_rb, cudaStream_t s);
+int augment_u8_to_ncthw_f32(const VfsAugItem* items_dev, float* out, long long clips, int T, int dst_h, int dst_w,
+                            const float* mean3, const double* stdinv3, int swap_rb, cudaStream_t s);
 int xcorr_nhwc(const float* z, const float* x, float* out, int nz, int nx, int C, int hz, int wz, int h, int w,
                float out_scale, cudaStream_t s);
 
@@ -265,16 +269,16 @@ int vfs_affine_act_f32(float* y, const float* scale, const float* shift, long lo
   return vfs::affine_act_f32(y, scale, shift, M, C, relu, s);
 }
 int vfs_bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32,
-                      const float* z, const float* mean, const float* invstd, double* sums, long long M, int C,
-                      vfs_stream_t s) {
-  return vfs::bn_bwd_reduce(dy_split, dy_f32, y_split, y_f32, z, mean, invstd, sums, M, C, s);
+                      const float* z, const void* z_split, const float* mean, const float* invstd, double* sums,
+                      long long M, int C, vfs_stream_t s) {
+  return vfs::bn_bwd_reduce(dy_split, dy_f32, y_split, y_f32, z, z_split, mean, invstd, sums, M, C, s);
 }
 int vfs_bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32,
-                     const float* z, const float* mean, const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
-                     float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
-                     long long M, int C, vfs_stream_t s) {
-  return vfs::bn_bwd_apply(dy_split, dy_f32, y_split, y_f32, z, mean, invstd, gamma, sums, count, dz_split, dz_f32, g_split,
-                           dgamma, dbeta, accumulate, param_scale, M, C, s);
+                     const float* z, const void* z_split, const float* mean, const float* invstd, const float* gamma,
+                     const double* sums, double count, void* dz_split, float* dz_f32, void* g_split, float* dgamma,
+                     float* dbeta, int accumulate, float param_scale, long long M, int C, vfs_stream_t s) {
+  return vfs::bn_bwd_apply(dy_split, dy_f32, y_split, y_f32, z, z_split, mean, invstd, gamma, sums, count, dz_split, dz_f32,
+                           g_split, dgamma, dbeta, accumulate, param_scale, M, C, s);
 }
 int vfs_relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, long long elems, vfs_stream_t s) {
   return vfs::relu_bwd_split(dy_split, y_split, g_split, elems, s);
@@ -343,9 +347,13 @@ int vfs_bn_finalize(double* stats, double count, const float* gamma, const float
   return vfs::bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift,
                           save_mean, save_invstd, C, s);
 }
-int vfs_bn_apply(const float* z, const float* scale, const float* shift, const void* residual_split,
-                 void* out_split, long long M, int C, int relu, vfs_stream_t s) {
-  return vfs::bn_apply(z, scale, shift, residual_split, out_split, M, C, relu, s);
+int vfs_bn_apply(const float* z, const void* z_split, const float* scale, const float* shift,
+                 const void* residual_split, void* out_split, long long M, int C, int relu, vfs_stream_t s) {
+  return vfs::bn_apply(z, z_split, scale, shift, residual_split, out_split, M, C, relu, s);
+}
+int vfs_conv_stats_split(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* ones,
+                         const float* zeros, void* z_split, double* stats, vfs_stream_t s) {
+  return vfs::conv_bn_act_tc(d, in_split, w_split, ones, zeros, nullptr, z_split, nullptr, stats, s);
 }
 int vfs_pack_blocks(int Cout, int Cin, int ksize) {
   const long long total = static_cast<long long>(Cout) * Cin * ksize * ksize;
@@ -462,6 +470,10 @@ int vfs_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W
 int vfs_xcorr_nhwc(const float* z, const float* x, float* out, int nz, int nx, int C, int hz, int wz, int h, int w,
                    float out_scale, vfs_stream_t s) {
   return vfs::xcorr_nhwc(z, x, out, nz, nx, C, hz, wz, h, w, out_scale, s);
+}
+int vfs_augment_u8_to_ncthw_f32(const VfsAugItem* items_dev, float* out, long long clips, int T, int dst_h, int dst_w,
+                                const float* mean3, const double* stdinv3, int swap_rb, vfs_stream_t s) {
+  return vfs::augment_u8_to_ncthw_f32(items_dev, out, clips, T, dst_h, dst_w, mean3, stdinv3, swap_rb, s);
 }
 
 }  // extern "C"

@@ -72,7 +72,8 @@ __global__ void bn_finalize_kernel(double* __restrict__ stats, double count, con
 }
 
 // y = z*scale + shift (+res) (relu) -> split; one thread per 8 channels
-__global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale,
+__global__ void bn_apply_kernel(const float* __restrict__ z, const h16* __restrict__ z_hi,
+                                const h16* __restrict__ z_lo, const float* __restrict__ scale,
                                 const float* __restrict__ shift, const h16* __restrict__ res_hi,
                                 const h16* __restrict__ res_lo, h16* __restrict__ out_hi,
                                 h16* __restrict__ out_lo, long long total8, int C, int relu) {
@@ -80,7 +81,17 @@ __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __rest
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long o = i * 8;
     const int c = static_cast<int>(o % C);
-    const float4 a = *reinterpret_cast<const float4*>(z + o), b = *reinterpret_cast<const float4*>(z + o + 4);
+    float4 a, b;
+    if (z != nullptr) {
+      a = *reinterpret_cast<const float4*>(z + o);
+      b = *reinterpret_cast<const float4*>(z + o + 4);
+    } else {   // raw conv output kept as a split tensor (train-mode forward through the TMA epilogue)
+      const uint4 zh = *reinterpret_cast<const uint4*>(z_hi + o), zl = *reinterpret_cast<const uint4*>(z_lo + o);
+      a = make_float4(lo16_to_float(zh.x) + lo16_to_float(zl.x), hi16_to_float(zh.x) + hi16_to_float(zl.x),
+                      lo16_to_float(zh.y) + lo16_to_float(zl.y), hi16_to_float(zh.y) + hi16_to_float(zl.y));
+      b = make_float4(lo16_to_float(zh.z) + lo16_to_float(zl.z), hi16_to_float(zh.z) + hi16_to_float(zl.z),
+                      lo16_to_float(zh.w) + lo16_to_float(zl.w), hi16_to_float(zh.w) + hi16_to_float(zl.w));
+    }
     const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
     const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
     float y[8] = {fmaf(a.x, s0.x, h0.x), fmaf(a.y, s0.y, h0.y), fmaf(a.z, s0.z, h0.z), fmaf(a.w, s0.w, h0.w),
@@ -159,17 +170,18 @@ int bn_finalize(double* stats, double count, const float* gamma, const float* be
   return VFS_OK;
 }
 
-int bn_apply(const float* z, const float* scale, const float* shift, const void* residual_split, void* out_split,
-             long long M, int C, int relu, cudaStream_t s) {
-  VFS_REQUIRE(z && scale && shift && out_split, VFS_EINVAL, "bn_apply: null argument");
+int bn_apply(const float* z, const void* z_split, const float* scale, const float* shift, const void* residual_split,
+             void* out_split, long long M, int C, int relu, cudaStream_t s) {
+  VFS_REQUIRE((z || z_split) && scale && shift && out_split, VFS_EINVAL, "bn_apply: null argument");
   VFS_REQUIRE(M > 0 && C > 0 && C % 8 == 0, VFS_ESHAPE, "bn_apply: C=%d must be a multiple of 8", C);
   const long long total8 = M * C / 8;
   const h16* rh = reinterpret_cast<const h16*>(residual_split);
   h16* oh = reinterpret_cast<h16*>(out_split);
   long long blocks = (total8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  bn_apply_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(z, scale, shift, rh, rh ? rh + M * C : nullptr, oh,
-                                                           oh + M * C, total8, C, relu);
+  const h16* zh = z ? nullptr : reinterpret_cast<const h16*>(z_split);
+  bn_apply_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(z, zh, zh ? zh + M * C : nullptr, scale, shift, rh,
+                                                           rh ? rh + M * C : nullptr, oh, oh + M * C, total8, C, relu);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }

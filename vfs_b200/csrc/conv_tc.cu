@@ -91,7 +91,7 @@ struct TraceCursor {
   }
 };
 
-template <int BN, int STAGES, int NBUF, bool PAIR = false>
+template <int BN, int STAGES, int NBUF, bool PAIR = false, bool STATS = false>
 struct ConvSmem {
   static constexpr int kRowsB = PAIR ? BN / 2 : BN;                       // weight rows this CTA stages
   static constexpr int kTileBBytes = kRowsB * kBlockK * 2;                // one plane of the weight tile
@@ -100,7 +100,7 @@ struct ConvSmem {
   static constexpr int kStagingBytes = (NBUF == 0) ? kBlockM * 64 * 4 : NBUF * kChunkBytes;
   // 8 B x (2*STAGES + 4 pipeline + tmem ptr + 3 x 4 epilogue) <= 200, then (legacy epilogue) 2 x BN fp32 per-tile
   // partial sums of the BatchNorm statistics
-  static constexpr int kBarrierBytes = 256 + (NBUF == 0 ? 2 * BN * 4 : 0);
+  static constexpr int kBarrierBytes = 256 + ((NBUF == 0 || STATS) ? 2 * BN * 4 : 0);
   static constexpr int kTotal = STAGES * kStageBytes + kStagingBytes + kBarrierBytes + 1024;  // +1024 align slack
 };
 
@@ -115,9 +115,45 @@ struct ConvSmem {
 //       (profiles/r01_conv_trace_v7.log: 1093 cycles per K-chunk against an MMA floor of 768).  Only the leader CTA's
 //       warp 1 issues MMAs; its commits are multicast to the barriers of both CTAs; the peer's TMA loads signal the
 //       leader's full barriers; the peer's epilogue releases accumulator stages on the leader's barrier.
-template <int BN, int STAGES, int NBUF, bool RES, bool PAIR = false>
+// Sum over the warp's 32 lanes (accumulator rows) of 8 per-lane values (columns): recursive halving over lane bits
+// 4, 3, 2 (7 shuffles) + a 2-step butterfly; every lane returns the total of column lane >> 2.
+__device__ __forceinline__ float warp_colsum8(float (&v)[8], int lane) {
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4];
+      const float keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2];
+      const float keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+
+// STATS (TMA epilogue only): per-channel sum / sum of squares of the epilogue output over the valid pixels of every
+// tile (train-mode BatchNorm statistics) -- column sums by warp shuffles, combined across the eight math warps in shared
+// memory, one fp64 atomic per channel and tile.  The raw conv output leaves as a split tensor through the TMA store.
+template <int BN, int STAGES, int NBUF, bool RES, bool PAIR = false, bool STATS = false>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
-  using S = ConvSmem<BN, STAGES, NBUF, PAIR>;
+  using S = ConvSmem<BN, STAGES, NBUF, PAIR, STATS>;
+  static_assert(!STATS || (NBUF > 0 && !RES), "statistics ride on the residual-free TMA epilogue");
   static_assert(!RES || NBUF >= 2, "the residual prefetch needs at least two staging buffers");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -374,8 +410,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     int as = 0;
     uint32_t aphase = 0;
     int g = 0;
+    const int et = threadIdx.x - 64;  // 0..255 over the math warps
+    float* s_stat = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
+    if constexpr (STATS) {
+      for (int i = et; i < 2 * BN; i += 256) s_stat[i] = 0.0f;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+    }
     for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
       const int n_tile = tile % p.num_n_tiles;
+      bool row_valid = true;
+      if constexpr (STATS) {   // rows beyond the image (ragged tiles, the phantom tile of an odd pair) do not count
+        const int m_tile = m_tile_of(tile);
+        const int tw_i = m_tile % p.tiles_w;
+        const int t2 = m_tile / p.tiles_w;
+        const int r2 = row / p.tw;
+        const int w = tw_i * p.tw + row % p.tw;
+        const int hh = (t2 % p.tiles_h) * p.th + r2 % p.th;
+        const int n = (t2 / p.tiles_h) * p.tn + r2 / p.th;
+        row_valid = (w < p.Wo) && (hh < p.Ho) && (n < p.N);
+      }
       // pull this tile's scale / shift lines into L1 while the accumulator is still being produced
       if (lane < BN / 16) {
         const float* base = (lane < BN / 32) ? p.scale : p.shift;
@@ -419,6 +472,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         }
         const float* sc_ptr = p.scale + n_tile * BN + c * 64 + ch * 32;
         const float* sh_ptr = p.shift + n_tile * BN + c * 64 + ch * 32;
+        float my_sum = 0.0f, my_sq = 0.0f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 sc0 = __ldg(reinterpret_cast<const float4*>(sc_ptr + 8 * j));
@@ -454,6 +508,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           }
           oh[j] = make_uint4(h2[0], h2[1], h2[2], h2[3]);
           ol[j] = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+          if constexpr (STATS) {
+            float v[8], q[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[2 * e] = row_valid ? y[e].x : 0.0f;
+              v[2 * e + 1] = row_valid ? y[e].y : 0.0f;
+              q[2 * e] = v[2 * e] * v[2 * e];
+              q[2 * e + 1] = v[2 * e + 1] * v[2 * e + 1];
+            }
+            const float cs = warp_colsum8(v, lane), cq = warp_colsum8(q, lane);
+            if ((lane & 3) == j) {   // lane keeps column 8 (lane & 3) + (lane >> 2) of this warp's 32 columns
+              my_sum = cs;
+              my_sq = cq;
+            }
+          }
+        }
+        if constexpr (STATS) {
+          const int col = c * 64 + ch * 32 + 8 * (lane & 3) + (lane >> 2);
+          atomicAdd(s_stat + col, my_sum);
+          atomicAdd(s_stat + BN + col, my_sq);
         }
         tr.mark(11);
         // RES: the landed residual implies the buffer was free; otherwise wait for the store NBUF chunks ago
@@ -469,6 +543,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(staged_bar(b));
         tr.mark(7);
+      }
+      if constexpr (STATS) {
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // every math warp's partial sums of this tile are in
+        if (et < BN) {
+          atomicAdd(p.stat_sum + n_tile * BN + et, static_cast<double>(s_stat[et]));
+          atomicAdd(p.stat_sqsum + n_tile * BN + et, static_cast<double>(s_stat[BN + et]));
+          s_stat[et] = 0.0f;
+          s_stat[BN + et] = 0.0f;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // zeroed before the next tile accumulates
       }
       if (++as == 2) {
         as = 0;
@@ -716,14 +800,14 @@ void conv_pair_policy(int* mode, int* min_tiles) {
 
 // Persistent launch: one CTA per SM (or one CTA pair per TPC) walking the tile list; p.num_m_tiles / num_n_tiles must
 // be final.
-template <int BN, int STAGES, int NBUF, bool RES, bool PAIR = false>
+template <int BN, int STAGES, int NBUF, bool RES, bool PAIR = false, bool STATS = false>
 int launch(ConvKernelParams p, cudaStream_t stream) {
-  using S = ConvSmem<BN, STAGES, NBUF, PAIR>;
+  using S = ConvSmem<BN, STAGES, NBUF, PAIR, STATS>;
   static_assert(S::kTotal <= 232448, "shared memory budget (227 KB) exceeded");
   static_assert(2 * BN <= 512, "two accumulator stages must fit the 512 TMEM columns");
   static bool configured = false;
   if (!configured) {
-    VFS_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, NBUF, RES, PAIR>,
+    VFS_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, NBUF, RES, PAIR, STATS>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
@@ -756,7 +840,7 @@ int launch(ConvKernelParams p, cudaStream_t stream) {
   attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = PAIR ? 2 : 1;
-  VFS_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, NBUF, RES, PAIR>, p));
+  VFS_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, NBUF, RES, PAIR, STATS>, p));
   return VFS_OK;
 }
 
@@ -896,7 +980,11 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
     const char* e = getenv("VFS_CONV_LEGACY_EPILOGUE");
     force_legacy = (e && atoi(e) != 0) ? 1 : 0;
   }
-  const bool legacy = force_legacy || c.out_f32 != nullptr || c.stats != nullptr || c.out_split == nullptr;
+  // (statistics with a split output and no residual ride on the TMA epilogue: the train-mode forward)
+  const bool tma_stats = c.stats != nullptr && c.out_split != nullptr && c.out_f32 == nullptr &&
+                         c.res_split == nullptr && !force_legacy;
+  const bool legacy = force_legacy || c.out_f32 != nullptr || (c.stats != nullptr && !tma_stats) ||
+                      c.out_split == nullptr;
   if (legacy) {
     if (BN == 256) {
       BN = 128;
@@ -947,6 +1035,10 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
           if (BNp == 256) return launch<256, 2, 3, true, true>(p, stream);
           return launch<128, 2, 3, true, true>(p, stream);
         }
+        if (tma_stats) {   // (two stages: the third would not leave room for the per-tile sums)
+          if (BNp == 256) return launch<256, 2, 1, false, true, true>(p, stream);
+          return launch<128, 4, 1, false, true, true>(p, stream);
+        }
         if (BNp == 256) return launch<256, 3, 1, false, true>(p, stream);
         return launch<128, 4, 1, false, true>(p, stream);
       }
@@ -961,6 +1053,16 @@ static int run_spec(const ConvSpec& c, cudaStream_t stream) {
     }
     if (BN == 128) return launch<128, 2, 3, true>(p, stream);
     return launch<64, 2, 3, true>(p, stream);
+  }
+  if (tma_stats) {
+    if (BN == 256) {   // (no room for the per-tile sums next to two 96 KB stages)
+      BN = 128;
+      p.num_n_tiles = c.Nout / 128;
+      int rc = set_weight_map(128);
+      if (rc != VFS_OK) return rc;
+    }
+    if (BN == 128) return launch<128, 3, 1, false, false, true>(p, stream);
+    return launch<64, 4, 1, false, false, true>(p, stream);
   }
   if (BN == 256) return launch<256, 2, 1, false>(p, stream);
   if (BN == 128) return launch<128, 3, 1, false>(p, stream);

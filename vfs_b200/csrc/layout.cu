@@ -297,6 +297,82 @@ __global__ void frames_u8_to_ncthw_kernel(const unsigned char* __restrict__ in, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Training data feed on the device: RandomResizedCrop (the crop box itself is drawn on the host) -> Resize(keep_ratio
+// False, cv2 bilinear) -> Flip(horizontal) -> Normalize -> FormatShape('NCTHW') of the reference's train_pipeline
+// (configs/*:48-92; augmentations.py:171-330, 487-597, 600-711, 711-757) as ONE kernel per batch.
+// The resize is cv2.resize(INTER_LINEAR) on uint8 bit for bit (resize.cpp: fx = float((dx+0.5)*scale-0.5); coefficients
+// saturate_cast<short>(x * 2048); horizontal pass in int32; vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2 >> 2;
+// left/right border columns collapse to one source pixel, rows clamp).  One thread = one output pixel, 3 channels.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cv_linear_coef(int d, double scale, int src_n, bool collapse, int& ofs, int& c0, int& c1) {
+  float f = static_cast<float>((d + 0.5) * scale - 0.5);
+  int s0 = static_cast<int>(floorf(f));
+  f -= static_cast<float>(s0);
+  if (collapse) {   // horizontal axis: outside [0, n-1) the sample is one source pixel
+    if (s0 < 0) { f = 0.0f; s0 = 0; }
+    if (s0 >= src_n - 1) { f = 0.0f; s0 = src_n - 1; }
+  }
+  ofs = s0;
+  c0 = __float2int_rn((1.0f - f) * 2048.0f);
+  c1 = __float2int_rn(f * 2048.0f);
+}
+
+__global__ void augment_u8_to_ncthw_kernel(const VfsAugItem* __restrict__ items, float* __restrict__ out, int T, int dst_h,
+                                           int dst_w, float m0, float m1, float m2, double s0, double s1, double s2,
+                                           int swap_rb) {
+  const int f = blockIdx.y;                       // frame = clip * T + t
+  const VfsAugItem it = items[f];
+  const int clip = f / T, t = f - clip * T;
+  const long long HW = static_cast<long long>(dst_h) * dst_w;
+  const double scale_x = static_cast<double>(it.crop_w) / dst_w, scale_y = static_cast<double>(it.crop_h) / dst_h;
+  const unsigned char* src = it.src + (static_cast<long long>(it.crop_y0) * it.W + it.crop_x0) * 3;
+  const long long row_pitch = static_cast<long long>(it.W) * 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < HW;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int oy = static_cast<int>(i / dst_w), ox = static_cast<int>(i - static_cast<long long>(oy) * dst_w);
+    const int dx = it.flip ? dst_w - 1 - ox : ox;     // Flip runs after Resize: mirrored column of the resized image
+    int xo, a0, a1, yo, b0, b1;
+    cv_linear_coef(dx, scale_x, it.crop_w, true, xo, a0, a1);
+    cv_linear_coef(oy, scale_y, it.crop_h, false, yo, b0, b1);
+    const int x1 = min(xo + 1, it.crop_w - 1);
+    const int y0 = min(max(yo, 0), it.crop_h - 1), y1 = min(max(yo + 1, 0), it.crop_h - 1);
+    const unsigned char* r0 = src + y0 * row_pitch;
+    const unsigned char* r1 = src + y1 * row_pitch;
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int h0 = r0[xo * 3 + c] * a0 + r0[x1 * 3 + c] * a1;
+      const int h1 = r1[xo * 3 + c] * a0 + r1[x1 * 3 + c] * a1;
+      int px = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      px = min(max(px, 0), 255);
+      v[c] = static_cast<float>(px);
+    }
+    auto norm = [](float x, float m, double sinv) {
+      return __double2float_rn(static_cast<double>(__fsub_rn(x, m)) * sinv);
+    };
+    float* dst = out + (static_cast<long long>(clip) * 3 * T + t) * HW + i;
+    const long long plane = static_cast<long long>(T) * HW;
+    dst[0] = norm(swap_rb ? v[2] : v[0], m0, s0);
+    dst[plane] = norm(v[1], m1, s1);
+    dst[2 * plane] = norm(swap_rb ? v[0] : v[2], m2, s2);
+  }
+}
+
+int augment_u8_to_ncthw_f32(const VfsAugItem* items_dev, float* out, long long clips, int T, int dst_h, int dst_w,
+                            const float* mean3, const double* stdinv3, int swap_rb, cudaStream_t s) {
+  VFS_REQUIRE(items_dev && out && mean3 && stdinv3, VFS_EINVAL, "augment_u8_to_ncthw_f32: null argument");
+  VFS_REQUIRE(clips > 0 && T > 0 && dst_h > 0 && dst_w > 0 && clips * T <= 65535, VFS_ESHAPE,
+              "augment_u8_to_ncthw_f32: bad shape (at most 65535 frames per call)");
+  const long long HW = static_cast<long long>(dst_h) * dst_w;
+  int bx = static_cast<int>((HW + 255) / 256);
+  if (bx > 64) bx = 64;
+  augment_u8_to_ncthw_kernel<<<dim3(bx, static_cast<unsigned>(clips * T)), 256, 0, s>>>(
+      items_dev, out, T, dst_h, dst_w, mean3[0], mean3[1], mean3[2], stdinv3[0], stdinv3[1], stdinv3[2], swap_rb);
+  VFS_CUDA_OK(cudaGetLastError());
+  return VFS_OK;
+}
+
 int frames_u8_to_ncthw_f32(const unsigned char* in, float* out, long long clips, int T, int H, int W, const float* mean3,
                            const double* stdinv3, int swap_rb, cudaStream_t s) {
   VFS_REQUIRE(in && out && mean3 && stdinv3, VFS_EINVAL, "frames_u8_to_ncthw_f32: null argument");

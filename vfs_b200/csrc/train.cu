@@ -261,7 +261,7 @@ __global__ void bn_bwd_param_kernel(const double* __restrict__ sums, float* __re
 }
 
 static int bn_bwd_fill(BnBwdArgs& a, const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32,
-                       const float* z,
+                       const float* z, const void* z_split,
                        const float* mean, const float* invstd, const float* gamma, double* sums, double count,
                        void* dz_split, float* dz_f32, void* g_split, long long M, int C) {
   memset(&a, 0, sizeof(a));
@@ -277,6 +277,10 @@ static int bn_bwd_fill(BnBwdArgs& a, const void* dy_split, const float* dy_f32, 
   }
   a.y_f32 = y_f32;
   a.z = z; a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.sums = sums; a.count = count;
+  if (!z && z_split) {
+    a.z_hi = reinterpret_cast<const h16*>(z_split);
+    a.z_lo = a.z_hi + plane;
+  }
   if (dz_split) {
     a.dz_hi = reinterpret_cast<h16*>(dz_split);
     a.dz_lo = a.dz_hi + plane;
@@ -314,13 +318,15 @@ static dim3 bn_grid(long long M, int C, int slab) {
 }
 
 int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32, const float* z,
-                  const float* mean, const float* invstd, double* sums, long long M, int C, cudaStream_t s) {
-  VFS_REQUIRE((dy_split || dy_f32) && z && mean && invstd && sums, VFS_EINVAL, "bn_bwd_reduce: null argument");
+                  const void* z_split, const float* mean, const float* invstd, double* sums, long long M, int C,
+                  cudaStream_t s) {
+  VFS_REQUIRE((dy_split || dy_f32) && (z || z_split) && mean && invstd && sums, VFS_EINVAL,
+              "bn_bwd_reduce: null argument");
   int slab = 0;
   VFS_REQUIRE(M > 0 && bn_slab(C, &slab), VFS_ESHAPE, "bn_bwd_reduce: C=%d unsupported", C);
   BnBwdArgs a;
-  bn_bwd_fill(a, dy_split, dy_f32, y_split, y_f32, z, mean, invstd, nullptr, sums, 1.0, nullptr, nullptr, nullptr, M,
-              C);
+  bn_bwd_fill(a, dy_split, dy_f32, y_split, y_f32, z, z_split, mean, invstd, nullptr, sums, 1.0, nullptr, nullptr,
+              nullptr, M, C);
   const dim3 grid = bn_grid(M, C, slab);
   bn_bwd_reduce_kernel<<<grid, kBnThreads, 0, s>>>(a, slab);
   VFS_CUDA_OK(cudaGetLastError());
@@ -328,16 +334,17 @@ int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split
 }
 
 int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split, const float* y_f32, const float* z,
-                 const float* mean, const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
+                 const void* z_split, const float* mean, const float* invstd, const float* gamma, const double* sums,
+                 double count, void* dz_split,
                  float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
                  long long M, int C, cudaStream_t s) {
-  VFS_REQUIRE((dy_split || dy_f32) && z && mean && invstd && sums && (dz_split || dz_f32), VFS_EINVAL,
+  VFS_REQUIRE((dy_split || dy_f32) && (z || z_split) && mean && invstd && sums && (dz_split || dz_f32), VFS_EINVAL,
               "bn_bwd_apply: null argument");
   int slab = 0;
   VFS_REQUIRE(M > 0 && count > 0 && bn_slab(C, &slab), VFS_ESHAPE, "bn_bwd_apply: C=%d unsupported", C);
   BnBwdArgs a;
-  bn_bwd_fill(a, dy_split, dy_f32, y_split, y_f32, z, mean, invstd, gamma, const_cast<double*>(sums), count, dz_split,
-              dz_f32, g_split, M, C);
+  bn_bwd_fill(a, dy_split, dy_f32, y_split, y_f32, z, z_split, mean, invstd, gamma, const_cast<double*>(sums), count,
+              dz_split, dz_f32, g_split, M, C);
   a.dgamma = dgamma;
   a.dbeta = dbeta;
   a.accumulate = accumulate;

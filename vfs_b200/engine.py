@@ -174,9 +174,11 @@ class BackboneEngine:
             # batch statistics: conv (+ per-channel sums in the epilogue) -> finalise (+ SyncBN all-reduce,
             # running-stat update) -> normalise + residual + ReLU
             assert not want_f32
-            z, stats = ops.conv_stats(xs, p.w_split, k, stride, dil,
-                                      stats=self.stats_vec(2 * cm.conv.out_channels, xs.device))
-            scale, shift, mean, invstd = ops.bn_finalize(stats, z.numel() // z.shape[-1], cm.norm, nbt_list=self._nbt)
+            # (z stays a split tensor: written by the TMA epilogue whose math warps also accumulate the statistics)
+            z, stats = ops.conv_stats_split(xs, p.w_split, k, stride, dil,
+                                            stats=self.stats_vec(2 * cm.conv.out_channels, xs.device))
+            scale, shift, mean, invstd = ops.bn_finalize(stats, z.numel() // (2 * z.shape[-1]), cm.norm,
+                                                         nbt_list=self._nbt)
             y = ops.bn_apply(z, scale, shift, residual, relu)
             if self.tape is not None:
                 self.tape.append(dict(cm=cm, xs=xs, z=z, mean=mean, invstd=invstd, y=y, relu=relu,

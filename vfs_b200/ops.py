@@ -236,13 +236,38 @@ def bn_finalize(stats, count, bn, nbt_list=None):
     return scale, shift, mean, invstd
 
 
+def _z_args(z):
+    """(fp32 pointer, split pointer, (N, H, W, C)) of a raw conv output kept as fp32 NHWC or as a split tensor."""
+    if z.dtype == torch.float16:
+        assert z.ndim == 5 and z.shape[0] == 2
+        return None, ptr(z), tuple(z.shape[1:])
+    return ptr(z), None, tuple(z.shape)
+
+
 def bn_apply(z, scale, shift, residual=None, relu=True):
-    """fp32 NHWC z -> split NHWC relu?(z*scale + shift (+residual))."""
-    N, H, W, C = z.shape
+    """Raw conv output z (fp32 NHWC, or split NHWC from conv_stats_split) -> split NHWC relu?(z*scale + shift
+    (+residual))."""
+    zf, zs, (N, H, W, C) = _z_args(z)
     out = torch.empty((2, N, H, W, C), dtype=torch.float16, device=z.device)
-    check(nat.lib().vfs_bn_apply(ptr(z), ptr(scale), ptr(shift), ptr(residual), ptr(out), N * H * W, C, int(relu),
+    check(nat.lib().vfs_bn_apply(zf, zs, ptr(scale), ptr(shift), ptr(residual), ptr(out), N * H * W, C, int(relu),
                                  current_stream()), 'bn_apply')
     return out
+
+
+def conv_stats_split(xs, w_split, ksize, stride=1, dilation=1, stats=None):
+    """Train-mode forward conv: raw output as a SPLIT tensor [2,N,Ho,Wo,Cout] (TMA epilogue) + per-channel
+    [sum | sum of squares] accumulated into ``stats`` (zeroed fp64 [2*Cout]) by the epilogue's math warps."""
+    Cout = w_split.shape[1]
+    _, N, H, W, Cin = xs.shape
+    Ho, Wo = conv_out_hw(H, W, ksize, stride, dilation)
+    z = torch.empty((2, N, Ho, Wo, Cout), dtype=torch.float16, device=xs.device)
+    if stats is None:
+        stats = torch.zeros((2 * Cout, ), dtype=torch.float64, device=xs.device)
+    d = _desc(xs, Cout, ksize, stride, dilation, False)
+    check(nat.lib().vfs_conv_stats_split(ctypes.byref(d), ptr(xs), ptr(w_split), ptr(_const_vec(1, Cout, xs.device)),
+                                         ptr(_const_vec(0, Cout, xs.device)), ptr(z), ptr(stats), current_stream()),
+          'conv_stats')
+    return z, stats
 
 
 def stem_conv_raw(x, weight):
@@ -432,7 +457,7 @@ def bn1d_backward(dy, pre, out, gamma, mean, invstd, training, relu, bn=None):
     if training and bn is not None and _is_cross_rank_syncbn(bn):
         sums = torch.zeros((2 * N, ), dtype=torch.float64, device=dy.device)
         yf = out if relu else None
-        check(nat.lib().vfs_bn_bwd_reduce(None, ptr(dy), None, ptr(yf), ptr(pre), ptr(mean), ptr(invstd), ptr(sums), M,
+        check(nat.lib().vfs_bn_bwd_reduce(None, ptr(dy), None, ptr(yf), ptr(pre), None, ptr(mean), ptr(invstd), ptr(sums), M,
                                           N, current_stream()), 'bn_bwd_reduce')
         world = _sync_sums(sums, bn)
         count = M * world
@@ -442,7 +467,7 @@ def bn1d_backward(dy, pre, out, gamma, mean, invstd, training, relu, bn=None):
         if not sunk:
             dg = torch.empty((N, ), dtype=torch.float32, device=dy.device)
             db = torch.empty_like(dg)
-        check(nat.lib().vfs_bn_bwd_apply(None, ptr(dy), None, ptr(yf), ptr(pre), ptr(mean), ptr(invstd), ptr(gamma),
+        check(nat.lib().vfs_bn_bwd_apply(None, ptr(dy), None, ptr(yf), ptr(pre), None, ptr(mean), ptr(invstd), ptr(gamma),
                                          ptr(sums), float(count), None, ptr(dpre), None, ptr(dg), ptr(db), int(sunk),
                                          1.0 / world, M, N, current_stream()), 'bn_bwd_apply')
         return (dpre, None, None) if sunk else (dpre, dg, db)
@@ -493,12 +518,12 @@ def bn_backward(dy, y_for_relu, z, mean, invstd, bn, want_g=False, dy_is_f32=Fal
     """BatchNorm(+ReLU) backward.  ``dy``: split [2,N,H,W,C] (or fp32 NHWC when dy_is_f32), ``y_for_relu``: forward
     output (split) or None, ``z`` raw conv output fp32 NHWC.  Returns (dz, g|None, dgamma, dbeta); dz is split (or
     fp32 when want_f32).  SyncBN: the two per-channel sums are all-reduced across ranks."""
-    N, H, W, C = z.shape
+    zf, zs, (N, H, W, C) = _z_args(z)
     M = N * H * W
     if sums is None:
         sums = torch.zeros((2 * C, ), dtype=torch.float64, device=z.device)
     dys, dyf = (None, dy) if dy_is_f32 else (dy, None)
-    check(nat.lib().vfs_bn_bwd_reduce(ptr(dys), ptr(dyf), ptr(y_for_relu), None, ptr(z), ptr(mean), ptr(invstd),
+    check(nat.lib().vfs_bn_bwd_reduce(ptr(dys), ptr(dyf), ptr(y_for_relu), None, zf, zs, ptr(mean), ptr(invstd),
                                       ptr(sums), M, C, current_stream()), 'bn_bwd_reduce')
     world = _sync_sums(sums, bn)
     count = M * world
@@ -514,7 +539,7 @@ def bn_backward(dy, y_for_relu, z, mean, invstd, bn, want_g=False, dy_is_f32=Fal
         dg = torch.empty((C, ), dtype=torch.float32, device=z.device)
         db = torch.empty_like(dg)
         acc = 0
-    check(nat.lib().vfs_bn_bwd_apply(ptr(dys), ptr(dyf), ptr(y_for_relu), None, ptr(z), ptr(mean), ptr(invstd),
+    check(nat.lib().vfs_bn_bwd_apply(ptr(dys), ptr(dyf), ptr(y_for_relu), None, zf, zs, ptr(mean), ptr(invstd),
                                      ptr(bn.weight.detach()) if bn.affine else None, ptr(sums), float(count),
                                      None if want_f32 else ptr(dz), ptr(dz) if want_f32 else None, ptr(g), ptr(dg),
                                      ptr(db), acc, float(param_scale), M, C, current_stream()), 'bn_bwd_apply')

@@ -47,3 +47,138 @@ class DeviceNormalizeFormat:
         check(nat.lib().vfs_frames_u8_to_ncthw_f32(ptr(dev), ptr(out), B, T, H, W, self._mean3, self._stdinv3,
                                                    int(self.to_bgr), current_stream()), 'frames_u8_to_ncthw_f32')
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Training feed: RandomResizedCrop -> Resize -> Flip -> Normalize -> FormatShape of the reference's train_pipeline
+# (configs/*:48-92).  The random decisions (crop boxes, flips) are drawn on the host with the reference's exact sequence of
+# numpy / random calls, so a seeded run reproduces the reference's augmentation; the pixel work is one CUDA kernel per
+# batch (csrc/layout.cu: vfs_augment_u8_to_ncthw_f32 -- cv2-exact bilinear resize of the crop, mirror, normalise).
+# ---------------------------------------------------------------------------------------------------------------------
+def random_crop_bbox(img_shape, area_range=(0.08, 1.0), aspect_ratio_range=(3 / 4, 4 / 3), max_attempts=10):
+    """RandomResizedCrop.get_crop_bbox (augmentations.py:214-262): same draws, same arithmetic."""
+    import random
+    assert 0 < area_range[0] <= area_range[1] <= 1
+    assert 0 < aspect_ratio_range[0] <= aspect_ratio_range[1]
+    img_h, img_w = img_shape
+    area = img_h * img_w
+    min_ar, max_ar = aspect_ratio_range
+    ratios = np.exp(np.random.uniform(np.log(min_ar), np.log(max_ar), size=max_attempts))
+    areas = np.random.uniform(*area_range, size=max_attempts) * area
+    cand_w = np.round(np.sqrt(areas * ratios)).astype(np.int32)
+    cand_h = np.round(np.sqrt(areas / ratios)).astype(np.int32)
+    for crop_w, crop_h in zip(cand_w, cand_h):
+        if crop_h <= img_h and crop_w <= img_w:
+            x0 = random.randint(0, img_w - crop_w)
+            y0 = random.randint(0, img_h - crop_h)
+            return x0, y0, x0 + int(crop_w), y0 + int(crop_h)
+    side = min(img_h, img_w)
+    x0, y0 = (img_w - side) // 2, (img_h - side) // 2
+    return x0, y0, x0 + side, y0 + side
+
+
+class DeviceTrainAugment:
+    """``RandomResizedCrop(area_range, aspect_ratio_range, same_on_clip, same_across_clip)`` +
+    ``Resize(scale, keep_ratio=False)`` + ``Flip(flip_ratio, same_on_clip, same_across_clip)`` + ``Normalize`` +
+    ``FormatShape('NCTHW')``: ``sample()`` draws the per-frame crop boxes and flip flags like the reference pipeline
+    would for one video, ``__call__`` runs the pixels on the device."""
+
+    def __init__(self, mean, std, to_bgr=False, scale=(224, 224), area_range=(0.08, 1.0),
+                 aspect_ratio_range=(3 / 4, 4 / 3), flip_ratio=0.5, same_on_clip=True, same_across_clip=True,
+                 device='cuda'):
+        self.norm = DeviceNormalizeFormat(mean, std, to_bgr, device)
+        self.scale = (int(scale[0]), int(scale[1]))            # (w, h) like mmcv
+        self.area_range, self.aspect_ratio_range = tuple(area_range), tuple(aspect_ratio_range)
+        self.flip_ratio, self.same_on_clip, self.same_across_clip = flip_ratio, same_on_clip, same_across_clip
+        self.device = torch.device(device)
+
+    def sample(self, img_shape, num_frames, clip_len):
+        """Crop boxes [num_frames, 4] (x0, y0, x1, y1) and flip flags [num_frames] of one video's frames, consuming
+        numpy's and random's global generators in the reference's order (all crops, then all flips)."""
+        boxes = []
+        box = random_crop_bbox(img_shape, self.area_range, self.aspect_ratio_range)
+        for i in range(num_frames):
+            is_new_clip = not self.same_across_clip and i % clip_len == 0 and i > 0
+            if not self.same_on_clip or is_new_clip:
+                box = random_crop_bbox(img_shape, self.area_range, self.aspect_ratio_range)
+            boxes.append(box)
+        flips = []
+        flip = bool(np.random.rand() < self.flip_ratio)
+        for i in range(num_frames):
+            is_new_clip = not self.same_across_clip and i % clip_len == 0 and i > 0
+            if not self.same_on_clip or is_new_clip:
+                flip = bool(np.random.rand() < self.flip_ratio)
+            flips.append(flip)
+        return np.asarray(boxes, dtype=np.int32), np.asarray(flips, dtype=bool)
+
+    def __call__(self, frames, boxes, flips, clip_len=1):
+        """``frames``: uint8 tensor [F, H, W, 3] (pinned host or CUDA; F = clips * clip_len) or a list of F uint8
+        [H_i, W_i, 3] tensors of different sizes; ``boxes`` [F, 4], ``flips`` [F] -> fp32 [clips, 3, clip_len, h, w]."""
+        if not torch.cuda.is_available():
+            raise RuntimeError('vfs_b200.DeviceTrainAugment needs a CUDA device (no CPU fallback)')
+        if torch.is_tensor(frames):
+            frames = list(frames.to(self.device, non_blocking=True).contiguous().unbind(0))
+        else:
+            frames = [f.to(self.device, non_blocking=True).contiguous() for f in frames]
+        F = len(frames)
+        assert F % clip_len == 0 and len(boxes) == F and len(flips) == F
+        items = (nat.VfsAugItem * F)()
+        for i, (f, b, fl) in enumerate(zip(frames, boxes, flips)):
+            if f.dtype != torch.uint8 or f.ndim != 3 or f.shape[2] != 3:
+                raise TypeError('DeviceTrainAugment expects uint8 HWC frames')
+            x0, y0, x1, y1 = (int(v) for v in b)
+            if not (0 <= x0 < x1 <= f.shape[1] and 0 <= y0 < y1 <= f.shape[0]):
+                raise ValueError(f'crop box {tuple(b)} outside a {f.shape[0]}x{f.shape[1]} frame')
+            items[i] = nat.VfsAugItem(src=f.data_ptr(), H=f.shape[0], W=f.shape[1], crop_x0=x0, crop_y0=y0,
+                                      crop_w=x1 - x0, crop_h=y1 - y0, flip=int(bool(fl)), reserved=0)
+        table = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).pin_memory().to(self.device,
+                                                                                             non_blocking=True)
+        w, h = self.scale
+        out = torch.empty((F // clip_len, 3, clip_len, h, w), dtype=torch.float32, device=self.device)
+        check(nat.lib().vfs_augment_u8_to_ncthw_f32(ptr(table), ptr(out), F // clip_len, clip_len, h, w,
+                                                    self.norm._mean3, self.norm._stdinv3, int(self.norm.to_bgr),
+                                                    current_stream()), 'augment_u8_to_ncthw_f32')
+        self._keep = (frames, table)      # the kernel reads them asynchronously
+        return out
+
+
+class PinnedRing:
+    """Double-buffered pinned host -> device feed: ``put(host_tensor)`` copies the tensor into the next pinned slot and
+    starts its H2D copy on a side stream; ``get()`` returns the oldest device tensor after making the current stream
+    wait for its copy.  Issuing ``put`` for batch i+1 before running batch i overlaps the PCIe transfer with compute
+    (the reference relies on DataLoader(pin_memory=True) + scatter, one blocking copy per step)."""
+
+    def __init__(self, slots=2, device='cuda'):
+        if not torch.cuda.is_available():
+            raise RuntimeError('vfs_b200.PinnedRing needs a CUDA device')
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [dict(host=None, dev=None, ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(slots)]
+        self._head = self._tail = self._count = 0
+
+    def put(self, t):
+        if self._count == len(self.slots):
+            raise RuntimeError('PinnedRing is full: call get() first')
+        s = self.slots[self._head]
+        if s['host'] is None or s['host'].shape != t.shape or s['host'].dtype != t.dtype:
+            s['host'] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            s['dev'] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        s['free'].synchronize()              # the previous H2D out of this pinned slot has finished
+        s['host'].copy_(t)                   # (a loader would decode straight into the pinned slot)
+        self.stream.wait_event(s['free'])
+        with torch.cuda.stream(self.stream):
+            s['dev'].copy_(s['host'], non_blocking=True)
+            s['ready'].record(self.stream)
+        self._head = (self._head + 1) % len(self.slots)
+        self._count += 1
+
+    def get(self):
+        if self._count == 0:
+            raise RuntimeError('PinnedRing is empty')
+        s = self.slots[self._tail]
+        torch.cuda.current_stream(self.device).wait_event(s['ready'])
+        self._tail = (self._tail + 1) % len(self.slots)
+        self._count -= 1
+        out = s['dev']
+        s['free'].record(torch.cuda.current_stream(self.device))   # consumers enqueued so far come before the reuse
+        return out
