@@ -901,6 +901,39 @@ def test_siamfc_tracker_matches_reference_golden(name):
 
 
 # --------------------------------------------------------------------------------------------- trackers
+def test_vanilla_tracker_multi_level_equals_single_level_runs():
+    """Several backbone out indices / test_cfg.all_blocks (reference vanilla_tracker.py:30-46, 92-93, 196-206): the
+    propagation runs once per feature level and the results are stacked [L,T,H,W]; every level must equal the
+    single-level tracker configured for it, all_blocks' last block of a stage equals that stage's output."""
+    import vfs_b200
+    name = sorted(cases.TRACKER_TEST_CASES)[0]
+    c = cases.TRACKER_TEST_CASES[name]
+    imgs, seg = cases.tracker_test_inputs(c)
+    meta = [dict(original_shape=(c['H'], c['W'], 3))]
+
+    def run(out_indices, **extra):
+        bb = dict(c['backbone'])
+        bb['out_indices'] = out_indices
+        tc = dict(c['test_cfg'])
+        tc['out_indices'] = out_indices
+        tc.update(extra)
+        m = vfs_b200.build_model(dict(type='VanillaTracker', backbone=bb), train_cfg=None,
+                                 test_cfg=vfs_b200.ConfigDict(tc))
+        m.backbone.load_state_dict(oracle.seeded_state_dict(m.backbone, seed=c['seed']))
+        m = m.cuda()
+        m.eval()
+        return np.asarray(m.forward_test(imgs.cuda(), seg.cuda(), meta)[0])
+
+    lvl1, lvl2 = run((1, )), run((2, ))
+    both = run((1, 2))
+    assert both.shape == (2, ) + lvl1.shape
+    np.testing.assert_array_equal(both[0], lvl1)
+    np.testing.assert_array_equal(both[1], lvl2)
+    blocks = run((2, ), all_blocks=True)
+    assert blocks.ndim == 4 and blocks.shape[1:] == lvl2.shape
+    np.testing.assert_array_equal(blocks[-1], lvl2)
+
+
 @pytest.mark.parametrize('name', sorted(cases.TRACKER_TEST_CASES))
 def test_vanilla_tracker_matches_reference_golden(golden, name):
     """End-to-end DAVIS-style propagation through build_model + the config dicts; label maps are argmaxes, so the
@@ -1011,6 +1044,60 @@ def test_simsiam_forward_eval_mode_matches_oracle(name):
     out = model.train_step(dict(imgs=imgs.cuda()), None)
     assert set(out) == {'loss', 'log_vars', 'num_samples'} and out['num_samples'] == imgs.shape[0]
     assert abs(out['log_vars']['loss'] - float(sum(v.mean() for v in exp.values()))) < 1e-3
+
+
+@pytest.mark.parametrize('depth', [18, 50])
+def test_backward_through_eval_mode_bn_matches_oracle_autograd(depth):
+    """norm_eval=True fine-tuning with a frozen prefix (reference resnet.py:593-609, 645-654; the SiamFC / transfer
+    setting): every BatchNorm runs on its running statistics, stage 1 and the stem are frozen, the rest trains.
+    Gradients of all trainable parameters against torch autograd over the CPU oracle, judged against an fp64 run."""
+    from vfs_b200.backbones import ResNet
+    net = ResNet(depth, norm_cfg=dict(type='BN', requires_grad=True), norm_eval=True, frozen_stages=1,
+                 out_indices=(3, ), zero_init_residual=True)
+    sd = oracle.seeded_state_dict(net, seed=60 + depth)
+    # zero-init-residual state on some blocks: dgamma must survive gamma == 0 (it cannot be recovered from y)
+    for k in list(sd):
+        if k.endswith(('layer2.1.conv2.bn.weight', 'layer3.0.conv3.bn.weight', 'layer3.1.conv2.bn.weight')):
+            sd[k] = torch.zeros_like(sd[k])
+    net = _load(net, sd)
+    net.train()                                   # norm_eval keeps the BNs in eval mode, frozen stages stay frozen
+    g = torch.Generator().manual_seed(depth)
+    x = torch.randn(4, 3, 96, 96, generator=g)
+    wout = torch.randn(4, 2048 if depth == 50 else 512, 3, 3, generator=g)
+
+    def oracle_grads(dtype):
+        params = {k: (v.to(dtype).clone() if v.dtype.is_floating_point else v.clone()) for k, v in sd.items()}
+        for k, v in params.items():
+            frozen = k.startswith(('conv1.', 'layer1.')) or 'running' in k or not v.dtype.is_floating_point
+            v.requires_grad_(not frozen)
+        y = oracle.resnet_forward(params, x.to(dtype), depth, out_indices=(3, ), bn_training=False)
+        (y * wout.to(dtype)).sum().backward()
+        return {k: v.grad for k, v in params.items() if v.requires_grad}
+
+    ref, ref64 = oracle_grads(torch.float32), oracle_grads(torch.float64)
+    y = net(x.cuda())
+    (y * wout.cuda()).sum().backward()
+    from vfs_b200 import ops
+    assert ops.overflow_count() == 0
+    got = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    assert set(got) == set(ref), set(got) ^ set(ref)
+    gnorm = max(float(r.norm()) for r in ref64.values())
+    bad = []
+    for k, gk in got.items():
+        r64 = ref64[k]
+        denom = max(float(r64.norm()), 1e-6 * gnorm)
+        mine = float((gk.cpu().double() - r64).norm()) / denom
+        base = float((ref[k].double() - r64).norm()) / denom
+        if mine > max(10 * base, 1e-3):
+            bad.append((k, mine, base))
+    assert not bad, bad[:6]
+    # frozen parameters received nothing, running statistics did not move
+    for k, p in net.named_parameters():
+        if k.startswith(('conv1.', 'layer1.')):
+            assert p.grad is None
+    for k, v in net.state_dict().items():
+        if 'running' in k:
+            assert torch.equal(v.cpu(), sd[k]), k
 
 
 @pytest.mark.parametrize('pair_mode', [0, 1], ids=['one_cta', 'cta_pair'])

@@ -222,13 +222,14 @@ class ResNet(nn.Module):
         return outs[0] if len(outs) == 1 else tuple(outs)
 
     def _check_trainable(self):
-        """The native backward pass covers the reference's pre-training setting (every BN in batch-statistics mode,
-        configs/*:9-11).  Eval-mode BN inside a trainable layer has no backward kernel yet: fail loudly."""
-        for m in self.modules():
-            if isinstance(m, ConvModule) and m.conv.weight.requires_grad and m.with_norm and not m.norm.training:
-                raise NotImplementedError('vfs_b200: backward through an eval-mode BatchNorm (norm_eval / partial_bn '
-                                          'with trainable convs) is not implemented; freeze the layer or call '
-                                          'under torch.no_grad()')
+        """The native backward pass covers batch-statistics BN (the configs' pre-training, configs/*:9-11) and
+        eval-mode BN inside the residual stages (norm_eval / frozen-BN fine-tuning).  The 7x7 stem with an eval-mode BN
+        and trainable parameters has no backward kernel (the reference freezes the stem whenever it freezes anything,
+        resnet.py:593-609): fail loudly."""
+        cm = self.conv1
+        if cm.conv.weight.requires_grad and cm.with_norm and not cm.norm.training:
+            raise NotImplementedError('vfs_b200: backward through the stem with an eval-mode BatchNorm is not '
+                                      'implemented; freeze the stem (frozen_stages >= 0) or keep its BN in train mode')
 
     def forward_block(self, x, index):
         return self.engine.forward(x, block_index=index)[0]

@@ -55,6 +55,10 @@ struct alignas(64) AttnParams {
   int non_mask_len;
   int q_tiles_x, q_tiles_y, splits;
   int num_units;
+  // key tile = kth x ktw pixels (kth * ktw <= 128 accumulator columns; the WIDE form picks the shape that covers the
+  // neighbour window of a query tile with the fewest tiles, e.g. 5 x 25 for radius 18: 18 tiles instead of 24 of 8 x 16)
+  int kth, ktw, kvalid;
+  int stage_tx_bytes;
   float* part_val;  // [problems*T*splits*kAttnEpiHalves][KMAX][HW]
   int* part_idx;
 };
@@ -77,8 +81,8 @@ __device__ __forceinline__ KeyWindow key_window(const AttnParams& p, int qy0, in
     wx1 = min(p.W - 1, min(qx0 + kQTileW - 1, p.W - 1) + ex);
   }
   const int wh = wy1 - w.wy0 + 1, ww = wx1 - w.wx0 + 1;
-  w.ny = wh > 0 ? (wh + kQTileH - 1) / kQTileH : 0;
-  w.nx = ww > 0 ? (ww + kQTileW - 1) / kQTileW : 0;
+  w.ny = wh > 0 ? (wh + p.kth - 1) / p.kth : 0;
+  w.nx = ww > 0 ? (ww + p.ktw - 1) / p.ktw : 0;
   if (w.ny == 0 || w.nx == 0) {
     w.ny = 0;
     w.nx = 1;  // keeps j / nx well defined for the (empty) tile loop
@@ -116,8 +120,8 @@ __device__ __forceinline__ UnitInfo decode_unit(const AttnParams& p, int unit) {
 // its TMA load is pure zero fill and the epilogue skips its columns
 __device__ __forceinline__ void key_tile_origin(const AttnParams& p, const UnitInfo& u, int j, int& ky0, int& kx0) {
   if (j < u.n) {
-    ky0 = u.w.wy0 + (j / u.w.nx) * kQTileH;
-    kx0 = u.w.wx0 + (j % u.w.nx) * kQTileW;
+    ky0 = u.w.wy0 + (j / u.w.nx) * p.kth;
+    kx0 = u.w.wx0 + (j % u.w.nx) * p.ktw;
   } else {
     ky0 = p.H;
     kx0 = 0;
@@ -155,6 +159,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
   const uint32_t scratch_base = bar_base + 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 2 * kNC;  // 2 accumulator stages
+  __shared__ unsigned short s_lut[128];    // accumulator column -> (row << 8 | column) inside the key tile
+  if (threadIdx.x < 128) s_lut[threadIdx.x] = static_cast<unsigned short>(((threadIdx.x / p.ktw) << 8) | (threadIdx.x % p.ktw));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_q);
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
           mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
           if (lane == 0) {
             const uint32_t sq = smem_base + stage * kAttnStageBytes;
-            mbar_arrive_expect_tx(full_bar(stage), kAttnStageBytes);
+            mbar_arrive_expect_tx(full_bar(stage), static_cast<uint32_t>(p.stage_tx_bytes));
             tma_load_5d(sq, &p.tmap_q, full_bar(stage), kc * 64, u.qx0, u.qy0, qframe, 0);
             if (WIDE) {
               // K hi = [tile 2j rows 0..127 | tile 2j+1 rows 128..255], then K lo likewise: one plane per load
@@ -293,48 +299,33 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
         mbar_wait(tfull_bar(as), aphase, 400 + as);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kNC + (WIDE ? 128 * half : 0);
-        // per key tile: squared horizontal distances and in-image flags of the 16 key columns (shared by all rows)
-        int dx2[16];
-        uint32_t xok = 0;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int dx = kx0 + c - qx;
-          dx2[c] = (p.mask_mode == 2) ? abs(dx) : dx * dx;
-          if (kx0 + c < p.W) xok |= (1u << c);
-        }
         const int c_begin = WIDE ? 0 : 64 * half;
-        const int c_end = (jt < u.n) ? (WIDE ? 128 : 64 * half + 64) : c_begin;   // phantom tile: nothing to scan
+        int c_end = (jt < u.n) ? (WIDE ? 128 : 64 * half + 64) : c_begin;   // phantom tile: nothing to scan
+        if (c_end > p.kvalid) c_end = p.kvalid;                               // columns past the tile's pixels: stale rows
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t acc[32];
           tmem_ld_32x32b_x32(t_row + c0, acc);
           tmem_ld_wait();
-          // 32 columns = 2 key rows x 16 key columns.  Two passes: (1) a bit mask of the columns that are inside the
-          // image / radius and beat the list's current k-th value -- a conservative filter, the k-th value only grows;
-          // (2) only those columns go through the sorted insertion, in ascending key order (identical result to
-          // testing every column, but the warp executes the ~40-instruction insertion max-over-lanes(#candidates)
-          // times instead of 32 times).  The dynamic column index of pass 2 reads the slab back from shared memory.
+          // Two passes: (1) a bit mask of the columns that are inside the image / radius and beat the list's current
+          // k-th value -- a conservative filter, the k-th value only grows; (2) only those columns go through the sorted
+          // insertion, in ascending column order (identical result to testing every column, but the warp executes the
+          // ~40-instruction insertion max-over-lanes(#candidates) times instead of 32 times).  The dynamic column index
+          // of pass 2 reads the slab back from shared memory.
           const float thr = tv[KMAX - 1];
           uint32_t cand = 0;
 #pragma unroll
-          for (int rr = 0; rr < 2; ++rr) {   // the slab's two key rows
-            const int ky = ky0 + (c0 >> 4) + rr;
-            const int dy = ky - qy;
-            // circle: dx^2 < r^2 - dy^2; square: |dx| <= rx (and |dy| <= ry); unmasked: always
-            int lim = 0x7fffffff;
-            bool rowok = ky < p.H;
+          for (int cc = 0; cc < 32; ++cc) {
+            const int lut = s_lut[c0 + cc];          // same address for the whole warp: a broadcast read
+            const int ky = ky0 + (lut >> 8), kx = kx0 + (lut & 255);
+            const int dy = ky - qy, dx = kx - qx;
+            bool ok = (c0 + cc < c_end) && (ky < p.H) && (kx < p.W);
             if (masked) {
-              if (p.mask_mode == 1) lim = r2 - dy * dy;
-              else {
-                lim = p.rx + 1;
-                rowok = rowok && (abs(dy) <= p.ry);
-              }
+              // circle: dy^2 + dx^2 < r^2 (integer form of sqrt(dy^2+dx^2) < r, affinity_utils.py:150); square: |dy| <= ry,
+              // |dx| <= rx
+              ok = ok && ((p.mask_mode == 1) ? (dy * dy + dx * dx < r2) : (abs(dy) <= p.ry && abs(dx) <= p.rx));
             }
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const bool ok = rowok && ((xok >> c) & 1u) && (dx2[c] < lim);
-              if (ok && __uint_as_float(acc[rr * 16 + c]) > thr) cand |= (1u << (rr * 16 + c));
-            }
+            if (ok && __uint_as_float(acc[cc]) > thr) cand |= (1u << cc);
           }
           if (__any_sync(0xffffffffu, cand != 0)) {
             const uint32_t slab = scratch_base + static_cast<uint32_t>(half) * (32 * 128 * 4) +
@@ -348,8 +339,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
               float sc;
               asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc) : "r"(slab + jj * 512));
               if (sc > tv[KMAX - 1]) {
-                const int ky = ky0 + ((c0 + jj) >> 4);
-                const int kx = kx0 + ((c0 + jj) & 15);
+                const int lut = s_lut[c0 + jj];
+                const int ky = ky0 + (lut >> 8), kx = kx0 + (lut & 255);
                 topk_insert<KMAX>(tv, ti, sc, u.t * HW + ky * p.W + kx);
               }
             }
@@ -714,8 +705,47 @@ int masked_attention_batched(const VfsAttnDesc* d, int B, const void* q_bank_spl
     if (rc != VFS_OK) return rc;
   }
   const bool wide = attn_use_wide();
+  p.kth = kQTileH;
+  p.ktw = kQTileW;
   if (wide) {
-    const uint32_t box1[5] = {64, kQTileW, kQTileH, 1, 1};
+    // key tile shape covering an interior query tile's window with the fewest tiles (then the widest rows)
+    int wh = d->H, ww = d->W;
+    if (d->mask_mode == 1) {
+      wh = kQTileH + 2 * (d->radius_y - 1);
+      ww = kQTileW + 2 * (d->radius_y - 1);
+    } else if (d->mask_mode == 2) {
+      wh = kQTileH + 2 * d->radius_y;
+      ww = kQTileW + 2 * d->radius_x;
+    }
+    if (wh > d->H) wh = d->H;
+    if (ww > d->W) ww = d->W;
+    if (wh < 1) wh = 1;
+    if (ww < 1) ww = 1;
+    static int fixed = -1;   // VFS_ATTN_KEYTILE=0 keeps the 8 x 16 key tiles (comparison runs)
+    if (fixed < 0) {
+      const char* e = getenv("VFS_ATTN_KEYTILE");
+      fixed = (e && atoi(e) == 0) ? 1 : 0;
+    }
+    if (!fixed) {
+      int best_tiles = ((wh + kQTileH - 1) / kQTileH) * ((ww + kQTileW - 1) / kQTileW);
+      for (int th = 1; th <= 128 && th <= wh; ++th) {
+        int tw = 128 / th;
+        if (tw > ww) tw = ww;
+        if (tw > 256) tw = 256;
+        if (tw < 1) continue;
+        const int tiles = ((wh + th - 1) / th) * ((ww + tw - 1) / tw);
+        if (tiles < best_tiles || (tiles == best_tiles && tw > p.ktw)) {
+          best_tiles = tiles;
+          p.kth = th;
+          p.ktw = tw;
+        }
+      }
+    }
+  }
+  p.kvalid = p.kth * p.ktw;
+  p.stage_tx_bytes = 2 * 16384 + (wide ? 4 * p.kvalid * 128 : 2 * 16384);
+  if (wide) {
+    const uint32_t box1[5] = {64, static_cast<uint32_t>(p.ktw), static_cast<uint32_t>(p.kth), 1, 1};
     const uint64_t dims[5] = {static_cast<uint64_t>(d->C), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
                               static_cast<uint64_t>(k_bank_frames), 2};
     const uint64_t strides[4] = {static_cast<uint64_t>(d->C) * 2, static_cast<uint64_t>(d->W) * d->C * 2,

@@ -7,10 +7,10 @@
 // mapped into every peer), and the exchanges are ordinary kernels on the caller's stream that store into / load from
 // peer memory over NVLink:
 //
-//   comm_allreduce_small   [<= 4096 fp64 | 8192 fp32 values]  SyncBN statistics / logged scalars.  Every rank PUSHES
-//                          its values into a slot of every peer's segment, raises a per-(slot, rank) epoch flag
-//                          there (st.release.sys) and waits for the flags of its own segment (ld.acquire.sys); the
-//                          sum is formed in rank order from local memory, so all ranks hold bit-identical results.
+//   comm_allreduce_small   [<= 4096 values, fp64 or fp32]  SyncBN statistics / logged scalars.  Every rank PUSHES its
+//                          values into a slot of every peer's segment as epoch-tagged 8-byte words (NCCL's LL
+//                          protocol: no fence, no separate flag) and polls the cells of its own segment; the sum is
+//                          formed in rank order from local memory, so all ranks hold bit-identical results.
 //   comm_barrier           flags only.
 //   comm_allreduce_f32     the gradient all-reduce over a range of the segment's data region: barrier, then rank r
 //                          reduces the r-th chunk reading the W peer copies (fixed order), scales it and writes the
@@ -28,8 +28,8 @@ namespace vfs {
 namespace {
 
 constexpr int kMaxWorld = 8;
-constexpr int kSlots = 64;                       // small-exchange slots, used round-robin by the host
-constexpr int kSmallBytes = 32 * 1024;           // per (slot, parity, rank) payload
+constexpr int kSlots = 32;                       // small-exchange slots, used round-robin by the host
+constexpr int kSmallBytes = 64 * 1024;           // per (slot, parity, rank): 4096 cells of 16 bytes
 constexpr unsigned long long kDefaultTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 // control block at the start of every segment
@@ -87,27 +87,62 @@ __device__ __forceinline__ void wait_flag(const CommDev& c, const unsigned int* 
   }
 }
 
+// LL ("low latency") exchange, the protocol NCCL uses for small messages: every 4-byte half of a value travels in an
+// 8-byte word {payload, epoch} -- 8-byte stores are single transactions over NVLink, so the receiver needs no separate
+// flag and the sender no system-scope fence: it polls each word until its epoch tag matches.  One one-way NVLink trip
+// instead of store -> fence (round trip) -> flag store -> flag poll.  A slot holds [parity][rank][n] 16-byte cells
+// {lo32, epoch, hi32, epoch} (fp32 values use the first word only).
+__device__ __forceinline__ void st_ll(uint4* p, unsigned int a, unsigned int b, unsigned int epoch) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(epoch), "r"(b), "r"(epoch)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_ll(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(1024) allreduce_small_kernel(const CommDev c, T* __restrict__ data, int n, int slot) {
   Control* me = ctl(c, c.rank);
   const unsigned int epoch = me->small_epoch[slot] + 1u;   // every thread reads it before thread 0 advances it
   const int parity = static_cast<int>(epoch & 1u);
-  // push my values into every rank's copy of the slot (own copy included)
+  // push my values into every rank's copy of the slot (own copy included), tagged with the epoch
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const T v = data[i];
-    for (int r = 0; r < c.world; ++r) reinterpret_cast<T*>(small_buf(c, r, slot, parity, c.rank))[i] = v;
+    unsigned int lo, hi = 0u;
+    if (sizeof(T) == 8) {
+      const unsigned long long bits = __double_as_longlong(static_cast<double>(data[i]));
+      lo = static_cast<unsigned int>(bits);
+      hi = static_cast<unsigned int>(bits >> 32);
+    } else {
+      lo = __float_as_uint(static_cast<float>(data[i]));
+    }
+    for (int r = 0; r < c.world; ++r)
+      st_ll(reinterpret_cast<uint4*>(small_buf(c, r, slot, parity, c.rank)) + i, lo, hi, epoch);
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < c.world) {
-    st_release_sys(&ctl(c, threadIdx.x)->small_flag[slot][c.rank], epoch);
-    wait_flag(c, &me->small_flag[slot][threadIdx.x], epoch);
-  }
-  __syncthreads();
+  // collect: poll every rank's cell until both tags carry this epoch, sum in rank order (bit-identical on all ranks)
+  const unsigned long long t0 = global_ns();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     T sum = static_cast<T>(0);
-    for (int r = 0; r < c.world; ++r)
-      sum += __ldcg(reinterpret_cast<const T*>(small_buf(c, c.rank, slot, parity, r)) + i);
+    for (int r = 0; r < c.world; ++r) {
+      const uint4* cell = reinterpret_cast<const uint4*>(small_buf(c, c.rank, slot, parity, r)) + i;
+      uint4 v = ld_ll(cell);
+      while (v.y != epoch || v.w != epoch) {
+        if (*reinterpret_cast<volatile unsigned int*>(&me->error)) break;
+        if (global_ns() - t0 > c.timeout_ns) {
+          *reinterpret_cast<volatile unsigned int*>(&me->error) = 1u;
+          break;
+        }
+        v = ld_ll(cell);
+      }
+      if (sizeof(T) == 8)
+        sum += static_cast<T>(__longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(v.z) << 32) | v.x)));
+      else
+        sum += static_cast<T>(__uint_as_float(v.x));
+    }
     data[i] = sum;
   }
   __syncthreads();
@@ -239,9 +274,8 @@ int comm_error(Comm* c) {
 int comm_allreduce_small(Comm* c, void* data, int n, int is_f64, cudaStream_t s) {
   VFS_REQUIRE(c && data, VFS_EINVAL, "comm_allreduce_small: null argument");
   VFS_REQUIRE(c->connected, VFS_EINVAL, "comm_allreduce_small: communicator is not connected");
-  const size_t bytes = static_cast<size_t>(n) * (is_f64 ? 8 : 4);
-  VFS_REQUIRE(n > 0 && bytes <= static_cast<size_t>(kSmallBytes), VFS_ESHAPE,
-              "comm_allreduce_small: %d values exceed the %d-byte slot", n, kSmallBytes);
+  VFS_REQUIRE(n > 0 && static_cast<size_t>(n) * 16 <= static_cast<size_t>(kSmallBytes), VFS_ESHAPE,
+              "comm_allreduce_small: %d values exceed the %d cells of a slot", n, kSmallBytes / 16);
   const int slot = c->next_slot;
   c->next_slot = (c->next_slot + 1) % kSlots;
   int threads = (n + 31) / 32 * 32;

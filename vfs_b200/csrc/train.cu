@@ -51,6 +51,7 @@ struct BnBwdArgs {
   h16* g_hi; h16* g_lo;                // optional: masked gradient for the residual branch
   float* dgamma; float* dbeta;         // optional (apply): parameter gradients = param_scale * sums, written by block row 0
   int accumulate; float param_scale;
+  int eval_mode;                       // BN ran on running statistics: dz = gamma * invstd * g (no batch-statistic terms)
   long long M; int C;
 };
 
@@ -192,10 +193,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const BnBwdArg
     mu[e] = a.mean[c + e];
     is[e] = a.invstd[c + e];
     ga[e] = (a.gamma ? a.gamma[c + e] : 1.0f) * is[e];
-    sgm[e] = static_cast<float>(a.sums[c + e]) * inv_count;
-    sxm[e] = static_cast<float>(a.sums[a.C + c + e]) * inv_count;
+    sgm[e] = a.eval_mode ? 0.0f : static_cast<float>(a.sums[c + e]) * inv_count;
+    sxm[e] = a.eval_mode ? 0.0f : static_cast<float>(a.sums[a.C + c + e]) * inv_count;
   }
-  if (blockIdx.x == 0 && rgrp == 0 && (a.dgamma || a.dbeta)) {
+  if (blockIdx.x == 0 && rgrp == 0 && (a.dgamma || a.dbeta) && a.sums != nullptr) {
     // dgamma = param_scale * sum g xhat, dbeta = param_scale * sum g (one writer per channel; formerly a third launch)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -338,8 +339,12 @@ int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split,
                  double count, void* dz_split,
                  float* dz_f32, void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale,
                  long long M, int C, cudaStream_t s) {
-  VFS_REQUIRE((dy_split || dy_f32) && (z || z_split) && mean && invstd && sums && (dz_split || dz_f32), VFS_EINVAL,
-              "bn_bwd_apply: null argument");
+  // count <= 0 selects the eval-mode form (running statistics): sums may then be NULL when no parameter gradient is
+  // wanted
+  const bool eval_mode = !(count > 0);
+  if (eval_mode) count = 1.0;
+  VFS_REQUIRE((dy_split || dy_f32) && (z || z_split) && mean && invstd && (sums || eval_mode) && (dz_split || dz_f32),
+              VFS_EINVAL, "bn_bwd_apply: null argument");
   int slab = 0;
   VFS_REQUIRE(M > 0 && count > 0 && bn_slab(C, &slab), VFS_ESHAPE, "bn_bwd_apply: C=%d unsupported", C);
   BnBwdArgs a;
@@ -349,6 +354,7 @@ int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split,
   a.dbeta = dbeta;
   a.accumulate = accumulate;
   a.param_scale = param_scale;
+  a.eval_mode = eval_mode ? 1 : 0;
   const dim3 grid = bn_grid(M, C, slab);
   bn_bwd_apply_kernel<<<grid, kBnThreads, 0, s>>>(a, slab);
   VFS_CUDA_OK(cudaGetLastError());

@@ -50,6 +50,7 @@ class BackboneEngine:
         self._arena_off = 0
         self._arena_size = None
         self._nbt = None            # num_batches_tracked tensors to bump at the end of the pass
+        self._region = None         # (requires_grad signature, ids of ConvModules inside the gradient region)
 
     # -------------------------------------------------------------- plans
     @staticmethod
@@ -186,6 +187,19 @@ class BackboneEngine:
             return y
         if p.scale is None:   # planned while the BN was in train mode
             p.scale, p.shift = fold_bn(cm, xs.device)
+        if self.tape is not None and cm.with_norm and not want_f32 and id(cm) in self._grad_region():
+            # Eval-mode BatchNorm inside a taped (training) forward -- norm_eval / frozen-BN fine-tuning, reference
+            # resnet.py:645-654: the raw conv output is kept (the BN backward needs xhat, and dgamma cannot be
+            # recovered from y when gamma == 0, the zero-init-residual state), BN on the running statistics is the folded
+            # scale / shift.  Gradients: dz = gamma * invstd_running * g, dgamma / dbeta from the running-statistics xhat.
+            bn = cm.norm
+            z, _ = ops.conv_bn_act(xs, p.w_split, ops._const_vec(1, cm.conv.out_channels, xs.device),
+                                   ops._const_vec(0, cm.conv.out_channels, xs.device), k, stride, dil, relu=False)
+            y = ops.bn_apply(z, p.scale, p.shift, residual, relu)
+            invstd = torch.rsqrt(bn.running_var.detach().double() + bn.eps).float()
+            self.tape.append(dict(cm=cm, xs=xs, z=z, mean=bn.running_mean.detach().float(), invstd=invstd, y=y,
+                                  relu=relu, residual=residual, k=k, stride=stride, dil=dil, eval_bn=True))
+            return y
         out, out32 = ops.conv_bn_act(xs, p.w_split, p.scale, p.shift, k, stride, dil, relu, residual,
                                      want_split=not want_f32, want_f32=want_f32)
         return out32 if want_f32 else out
@@ -257,6 +271,21 @@ class BackboneEngine:
             self._end_stats_arena()
         return outs, out_splits
 
+    def _grad_region(self):
+        """ids of the ConvModules a gradient has to flow through: everything from the first residual block that owns a
+        trainable parameter onwards (frozen_stages freezes a prefix of the network, resnet.py:593-609; layers in front of
+        the first trainable one keep the fused inference kernel and stay off the tape)."""
+        key = tuple(p.requires_grad for p in self.net.parameters())
+        if self._region is None or self._region[0] != key:
+            ids, started = set(), False
+            for name in self.net.res_layers:
+                for block in getattr(self.net, name):
+                    started = started or any(p.requires_grad for p in block.parameters())
+                    if started:
+                        ids.update(id(m) for m in block.modules() if isinstance(m, ConvModule))
+            self._region = (key, ids)
+        return self._region[1]
+
     # -- per-pass arena of zero-initialised fp64 statistics vectors: one fill per pass instead of one per BN layer
     def _arena_total(self):
         if self._arena_size is None:
@@ -327,7 +356,8 @@ class BackboneEngine:
             want_g = op['residual'] is not None
             dz, g, dgam, dbet = ops.bn_backward(dy, op['y'] if op['relu'] else None, op['z'], op['mean'], op['invstd'],
                                                 bn, want_g=want_g, param_scale=inv,
-                                                sums=self.stats_vec(2 * op['z'].shape[-1], dy.device))
+                                                sums=self.stats_vec(2 * op['z'].shape[-1], dy.device),
+                                                eval_mode=op.get('eval_bn', False))
             if want_g:
                 if id(op['residual']) in grad:
                     raise NotImplementedError('vfs_b200: unexpected second gradient for a residual input')
@@ -365,6 +395,25 @@ class BackboneEngine:
         xs = self.run_stages(xs, stage)
         self._mark('convs_end')
         return xs
+
+    def forward_split_taps(self, x, stages, all_blocks=False):
+        """Split-format features of several tap points from one pass: the outputs of the stages in ``stages``, or
+        with ``all_blocks`` of every residual block inside those stages (VanillaTracker.extract_feat_test,
+        vanilla_tracker.py:30-46)."""
+        if not x.is_cuda:
+            raise RuntimeError('vfs_b200 backbone needs a CUDA tensor: the B200 path has no CPU fallback')
+        xs = self.stem(x.contiguous().float())
+        outs = []
+        for i, name in enumerate(self.net.res_layers):
+            if i > max(stages):
+                break
+            for block in getattr(self.net, name):
+                xs = block.native_forward(self, xs)
+                if all_blocks and i in stages:
+                    outs.append(xs)
+            if not all_blocks and i in stages:
+                outs.append(xs)
+        return outs
 
     def run_stages(self, xs, stage):
         """Residual stages 0..``stage`` on a split NHWC tensor (all tcgen05 conv launches)."""

@@ -514,7 +514,7 @@ def _sync_sums(sums, bn):
 
 
 def bn_backward(dy, y_for_relu, z, mean, invstd, bn, want_g=False, dy_is_f32=False, want_f32=False,
-                param_scale=1.0, sums=None):
+                param_scale=1.0, sums=None, eval_mode=False):
     """BatchNorm(+ReLU) backward.  ``dy``: split [2,N,H,W,C] (or fp32 NHWC when dy_is_f32), ``y_for_relu``: forward
     output (split) or None, ``z`` raw conv output fp32 NHWC.  Returns (dz, g|None, dgamma, dbeta); dz is split (or
     fp32 when want_f32).  SyncBN: the two per-channel sums are all-reduced across ranks."""
@@ -523,10 +523,19 @@ def bn_backward(dy, y_for_relu, z, mean, invstd, bn, want_g=False, dy_is_f32=Fal
     if sums is None:
         sums = torch.zeros((2 * C, ), dtype=torch.float64, device=z.device)
     dys, dyf = (None, dy) if dy_is_f32 else (dy, None)
-    check(nat.lib().vfs_bn_bwd_reduce(ptr(dys), ptr(dyf), ptr(y_for_relu), None, zf, zs, ptr(mean), ptr(invstd),
-                                      ptr(sums), M, C, current_stream()), 'bn_bwd_reduce')
-    world = _sync_sums(sums, bn)
-    count = M * world
+    need_param = bn.affine and bn.weight.requires_grad
+    if eval_mode:
+        # BN on running statistics (norm_eval / frozen-BN fine-tuning): no batch-statistic terms, nothing to exchange
+        # between ranks; the two sums are only needed for dgamma / dbeta
+        if need_param:
+            check(nat.lib().vfs_bn_bwd_reduce(ptr(dys), ptr(dyf), ptr(y_for_relu), None, zf, zs, ptr(mean), ptr(invstd),
+                                              ptr(sums), M, C, current_stream()), 'bn_bwd_reduce')
+        world, count = 1, 0.0
+    else:
+        check(nat.lib().vfs_bn_bwd_reduce(ptr(dys), ptr(dyf), ptr(y_for_relu), None, zf, zs, ptr(mean), ptr(invstd),
+                                          ptr(sums), M, C, current_stream()), 'bn_bwd_reduce')
+        world = _sync_sums(sums, bn)
+        count = M * world
     # dgamma/dbeta come out of the all-reduced sums, i.e. already summed over ranks; the data-parallel gradient
     # all-reduce averages parameter gradients afterwards, so hand it this rank's 1/world share.
     param_scale = param_scale / world
@@ -535,12 +544,16 @@ def bn_backward(dy, y_for_relu, z, mean, invstd, bn, want_g=False, dy_is_f32=Fal
     g = torch.empty((2, N, H, W, C), dtype=torch.float16, device=z.device) if want_g else None
     dg, db, acc = (grad_sink(bn.weight), grad_sink(bn.bias), 1) if bn.affine else (None, None, 0)
     sunk = dg is not None and db is not None
-    if not sunk:
+    if eval_mode and not need_param:
+        dg = db = None
+        sunk, acc = True, 0
+    elif not sunk:
         dg = torch.empty((C, ), dtype=torch.float32, device=z.device)
         db = torch.empty_like(dg)
         acc = 0
     check(nat.lib().vfs_bn_bwd_apply(ptr(dys), ptr(dyf), ptr(y_for_relu), None, zf, zs, ptr(mean), ptr(invstd),
-                                     ptr(bn.weight.detach()) if bn.affine else None, ptr(sums), float(count),
+                                     ptr(bn.weight.detach()) if bn.affine else None,
+                                     ptr(sums) if (not eval_mode or need_param) else None, float(count),
                                      None if want_f32 else ptr(dz), ptr(dz) if want_f32 else None, ptr(g), ptr(dg),
                                      ptr(db), acc, float(param_scale), M, C, current_stream()), 'bn_bwd_apply')
     if sunk:

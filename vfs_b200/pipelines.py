@@ -145,16 +145,25 @@ class DeviceTrainAugment:
 class PinnedRing:
     """Double-buffered pinned host -> device feed: ``put(host_tensor)`` copies the tensor into the next pinned slot and
     starts its H2D copy on a side stream; ``get()`` returns the oldest device tensor after making the current stream
-    wait for its copy.  Issuing ``put`` for batch i+1 before running batch i overlaps the PCIe transfer with compute
-    (the reference relies on DataLoader(pin_memory=True) + scatter, one blocking copy per step)."""
+    wait for its copy.  Calling ``put`` for batch i+1 right after ``get`` of batch i -- before enqueuing batch i's
+    kernels -- overlaps the PCIe transfer of i+1 with the compute of i (the reference relies on
+    DataLoader(pin_memory=True) + scatter: one blocking copy per step).
+
+    Slot life cycle: the pinned buffer may be rewritten once its own H2D has finished (``h2d`` event, host wait); the
+    device buffer may be overwritten once the kernels that consumed it have finished (``free`` event, recorded on the
+    consumer stream at the NEXT ``get`` -- by then the consumers of the previously returned slot have been enqueued --
+    and waited for on the copy stream, not on the host)."""
 
     def __init__(self, slots=2, device='cuda'):
         if not torch.cuda.is_available():
             raise RuntimeError('vfs_b200.PinnedRing needs a CUDA device')
+        if slots < 2:
+            raise ValueError('PinnedRing needs at least two slots')
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
-        self.slots = [dict(host=None, dev=None, ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(slots)]
+        self.slots = [dict(host=None, dev=None, h2d=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(slots)]
         self._head = self._tail = self._count = 0
+        self._last = None
 
     def put(self, t):
         if self._count == len(self.slots):
@@ -163,22 +172,24 @@ class PinnedRing:
         if s['host'] is None or s['host'].shape != t.shape or s['host'].dtype != t.dtype:
             s['host'] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             s['dev'] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
-        s['free'].synchronize()              # the previous H2D out of this pinned slot has finished
+        s['h2d'].synchronize()               # the previous copy out of this pinned buffer has finished
         s['host'].copy_(t)                   # (a loader would decode straight into the pinned slot)
-        self.stream.wait_event(s['free'])
+        self.stream.wait_event(s['free'])    # the kernels that read the old device contents are done
         with torch.cuda.stream(self.stream):
             s['dev'].copy_(s['host'], non_blocking=True)
-            s['ready'].record(self.stream)
+            s['h2d'].record(self.stream)
         self._head = (self._head + 1) % len(self.slots)
         self._count += 1
 
     def get(self):
         if self._count == 0:
             raise RuntimeError('PinnedRing is empty')
+        cur = torch.cuda.current_stream(self.device)
+        if self._last is not None:
+            self._last['free'].record(cur)   # everything enqueued since the last get() consumed that slot
         s = self.slots[self._tail]
-        torch.cuda.current_stream(self.device).wait_event(s['ready'])
+        cur.wait_event(s['h2d'])
         self._tail = (self._tail + 1) % len(self.slots)
         self._count -= 1
-        out = s['dev']
-        s['free'].record(torch.cuda.current_stream(self.device))   # consumers enqueued so far come before the reuse
-        return out
+        self._last = s
+        return s['dev']

@@ -39,8 +39,12 @@ class VanillaTracker(BaseTracker):
         return np.prod(self.backbone.strides[:end_index + 1]) * 4
 
     def extract_feat_test(self, imgs):
+        """reference vanilla_tracker.py:30-46: the backbone's outputs, or with ``test_cfg.all_blocks`` the output of
+        every residual block of the stages listed in ``test_cfg.out_indices`` (NCHW fp32 tensors)."""
         if self.test_cfg.get('all_blocks', False):
-            raise NotImplementedError('vfs_b200 VanillaTracker: test_cfg.all_blocks is not used by any VFS config')
+            stages = tuple(self.test_cfg.out_indices)
+            return tuple(ops.from_split(xs) for xs in
+                         self.backbone.engine.forward_split_taps(imgs.contiguous().float(), stages, True))
         return self.extract_feat(imgs)
 
     def extract_single_feat(self, imgs, idx):
@@ -49,10 +53,32 @@ class VanillaTracker(BaseTracker):
 
     # ------------------------------------------------------------------ device-resident feature bank
     def _feature_stage(self):
-        out_indices = tuple(self.backbone.out_indices)
-        if len(out_indices) != 1:
-            raise NotImplementedError('vfs_b200 VanillaTracker: exactly one backbone out index is supported')
-        return out_indices[0]
+        return tuple(self.backbone.out_indices)[0]
+
+    def _multi_level(self):
+        """True when the propagation runs on several feature levels (several out indices, or ``all_blocks``)."""
+        return bool(self.test_cfg.get('all_blocks', False)) or len(tuple(self.backbone.out_indices)) != 1
+
+    def get_feat_banks(self, imgs):
+        """Several feature levels (reference get_feats with num_feats > 1, vanilla_tracker.py:55-75): a list of
+        normalised split banks [2,B*T,h_l,w_l,C_l], one per level, from ONE backbone pass per chunk of frames."""
+        batch_step = self.test_cfg.get('batch_step', 10)
+        frames = video2images(imgs)
+        all_blocks = bool(self.test_cfg.get('all_blocks', False))
+        stages = tuple(self.test_cfg.out_indices) if all_blocks else tuple(self.backbone.out_indices)
+        with_norm = self.test_cfg.get('with_norm', True)
+        banks = None
+        for ptr in range(0, frames.size(0), batch_step):
+            chunk = frames[ptr:ptr + batch_step].contiguous().float()
+            levels = self.backbone.engine.forward_split_taps(chunk, stages, all_blocks)
+            if with_norm:
+                levels = [ops.normalize_split(xs) for xs in levels]
+            if banks is None:
+                banks = [torch.empty((2, frames.size(0)) + tuple(xs.shape[2:]), dtype=torch.float16, device=xs.device)
+                         for xs in levels]
+            for bank, xs in zip(banks, levels):
+                bank[:, ptr:ptr + xs.shape[1]].copy_(xs)
+        return banks
 
     def get_feat_bank(self, imgs):
         """imgs [B,3,T,H,W] -> normalised split-fp16 bank [2,B*T,h,w,C] on the device, frame (b, t) at index b*T+t
@@ -97,7 +123,33 @@ class VanillaTracker(BaseTracker):
         raise NotImplementedError
 
     def forward_test(self, imgs, ref_seg_map, img_meta):
-        """imgs [B,1,3,T,H,W], ref_seg_map [B,H,W] (label ids) or [B,Cv,H,W] (one-hot) -> list of B arrays [T,H,W].
+        """imgs [B,1,3,T,H,W], ref_seg_map [B,H,W] (label ids) or [B,Cv,H,W] (one-hot) -> list of B arrays [T,H,W]
+        (``[L,T,H,W]`` when the propagation runs on L > 1 feature levels: several out indices or
+        ``test_cfg.all_blocks``, reference vanilla_tracker.py:92-93,196-206)."""
+        if not self._multi_level():
+            preds = self._forward_test_level(imgs, ref_seg_map, img_meta)
+        else:
+            if not imgs.is_cuda:
+                raise RuntimeError('vfs_b200 VanillaTracker needs CUDA tensors (no CPU fallback)')
+            banks = self.get_feat_banks(imgs.reshape((-1, ) + imgs.shape[2:]))
+            per_level = [self._forward_test_level(imgs, ref_seg_map, img_meta, bank=bank) for bank in banks]
+            preds = per_level[0] if len(per_level) == 1 else np.stack(per_level, axis=1)       # [B,L,T,H,W]
+        if self.save_np:
+            assert preds.shape[0] == 1
+            import os
+            eval_dir = '.eval'
+            os.makedirs(eval_dir, exist_ok=True)
+            paths = []
+            for arr in (preds[0] if preds.ndim == 5 else [preds[0]]):
+                temp_file = tempfile.NamedTemporaryFile(dir=eval_dir, suffix='.npy', delete=False)
+                file_path = osp.join(eval_dir, temp_file.name)
+                np.save(file_path, arr)
+                paths.append(file_path)
+            return [paths] if len(paths) > 1 else [paths[0]]
+        return list(preds)
+
+    def _forward_test_level(self, imgs, ref_seg_map, img_meta, bank=None):
+        """One feature level: imgs [B,1,3,T,H,W] -> predictions [B,T,H,W] (host array).
 
         The reference handles one video per call (``get_feats`` asserts B == 1, vanilla_tracker.py:56).  Here B
         videos of equal length are propagated together -- one backbone pass over the B*T frames, one attention
@@ -110,7 +162,7 @@ class VanillaTracker(BaseTracker):
         imgs = imgs.reshape((-1, ) + imgs.shape[2:])
         num_videos, clip_len = imgs.size(0), imgs.size(2)
         cfg = self.test_cfg
-        fh, fw = self._feature_hw(imgs.shape[-2:])
+        fh, fw = self._feature_hw(imgs.shape[-2:]) if bank is None else tuple(bank.shape[2:4])
         hw = fh * fw
         orig_hw = tuple(img_meta[0]['original_shape'][:2])
         # First-frame labels before the backbone: F.one_hot sizes its output from the largest label id, which is
@@ -142,7 +194,8 @@ class VanillaTracker(BaseTracker):
         seg_bank = torch.empty((num_videos, clip_len, cv, hw), dtype=torch.float32, device=imgs.device)
         seg_bank[:, 0] = first.reshape(num_videos, cv, hw)
 
-        bank = self.get_feat_bank(imgs)                      # [2,B*T,h,w,C]
+        if bank is None:
+            bank = self.get_feat_bank(imgs)                  # [2,B*T,h,w,C]
         assert tuple(bank.shape[2:4]) == (fh, fw), (bank.shape, fh, fw)
 
         neighbor_range = cfg.get('neighbor_range', None)
@@ -182,14 +235,4 @@ class VanillaTracker(BaseTracker):
         host = torch.empty(preds.shape, dtype=preds.dtype, pin_memory=True)
         host.copy_(preds, non_blocking=True)
         torch.cuda.current_stream(imgs.device).synchronize()
-        seg_preds = host.numpy()
-        if self.save_np:
-            assert seg_preds.shape[0] == 1
-            eval_dir = '.eval'
-            import os
-            os.makedirs(eval_dir, exist_ok=True)
-            temp_file = tempfile.NamedTemporaryFile(dir=eval_dir, suffix='.npy', delete=False)
-            file_path = osp.join(eval_dir, temp_file.name)
-            np.save(file_path, seg_preds[0])
-            return [file_path]
-        return list(seg_preds)
+        return host.numpy()
