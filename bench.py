@@ -352,6 +352,57 @@ def dp_rank_check(torch, dist, dev, rank, world):
     return res
 
 
+def bench_siamfc(torch, dev, steps=30):
+    """SURVEY cfg-5: SiamFC object-level tracking, R18 backbone with the default_config_base.py overrides (dilations
+    (1,1,2,4), strides (1,2,1,1), frozen, eval BN), 127 px exemplar / three 255 px search crops, SiamConvFC head.
+    ``updates_per_s``: TrackerSiamFC.update(img) end to end (cv2 crops on the host, H2D, backbone, head, fused response
+    peak, 12-byte D2H); ``device_us_per_update``: backbone + head + peak on pre-staged crops (CUDA events)."""
+    import numpy as np
+    from vfs_b200 import ops
+    from vfs_b200.siamfc import TrackerSiamFC, build_cfg
+    from vfs_b200.synthetic import seeded_state_dict
+    cfg = build_cfg(dict(type='ResNet', depth=18, pretrained=None, norm_cfg=dict(type='BN', requires_grad=True)),
+                    exemplar_sz=127, out_scale=1e-3)
+    trk = TrackerSiamFC(cfg, device=dev)
+    trk.net.backbone.load_state_dict(seeded_state_dict(trk.net.backbone, seed=3))
+    trk.net.head.load_state_dict(seeded_state_dict(trk.net.head, seed=4))
+    trk.net.to(dev)
+    rng = np.random.RandomState(0)
+    frames = [rng.randint(0, 256, (480, 640, 3)).astype(np.uint8) for _ in range(4)]
+    box = [300, 200, 80, 60]
+    trk.init(frames[0], box)
+    for i in range(5):
+        trk.update(frames[i % 4])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        trk.update(frames[i % 4])
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / steps
+    crops = np.stack([rng.randint(0, 256, (255, 255, 3)).astype(np.uint8) for _ in range(3)])
+    x = trk._to_device(crops)
+
+    def device_part():
+        feats = trk.net.backbone(x)
+        r = trk.net.head(trk.kernel, feats).squeeze(1)
+        return ops.siamfc_response_peak(r, trk._hann_dev, trk.upscale_sz, cfg.scale_penalty, cfg.window_influence)
+
+    with torch.no_grad():
+        for _ in range(5):
+            device_part()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            device_part()
+        e1.record()
+        torch.cuda.synchronize()
+    return dict(workload='SiamFC R18 (dilated, frozen) 127/255 exemplar/search, 3 scales, SiamConvFC head',
+                updates_per_s=1.0 / wall, ms_per_update=wall * 1e3,
+                device_us_per_update=e0.elapsed_time(e1) / steps * 1e3,
+                api='TrackerSiamFC.update(img): host cv2 crops + H2D + backbone + x-corr head + fused response peak')
+
+
 def bench_affinity_480p(torch, dev, T, peaks, peak_tf, flush):
     """SURVEY cfg-3: DAVIS-style propagation of one 480p query frame (R50 res4 map 60x107, C = 1024, Cv = 4, radius 18,
     top-k 10) against T key frames; T = 21 is the steady state of VanillaTracker.forward_test with frame 0 in the key
@@ -683,6 +734,7 @@ def main():
         if world == 1:
             line['affinity_480p'] = dict(T1=bench_affinity_480p(torch, dev, 1, peaks, peak_tf, flush),
                                          T21=bench_affinity_480p(torch, dev, 21, peaks, peak_tf, flush))
+            line['siamfc'] = bench_siamfc(torch, dev)
             line['train_cfg2'] = bench_train(torch, dist, dev, rank, world, 8, 256, max(3, min(a.steps, 10)), peak_tf,
                                              'SURVEY cfg-2: R50 SimSiam train step, 8 clips x 2 views x 256^2, 1 GPU')
         if world > 1:

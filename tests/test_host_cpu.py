@@ -422,3 +422,57 @@ def test_multi_gpu_test_orders_results_like_the_reference_gloo_world2():
     assert res[1] is None
     assert [r['sample'] for r in res[0]] == list(range(7))
     assert all(r['doubled'] == 2 * r['sample'] for r in res[0])
+
+
+# --------------------------------------------------------------------------------------------- data-parallel plumbing
+def test_flat_layout_is_16_byte_aligned_and_dense():
+    """dp.FlatTrainState places every parameter at a 4-float (16-byte) aligned offset: the peer-memory all-reduce and
+    the vectorised flat SGD kernel rely on it; padding stays below 3 floats per tensor."""
+    from vfs_b200.dp import _layout
+    params = [torch.zeros(s) for s in [(64, 3, 7, 7), (64, ), (5, ), (2048, 512), (3, ), (1, )]]
+    offs, total = _layout(params)
+    assert offs[0] == 0 and all(o % 4 == 0 for o in offs) and total % 4 == 0
+    for (o, p), nxt in zip(zip(offs, params), offs[1:] + [total]):
+        assert 0 <= nxt - (o + p.numel()) < 4
+
+
+def _cross_rank_sum_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from vfs_b200 import ops, peer
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    assert peer.active() is None               # no communicator installed: torch.distributed carries the exchange
+    stats = torch.arange(6, dtype=torch.float64) * (rank + 1)
+    w = ops.cross_rank_sum_(stats)
+    q.put((rank, w, stats.clone()))
+    dist.destroy_process_group()
+
+
+def test_syncbn_statistics_exchange_falls_back_to_torch_distributed_gloo_world2():
+    """The SyncBN [sum | sum of squares] exchange (ops.cross_rank_sum_): without an installed peer communicator it is a
+    plain all-reduce over the default group -- the path the eager multi-rank step and these CPU tests take."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 33700 + os.getpid() % 2000
+    procs = [ctx.Process(target=_cross_rank_sum_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    for _, w, stats in res:
+        assert w == 2
+        assert torch.equal(stats, torch.arange(6, dtype=torch.float64) * 3)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU behaviour')
+def test_peer_communicator_and_device_feeds_fail_loudly_without_cuda():
+    import vfs_b200
+    from vfs_b200 import peer
+    with pytest.raises(RuntimeError):
+        peer.PeerComm(data_bytes=1024, rank=0, world=1)
+    with pytest.raises(RuntimeError):
+        vfs_b200.PinnedRing()
+    aug = vfs_b200.DeviceTrainAugment(mean=[0, 0, 0], std=[1, 1, 1], device='cpu')
+    with pytest.raises(RuntimeError):
+        aug(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), [(0, 0, 8, 8)], [False])

@@ -36,8 +36,10 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for C, H, W, res in SHAPES:
         M = N * H * W
-        z = torch.randn(N, H, W, C, device=dev)
-        y = ops.bn_apply(z, torch.ones(C, device=dev), torch.zeros(C, device=dev), None, True)
+        z32 = torch.randn(N, H, W, C, device=dev)
+        y = ops.bn_apply(z32, torch.ones(C, device=dev), torch.zeros(C, device=dev), None, True)
+        z = ops.bn_apply(z32, torch.ones(C, device=dev), torch.zeros(C, device=dev), None, False)   # split, like the engine
+        del z32
         dy = ops.bn_apply(torch.randn(N, H, W, C, device=dev), torch.ones(C, device=dev), torch.zeros(C, device=dev),
                           None, False)
         mean = torch.zeros(C, device=dev)
@@ -53,7 +55,7 @@ def main():
         sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
 
         def red():
-            nat.lib().vfs_bn_bwd_reduce(ptr(dy), None, ptr(y), None, ptr(z), None, ptr(mean), ptr(invstd), ptr(sums), M, C,
+            nat.lib().vfs_bn_bwd_reduce(ptr(dy), None, ptr(y), None, None, ptr(z), ptr(mean), ptr(invstd), ptr(sums), M, C,
                                         current_stream())
 
         dz = torch.empty_like(dy)
@@ -62,7 +64,7 @@ def main():
         db = torch.empty(C, device=dev)
 
         def app():
-            nat.lib().vfs_bn_bwd_apply(ptr(dy), None, ptr(y), None, ptr(z), None, ptr(mean), ptr(invstd), ptr(bn.weight),
+            nat.lib().vfs_bn_bwd_apply(ptr(dy), None, ptr(y), None, None, ptr(z), ptr(mean), ptr(invstd), ptr(bn.weight),
                                        ptr(sums), float(M), ptr(dz), None, ptr(g), ptr(dg), ptr(db), 0, 1.0, M, C,
                                        current_stream())
 
@@ -82,8 +84,8 @@ def main():
         t_app = timed(with_flush(app)) - t_flush
         t_fa = timed(with_flush(fapp)) - t_flush
         e = M * C
-        print(f'C={C:5d} {H:3d}x{W:<3d} res={int(res)} M={M:8d}: reduce {t_red:7.1f} us {12 * e / t_red / 1e3:7.0f} GB/s | '
-              f'apply {t_app:7.1f} us {(16 + 4 * res) * e / t_app / 1e3:7.0f} GB/s | fwd apply {t_fa:7.1f} us '
+        print(f'C={C:5d} {H:3d}x{W:<3d} res={int(res)} M={M:8d}: reduce {t_red:7.1f} us {10 * e / t_red / 1e3:7.0f} GB/s | '
+              f'apply {t_app:7.1f} us {(14 + 4 * res) * e / t_app / 1e3:7.0f} GB/s | fwd apply {t_fa:7.1f} us '
               f'{(8 + 4 * res) * e / t_fa / 1e3:7.0f} GB/s', flush=True)
         tot['reduce'] += t_red
         tot['apply'] += t_app

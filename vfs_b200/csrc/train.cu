@@ -295,6 +295,16 @@ static int bn_bwd_fill(BnBwdArgs& a, const void* dy_split, const float* dy_f32, 
   return VFS_OK;
 }
 
+// bulk-copy pipelined forms (csrc/bn_stream.cu) for the residual-stage layout: split dy / z / y, split outputs
+bool bn_stream_eligible(const void* dy_split, const float* dy_f32, const float* y_f32, const float* z, const void* z_split,
+                        float* dz_f32, long long M, int C);
+int bn_bwd_reduce_stream(const void* dy_split, const void* y_split, const void* z_split, const float* mean,
+                         const float* invstd, double* sums, long long M, int C, cudaStream_t s);
+int bn_bwd_apply_stream(const void* dy_split, const void* y_split, const void* z_split, const float* mean,
+                        const float* invstd, const float* gamma, const double* sums, double count, void* dz_split,
+                        void* g_split, float* dgamma, float* dbeta, int accumulate, float param_scale, int eval_mode,
+                        long long M, int C, cudaStream_t s);
+
 // channel slab of a block: the whole C when C <= 512 (C/8 must divide kBnThreads), else 512-channel slabs
 static bool bn_slab(int C, int* slab) {
   if (C <= 0 || C % 8 != 0) return false;
@@ -323,6 +333,8 @@ int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split
                   cudaStream_t s) {
   VFS_REQUIRE((dy_split || dy_f32) && (z || z_split) && mean && invstd && sums, VFS_EINVAL,
               "bn_bwd_reduce: null argument");
+  if (M > 0 && bn_stream_eligible(dy_split, dy_f32, y_f32, z, z_split, nullptr, M, C))
+    return bn_bwd_reduce_stream(dy_split, y_split, z_split, mean, invstd, sums, M, C, s);
   int slab = 0;
   VFS_REQUIRE(M > 0 && bn_slab(C, &slab), VFS_ESHAPE, "bn_bwd_reduce: C=%d unsupported", C);
   BnBwdArgs a;
@@ -345,6 +357,9 @@ int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split,
   if (eval_mode) count = 1.0;
   VFS_REQUIRE((dy_split || dy_f32) && (z || z_split) && mean && invstd && (sums || eval_mode) && (dz_split || dz_f32),
               VFS_EINVAL, "bn_bwd_apply: null argument");
+  if (M > 0 && dz_split && bn_stream_eligible(dy_split, dy_f32, y_f32, z, z_split, dz_f32, M, C))
+    return bn_bwd_apply_stream(dy_split, y_split, z_split, mean, invstd, gamma, sums, count, dz_split, g_split, dgamma,
+                               dbeta, accumulate, param_scale, eval_mode ? 1 : 0, M, C, s);
   int slab = 0;
   VFS_REQUIRE(M > 0 && count > 0 && bn_slab(C, &slab), VFS_ESHAPE, "bn_bwd_apply: C=%d unsupported", C);
   BnBwdArgs a;
