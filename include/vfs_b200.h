@@ -394,6 +394,22 @@ int vfs_nchw_to_nhwc_f32(const float* in, float* out, int N, int C, int H, int W
 int vfs_xcorr_nhwc(const float* z, const float* x, float* out, int nz, int nx, int C, int hz, int wz, int h, int w,
                    float out_scale, vfs_stream_t s);
 
+/* ------------------------------------------------------------------------------------------------
+ * SiamFC linear-probe training (TrackerSiamFC.train_step, projects/siamfc-pytorch/siamfc/siamfc_tracker_base.py:364-386;
+ * the backbone is frozen, default_config_base.py:40-49, so only the head trains).
+ *   vfs_siamfc_loss          FocalLoss (mode 0, losses.py:43-64) / BalancedLoss (mode 1, :27-40) of responses vs labels
+ *                            (n values each): loss[0] and, when grad != NULL, d loss / d responses, one launch
+ *   vfs_xcorr_backward_nhwc  gradients of vfs_xcorr_nhwc for n (exemplar, search) pairs: dz [n,hz,wz,C], dx [n,h,w,C]
+ *                            from dr [n,1,h-hz+1,w-wz+1] (either output may be NULL)
+ *   vfs_adam_step            torch.optim.Adam update (no amsgrad), `step` = 1-based step count
+ * The 1x1 adapter convolutions and their weight gradients use vfs_conv_bn_act / vfs_conv_wgrad. */
+int vfs_siamfc_loss(const float* responses, const float* labels, float* loss, float* grad, int n, int mode,
+                    float gamma, float neg_weight, vfs_stream_t s);
+int vfs_xcorr_backward_nhwc(const float* dr, const float* z, const float* x, float* dz, float* dx, int n, int C, int hz,
+                            int wz, int h, int w, float out_scale, vfs_stream_t s);
+int vfs_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, vfs_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,3 +147,79 @@ class TrackerOracle:
         self.x_sz *= scale
         return np.array([self.center[1] + 1 - (self.target_sz[1] - 1) / 2,
                          self.center[0] + 1 - (self.target_sz[0] - 1) / 2, self.target_sz[1], self.target_sz[0]])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# TrackerSiamFC.train_step (siamfc_tracker_base.py:364-386) with the frozen backbone of default_config_base.py:40-49:
+# labels (_create_labels :468-500), FocalLoss / BalancedLoss (siamfc/losses.py:27-64), torch.optim.Adam / SGD.
+# PINNED by tests/golden/siamfc_train_golden.npz (the unmodified reference class, oracle/ref_shim.py).
+# ----------------------------------------------------------------------------------------------------------------
+def create_labels(size, r_pos, r_neg, total_stride):
+    import numpy as np
+    n, c, h, w = size
+    x = np.arange(w) - (w - 1) / 2
+    y = np.arange(h) - (h - 1) / 2
+    x, y = np.meshgrid(x, y)
+    dist = np.abs(x) + np.abs(y)
+    rp, rn = r_pos / total_stride, r_neg / total_stride
+    labels = np.where(dist <= rp, np.ones_like(x), np.where(dist < rn, np.ones_like(x) * 0.5, np.zeros_like(x)))
+    return np.tile(labels.reshape((1, 1, h, w)), (n, c, 1, 1))
+
+
+def focal_loss(input, target, gamma=2):
+    import torch
+    pos_log_sig = torch.clamp(input, max=0) - torch.log(1 + torch.exp(-torch.abs(input))) + \
+        0.5 * torch.clamp(input, min=0, max=0)
+    neg_log_sig = torch.clamp(-input, max=0) - torch.log(1 + torch.exp(-torch.abs(input))) + \
+        0.5 * torch.clamp(input, min=0, max=0)
+    prob = torch.sigmoid(input)
+    pos_weight = torch.pow(1 - prob, gamma)
+    neg_weight = torch.pow(prob, gamma)
+    loss = -(target * pos_weight * pos_log_sig + (1 - target) * neg_weight * neg_log_sig)
+    avg_weight = target * pos_weight + (1 - target) * neg_weight
+    loss = loss / avg_weight.mean()
+    return loss.mean()
+
+
+def balanced_loss(input, target, neg_weight=1.0):
+    import torch
+    pos_mask, neg_mask = (target == 1), (target == 0)
+    pos_num, neg_num = pos_mask.sum().float(), neg_mask.sum().float()
+    weight = target.new_zeros(target.size())
+    weight[pos_mask] = 1 / pos_num
+    weight[neg_mask] = 1 / neg_num * neg_weight
+    weight /= weight.sum()
+    return F.binary_cross_entropy_with_logits(input, target, weight, reduction='sum')
+
+
+def train_steps(cfg, backbone_sd, head_sd, depth, batches):
+    """Runs ``len(batches)`` reference train steps on the CPU; returns (losses, gradients of the first step keyed like
+    the head's state dict, head state dict after the last step)."""
+    import numpy as np
+    import torch
+    from .resnet import resnet_forward
+    params = {k: v.clone().requires_grad_(True) for k, v in head_sd.items()}
+    lr = cfg['initial_lr']
+    if cfg['optimizer'] == 'Adam':
+        opt = torch.optim.Adam(list(params.values()), lr=lr, weight_decay=0)
+    else:
+        opt = torch.optim.SGD(list(params.values()), lr=lr, weight_decay=0, momentum=cfg['momentum'])
+    mean = torch.tensor([123.675, 116.28, 103.53]).view(1, 3, 1, 1)
+    std = torch.tensor([58.395, 57.12, 57.375]).view(1, 3, 1, 1)
+    b = cfg['model']['backbone']
+    losses, first_grads = [], None
+    for z, x in batches:
+        with torch.no_grad():
+            fz = resnet_forward(backbone_sd, (z.float() - mean) / std, depth, b['strides'], b['dilations'], b['out_indices'])
+            fx = resnet_forward(backbone_sd, (x.float() - mean) / std, depth, b['strides'], b['dilations'], b['out_indices'])
+        responses = siam_conv_fc(params, fz, fx, cfg['out_scale'])
+        labels = torch.from_numpy(create_labels(tuple(responses.shape), cfg['r_pos'], cfg['r_neg'],
+                                                cfg['total_stride'])).float()
+        loss = focal_loss(responses, labels) if cfg['loss'] == 'focal' else balanced_loss(responses, labels)
+        opt.zero_grad()
+        loss.backward()
+        if first_grads is None:
+            first_grads = {k: v.grad.detach().clone() for k, v in params.items()}
+        opt.step()
+        losses.append(float(loss))
+    return np.asarray(losses), first_grads, {k: v.detach().clone() for k, v in params.items()}

@@ -237,6 +237,31 @@ def siamfc_tracker_cfg(c):
     return cfg
 
 
+SIAMFC_TRAIN_CASES = {
+    'focal_adam': dict(depth=18, exemplar_sz=127, extra_conv=True, out_scale=1e-3, seed=81, loss='focal',
+                       optimizer='Adam', batch=2),
+    'balance_sgd': dict(depth=18, exemplar_sz=127, extra_conv=True, out_scale=1e-3, seed=83, loss='balance',
+                        optimizer='SGD', batch=3),
+}
+
+
+def siamfc_train_batches(c, steps=2):
+    """(z [B,3,127,127], x [B,3,255,255]) float batches of 0..255 pixel values, like the GOT-10k pair loader yields."""
+    g = _gen(1500 + c['seed'])
+    out = []
+    for _ in range(steps):
+        z = torch.rand(c['batch'], 3, c['exemplar_sz'], c['exemplar_sz'], generator=g) * 255
+        x = torch.rand(c['batch'], 3, 255, 255, generator=g) * 255
+        out.append((z, x))
+    return out
+
+
+def siamfc_train_cfg(c):
+    cfg = siamfc_tracker_cfg(c)
+    cfg.update(loss=c['loss'], optimizer=c['optimizer'], lr_schedule='fixed', gpus=None)
+    return cfg
+
+
 def siamfc_image():
     import numpy as np
     return np.random.RandomState(900).randint(0, 256, (180, 240, 3)).astype(np.uint8)

@@ -176,6 +176,36 @@ def train_pipeline_outputs():
     return out
 
 
+def siamfc_train_outputs():
+    """The UNMODIFIED reference ``TrackerSiamFC.train_step`` (siamfc_tracker_base.py:364-386: frozen R18 backbone,
+    SiamConvFC head, Focal / Balanced loss, Adam / SGD) for two steps -> tests/golden/siamfc_train_golden.npz: losses,
+    head gradients of the first step (recovered from the optimiser state) and head parameters after the second."""
+    import logging
+    import oracle
+    from vfs_b200.mmcv_lite import ConfigDict
+    mod = ref_shim.load_reference_siamfc_tracker()
+    out = {}
+    for name, c in cases.SIAMFC_TRAIN_CASES.items():
+        trk = mod.TrackerSiamFC(ConfigDict(cases.siamfc_train_cfg(c)), logging.getLogger('ref_siamfc'))
+        trk.net.backbone.load_state_dict(oracle.seeded_state_dict(trk.net.backbone, seed=c['seed']))
+        trk.net.head.load_state_dict(oracle.seeded_state_dict(trk.net.head, seed=c['seed'] + 1))
+        trk.net.cpu()
+        trk.device, trk.cuda = torch.device('cpu'), False
+        head_params = dict(trk.net.head.named_parameters())
+        losses = []
+        for i, batch in enumerate(cases.siamfc_train_batches(c)):
+            losses.append(trk.train_step(batch, backward=True))
+            if i == 0:
+                for k, p in head_params.items():
+                    st = trk.optimizer.state[p]
+                    g = st['exp_avg'] / 0.1 if c['optimizer'] == 'Adam' else st['momentum_buffer']
+                    out[f'{name}/grad/{k}'] = g.detach().numpy().copy()
+        out[f'{name}/losses'] = np.asarray(losses, dtype=np.float64)
+        for k, p in head_params.items():
+            out[f'{name}/param/{k}'] = p.detach().numpy().copy()
+    return out
+
+
 def attention_extra_outputs():
     """masked_attention_efficient of the unmodified reference for arbitrary bool masks / topk=None / rectangular maps
     -> tests/golden/attention_extra_golden.npz."""
@@ -205,6 +235,10 @@ def main():
     tp_path = os.path.join(ROOT, 'tests', 'golden', 'train_pipeline_golden.npz')
     np.savez_compressed(tp_path, **tp)
     print(f'wrote {tp_path}: {len(tp)} arrays', {k: v.shape for k, v in tp.items()})
+    st = siamfc_train_outputs()
+    st_path = os.path.join(ROOT, 'tests', 'golden', 'siamfc_train_golden.npz')
+    np.savez_compressed(st_path, **st)
+    print(f'wrote {st_path}: {len(st)} arrays')
     trk = siamfc_tracker_outputs()
     trk_path = os.path.join(ROOT, 'tests', 'golden', 'siamfc_tracker_golden.npz')
     np.savez_compressed(trk_path, **trk)

@@ -1063,7 +1063,8 @@ def test_backward_through_eval_mode_bn_matches_oracle_autograd(depth):
     net.train()                                   # norm_eval keeps the BNs in eval mode, frozen stages stay frozen
     g = torch.Generator().manual_seed(depth)
     x = torch.randn(4, 3, 96, 96, generator=g)
-    wout = torch.randn(4, 2048 if depth == 50 else 512, 3, 3, generator=g)
+    # (a loss weight of realistic size: gradients travel scaled by 2^12 in fp16 planes, see autograd.GRAD_SCALE)
+    wout = torch.randn(4, 2048 if depth == 50 else 512, 3, 3, generator=g) * 1e-3
 
     def oracle_grads(dtype):
         params = {k: (v.to(dtype).clone() if v.dtype.is_floating_point else v.clone()) for k, v in sd.items()}

@@ -120,6 +120,9 @@ PROTOTYPES = {
                                         ctypes.POINTER(ctypes.c_double), _i, _vp]),
     'vfs_augment_u8_to_ncthw_f32': (_i, [_vp, _vp, _ll, _i, _i, _i, ctypes.POINTER(ctypes.c_float),
                                          ctypes.POINTER(ctypes.c_double), _i, _vp]),
+    'vfs_siamfc_loss': (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp]),
+    'vfs_xcorr_backward_nhwc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    'vfs_adam_step': (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _vp]),
     'vfs_xcorr_nhwc': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
 }
 

@@ -142,8 +142,11 @@ __device__ __forceinline__ void topk_insert(float (&v)[KMAX], int (&id)[KMAX], f
   }
 }
 
-template <int KMAX, bool WIDE>
+// KTH x KTW: key tile shape (compile time, so that the epilogue's column -> (row, column) map unrolls into constants;
+// a run-time shape with a lookup table was measured 12 % slower end to end: the top-k epilogue then paces the loop)
+template <int KMAX, bool WIDE, int KTH, int KTW>
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const __grid_constant__ AttnParams p) {
+  static_assert(KTH * KTW <= 128 && KTW <= 32, "key tile: at most 128 pixels, rows of at most 32");
   using A = AttnCfg<WIDE>;
   constexpr int kAttnStages = A::kStages;
   constexpr int kAttnStageBytes = A::kStageBytes;
@@ -159,8 +162,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
   const uint32_t scratch_base = bar_base + 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kTmemCols = 2 * kNC;  // 2 accumulator stages
-  __shared__ unsigned short s_lut[128];    // accumulator column -> (row << 8 | column) inside the key tile
-  if (threadIdx.x < 128) s_lut[threadIdx.x] = static_cast<unsigned short>(((threadIdx.x / p.ktw) << 8) | (threadIdx.x % p.ktw));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_q);
@@ -299,11 +300,40 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
         mbar_wait(tfull_bar(as), aphase, 400 + as);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kNC + (WIDE ? 128 * half : 0);
+        // per key tile: squared horizontal distances / in-image flags of its KTW columns and the per-row limits
+        // (circle: dx^2 < r^2 - dy^2; square: |dx| <= rx and |dy| <= ry; unmasked: always), shared by all slabs
+        int dx2[KTW], lim[KTH];
+        uint32_t xok = 0, rowok = 0;
+#pragma unroll
+        for (int c = 0; c < KTW; ++c) {
+          const int dx = kx0 + c - qx;
+          dx2[c] = (p.mask_mode == 2) ? abs(dx) : dx * dx;
+          if (kx0 + c < p.W) xok |= (1u << c);
+        }
+#pragma unroll
+        for (int r = 0; r < KTH; ++r) {
+          const int ky = ky0 + r;
+          const int dy = ky - qy;
+          bool ok = ky < p.H;
+          int l = 0x7fffffff;
+          if (masked) {
+            if (p.mask_mode == 1) l = r2 - dy * dy;
+            else {
+              l = p.rx + 1;
+              ok = ok && (abs(dy) <= p.ry);
+            }
+          }
+          lim[r] = l;
+          if (ok) rowok |= (1u << r);
+        }
+        constexpr int kValid = KTH * KTW;
         const int c_begin = WIDE ? 0 : 64 * half;
         int c_end = (jt < u.n) ? (WIDE ? 128 : 64 * half + 64) : c_begin;   // phantom tile: nothing to scan
-        if (c_end > p.kvalid) c_end = p.kvalid;                               // columns past the tile's pixels: stale rows
-#pragma unroll 1
-        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        if (c_end > kValid) c_end = kValid;                                  // columns past the tile's pixels: stale rows
+#pragma unroll
+        for (int slab_i = 0; slab_i < 4; ++slab_i) {
+          const int c0 = slab_i * 32;                                        // compile-time after unrolling
+          if (c0 < c_begin || c0 >= c_end) continue;
           uint32_t acc[32];
           tmem_ld_32x32b_x32(t_row + c0, acc);
           tmem_ld_wait();
@@ -316,16 +346,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
           uint32_t cand = 0;
 #pragma unroll
           for (int cc = 0; cc < 32; ++cc) {
-            const int lut = s_lut[c0 + cc];          // same address for the whole warp: a broadcast read
-            const int ky = ky0 + (lut >> 8), kx = kx0 + (lut & 255);
-            const int dy = ky - qy, dx = kx - qx;
-            bool ok = (c0 + cc < c_end) && (ky < p.H) && (kx < p.W);
-            if (masked) {
-              // circle: dy^2 + dx^2 < r^2 (integer form of sqrt(dy^2+dx^2) < r, affinity_utils.py:150); square: |dy| <= ry,
-              // |dx| <= rx
-              ok = ok && ((p.mask_mode == 1) ? (dy * dy + dx * dx < r2) : (abs(dy) <= p.ry && abs(dx) <= p.rx));
+            const int r = c0 + cc;                                           // constants: r, r / KTW, r % KTW
+            if (r < kValid) {
+              const bool ok = ((rowok >> (r / KTW)) & 1u) && ((xok >> (r % KTW)) & 1u) && (dx2[r % KTW] < lim[r / KTW]);
+              if (ok && __uint_as_float(acc[cc]) > thr) cand |= (1u << cc);
             }
-            if (ok && __uint_as_float(acc[cc]) > thr) cand |= (1u << cc);
           }
           if (__any_sync(0xffffffffu, cand != 0)) {
             const uint32_t slab = scratch_base + static_cast<uint32_t>(half) * (32 * 128 * 4) +
@@ -339,8 +364,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_scores_topk_kernel(const
               float sc;
               asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc) : "r"(slab + jj * 512));
               if (sc > tv[KMAX - 1]) {
-                const int lut = s_lut[c0 + jj];
-                const int ky = ky0 + (lut >> 8), kx = kx0 + (lut & 255);
+                const int r = c0 + jj;
+                const int ky = ky0 + r / KTW, kx = kx0 + r % KTW;
                 topk_insert<KMAX>(tv, ti, sc, u.t * HW + ky * p.W + kx);
               }
             }
@@ -727,14 +752,14 @@ int masked_attention_batched(const VfsAttnDesc* d, int B, const void* q_bank_spl
       fixed = (e && atoi(e) == 0) ? 1 : 0;
     }
     if (!fixed) {
-      int best_tiles = ((wh + kQTileH - 1) / kQTileH) * ((ww + kQTileW - 1) / kQTileW);
-      for (int th = 1; th <= 128 && th <= wh; ++th) {
-        int tw = 128 / th;
-        if (tw > ww) tw = ww;
-        if (tw > 256) tw = 256;
-        if (tw < 1) continue;
+      // instantiated shapes: 8 x 16 (general), 5 x 25 (radius 18: 42 x 50 window -> 18 tiles instead of 24),
+      // 6 x 19 (radius 12: 30 x 38 window -> 10 instead of 12), 4 x 32
+      const int shapes[4][2] = {{8, 16}, {5, 25}, {6, 19}, {4, 32}};
+      int best_tiles = 1 << 30;
+      for (int k = 0; k < 4; ++k) {
+        const int th = shapes[k][0], tw = shapes[k][1];
         const int tiles = ((wh + th - 1) / th) * ((ww + tw - 1) / tw);
-        if (tiles < best_tiles || (tiles == best_tiles && tw > p.ktw)) {
+        if (tiles < best_tiles) {
           best_tiles = tiles;
           p.kth = th;
           p.ktw = tw;
@@ -755,24 +780,40 @@ int masked_attention_batched(const VfsAttnDesc* d, int B, const void* q_bank_spl
   }
   const int sms = device_sm_count();
   const int grid = p.num_units < sms ? p.num_units : sms;
-  static bool configured = false;
-  if (!configured) {
-    VFS_CUDA_OK(cudaFuncSetAttribute(attn_scores_topk_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kAttnSmemBytes));
-    VFS_CUDA_OK(cudaFuncSetAttribute(attn_scores_topk_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kAttnSmemBytes));
-    VFS_CUDA_OK(cudaFuncSetAttribute(attn_scores_topk_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kAttnSmemBytes));
-    VFS_CUDA_OK(cudaFuncSetAttribute(attn_scores_topk_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kAttnSmemBytes));
-    configured = true;
-  }
-  if (wide) {
-    if (KMAX == 10) attn_scores_topk_kernel<10, true><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
-    else attn_scores_topk_kernel<16, true><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
-  } else {
-    if (KMAX == 10) attn_scores_topk_kernel<10, false><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
-    else attn_scores_topk_kernel<16, false><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
+  {
+    const int shape_id = (p.kth == 5) ? 1 : (p.kth == 6) ? 2 : (p.kth == 4) ? 3 : 0;
+    int rc = VFS_OK;
+#define VFS_ATTN_LAUNCH(K, WD, TH, TW)                                                                          \
+  do {                                                                                                            \
+    static bool cfgd = false;                                                                                     \
+    if (!cfgd) {                                                                                                  \
+      rc = check_cuda(cudaFuncSetAttribute(attn_scores_topk_kernel<K, WD, TH, TW>,                               \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes),          \
+                      "cudaFuncSetAttribute(attn_scores_topk_kernel)");                                           \
+      cfgd = (rc == VFS_OK);                                                                                      \
+    }                                                                                                             \
+    if (rc == VFS_OK) attn_scores_topk_kernel<K, WD, TH, TW><<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p); \
+  } while (0)
+    if (!wide) {
+      if (KMAX == 10) VFS_ATTN_LAUNCH(10, false, 8, 16);
+      else VFS_ATTN_LAUNCH(16, false, 8, 16);
+    } else if (KMAX == 10) {
+      switch (shape_id) {
+        case 1: VFS_ATTN_LAUNCH(10, true, 5, 25); break;
+        case 2: VFS_ATTN_LAUNCH(10, true, 6, 19); break;
+        case 3: VFS_ATTN_LAUNCH(10, true, 4, 32); break;
+        default: VFS_ATTN_LAUNCH(10, true, 8, 16); break;
+      }
+    } else {
+      switch (shape_id) {
+        case 1: VFS_ATTN_LAUNCH(16, true, 5, 25); break;
+        case 2: VFS_ATTN_LAUNCH(16, true, 6, 19); break;
+        case 3: VFS_ATTN_LAUNCH(16, true, 4, 32); break;
+        default: VFS_ATTN_LAUNCH(16, true, 8, 16); break;
+      }
+    }
+#undef VFS_ATTN_LAUNCH
+    if (rc != VFS_OK) return rc;
   }
   VFS_CUDA_OK(cudaGetLastError());
 

@@ -187,6 +187,12 @@ int frames_u8_to_ncthw_f32(const unsigned char* in, float* out, long long clips,
                            const double* stdinv3, int swap_rb, cudaStream_t s);
 int augment_u8_to_ncthw_f32(const VfsAugItem* items_dev, float* out, long long clips, int T, int dst_h, int dst_w,
                             const float* mean3, const double* stdinv3, int swap_rb, cudaStream_t s);
+int siamfc_loss(const float* responses, const float* labels, float* loss, float* grad, int n, int mode, float gamma,
+                float neg_weight, cudaStream_t s);
+int xcorr_backward_nhwc(const float* dr, const float* z, const float* x, float* dz, float* dx, int n, int C, int hz, int wz,
+                        int h, int w, float out_scale, cudaStream_t s);
+int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+              float weight_decay, int step, cudaStream_t s);
 int xcorr_nhwc(const float* z, const float* x, float* out, int nz, int nx, int C, int hz, int wz, int h, int w,
                float out_scale, cudaStream_t s);
 
@@ -474,6 +480,18 @@ int vfs_xcorr_nhwc(const float* z, const float* x, float* out, int nz, int nx, i
 int vfs_augment_u8_to_ncthw_f32(const VfsAugItem* items_dev, float* out, long long clips, int T, int dst_h, int dst_w,
                                 const float* mean3, const double* stdinv3, int swap_rb, vfs_stream_t s) {
   return vfs::augment_u8_to_ncthw_f32(items_dev, out, clips, T, dst_h, dst_w, mean3, stdinv3, swap_rb, s);
+}
+int vfs_siamfc_loss(const float* responses, const float* labels, float* loss, float* grad, int n, int mode,
+                    float gamma, float neg_weight, vfs_stream_t s) {
+  return vfs::siamfc_loss(responses, labels, loss, grad, n, mode, gamma, neg_weight, s);
+}
+int vfs_xcorr_backward_nhwc(const float* dr, const float* z, const float* x, float* dz, float* dx, int n, int C, int hz,
+                            int wz, int h, int w, float out_scale, vfs_stream_t s) {
+  return vfs::xcorr_backward_nhwc(dr, z, x, dz, dx, n, C, hz, wz, h, w, out_scale, s);
+}
+int vfs_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, vfs_stream_t s) {
+  return vfs::adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, s);
 }
 
 }  // extern "C"

@@ -18,12 +18,16 @@ from ..builder import build_backbone
 from ..mmcv_lite import ConfigDict
 from . import image_ops
 from .heads import SiamConvFC, SiamFC
+from .train import TrainingMixin
 
 # projects/siamfc-pytorch/siamfc/default_config_base.py:2-51 (inference-relevant keys)
 DEFAULT_CFG = dict(
     out_scale=0.001, exemplar_sz=120, instance_sz=255, context=0.5, scale_num=3, scale_step=1.0375, scale_lr=0.59,
     scale_penalty=0.9745, window_influence=0.176, response_sz=17, response_up=16, total_stride=8, extra_conv=True,
     out_channels=512, reduction=1, out_block_index=None,
+    # training keys (default_config_base.py:18-38)
+    epoch_num=50, batch_size=8, initial_lr=1e-3, ultimate_lr=1e-5, weight_decay=5e-4, momentum=0.9, r_pos=16, r_neg=0,
+    optimizer='Adam', loss='focal', lr_schedule='exp', lr_step_size=10, force_wd=False,
     model=dict(backbone=dict(frozen_stages=4, dilations=(1, 1, 2, 4), strides=(1, 2, 1, 1), out_indices=(3, ),
                              with_cp=False, norm_eval=True)))
 
@@ -53,7 +57,7 @@ def build_cfg(backbone, **overrides):
     return ConfigDict(cfg)
 
 
-class TrackerSiamFC:
+class TrackerSiamFC(TrainingMixin):
     """``init(img, box)`` / ``update(img)`` / ``track(frames, box)`` with the reference's state variables
     (``center``, ``target_sz``, ``z_sz``, ``x_sz``, ``scale_factors``, ``hann_window``, ``kernel``).  ``img`` is an
     RGB uint8 array [H,W,3]; ``box`` is 1-indexed (x, y, w, h) like the OTB / GOT-10k annotations."""
