@@ -215,6 +215,14 @@ int vfs_comm_allreduce_small_f32(VfsComm* c, float* data, int n, vfs_stream_t s)
 int vfs_comm_barrier(VfsComm* c, vfs_stream_t s);
 int vfs_comm_allreduce_f32(VfsComm* c, size_t offset_bytes, size_t n, float scale, vfs_stream_t s);
 
+/* The packers with a power-of-two weight scale: w * wscale is split.  Weights of ~0.02 (kaiming initialisation) have
+ * their lo plane in the fp16 subnormal range and keep ~17 significant bits; scaled by 256 both planes are normal for
+ * |w| >= 5e-4 and the pair keeps 22.  The caller multiplies the conv epilogue's scale vector (vfs_conv_bn_act `scale`,
+ * the `ones` of vfs_conv_stats_split / vfs_conv_dgrad) by 1 / wscale -- exact, a power of two. */
+int vfs_pack_conv_weight_scaled(const float* w_oihw, void* w_split, int Cout, int Cin, int ksize, float wscale,
+                                vfs_stream_t s);
+int vfs_pack_conv_weight_dgrad_scaled(const float* w_oihw, void* wt_split, int Cout, int Cin, int ksize, float wscale,
+                                      vfs_stream_t s);
 /* OIHW fp32 [Cout,Cin,k,k] -> split [2][Cout][k*k*Cin] (device to device). */
 int vfs_pack_conv_weight(const float* w_oihw, void* w_split, int Cout, int Cin, int ksize, vfs_stream_t s);
 
@@ -226,7 +234,8 @@ typedef struct VfsPackItem {
   const float* w;   /* OIHW fp32 [Cout,Cin,k,k] */
   void* dst_split;  /* split [2][...] */
   int32_t Cout, Cin, ksize, mode;
-  int32_t first_block, reserved;
+  int32_t first_block;
+  int32_t scale_log2; /* the weights are multiplied by 2^scale_log2 before the split (see vfs_pack_conv_weight_scaled) */
 } VfsPackItem;
 int vfs_pack_blocks(int Cout, int Cin, int ksize);
 int vfs_pack_conv_weights_multi(const VfsPackItem* items_dev, int n, int total_blocks, vfs_stream_t s);

@@ -372,3 +372,41 @@ def test_train_pipeline_golden_is_current_vs_live_reference(train_pipeline_golde
     assert set(ref) == set(train_pipeline_golden)
     for k in ref:
         np.testing.assert_array_equal(ref[k], train_pipeline_golden[k])
+
+
+# --------------------------------------------------------------------------------------------- SiamFC training step
+@pytest.fixture(scope='module')
+def siamfc_train_golden():
+    import os
+    with np.load(os.path.join(os.path.dirname(__file__), 'golden', 'siamfc_train_golden.npz')) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _oracle_siamfc_train(name):
+    from oracle import siamfc as o_siamfc
+    from vfs_b200.backbones import ResNet
+    from vfs_b200.siamfc import SiamConvFC
+    c = cases.SIAMFC_TRAIN_CASES[name]
+    cfg = cases.siamfc_train_cfg(c)
+    b = cfg['model']['backbone']
+    net = ResNet(c['depth'], norm_cfg=dict(type='BN', requires_grad=True), strides=b['strides'],
+                 dilations=b['dilations'], out_indices=b['out_indices'])
+    bsd = oracle.seeded_state_dict(net, seed=c['seed'])
+    hsd = oracle.seeded_state_dict(SiamConvFC(512, 512, out_scale=c['out_scale']), seed=c['seed'] + 1)
+    return o_siamfc.train_steps(cfg, bsd, hsd, c['depth'], cases.siamfc_train_batches(c))
+
+
+@pytest.mark.parametrize('name', sorted(cases.SIAMFC_TRAIN_CASES))
+def test_siamfc_train_step_oracle_matches_reference_golden(siamfc_train_golden, name):
+    """TrackerSiamFC.train_step (siamfc_tracker_base.py:364-386): labels, Focal / Balanced loss, head gradients and
+    the Adam / SGD update of the oracle restatement against two steps of the unmodified reference class."""
+    losses, grads, params = _oracle_siamfc_train(name)
+    g = siamfc_train_golden
+    np.testing.assert_allclose(losses, g[f'{name}/losses'], rtol=2e-4)
+    for k, v in grads.items():
+        ref = g[f'{name}/grad/{k}']
+        assert float(np.abs(v.numpy() - ref).max()) <= 2e-4 * float(np.abs(ref).max()) + 1e-12, k
+    if cases.SIAMFC_TRAIN_CASES[name]['optimizer'] == 'SGD':   # (Adam's first steps are +-lr per element: sign noise)
+        for k, v in params.items():
+            ref = g[f'{name}/param/{k}']
+            assert float(np.abs(v.numpy() - ref).max()) <= 1e-6 * float(np.abs(ref).max()) + 1e-9, k

@@ -19,7 +19,7 @@ class VfsConvDesc(ctypes.Structure):
 
 class VfsPackItem(ctypes.Structure):
     _fields_ = [('w', ctypes.c_void_p), ('dst_split', ctypes.c_void_p)] + \
-        [(n, ctypes.c_int32) for n in ('Cout', 'Cin', 'ksize', 'mode', 'first_block', 'reserved')]
+        [(n, ctypes.c_int32) for n in ('Cout', 'Cin', 'ksize', 'mode', 'first_block', 'scale_log2')]
 
 
 class VfsAugItem(ctypes.Structure):
@@ -51,6 +51,8 @@ PROTOTYPES = {
     'vfs_stem_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'vfs_conv_bn_act': (_i, [ctypes.POINTER(VfsConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'vfs_pack_conv_weight': (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    'vfs_pack_conv_weight_scaled': (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),
+    'vfs_pack_conv_weight_dgrad_scaled': (_i, [_vp, _vp, _i, _i, _i, _f, _vp]),
     'vfs_pack_blocks': (_i, [_i, _i, _i]),
     'vfs_pack_conv_weights_multi': (_i, [_vp, _i, _i, _vp]),
     'vfs_debug_conv_trace': (_i, [_vp, _i]),

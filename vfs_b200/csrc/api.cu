@@ -86,7 +86,7 @@ int conv_set_trace(long long* buffer, int events_per_role);
 int conv_set_pair_policy(int mode, int min_pair_tiles);
 int conv_dgrad_tc(const VfsConvDesc* d, const void* dz_split, const void* wt_split, const float* ones,
                   const float* zeros, const void* add_split, void* dx_split, cudaStream_t stream);
-int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, int k, cudaStream_t s);
+int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, int k, float wscale, cudaStream_t s);
 size_t wgrad_workspace_bytes(int Cout, int Cin, int ksize);
 int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_split, void* workspace, float* dw_oihw,
                   int accumulate, float out_scale, cudaStream_t stream);
@@ -137,7 +137,7 @@ int conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const void* w_s
                      const float* shift, const void* residual_split, float* out_f32, cudaStream_t stream);
 int nchw_f32_to_split(const float* in, void* out_split, int N, int C, int H, int W, float scale, cudaStream_t s);
 int split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H, int W, cudaStream_t s);
-int pack_conv_weight(const float* w, void* w_split, int Cout, int Cin, int k, cudaStream_t s);
+int pack_conv_weight(const float* w, void* w_split, int Cout, int Cin, int k, float wscale, cudaStream_t s);
 int pack_conv_weights_multi(const VfsPackItem* items_dev, int n, int total_blocks, cudaStream_t s);
 size_t stem_workspace_bytes(int N, int H, int W);
 int stem_forward(const float* in, const void* weight, const float* scale, const float* shift, void* out_split,
@@ -261,7 +261,11 @@ int vfs_conv_dgrad(const VfsConvDesc* d, const void* dz_split, const void* wt_sp
   return vfs::conv_dgrad_tc(d, dz_split, wt_split, ones, zeros, add_split, dx_split, s);
 }
 int vfs_pack_conv_weight_dgrad(const float* w_oihw, void* wt_split, int Cout, int Cin, int ksize, vfs_stream_t s) {
-  return vfs::pack_conv_weight_dgrad(w_oihw, wt_split, Cout, Cin, ksize, s);
+  return vfs::pack_conv_weight_dgrad(w_oihw, wt_split, Cout, Cin, ksize, 1.0f, s);
+}
+int vfs_pack_conv_weight_dgrad_scaled(const float* w_oihw, void* wt_split, int Cout, int Cin, int ksize, float wscale,
+                                      vfs_stream_t s) {
+  return vfs::pack_conv_weight_dgrad(w_oihw, wt_split, Cout, Cin, ksize, wscale, s);
 }
 size_t vfs_conv_wgrad_workspace_bytes(int Cout, int Cin, int ksize) {
   return vfs::wgrad_workspace_bytes(Cout, Cin, ksize);
@@ -369,7 +373,11 @@ int vfs_pack_conv_weights_multi(const VfsPackItem* items_dev, int n, int total_b
   return vfs::pack_conv_weights_multi(items_dev, n, total_blocks, s);
 }
 int vfs_pack_conv_weight(const float* w_oihw, void* w_split, int Cout, int Cin, int ksize, vfs_stream_t s) {
-  return vfs::pack_conv_weight(w_oihw, w_split, Cout, Cin, ksize, s);
+  return vfs::pack_conv_weight(w_oihw, w_split, Cout, Cin, ksize, 1.0f, s);
+}
+int vfs_pack_conv_weight_scaled(const float* w_oihw, void* w_split, int Cout, int Cin, int ksize, float wscale,
+                                vfs_stream_t s) {
+  return vfs::pack_conv_weight(w_oihw, w_split, Cout, Cin, ksize, wscale, s);
 }
 int vfs_debug_conv_bn_act_simt(const VfsConvDesc* d, const void* in_split, const void* w_split, const float* scale,
                                const float* shift, const void* residual_split, float* out_f32_nhwc,

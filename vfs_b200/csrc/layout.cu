@@ -80,8 +80,11 @@ int split_to_nchw_f32(const void* in_split, float* out, int N, int C, int H, int
 // ------------------------------------------------------------------------------------------------
 // OIHW fp32 -> split [2][Cout][(r*k+s)*Cin + ci]
 // ------------------------------------------------------------------------------------------------
+// ``wscale`` (a power of two) multiplies the weights before the split: kaiming-initialised weights are ~0.02, where
+// the lo plane (2^-11 of the value) is an fp16 subnormal and the pair keeps ~17 instead of 22 significant bits; scaled
+// by 256 both planes are normal numbers for |w| >= 5e-4.  The caller folds 1 / wscale into the epilogue's scale vector.
 __global__ void pack_weight_kernel(const float* __restrict__ w, h16* __restrict__ hi,
-                                   h16* __restrict__ lo, int Cout, int Cin, int k) {
+                                   h16* __restrict__ lo, int Cout, int Cin, int k, float wscale) {
   const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -90,7 +93,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, h16* __restrict_
     const size_t t = i / Cin;
     const int tap = static_cast<int>(t % (k * k));
     const int co = static_cast<int>(t / (k * k));
-    const float v = w[(static_cast<size_t>(co) * Cin + ci) * k * k + tap];
+    const float v = w[(static_cast<size_t>(co) * Cin + ci) * k * k + tap] * wscale;
     h16 h, l;
     split16(v, h, l);
     hi[i] = h;
@@ -100,7 +103,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, h16* __restrict_
 
 // OIHW fp32 -> split [2][Cin][(r'*k+s')*Cout + co] with the kernel flipped (operand of the data-gradient conv)
 __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, h16* __restrict__ hi,
-                                         h16* __restrict__ lo, int Cout, int Cin, int k) {
+                                         h16* __restrict__ lo, int Cout, int Cin, int k, float wscale) {
   const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -110,7 +113,7 @@ __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, h16* __res
     const int tap = static_cast<int>(t % (k * k));
     const int ci = static_cast<int>(t / (k * k));
     const int src_tap = k * k - 1 - tap;  // (k-1-r', k-1-s')
-    const float v = w[(static_cast<size_t>(co) * Cin + ci) * k * k + src_tap];
+    const float v = w[(static_cast<size_t>(co) * Cin + ci) * k * k + src_tap] * wscale;
     h16 h, l;
     split16(v, h, l);
     hi[i] = h;
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const VfsPackIt
     else hi_i = mid - 1;
   }
   const VfsPackItem it = items[lo_i];
+  const float wscale = exp2f(static_cast<float>(it.scale_log2));
   const int Cout = it.Cout, Cin = it.Cin, kk = it.ksize * it.ksize;
   const size_t total = static_cast<size_t>(Cout) * Cin * kk;
   h16* hi = reinterpret_cast<h16*>(it.dst_split);
@@ -144,13 +148,13 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const VfsPackIt
       const size_t t = i / Cin;
       const int tap = static_cast<int>(t % kk);
       const int co = static_cast<int>(t / kk);
-      v = it.w[(static_cast<size_t>(co) * Cin + ci) * kk + tap];
+      v = it.w[(static_cast<size_t>(co) * Cin + ci) * kk + tap] * wscale;
     } else {              // data-gradient operand: i = (ci * k*k + tap') * Cout + co, kernel flipped
       const int co = static_cast<int>(i % Cout);
       const size_t t = i / Cout;
       const int tap = static_cast<int>(t % kk);
       const int ci = static_cast<int>(t / kk);
-      v = it.w[(static_cast<size_t>(co) * Cin + ci) * kk + (kk - 1 - tap)];
+      v = it.w[(static_cast<size_t>(co) * Cin + ci) * kk + (kk - 1 - tap)] * wscale;
     }
     h16 h, l;
     split16(v, h, l);
@@ -166,24 +170,24 @@ int pack_conv_weights_multi(const VfsPackItem* items_dev, int n, int total_block
   return VFS_OK;
 }
 
-int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, int k, cudaStream_t s) {
+int pack_conv_weight_dgrad(const float* w, void* wt_split, int Cout, int Cin, int k, float wscale, cudaStream_t s) {
   VFS_REQUIRE(w && wt_split, VFS_EINVAL, "pack_conv_weight_dgrad: null argument");
   VFS_REQUIRE(Cout > 0 && Cin > 0 && k > 0, VFS_ESHAPE, "pack_conv_weight_dgrad: bad shape");
   const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
   h16* hi = reinterpret_cast<h16*>(wt_split);
   const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  pack_weight_dgrad_kernel<<<blocks, 256, 0, s>>>(w, hi, hi + total, Cout, Cin, k);
+  pack_weight_dgrad_kernel<<<blocks, 256, 0, s>>>(w, hi, hi + total, Cout, Cin, k, wscale);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }
 
-int pack_conv_weight(const float* w, void* w_split, int Cout, int Cin, int k, cudaStream_t s) {
+int pack_conv_weight(const float* w, void* w_split, int Cout, int Cin, int k, float wscale, cudaStream_t s) {
   VFS_REQUIRE(w && w_split, VFS_EINVAL, "pack_conv_weight: null argument");
   VFS_REQUIRE(Cout > 0 && Cin > 0 && k > 0, VFS_ESHAPE, "pack_conv_weight: bad shape");
   const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
   h16* hi = reinterpret_cast<h16*>(w_split);
   const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  pack_weight_kernel<<<blocks, 256, 0, s>>>(w, hi, hi + total, Cout, Cin, k);
+  pack_weight_kernel<<<blocks, 256, 0, s>>>(w, hi, hi + total, Cout, Cin, k, wscale);
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }

@@ -32,6 +32,7 @@ struct alignas(64) WgradParams {
   int tap_view[kWgMaxTaps], tap_dh[kWgMaxTaps], tap_dw[kWgMaxTaps];
   int Cin, Cout, taps_total;
   float* dw;  // fp32 [Cout][taps][Cin], accumulated
+  float out_scale;  // applied to the partial tiles before the atomics (1 when an unpack pass scales instead)
 };
 
 struct WgUnit {
@@ -186,8 +187,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         if (co_ok) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            red_add_v4(dst + c0 + j, __uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
-                       __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+            red_add_v4(dst + c0 + j, __uint_as_float(acc[j]) * p.out_scale, __uint_as_float(acc[j + 1]) * p.out_scale,
+                       __uint_as_float(acc[j + 2]) * p.out_scale, __uint_as_float(acc[j + 3]) * p.out_scale);
         }
       }
       tc_fence_before();
@@ -347,7 +348,12 @@ int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_spli
   for (int v = 0; v < kWgMaxViews; ++v)
     if (!built[v]) p.tmap_x[v] = p.tmap_x[first_valid];
 
-  VFS_CUDA_OK(cudaMemsetAsync(workspace, 0, wgrad_workspace_bytes(Cout, Cin, k), stream));
+  // 1x1 convolutions: [Cout][1][Cin] IS the OIHW layout -- when the caller accumulates (the flat gradient buffer of
+  // the training step, zeroed once per step) the partial tiles go straight into dW: no workspace memset, no unpack pass
+  const bool direct = (k == 1) && accumulate != 0;
+  p.out_scale = direct ? out_scale : 1.0f;
+  if (direct) p.dw = dw_oihw;
+  else VFS_CUDA_OK(cudaMemsetAsync(workspace, 0, wgrad_workspace_bytes(Cout, Cin, k), stream));
   static bool configured = false;
   if (!configured) {
     VFS_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
@@ -356,6 +362,7 @@ int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_spli
   const int grid = p.num_units < sms ? p.num_units : sms;
   wgrad_tc_kernel<<<grid, kWgThreads, kWgSmemBytes, stream>>>(p);
   VFS_CUDA_OK(cudaGetLastError());
+  if (direct) return VFS_OK;
   const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
   const int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
   wgrad_unpack_kernel<<<blocks, 256, 0, stream>>>(p.dw, dw_oihw, Cout, Cin, k * k, accumulate, out_scale);

@@ -30,6 +30,8 @@ def fold_bn(conv_module, device):
         shift = torch.zeros(cout, dtype=torch.float64)
     if conv_module.conv.bias is not None:
         shift = shift + conv_module.conv.bias.detach().double().to(shift.device) * scale
+    if conv_module.conv.in_channels % 64 == 0:
+        scale = scale / ops.WEIGHT_SCALE      # residual-stage weights are packed scaled by WEIGHT_SCALE (exact: 2^-8)
     return (scale.float().to(device).contiguous(), shift.float().to(device).contiguous())
 
 
@@ -87,7 +89,7 @@ class BackboneEngine:
             w = cm.conv.weight.detach().to(device=device, dtype=torch.float32).contiguous()
             p.ksize = w.shape[2]
             # residual-stage convs: [2][Cout][k*k*Cin]; the 7x7 stem: [2][64][192] (K = 147 zero-padded)
-            p.w_split = ops.pack_conv_weight(w) if w.shape[1] % 64 == 0 else ops.stem_pack_weight(w)
+            p.w_split = ops.pack_conv_weight(w, ops.WEIGHT_SCALE) if w.shape[1] % 64 == 0 else ops.stem_pack_weight(w)
             p.wt_split = None  # dgrad packing, built on first use by the backward pass
             p.scale = p.shift = None
             p.w_version = wv if wv is not None else self._w_version(cm)
@@ -134,7 +136,7 @@ class BackboneEngine:
                 nb = int(nat.lib().vfs_pack_blocks(cout, cin, k))
                 for mode, dst in ((0, ws), (1, wt)):
                     items.append(nat.VfsPackItem(w=w.data_ptr(), dst_split=dst.data_ptr(), Cout=cout, Cin=cin, ksize=k,
-                                                 mode=mode, first_block=first, reserved=0))
+                                                 mode=mode, first_block=first, scale_log2=ops.WEIGHT_SCALE_LOG2))
                     first += nb
             arr = (nat.VfsPackItem * len(items))(*items)
             table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
@@ -177,7 +179,8 @@ class BackboneEngine:
             assert not want_f32
             # (z stays a split tensor: written by the TMA epilogue whose math warps also accumulate the statistics)
             z, stats = ops.conv_stats_split(xs, p.w_split, k, stride, dil,
-                                            stats=self.stats_vec(2 * cm.conv.out_channels, xs.device))
+                                            stats=self.stats_vec(2 * cm.conv.out_channels, xs.device),
+                                            wscale=ops.WEIGHT_SCALE)
             scale, shift, mean, invstd = ops.bn_finalize(stats, z.numel() // (2 * z.shape[-1]), cm.norm,
                                                          nbt_list=self._nbt)
             y = ops.bn_apply(z, scale, shift, residual, relu)
@@ -193,9 +196,10 @@ class BackboneEngine:
             # recovered from y when gamma == 0, the zero-init-residual state), BN on the running statistics is the folded
             # scale / shift.  Gradients: dz = gamma * invstd_running * g, dgamma / dbeta from the running-statistics xhat.
             bn = cm.norm
-            z, _ = ops.conv_bn_act(xs, p.w_split, ops._const_vec(1, cm.conv.out_channels, xs.device),
+            z, _ = ops.conv_bn_act(xs, p.w_split, ops._const_vec(1.0 / ops.WEIGHT_SCALE, cm.conv.out_channels, xs.device),
                                    ops._const_vec(0, cm.conv.out_channels, xs.device), k, stride, dil, relu=False)
-            y = ops.bn_apply(z, p.scale, p.shift, residual, relu)
+            # (p.scale carries 1 / WEIGHT_SCALE for the fused kernel; z here is the true conv output)
+            y = ops.bn_apply(z, p.scale * ops.WEIGHT_SCALE, p.shift, residual, relu)
             invstd = torch.rsqrt(bn.running_var.detach().double() + bn.eps).float()
             self.tape.append(dict(cm=cm, xs=xs, z=z, mean=bn.running_mean.detach().float(), invstd=invstd, y=y,
                                   relu=relu, residual=residual, k=k, stride=stride, dil=dil, eval_bn=True))
@@ -373,10 +377,10 @@ class BackboneEngine:
             plan = self.plan(cm, dz.device)
             if plan.wt_split is None:
                 plan.wt_split = ops.pack_conv_weight_dgrad(
-                    cm.conv.weight.detach().to(device=dz.device, dtype=torch.float32).contiguous())
+                    cm.conv.weight.detach().to(device=dz.device, dtype=torch.float32).contiguous(), ops.WEIGHT_SCALE)
             prev = grad.get(id(op['xs']))
             grad[id(op['xs'])] = ops.conv_dgrad(dz, plan.wt_split, tuple(op['xs'].shape[2:4]), op['k'], op['stride'],
-                                                op['dil'], add=prev)
+                                                op['dil'], add=prev, wscale=ops.WEIGHT_SCALE)
         return pgrads
 
     def _mark(self, tag):

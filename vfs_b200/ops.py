@@ -73,13 +73,20 @@ def from_split(xs):
     return out
 
 
-def pack_conv_weight(w):
-    """OIHW fp32 -> split [2, Cout, k*k*Cin] with K index (r*k+s)*Cin + ci."""
+# Power-of-two factor the engine multiplies conv weights by before the split (1 / WEIGHT_SCALE goes into the epilogue's
+# scale vector): keeps both fp16 planes of kaiming-sized weights (~0.02) in the normal range -> 22 instead of ~17 bits.
+WEIGHT_SCALE = 256.0
+WEIGHT_SCALE_LOG2 = 8
+
+
+def pack_conv_weight(w, wscale=1.0):
+    """OIHW fp32 -> split [2, Cout, k*k*Cin] of ``wscale * w`` with K index (r*k+s)*Cin + ci."""
     _require_cuda(w, 'w')
     assert w.dtype == torch.float32 and w.ndim == 4 and w.shape[2] == w.shape[3]
     Cout, Cin, k, _ = w.shape
     out = torch.empty((2, Cout, k * k * Cin), dtype=torch.float16, device=w.device)
-    check(nat.lib().vfs_pack_conv_weight(ptr(w), ptr(out), Cout, Cin, k, current_stream()), 'pack_conv_weight')
+    check(nat.lib().vfs_pack_conv_weight_scaled(ptr(w), ptr(out), Cout, Cin, k, float(wscale), current_stream()),
+          'pack_conv_weight')
     return out
 
 
@@ -254,7 +261,7 @@ def bn_apply(z, scale, shift, residual=None, relu=True):
     return out
 
 
-def conv_stats_split(xs, w_split, ksize, stride=1, dilation=1, stats=None):
+def conv_stats_split(xs, w_split, ksize, stride=1, dilation=1, stats=None, wscale=1.0):
     """Train-mode forward conv: raw output as a SPLIT tensor [2,N,Ho,Wo,Cout] (TMA epilogue) + per-channel
     [sum | sum of squares] accumulated into ``stats`` (zeroed fp64 [2*Cout]) by the epilogue's math warps."""
     Cout = w_split.shape[1]
@@ -264,7 +271,8 @@ def conv_stats_split(xs, w_split, ksize, stride=1, dilation=1, stats=None):
     if stats is None:
         stats = torch.zeros((2 * Cout, ), dtype=torch.float64, device=xs.device)
     d = _desc(xs, Cout, ksize, stride, dilation, False)
-    check(nat.lib().vfs_conv_stats_split(ctypes.byref(d), ptr(xs), ptr(w_split), ptr(_const_vec(1, Cout, xs.device)),
+    check(nat.lib().vfs_conv_stats_split(ctypes.byref(d), ptr(xs), ptr(w_split),
+                                         ptr(_const_vec(1.0 / wscale, Cout, xs.device)),
                                          ptr(_const_vec(0, Cout, xs.device)), ptr(z), ptr(stats), current_stream()),
           'conv_stats')
     return z, stats
@@ -290,17 +298,18 @@ def stem_bn_relu_pool(z, scale, shift, in_hw):
     return out
 
 
-def pack_conv_weight_dgrad(w):
-    """OIHW fp32 -> split [2, Cin, k*k*Cout] (flipped kernel, roles of Cin/Cout swapped) for conv_dgrad."""
+def pack_conv_weight_dgrad(w, wscale=1.0):
+    """OIHW fp32 -> split [2, Cin, k*k*Cout] of ``wscale * w`` (flipped kernel, roles of Cin/Cout swapped) for
+    conv_dgrad."""
     _require_cuda(w, 'w')
     Cout, Cin, k, _ = w.shape
     out = torch.empty((2, Cin, k * k * Cout), dtype=torch.float16, device=w.device)
-    check(nat.lib().vfs_pack_conv_weight_dgrad(ptr(w), ptr(out), Cout, Cin, k, current_stream()),
-          'pack_conv_weight_dgrad')
+    check(nat.lib().vfs_pack_conv_weight_dgrad_scaled(ptr(w), ptr(out), Cout, Cin, k, float(wscale),
+                                                      current_stream()), 'pack_conv_weight_dgrad')
     return out
 
 
-def conv_dgrad(dz, wt_split, in_hw, ksize, stride=1, dilation=1, add=None):
+def conv_dgrad(dz, wt_split, in_hw, ksize, stride=1, dilation=1, add=None, wscale=1.0):
     """dX = conv_transpose(dZ, W) (+ add): ``dz`` split [2,N,Ho,Wo,Cout], ``wt_split`` from pack_conv_weight_dgrad,
     ``in_hw`` the forward input (H, W); returns split [2,N,H,W,Cin]."""
     _, N, Ho, Wo, Cout = dz.shape
@@ -311,7 +320,7 @@ def conv_dgrad(dz, wt_split, in_hw, ksize, stride=1, dilation=1, add=None):
     if add is not None:
         assert tuple(add.shape) == tuple(dx.shape)
     d = VfsConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, ksize=ksize, stride=stride, dilation=dilation, relu=0)
-    check(nat.lib().vfs_conv_dgrad(ctypes.byref(d), ptr(dz), ptr(wt_split), ptr(_const_vec(1, Cin, dz.device)),
+    check(nat.lib().vfs_conv_dgrad(ctypes.byref(d), ptr(dz), ptr(wt_split), ptr(_const_vec(1.0 / wscale, Cin, dz.device)),
                                    ptr(_const_vec(0, Cin, dz.device)), ptr(add), ptr(dx), current_stream()),
           'conv_dgrad')
     return dx
@@ -649,8 +658,8 @@ def conv_stack_nhwc(x, convs):
     for i, m in enumerate(mods):
         assert isinstance(m, torch.nn.Conv2d) and m.kernel_size == (1, 1) and m.stride == (1, 1), \
             'vfs_b200 SiamConvFC supports 1x1 adapters (the reference default)'
-        w = pack_conv_weight(m.weight.detach().float().contiguous())
-        scale = torch.ones(m.out_channels, dtype=torch.float32, device=x.device)
+        w = pack_conv_weight(m.weight.detach().float().contiguous(), WEIGHT_SCALE)
+        scale = torch.full((m.out_channels, ), 1.0 / WEIGHT_SCALE, dtype=torch.float32, device=x.device)
         shift = (m.bias.detach().float() if m.bias is not None else torch.zeros_like(scale)).contiguous()
         last = i == len(mods) - 1
         xs, out32 = conv_bn_act(xs, w, scale, shift, 1, 1, 1, relu=False, want_split=not last, want_f32=last)

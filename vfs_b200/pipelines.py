@@ -169,15 +169,23 @@ class PinnedRing:
         if self._count == len(self.slots):
             raise RuntimeError('PinnedRing is full: call get() first')
         s = self.slots[self._head]
-        if s['host'] is None or s['host'].shape != t.shape or s['host'].dtype != t.dtype:
-            s['host'] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        if s['dev'] is None or s['dev'].shape != t.shape or s['dev'].dtype != t.dtype:
+            s['host'] = None
             s['dev'] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
-        s['h2d'].synchronize()               # the previous copy out of this pinned buffer has finished
-        s['host'].copy_(t)                   # (a loader would decode straight into the pinned slot)
+        src = t
+        if not t.is_pinned():
+            # pageable source: stage through this slot's pinned buffer (a loader that decodes straight into pinned
+            # memory -- DataLoader(pin_memory=True) -- skips this copy)
+            if s['host'] is None:
+                s['host'] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            s['h2d'].synchronize()           # the previous copy out of this pinned buffer has finished
+            s['host'].copy_(t)
+            src = s['host']
         self.stream.wait_event(s['free'])    # the kernels that read the old device contents are done
         with torch.cuda.stream(self.stream):
-            s['dev'].copy_(s['host'], non_blocking=True)
+            s['dev'].copy_(src, non_blocking=True)
             s['h2d'].record(self.stream)
+        s['src'] = src                       # keep the pinned source alive until its copy has run
         self._head = (self._head + 1) % len(self.slots)
         self._count += 1
 

@@ -141,8 +141,8 @@ class TrainingMixin:
                 m = convs[0]
                 assert m.kernel_size == (1, 1) and m.stride == (1, 1)
                 xs = ops.to_split(feat.contiguous().float())
-                w = ops.pack_conv_weight(m.weight.detach().float().contiguous())
-                ones = ops._const_vec(1, m.out_channels, feat.device)
+                w = ops.pack_conv_weight(m.weight.detach().float().contiguous(), ops.WEIGHT_SCALE)
+                ones = ops._const_vec(1.0 / ops.WEIGHT_SCALE, m.out_channels, feat.device)
                 shift = m.bias.detach().float().contiguous() if m.bias is not None else \
                     ops._const_vec(0, m.out_channels, feat.device)
                 _, a = ops.conv_bn_act(xs, w, ones, shift, 1, 1, 1, relu=False, want_split=False, want_f32=True)
