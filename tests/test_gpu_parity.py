@@ -1026,6 +1026,76 @@ def test_vanilla_tracker_batched_videos_equal_single_video_calls():
         assert set(np.unique(batched[b])) <= set(range(b + 2))
 
 
+@pytest.mark.parametrize('M,N,K', [(32, 2048, 2048), (8, 512, 2048), (20, 48, 64), (5, 16, 128), (33, 64, 192),
+                                   (7, 24, 36)])
+def test_linear_forward_backward_against_fp64(M, N, K):
+    """Head Linear layers (csrc/linear_mma.cu: warp-MMA 3xTF32 kernels when N % 16 == 0 and K % 64 == 0, csrc/head.cu /
+    train.cu SIMT kernels otherwise -- the last shape) against fp64: fp32-grade error (the fp32 matmul of the oracle
+    itself is 1e-6..1e-5 from fp64 at K = 2048), with and without accumulation into existing gradients."""
+    from vfs_b200 import ops
+    g = torch.Generator().manual_seed(M * 7 + N)
+    x = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    dy = torch.randn(M, N, generator=g)
+    y = ops.linear_forward(x.cuda(), W.cuda(), b.cuda()).cpu().double()
+    ref = x.double() @ W.double().t() + b.double()
+    f32 = (x @ W.t() + b).double()
+    tol = max(4.0 * float((f32 - ref).abs().max()), 2e-6 * float(ref.abs().max()))
+    assert float((y - ref).abs().max()) <= tol, (float((y - ref).abs().max()), tol)
+    dx, dW, db = ops.linear_backward(dy.cuda(), x.cuda(), W.cuda())
+    for got, want64, want32 in ((dx, dy.double() @ W.double(), dy @ W), (dW, dy.double().t() @ x.double(), dy.t() @ x),
+                                (db, dy.double().sum(0), dy.sum(0))):
+        err = float((got.cpu().double() - want64).abs().max())
+        tol = max(4.0 * float((want32.double() - want64).abs().max()), 2e-6 * float(want64.abs().max()))
+        assert err <= tol, (tuple(got.shape), err, tol)
+    # accumulate into existing gradient tensors (flat-gradient sinks), no dx
+    dW0, db0 = torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    dWa, dba = dW0.cuda(), db0.cuda()
+    none_dx, _, _ = ops.linear_backward(dy.cuda(), x.cuda(), W.cuda(), need_dx=False, dW_out=dWa, db_out=dba)
+    assert none_dx is None
+    np.testing.assert_allclose(dWa.cpu().numpy(), (dW0 + dW.cpu()).numpy(), rtol=0, atol=1e-6 * float(dW.abs().max()) + 1e-6)
+    np.testing.assert_allclose(dba.cpu().numpy(), (db0 + db.cpu()).numpy(), rtol=0, atol=1e-5)
+
+
+def test_single_gpu_test_pipelined_driver_equals_blocking_calls():
+    """vfs_b200.apis.single_gpu_test (reference mmaction/apis/test.py:15-45) over a loader of HOST batches: the
+    prefetching device feed + two calls in flight must return exactly what one blocking forward_test call per batch on
+    device tensors returns, in loader order -- pinned and pageable sources, uint8 label maps (loader dtype)."""
+    import vfs_b200
+    from vfs_b200.apis import single_gpu_test
+    c = cases.TRACKER_TEST_CASES['r18_clip5']
+    model = vfs_b200.build_model(dict(type='VanillaTracker', backbone=c['backbone']), train_cfg=None,
+                                 test_cfg=vfs_b200.ConfigDict(c['test_cfg']))
+    model.backbone.load_state_dict(oracle.seeded_state_dict(model.backbone, seed=c['seed']))
+    model = model.cuda()
+    g = torch.Generator().manual_seed(78)
+    meta = [dict(original_shape=(c['H'], c['W'], 3))]
+    loader = []
+    for i in range(5):
+        B = 1 + i % 2
+        imgs = torch.randn(B, 1, 3, c['T'], c['H'], c['W'], generator=g)
+        seg = torch.zeros(B, c['H'], c['W'], dtype=torch.uint8)
+        for b in range(B):
+            seg[b, 5 + 3 * i:30 + 3 * i, 8 + 2 * b:40 + 2 * b] = 1 + (i + b) % 3
+        if i % 2 == 0:
+            imgs, seg = imgs.pin_memory(), seg.pin_memory()
+        loader.append(dict(imgs=imgs, ref_seg_map=seg, img_meta=meta * B))
+    model.eval()
+    expect = []
+    for d in loader:
+        expect.extend(model.forward_test(d['imgs'].cuda(), d['ref_seg_map'].cuda(), d['img_meta']))
+    for depth in (1, 2, 3):
+        got = single_gpu_test(model, loader, pipeline_depth=depth)
+        assert len(got) == len(expect) == 7
+        for a_, b_ in zip(got, expect):
+            assert a_.dtype == np.uint8 and a_.shape == b_.shape
+            np.testing.assert_array_equal(a_, b_)
+    handle = model.forward_test_async(loader[0]['imgs'].cuda(), loader[0]['ref_seg_map'], loader[0]['img_meta'])
+    np.testing.assert_array_equal(handle.result()[0], expect[0])
+    assert handle.result() is handle.result()
+
+
 @pytest.mark.parametrize('P', [1, 3])
 def test_seg_postprocess_matches_torch(P):
     """Fused bilinear upsample + min-max + arg-max (csrc/post.cu) against the reference's torch sequence

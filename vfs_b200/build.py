@@ -17,7 +17,7 @@ LIB_DIR = os.path.join(HERE, '_lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libvfs_b200.so')
 STAMP = os.path.join(LIB_DIR, 'build.stamp')
 
-SOURCES = ['api.cu', 'conv_tc.cu', 'layout.cu', 'stem.cu', 'affinity.cu', 'head.cu', 'xcorr.cu', 'bn.cu', 'wgrad_tc.cu', 'train.cu', 'dense.cu', 'post.cu', 'comm.cu', 'bn_stream.cu', 'siamfc_train.cu']
+SOURCES = ['api.cu', 'conv_tc.cu', 'layout.cu', 'stem.cu', 'affinity.cu', 'head.cu', 'xcorr.cu', 'bn.cu', 'wgrad_tc.cu', 'train.cu', 'dense.cu', 'post.cu', 'comm.cu', 'bn_stream.cu', 'siamfc_train.cu', 'linear_mma.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
     '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr',

@@ -5,6 +5,8 @@
 // HBM; tensor cores would not help.  Exact fp32 FMAs with a fixed summation order.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -22,9 +24,7 @@ __global__ void avgpool_nchw_kernel(const float* __restrict__ in, float* __restr
   if (lane == 0) out[w] = s / static_cast<float>(HW);
 }
 
-// ---- y[m, n] = sum_k x[m,k] W[n,k] + bias[n];  block = 8 warps x 2 output features each, rows tiled by MT.
-// Every 16-byte read of the staged activations feeds two weight rows (the loop is bound by shared-memory reads of x:
-// one output per warp ran 36 us per 2048 x 2048 layer at M = 32, profiles/r02_train_profile_graph_v4.log).
+// ---- y[m, n] = sum_k x[m,k] W[n,k] + bias[n];  block = 8 warps = 8 output features, rows tiled by MT
 template <int MT>
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                      const float* __restrict__ bias, float* __restrict__ y, int M,
@@ -32,57 +32,42 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
   constexpr int KC = 8192 / MT;  // floats of K staged per iteration (32 KB of shared memory)
   __shared__ __align__(16) float xs[MT * KC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * 16 + warp * 2;
-  const int n1 = n0 + 1;
+  const int n = blockIdx.x * 8 + warp;
   const int m0 = blockIdx.y * MT;
-  float acc0[MT], acc1[MT];
+  float acc[MT];
 #pragma unroll
-  for (int m = 0; m < MT; ++m) acc0[m] = acc1[m] = 0.0f;
-  const float* w0 = W + static_cast<size_t>(n0 < N ? n0 : 0) * K;
-  const float* w1 = W + static_cast<size_t>(n1 < N ? n1 : 0) * K;
+  for (int m = 0; m < MT; ++m) acc[m] = 0.0f;
   for (int k0 = 0; k0 < K; k0 += KC) {
     for (int i = threadIdx.x; i < MT * KC; i += 256) {
       const int m = i / KC, kk = i - m * KC;
       xs[i] = (m0 + m < M && k0 + kk < K) ? x[static_cast<size_t>(m0 + m) * K + k0 + kk] : 0.0f;
     }
     __syncthreads();
-    if (n0 < N) {
+    if (n < N) {
       for (int kk = lane * 4; kk < KC; kk += 128) {
         if (k0 + kk < K) {
-          const float4 a4 = __ldg(reinterpret_cast<const float4*>(w0 + k0 + kk));
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(w1 + k0 + kk));
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K + k0 + kk));
 #pragma unroll
           for (int m = 0; m < MT; ++m) {
             const float4 x4 = *reinterpret_cast<const float4*>(xs + m * KC + kk);
-            acc0[m] = fmaf(a4.x, x4.x, acc0[m]);
-            acc0[m] = fmaf(a4.y, x4.y, acc0[m]);
-            acc0[m] = fmaf(a4.z, x4.z, acc0[m]);
-            acc0[m] = fmaf(a4.w, x4.w, acc0[m]);
-            acc1[m] = fmaf(b4.x, x4.x, acc1[m]);
-            acc1[m] = fmaf(b4.y, x4.y, acc1[m]);
-            acc1[m] = fmaf(b4.z, x4.z, acc1[m]);
-            acc1[m] = fmaf(b4.w, x4.w, acc1[m]);
+            acc[m] = fmaf(w4.x, x4.x, acc[m]);
+            acc[m] = fmaf(w4.y, x4.y, acc[m]);
+            acc[m] = fmaf(w4.z, x4.z, acc[m]);
+            acc[m] = fmaf(w4.w, x4.w, acc[m]);
           }
         }
       }
     }
     __syncthreads();
   }
-  if (n0 >= N) return;
-  const float b0 = bias ? bias[n0] : 0.0f;
-  const float b1 = (bias && n1 < N) ? bias[n1] : 0.0f;
+  if (n >= N) return;
+  const float b = bias ? bias[n] : 0.0f;
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
-    float v0 = acc0[m], v1 = acc1[m];
+    float v = acc[m];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-    }
-    if (lane == (m & 31) && m0 + m < M) {
-      y[static_cast<size_t>(m0 + m) * N + n0] = v0 + b0;
-      if (n1 < N) y[static_cast<size_t>(m0 + m) * N + n1] = v1 + b1;
-    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == (m & 31) && m0 + m < M) y[static_cast<size_t>(m0 + m) * N + n] = v + b;
   }
 }
 
@@ -179,12 +164,25 @@ int global_avg_pool_nchw(const float* in, float* out, int B, int C, int HW, cuda
   return VFS_OK;
 }
 
+// csrc/linear_mma.cu: warp-MMA (3xTF32) kernels for N % 16 == 0, K % 64 == 0; VFS_LINEAR_MMA=0 keeps the SIMT kernels
+bool linear_mma_eligible(int M, int N, int K);
+int linear_forward_mma(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, cudaStream_t s);
+bool linear_mma_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VFS_LINEAR_MMA");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 int linear_forward(const float* x, const float* W, const float* bias, float* y, int M, int N, int K,
                    cudaStream_t s) {
   VFS_REQUIRE(x && W && y, VFS_EINVAL, "linear: null argument");
   VFS_REQUIRE(M > 0 && N > 0 && K > 0 && K % 4 == 0, VFS_ESHAPE, "linear: bad shape M=%d N=%d K=%d (K %% 4 == 0)", M,
               N, K);
-  const int nb = (N + 15) / 16;
+  if (linear_mma_enabled() && linear_mma_eligible(M, N, K)) return linear_forward_mma(x, W, bias, y, M, N, K, s);
+  const int nb = (N + 7) / 8;
   if (M <= 8) linear_kernel<8><<<dim3(nb, 1), 256, 0, s>>>(x, W, bias, y, M, N, K);
   else if (M <= 16) linear_kernel<16><<<dim3(nb, 1), 256, 0, s>>>(x, W, bias, y, M, N, K);
   else linear_kernel<32><<<dim3(nb, (M + 31) / 32), 256, 0, s>>>(x, W, bias, y, M, N, K);

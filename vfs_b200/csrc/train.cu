@@ -913,15 +913,26 @@ int relu_bwd_split(const void* dy_split, const void* y_split, void* g_split, lon
   return VFS_OK;
 }
 
+bool linear_mma_eligible(int M, int N, int K);
+bool linear_mma_enabled();
+int linear_bwd_data_mma(const float* dy, const float* W, float* dx, int M, int N, int K, cudaStream_t s);
+int linear_bwd_weight_mma(const float* dy, const float* x, float* dW, float* db, int M, int N, int K, int accumulate,
+                          cudaStream_t s);
+
 int linear_backward(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db, int M, int N,
                     int K, int accumulate, cudaStream_t s) {
   VFS_REQUIRE(dy && x && W, VFS_EINVAL, "linear_backward: null argument");
   VFS_REQUIRE(M > 0 && N > 0 && K > 0, VFS_ESHAPE, "linear_backward: bad shape");
-  if (dx) {
+  const bool mma = linear_mma_enabled() && linear_mma_eligible(M, N, K);
+  if (dx && mma) {
+    const int rc = linear_bwd_data_mma(dy, W, dx, M, N, K, s);
+    if (rc != VFS_OK) return rc;
+  } else if (dx) {
     VFS_CUDA_OK(cudaMemsetAsync(dx, 0, static_cast<size_t>(M) * K * sizeof(float), s));
     linear_bwd_data_kernel<<<dim3((K + 255) / 256, (M + 15) / 16, (N + 127) / 128), 256, 0, s>>>(dy, W, dx, M, N, K);
     VFS_CUDA_OK(cudaGetLastError());
   }
+  if (dW && mma && M <= 32) return linear_bwd_weight_mma(dy, x, dW, db, M, N, K, accumulate, s);
   if (dW) {
     linear_bwd_weight_kernel<<<dim3((K + 255) / 256, (N + 7) / 8), 256, 0, s>>>(dy, x, dW, db, M, N, K, accumulate);
     VFS_CUDA_OK(cudaGetLastError());

@@ -24,6 +24,43 @@ from ..registry import TRACKERS
 from .base import BaseTracker
 
 
+class PendingPredictions:
+    """Handle of an enqueued ``forward_test`` call (see ``VanillaTracker.forward_test_async``)."""
+
+    def __init__(self, host, done, pool=None):
+        self._host, self._done, self._pool, self._value = host, done, pool, None
+
+    @classmethod
+    def finished(cls, value):
+        self = cls(None, None)
+        self._value = value
+        return self
+
+    def result(self):
+        if self._value is None:
+            self._done.synchronize()
+            self._value = list(_unstage(self._host, self._pool))
+            self._host = None
+        return self._value
+
+
+def _stage(pool, shape, dtype):
+    """Pinned staging buffer for one call's predictions.  Buffers are recycled through ``pool``: callers keep the
+    returned arrays (an evaluation run holds every video's predictions), and pinned memory that stays referenced forces
+    a fresh cudaHostAlloc -- a device-synchronising driver call of ~1 ms -- on every call."""
+    free = pool.setdefault((tuple(shape), dtype), [])
+    return free.pop() if free else torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+def _unstage(host, pool):
+    out = host.numpy().copy()           # ordinary host array for the caller (1 MB: tens of microseconds)
+    if pool is not None:
+        free = pool.setdefault((tuple(host.shape), host.dtype), [])
+        if len(free) < 4:
+            free.append(host)
+    return out
+
+
 @TRACKERS.register_module()
 class VanillaTracker(BaseTracker):
     """Pixel tracker: first-frame labels are propagated frame by frame through restricted attention."""
@@ -31,6 +68,7 @@ class VanillaTracker(BaseTracker):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.save_np = self.test_cfg.get('save_np', False)
+        self._result_pool = {}
 
     @property
     def stride(self):
@@ -122,6 +160,22 @@ class VanillaTracker(BaseTracker):
     def forward_train(self, imgs, labels=None):
         raise NotImplementedError
 
+    # inputs the evaluation driver leaves on the host (vfs_b200.apis.single_gpu_test): forward_test reads the class
+    # count from a host label map for free and copies it itself
+    host_inputs = ('ref_seg_map', )
+
+    def forward_test_async(self, imgs, ref_seg_map, img_meta):
+        """``forward_test`` without the final host wait: everything (backbone, propagation, post-processing, the
+        device->host copy of the predictions into pinned memory) is enqueued and a ``PendingPredictions`` is
+        returned; ``.result()`` waits for the copy and returns what ``forward_test`` returns.  Calls are ordered by
+        the stream, so a driver can enqueue call i+1 before collecting call i and keep the device busy
+        (vfs_b200.apis.single_gpu_test does).  Paths that need the host in the middle (several feature levels,
+        ``save_np``) run synchronously and return a finished handle."""
+        if self._multi_level() or self.save_np:
+            return PendingPredictions.finished(self.forward_test(imgs, ref_seg_map, img_meta))
+        host, done = self._forward_test_level(imgs, ref_seg_map, img_meta, defer=True)
+        return PendingPredictions(host, done, self._result_pool)
+
     def forward_test(self, imgs, ref_seg_map, img_meta):
         """imgs [B,1,3,T,H,W], ref_seg_map [B,H,W] (label ids) or [B,Cv,H,W] (one-hot) -> list of B arrays [T,H,W]
         (``[L,T,H,W]`` when the propagation runs on L > 1 feature levels: several out indices or
@@ -148,8 +202,9 @@ class VanillaTracker(BaseTracker):
             return [paths] if len(paths) > 1 else [paths[0]]
         return list(preds)
 
-    def _forward_test_level(self, imgs, ref_seg_map, img_meta, bank=None):
-        """One feature level: imgs [B,1,3,T,H,W] -> predictions [B,T,H,W] (host array).
+    def _forward_test_level(self, imgs, ref_seg_map, img_meta, bank=None, defer=False):
+        """One feature level: imgs [B,1,3,T,H,W] -> predictions [B,T,H,W] (host array; with ``defer`` the pinned host
+        tensor and the event that marks the end of its device->host copy).
 
         The reference handles one video per call (``get_feats`` asserts B == 1, vanilla_tracker.py:56).  Here B
         videos of equal length are propagated together -- one backbone pass over the B*T frames, one attention
@@ -230,9 +285,13 @@ class VanillaTracker(BaseTracker):
                     preds[b0:b0 + len(vids), frame_idx] = F.interpolate(
                         seg_logit.view(len(vids), cv, fh, fw), size=orig_hw, mode='bilinear', align_corners=False)
 
-        # one device->host copy per call, into pinned memory from torch's caching host allocator (a pageable
-        # destination makes the copy several times slower); the returned arrays are views that keep the block alive
-        host = torch.empty(preds.shape, dtype=preds.dtype, pin_memory=True)
+        # one device->host copy per call, into a recycled pinned staging buffer (a pageable destination makes the copy
+        # several times slower)
+        host = _stage(self._result_pool, preds.shape, preds.dtype)
         host.copy_(preds, non_blocking=True)
+        if defer:
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(imgs.device))
+            return host, done
         torch.cuda.current_stream(imgs.device).synchronize()
-        return host.numpy()
+        return _unstage(host, self._result_pool)
