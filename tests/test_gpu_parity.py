@@ -1210,13 +1210,16 @@ def test_backward_through_eval_mode_bn_matches_oracle_autograd(depth):
         denom = max(float(r64.norm()), 1e-6 * gnorm)
         mine = float((gk.cpu().double() - r64).norm()) / denom
         base = float((ref[k].double() - r64).norm()) / denom
-        # Floor 2e-2: the tcgen05 forward is ~7e-5 (max-relative) away from fp64 (fp32 accumulation in the tensor core
+        # Floor 4e-2: the tcgen05 forward is ~7e-5 (max-relative) away from fp64 (fp32 accumulation in the tensor core
         # truncates; the fp32 oracle is at 4e-6), which flips the ReLU mask of the few activations that sit within 1e-4
         # of zero.  On these small maps ONE flipped element moves every upstream gradient by ~1e-2: the error is a step
         # function of depth that starts at the flipped layer with d(beta) hit 20x harder than d(gamma)
         # (tools/evalbn_debug.py) -- not a rounding drift.  A wrong formula (missing gamma or invstd, batch-statistic
-        # terms left in) is O(1) and a wrong parameter set is caught above.
-        if mine > max(10 * base, 2e-2):
+        # terms left in) is O(1) and a wrong parameter set is caught above.  Measured over repeated runs: R18 <= 1.2e-2,
+        # R50 up to 2.4e-2 (layer4.1.conv2.bn.bias: 4 images x 3 x 3 positions = 36 terms per channel, one flipped
+        # term changes that channel's d(beta) by a full summand); the cosine check below bounds the same quantity at
+        # 6e-2.
+        if mine > max(10 * base, 4e-2):
             bad.append((k, mine, base))
     assert not bad, bad[:6]
     cos = []

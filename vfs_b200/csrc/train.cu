@@ -632,11 +632,19 @@ int stem_pool_relu_bwd(const void* dpool_split, const float* z, const float* sca
   return VFS_OK;
 }
 
+int stem_wgrad_tc(const float* x, const float* dz, float* dw, float out_scale, int N, int H, int W, cudaStream_t s);
+
 int stem_wgrad(const float* x, const float* dz, float* dw, int accumulate, float out_scale, int N, int H, int W,
                cudaStream_t s) {
   VFS_REQUIRE(x && dz && dw, VFS_EINVAL, "stem_wgrad: null argument");
   const int Hc = (H + 6 - 7) / 2 + 1, Wc = (W + 6 - 7) / 2 + 1;
   if (!accumulate) VFS_CUDA_OK(cudaMemsetAsync(dw, 0, 64 * 147 * sizeof(float), s));
+  static int simt = -1;
+  if (simt < 0) {
+    const char* e = getenv("VFS_STEM_WGRAD_SIMT");
+    simt = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!simt) return stem_wgrad_tc(x, dz, dw, out_scale, N, H, W, s);   // csrc/stem.cu: tcgen05 version
   const int segs = (Wc + kStemSegMax - 1) / kStemSegMax;
   const int seg_w = (Wc + segs - 1) / segs;          // e.g. Wc = 112 -> 4 segments of 28 pixels
   stem_wgrad_kernel<<<148 * 3, 256, 0, s>>>(x, dz, dw, N, H, W, Hc, Wc, seg_w, out_scale);

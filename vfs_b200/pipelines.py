@@ -169,9 +169,9 @@ class PinnedRing:
         if self._count == len(self.slots):
             raise RuntimeError('PinnedRing is full: call get() first')
         s = self.slots[self._head]
-        if s['dev'] is None or s['dev'].shape != t.shape or s['dev'].dtype != t.dtype:
+        fresh = s['dev'] is None or s['dev'].shape != t.shape or s['dev'].dtype != t.dtype
+        if fresh:
             s['host'] = None
-            s['dev'] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
         src = t
         if not t.is_pinned():
             # pageable source: stage through this slot's pinned buffer (a loader that decodes straight into pinned
@@ -183,6 +183,10 @@ class PinnedRing:
             src = s['host']
         self.stream.wait_event(s['free'])    # the kernels that read the old device contents are done
         with torch.cuda.stream(self.stream):
+            if fresh:
+                # allocated under the copy stream: the caching allocator orders block reuse per stream, and a block of
+                # the caller's stream may still be referenced by kernels queued there when the copy stream writes it
+                s['dev'] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
             s['dev'].copy_(src, non_blocking=True)
             s['h2d'].record(self.stream)
         s['src'] = src                       # keep the pinned source alive until its copy has run
@@ -197,6 +201,7 @@ class PinnedRing:
             self._last['free'].record(cur)   # everything enqueued since the last get() consumed that slot
         s = self.slots[self._tail]
         cur.wait_event(s['h2d'])
+        s['dev'].record_stream(cur)          # consumed on the caller's stream: keep the block until that work is done
         self._tail = (self._tail + 1) % len(self.slots)
         self._count -= 1
         self._last = s

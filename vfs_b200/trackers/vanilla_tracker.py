@@ -285,13 +285,17 @@ class VanillaTracker(BaseTracker):
                     preds[b0:b0 + len(vids), frame_idx] = F.interpolate(
                         seg_logit.view(len(vids), cv, fh, fw), size=orig_hw, mode='bilinear', align_corners=False)
 
-        # one device->host copy per call, into a recycled pinned staging buffer (a pageable destination makes the copy
-        # several times slower)
-        host = _stage(self._result_pool, preds.shape, preds.dtype)
-        host.copy_(preds, non_blocking=True)
+        # one device->host copy per call, into pinned memory (a pageable destination makes the copy several times
+        # slower); deferred calls stage through recycled buffers, see _stage
         if defer:
+            host = _stage(self._result_pool, preds.shape, preds.dtype)
+            host.copy_(preds, non_blocking=True)
             done = torch.cuda.Event()
             done.record(torch.cuda.current_stream(imgs.device))
             return host, done
+        # blocking call: pinned memory from torch's caching host allocator, returned as views (no host copy; the
+        # device is idle by the time a fresh block would have to be allocated)
+        host = torch.empty(preds.shape, dtype=preds.dtype, pin_memory=True)
+        host.copy_(preds, non_blocking=True)
         torch.cuda.current_stream(imgs.device).synchronize()
-        return _unstage(host, self._result_pool)
+        return host.numpy()
