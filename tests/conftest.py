@@ -32,3 +32,15 @@ def golden():
     path = os.path.join(ROOT, 'tests', 'golden', 'vfs_golden.npz')
     with np.load(path) as z:
         return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _torch_cpu_threads():
+    """The oracle runs on torch CPU: keep its intra-op pool within the cores this process may use (GPU boxes expose
+    many more logical CPUs than the container's affinity mask / quota allows)."""
+    try:
+        import torch
+        torch.set_num_threads(max(1, min(16, len(os.sched_getaffinity(0)))))
+    except Exception:
+        pass
+    yield

@@ -18,6 +18,23 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-3  # north_star: "within 1e-3 rel fp32"
 
 
+def stable_oracle(fn, tries=5):
+    """Evaluate a CPU-oracle expression until two consecutive evaluations are bit-identical.  On the GPU boxes the
+    FIRST torch-CPU evaluation of the dense-softmax oracle in a fresh process came back wrong in about 1 of 30
+    processes (tools/dense_flake_probe.py: the CUDA output matched an fp64 re-evaluation of the same inputs to 1e-7,
+    the oracle's own second evaluation differed from its first by 0.12 -- a host-side torch threading artefact, not
+    reproducible in 40 cold processes in the build container).  The GPU result is not involved in the vote."""
+    prev = fn()
+    for _ in range(tries):
+        cur = fn()
+        if torch.equal(prev, cur):
+            return cur
+        print('[oracle] two CPU evaluations of the oracle disagreed (max abs diff %.3e); re-evaluating'
+              % float((prev - cur).abs().max()))
+        prev = cur
+    raise AssertionError('the CPU oracle does not give a reproducible result')
+
+
 def rel_err(got, ref):
     got = torch.as_tensor(got).detach().double().cpu()
     ref = torch.as_tensor(ref).detach().double().cpu()
@@ -502,8 +519,8 @@ def test_attention_general_masks_and_dense_softmax_match_oracle(case):
     out = masked_attention_efficient(q.cuda(), k.cuda(), v.cuda(), mask.cuda() if torch.is_tensor(mask) else mask,
                                      temperature=0.07 if mode == 'softmax' else 1.0, topk=topk, non_mask_len=nml,
                                      mode=mode)
-    ref = oracle.masked_attention_efficient(q, k, v, ref_mask, temperature=0.07 if mode == 'softmax' else 1.0,
-                                            topk=topk, non_mask_len=nml, mode=mode)
+    ref = stable_oracle(lambda: oracle.masked_attention_efficient(
+        q, k, v, ref_mask, temperature=0.07 if mode == 'softmax' else 1.0, topk=topk, non_mask_len=nml, mode=mode))
     assert tuple(out.shape) == tuple(ref.shape) == (N, Cv, Hq, Wq)
     assert rel_err(out, ref) < REL_TOL
 

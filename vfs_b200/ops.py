@@ -783,6 +783,9 @@ def masked_attention(query, key, value, mask, temperature, topk, normalize=True,
     return out
 
 
+GENERIC_ATTN_DEBUG = None
+
+
 def masked_attention_generic(query, key, value, mask, temperature, topk, normalize=True, non_mask_len=0,
                              mode='softmax'):
     """masked_attention_efficient for an arbitrary boolean ``mask`` tensor ([HWk,HWq], or [N,HWk,HWq] with T == 1)
@@ -821,12 +824,16 @@ def masked_attention_generic(query, key, value, mask, temperature, topk, normali
                                                  1, C, Hq, Wq, int(normalize), Cp, w_split.stride(0),
                                                  current_stream()), what)
         _, aff = conv_bn_act(a_split, w_split, scale, shift, 1, 1, 1, relu=False, want_split=False, want_f32=True)
+        if GENERIC_ATTN_DEBUG is not None:      # tools/dense_flake_probe.py: intermediates of the last call
+            GENERIC_ATTN_DEBUG.update(a_split=a_split, w_split=w_split, aff=aff, scale=scale, shift=shift)
         # reference quirk (local_attention.py:320-326): with top-k every batch item gathers the values of item 0
         vals = value[0 if topk is not None else b].float().reshape(Cv, rows).contiguous()
         mb = None if m8 is None else (m8 if m8.ndim == 2 else m8[b])
         check(nat.lib().vfs_generic_attention(ptr(aff), rows, HWqp, HWk, HWq, ptr(mb), int(non_mask_len), ptr(vals),
                                               Cv, int(topk or 0), 0 if mode == 'softmax' else 1, ptr(out[b]),
                                               current_stream()), 'generic_attention')
+        if GENERIC_ATTN_DEBUG is not None:
+            GENERIC_ATTN_DEBUG.update(mask=mb, vals=vals, out=out[b])
     return out.reshape(N, Cv, Hq, Wq)
 
 
