@@ -99,13 +99,18 @@ struct UnitInfo {
 template <bool WIDE>
 __device__ __forceinline__ UnitInfo decode_unit(const AttnParams& p, int unit) {
   UnitInfo u;
+  // unit order: window slice fastest, then query tile, then key frame, then problem.  The CTAs of a wave then work
+  // on ONE key frame (26 MB of split features at 480p: L2-resident) and every frame is read from DRAM about once;
+  // with the key frame varying faster than the query tile all T frames were live at once (550 MB at T = 21) and
+  // the window overlap of neighbouring query tiles was re-read from DRAM: 2.63 GB per launch against 0.58 GB of
+  // compulsory bytes (profiles/r02_affinity_480p_ncu.csv).
   const int s = unit % p.splits;
   const int r = unit / p.splits;
-  u.t = r % p.T;
-  const int r3 = r / p.T;
   const int q_tiles = p.q_tiles_x * p.q_tiles_y;
-  const int qt = r3 % q_tiles;
-  u.b = r3 / q_tiles;
+  const int qt = r % q_tiles;
+  const int r3 = r / q_tiles;
+  u.t = r3 % p.T;
+  u.b = r3 / p.T;
   u.qx0 = (qt % p.q_tiles_x) * kQTileW;
   u.qy0 = (qt / p.q_tiles_x) * kQTileH;
   u.w = key_window(p, u.qy0, u.qx0, u.t);

@@ -45,9 +45,10 @@ class PendingPredictions:
 
 
 def _stage(pool, shape, dtype):
-    """Pinned staging buffer for one call's predictions.  Buffers are recycled through ``pool``: callers keep the
-    returned arrays (an evaluation run holds every video's predictions), and pinned memory that stays referenced forces
-    a fresh cudaHostAlloc -- a device-synchronising driver call of ~1 ms -- on every call."""
+    """Pinned staging buffer for one call's predictions.  Buffers are recycled through ``pool`` and the caller gets an
+    ordinary host array: an evaluation run keeps every video's predictions, and returning views of pinned memory would
+    force a fresh cudaHostAlloc -- a device-synchronising driver call, measured 4 ms -- on every call
+    (bench.py e2e.blocking_driver: 1378 -> ~4000 frame-pairs/s)."""
     free = pool.setdefault((tuple(shape), dtype), [])
     return free.pop() if free else torch.empty(shape, dtype=dtype, pin_memory=True)
 
@@ -287,15 +288,11 @@ class VanillaTracker(BaseTracker):
 
         # one device->host copy per call, into pinned memory (a pageable destination makes the copy several times
         # slower); deferred calls stage through recycled buffers, see _stage
+        host = _stage(self._result_pool, preds.shape, preds.dtype)
+        host.copy_(preds, non_blocking=True)
         if defer:
-            host = _stage(self._result_pool, preds.shape, preds.dtype)
-            host.copy_(preds, non_blocking=True)
             done = torch.cuda.Event()
             done.record(torch.cuda.current_stream(imgs.device))
             return host, done
-        # blocking call: pinned memory from torch's caching host allocator, returned as views (no host copy; the
-        # device is idle by the time a fresh block would have to be allocated)
-        host = torch.empty(preds.shape, dtype=preds.dtype, pin_memory=True)
-        host.copy_(preds, non_blocking=True)
         torch.cuda.current_stream(imgs.device).synchronize()
-        return host.numpy()
+        return _unstage(host, self._result_pool)
