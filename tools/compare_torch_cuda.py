@@ -16,8 +16,56 @@ import oracle  # noqa: E402
 from vfs_b200.backbones import ResNet  # noqa: E402  (state-dict names only)
 
 
+def train_comparator(dev):
+    """SimSiam R50 train step (SURVEY cfg-2 / cfg-4 per-GPU shape) on stock torch-CUDA: forward + loss + autograd
+    backward (cuDNN / cuBLAS) through the oracle functions + torch.optim.SGD, eager launches, TF32 on / off."""
+    import vfs_b200
+    out = {}
+    model = vfs_b200.build_model(bench.TRAIN_MODEL, train_cfg=vfs_b200.ConfigDict(dict(intra_video=False)), test_cfg=None)
+    sd0 = oracle.seeded_state_dict(model, seed=0)
+    del model
+    for label, clips, size in (('cfg2_8x2x256', 8, 256), ('cfg4_32x2x224', 32, 224)):
+        g = torch.Generator().manual_seed(4321)
+        imgs = torch.randn(clips, 2, 3, 1, size, size, generator=g).to(dev)
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            params = {k: v.clone().to(dev).requires_grad_(v.dtype.is_floating_point and 'running' not in k)
+                      for k, v in sd0.items()}
+            opt = torch.optim.SGD([p for p in params.values() if p.requires_grad], lr=0.05, momentum=0.9,
+                                  weight_decay=1e-4)
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                losses = oracle.simsiam_forward_train(params, imgs, 50, intra_video=False, bn_training=True)
+                loss = sum(v.mean() for v in losses.values())
+                loss.backward()
+                opt.step()
+                return loss
+
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            out[f'{label}_{"tf32" if tf32 else "fp32"}'] = dict(ms_per_step=ms, frame_pairs_per_s=clips / (ms * 1e-3),
+                                                               loss=float(loss))
+            del params, opt
+            torch.cuda.empty_cache()
+    print(json.dumps(dict(what='stock torch-CUDA SimSiam R50 train step (cuDNN/cuBLAS autograd through the oracle modules '
+                          '+ torch.optim.SGD), eager, 1 GPU, device-timed over 10 steps; channels-first fp32 tensors, '
+                          'BN running statistics not updated (the oracle clones them)', **out)))
+
+
 def main():
     dev = torch.device('cuda', 0)
+    if '--train' in sys.argv:
+        return train_comparator(dev)
     net = ResNet(50, norm_cfg=dict(type='SyncBN', requires_grad=True), strides=(1, 2, 1, 1), out_indices=(2, ))
     sd = {k: v.to(dev) for k, v in oracle.seeded_state_dict(net, seed=0).items()}
     g = torch.Generator().manual_seed(1234)

@@ -64,6 +64,22 @@ def main():
     torch.cuda.synchronize()
     print('   host enqueue time of the same: %.3f ms' % t_host)
 
+    # device-side view of the pipelined driver: kernel table of 20 calls (two in flight)
+    from torch.profiler import ProfilerActivity, profile
+    from vfs_b200.apis import single_gpu_test
+    loader = [dict(imgs=imgs_host, ref_seg_map=seg_u8, img_meta=meta) for _ in range(20)]
+    single_gpu_test(model, loader[:4])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    single_gpu_test(model, loader)
+    torch.cuda.synchronize()
+    print('pipelined driver: %.3f ms per call' % ((time.perf_counter() - t0) / 20 * 1e3))
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        single_gpu_test(model, loader)
+        torch.cuda.synchronize()
+    tab = prof.key_averages().table(sort_by='cuda_time_total', row_limit=40, max_name_column_width=70)
+    print('\n'.join(line[:70] + line[-60:] for line in tab.splitlines()))
+
     pr = cProfile.Profile()
     for _ in range(5):
         call(seg_u8)
