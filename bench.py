@@ -739,8 +739,16 @@ def main():
     attn_med = statistics.median(attn_ms)
     attn_tf = attn_flops / (attn_med * 1e-3) / 1e12
     attn_bytes = 4.0 * CLIPS * (2 * 1024 * hw + 2 * CV * hw)          # q + k features, values in, labels out
+    attn_traffic = None        # ncu dram__bytes of the two attention kernels of one step (profiles/r02_ncu_step.json)
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_ncu_step.json')) as fh_:
+            attn_traffic = sum(k_.get('dram_read_bytes', 0.0) + k_.get('dram_write_bytes', 0.0)
+                               for k_ in json.load(fh_)['kernels'] if k_['kernel'].startswith('attn_'))
+    except Exception:
+        pass
     roofline_affinity = dict(bound='tensor', kernel='attn_scores_topk_kernel + attn_merge_propagate_kernel',
-                             achieved=attn_tf, peak=peak_tf, unit='TFLOP/s', frac=attn_tf / peak_tf, traffic=None,
+                             achieved=attn_tf, peak=peak_tf, unit='TFLOP/s', frac=attn_tf / peak_tf,
+                             traffic=attn_traffic,
                              segment_ms_median=attn_med, flops_per_step=attn_flops,
                              hbm_gbs_algorithmic=attn_bytes / (attn_med * 1e-3) / 1e9,
                              note='window-restricted fp32-equivalent FLOPs (3 MMAs issued per product, and whole '

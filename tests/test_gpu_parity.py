@@ -1102,8 +1102,8 @@ def test_single_gpu_test_pipelined_driver_equals_blocking_calls():
     expect = []
     for d in loader:
         expect.extend(model.forward_test(d['imgs'].cuda(), d['ref_seg_map'].cuda(), d['img_meta']))
-    for depth in (1, 2, 3):
-        got = single_gpu_test(model, loader, pipeline_depth=depth)
+    for depth, coalesce in ((1, None), (2, None), (3, None), (2, 1), (2, 3)):   # None: 8 videos per call at depth > 1
+        got = single_gpu_test(model, loader, pipeline_depth=depth, coalesce=coalesce)
         assert len(got) == len(expect) == 7
         for a_, b_ in zip(got, expect):
             assert a_.dtype == np.uint8 and a_.shape == b_.shape

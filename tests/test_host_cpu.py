@@ -476,3 +476,25 @@ def test_peer_communicator_and_device_feeds_fail_loudly_without_cuda():
     aug = vfs_b200.DeviceTrainAugment(mean=[0, 0, 0], std=[1, 1, 1], device='cpu')
     with pytest.raises(RuntimeError):
         aug(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), [(0, 0, 8, 8)], [False])
+
+
+def test_evaluation_driver_coalesces_only_batches_of_identical_layout():
+    """vfs_b200.apis._coalesced: consecutive loader batches are merged along the batch axis up to the limit, never
+    across a change of clip length / resolution / dtype, and a batch that already reaches the limit passes through."""
+    import torch
+    from vfs_b200.apis import _coalesced
+
+    def mk(b, t=3, tag=0):
+        return dict(imgs=torch.full((b, 1, 3, t, 4, 4), float(tag)), ref_seg_map=torch.zeros(b, 4, 4, dtype=torch.uint8),
+                    img_meta=[dict(tag=tag)] * b)
+
+    batches = [mk(1, tag=0), mk(2, tag=1), mk(1, tag=2), mk(1, 5, tag=3), mk(8, tag=4), mk(3, tag=5), mk(3, tag=6),
+               mk(3, tag=7)]
+    out = list(_coalesced(batches, 8))
+    assert [(d['imgs'].shape[0], d['imgs'].shape[3]) for d in out] == [(4, 3), (1, 5), (8, 3), (6, 3), (3, 3)]
+    assert [m['tag'] for m in out[0]['img_meta']] == [0, 1, 1, 2]
+    assert out[0]['imgs'][:, 0, 0, 0, 0, 0].tolist() == [0.0, 1.0, 1.0, 2.0]          # sample order is kept
+    assert out[2] is batches[4]
+    assert [d['imgs'].shape[0] for d in _coalesced(batches[:3], 1)] == [1, 2, 1]
+    odd = dict(imgs=torch.zeros(1, 1, 3, 3, 4, 4), extra=7)                           # a non-list, non-tensor entry
+    assert list(_coalesced([mk(1), odd, mk(1)], 8))[1] is odd

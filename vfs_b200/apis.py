@@ -73,15 +73,72 @@ def _batches_on_device(model, data_loader):
         cur = nxt
 
 
-def single_gpu_test(model, data_loader, pipeline_depth=2):
+def _signature(data):
+    """What must agree for two loader batches to be merged along the batch axis."""
+    sig = []
+    for k in sorted(data):
+        v = data[k]
+        if torch.is_tensor(v):
+            sig.append((k, 'tensor', tuple(v.shape[1:]), v.dtype, v.device))
+        elif isinstance(v, list):
+            sig.append((k, 'list'))
+        else:
+            return None
+    return tuple(sig)
+
+
+def _merge(group):
+    """Concatenate loader batches along the batch axis.  Device tensors are copied piece by piece into one buffer as
+    they arrive (the feed's ring slots are recycled after a few batches), host tensors and lists are concatenated."""
+    if len(group) == 1:
+        return group[0]
+    out = {}
+    for k, v in group[0].items():
+        if torch.is_tensor(v):
+            out[k] = torch.cat([d[k] for d in group], dim=0)
+        else:
+            out[k] = [x for d in group for x in d[k]]
+    return out
+
+
+def _coalesced(batches, max_videos):
+    """Group consecutive batches of identical layout into one call of at most ``max_videos`` samples.  The reference
+    configs evaluate with videos_per_gpu = 1 (configs/*:106), i.e. one two-to-hundred-frame video per forward_test call;
+    VanillaTracker.forward_test takes B equal-length videos per call with results identical to B separate calls
+    (tests: test_vanilla_tracker_batched_videos_equal_single_video_calls), and small launches are what a per-video call
+    loses on 148 SMs.  Videos of different length or resolution are never merged."""
+    group, sig, count = [], None, 0
+    for data in batches:
+        s = _signature(data)
+        n = len(next((v for v in data.values() if torch.is_tensor(v)), [0]))
+        if group and (s is None or s != sig or count + n > max_videos):
+            yield _merge(group)
+            group, count = [], 0
+        if s is None or (not group and n >= max_videos):
+            yield data
+            continue
+        # device tensors are cloned out of the feed's ring right away: the slot is recycled a few batches later
+        group.append({k: (v.clone() if (torch.is_tensor(v) and v.is_cuda) else v) for k, v in data.items()})
+        sig, count = s, count + n
+        if count >= max_videos:
+            yield _merge(group)
+            group, count = [], 0
+    if group:
+        yield _merge(group)
+
+
+def single_gpu_test(model, data_loader, pipeline_depth=2, coalesce=None):
     """mmaction/apis/test.py:15-45: list of per-sample results.
 
     Batches are moved to the model's device like the reference's MMDataParallel does, and a model that offers
     ``forward_test_async`` (VanillaTracker) is driven ``pipeline_depth`` calls deep: call i+1 is enqueued before the
-    predictions of call i are collected, so the host-side waits (H2D, D2H, launch latency) overlap device work.  Results
-    and their order are those of the plain loop."""
+    predictions of call i are collected, so the host-side waits (H2D, D2H, launch latency) overlap device work.
+    ``coalesce`` (default: the model's ``coalesce_videos`` attribute, 8 for VanillaTracker, 1 = off) merges consecutive
+    loader batches of identical layout into one call.  Results and their order are those of the plain loop."""
     model.eval()
     results, pending = [], []
+    if coalesce is None:
+        coalesce = int(getattr(model, 'coalesce_videos', 1)) if pipeline_depth > 1 else 1
 
     def collect(result):
         if isinstance(result, list):        # reference test.py:36-39: lists are flattened, anything else is one result
@@ -90,7 +147,10 @@ def single_gpu_test(model, data_loader, pipeline_depth=2):
             results.append(result)
 
     enqueue = getattr(model, 'forward_test_async', None) if pipeline_depth > 1 else None
-    for data in _batches_on_device(model, data_loader):
+    batches = _batches_on_device(model, data_loader)
+    if coalesce > 1:
+        batches = _coalesced(batches, coalesce)
+    for data in batches:
         with torch.no_grad():
             if enqueue is None:
                 collect(model(return_loss=False, **data))

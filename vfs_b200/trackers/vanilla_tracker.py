@@ -164,6 +164,9 @@ class VanillaTracker(BaseTracker):
     # inputs the evaluation driver leaves on the host (vfs_b200.apis.single_gpu_test): forward_test reads the class
     # count from a host label map for free and copies it itself
     host_inputs = ('ref_seg_map', )
+    # the evaluation driver may merge up to this many consecutive single-video batches of identical layout into one call
+    # (B videos per call give the same predictions as B calls)
+    coalesce_videos = 8
 
     def forward_test_async(self, imgs, ref_seg_map, img_meta):
         """``forward_test`` without the final host wait: everything (backbone, propagation, post-processing, the
