@@ -1108,6 +1108,11 @@ def test_single_gpu_test_pipelined_driver_equals_blocking_calls():
         for a_, b_ in zip(got, expect):
             assert a_.dtype == np.uint8 and a_.shape == b_.shape
             np.testing.assert_array_equal(a_, b_)
+    # an unsupported test_cfg.topk is a clear error, not a ctypes TypeError
+    dense = vfs_b200.build_model(dict(type='VanillaTracker', backbone=c['backbone']), train_cfg=None,
+                                 test_cfg=vfs_b200.ConfigDict(dict(c['test_cfg'], topk=None))).cuda()
+    with pytest.raises(NotImplementedError, match='topk'):
+        dense.forward_test(loader[0]['imgs'].cuda(), loader[0]['ref_seg_map'], loader[0]['img_meta'])
     handle = model.forward_test_async(loader[0]['imgs'].cuda(), loader[0]['ref_seg_map'], loader[0]['img_meta'])
     np.testing.assert_array_equal(handle.result()[0], expect[0])
     assert handle.result() is handle.result()

@@ -221,6 +221,11 @@ class VanillaTracker(BaseTracker):
         imgs = imgs.reshape((-1, ) + imgs.shape[2:])
         num_videos, clip_len = imgs.size(0), imgs.size(2)
         cfg = self.test_cfg
+        if cfg.get('topk', None) is None or not 1 <= int(cfg.topk) <= 16:
+            raise NotImplementedError(
+                'vfs_b200 VanillaTracker: test_cfg.topk must be an integer in [1, 16] (the fused bank kernel keeps the '
+                f'k best keys per query in registers), got {cfg.get("topk", None)!r}; softmax over every key of the '
+                'window is available through vfs_b200.common.masked_attention_efficient(..., topk=None)')
         fh, fw = self._feature_hw(imgs.shape[-2:]) if bank is None else tuple(bank.shape[2:4])
         hw = fh * fw
         orig_hw = tuple(img_meta[0]['original_shape'][:2])
