@@ -1,6 +1,8 @@
 // C-ABI surface of libvfs_b200.so (see include/vfs_b200.h) + host helpers.
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "host_common.h"
 
 namespace vfs {
@@ -18,6 +20,15 @@ int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return VFS_OK;
   set_last_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
   return VFS_ECUDA;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VFS_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 int device_sm_count() {

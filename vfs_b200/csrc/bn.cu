@@ -52,6 +52,7 @@ __global__ void bn_finalize_kernel(double* __restrict__ stats, double count, con
                                    float* __restrict__ running_var, float momentum, float eps,
                                    float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd, int C) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = stats[c] / count;
@@ -77,6 +78,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ z, const h16* __restri
                                 const float* __restrict__ shift, const h16* __restrict__ res_hi,
                                 const h16* __restrict__ res_lo, h16* __restrict__ out_hi,
                                 h16* __restrict__ out_lo, long long total8, int C, int relu) {
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long o = i * 8;
@@ -164,9 +166,8 @@ int bn_finalize(double* stats, double count, const float* gamma, const float* be
                 float* save_invstd, int C, cudaStream_t s) {
   VFS_REQUIRE(stats && scale && shift, VFS_EINVAL, "bn_finalize: null argument");
   VFS_REQUIRE(count > 1.0, VFS_ESHAPE, "bn_finalize: Expected more than 1 value per channel when training");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, count, gamma, beta, running_mean, running_var, momentum,
-                                                     eps, scale, shift, save_mean, save_invstd, C);
-  VFS_CUDA_OK(cudaGetLastError());
+  VFS_CUDA_OK(launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, s, stats, count, gamma, beta,
+                         running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd, C));
   return VFS_OK;
 }
 
@@ -180,9 +181,9 @@ int bn_apply(const float* z, const void* z_split, const float* scale, const floa
   long long blocks = (total8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   const h16* zh = z ? nullptr : reinterpret_cast<const h16*>(z_split);
-  bn_apply_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(z, zh, zh ? zh + M * C : nullptr, scale, shift, rh,
-                                                           rh ? rh + M * C : nullptr, oh, oh + M * C, total8, C, relu);
-  VFS_CUDA_OK(cudaGetLastError());
+  VFS_CUDA_OK(launch_pdl(bn_apply_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, z, zh,
+                         zh ? zh + M * C : nullptr, scale, shift, rh, rh ? rh + M * C : nullptr, oh, oh + M * C, total8,
+                         C, relu));
   return VFS_OK;
 }
 

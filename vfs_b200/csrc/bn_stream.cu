@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) bn_bwd_stream_kernel(const Stream
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();   // launched with launch_pdl: the barrier set-up above overlaps the tail of the previous kernel
   const long long num_tiles = (a.total + kTile - 1) / kTile;
 
   if (warp == kConsumers / 32) {
@@ -219,7 +220,7 @@ int launch_stream(const StreamArgs& a, cudaStream_t s) {
   const long long num_tiles = (a.total + kTile - 1) / kTile;
   long long grid = device_sm_count();
   if (grid > num_tiles) grid = num_tiles;
-  bn_bwd_stream_kernel<APPLY><<<static_cast<int>(grid), kThreads, kSmemBytes, s>>>(a);
+  VFS_CUDA_OK(launch_pdl(bn_bwd_stream_kernel<APPLY>, dim3(static_cast<unsigned>(grid)), dim3(kThreads), kSmemBytes, s, a));
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }

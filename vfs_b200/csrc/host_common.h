@@ -35,4 +35,27 @@ int make_tmap_16b_sw128(CUtensorMap* out, const void* base, int rank, const uint
 
 int device_sm_count();
 
+// Programmatic dependent launch for kernels that start with pdl_wait() (ptx.cuh): the grid may be scheduled while its
+// predecessor in the stream drains and waits on the device for the predecessor's completion, which hides the ~1 us
+// launch latency between dependent kernels (also as programmatic edges inside a captured CUDA graph -- the training
+// step is ~900 dependent launches).  VFS_PDL=0 turns the attribute off.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace vfs

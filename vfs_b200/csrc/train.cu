@@ -118,6 +118,7 @@ constexpr int kBnThreads = 512;
 // 256-thread blocks without unrolling and a serial 8-thread fold = 2.4 TB/s, profiles/r02_bn_bench_v1.log.)
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const BnBwdArgs a, int slab) {
   __shared__ float red[kBnThreads][17];
+  pdl_wait();
   const int pieces = slab / 8;
   const int piece = threadIdx.x % pieces, rgrp = threadIdx.x / pieces;
   const int rows_per_block = kBnThreads / pieces;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const BnBwdAr
 }
 
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const BnBwdArgs a, int slab) {
+  pdl_wait();
   const int pieces = slab / 8;
   const int piece = threadIdx.x % pieces, rgrp = threadIdx.x / pieces;
   const int rows_per_block = kBnThreads / pieces;
@@ -341,7 +343,7 @@ int bn_bwd_reduce(const void* dy_split, const float* dy_f32, const void* y_split
   bn_bwd_fill(a, dy_split, dy_f32, y_split, y_f32, z, z_split, mean, invstd, nullptr, sums, 1.0, nullptr, nullptr,
               nullptr, M, C);
   const dim3 grid = bn_grid(M, C, slab);
-  bn_bwd_reduce_kernel<<<grid, kBnThreads, 0, s>>>(a, slab);
+  VFS_CUDA_OK(launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(kBnThreads), 0, s, a, slab));
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }
@@ -371,7 +373,7 @@ int bn_bwd_apply(const void* dy_split, const float* dy_f32, const void* y_split,
   a.param_scale = param_scale;
   a.eval_mode = eval_mode ? 1 : 0;
   const dim3 grid = bn_grid(M, C, slab);
-  bn_bwd_apply_kernel<<<grid, kBnThreads, 0, s>>>(a, slab);
+  VFS_CUDA_OK(launch_pdl(bn_bwd_apply_kernel, dim3(grid), dim3(kBnThreads), 0, s, a, slab));
   VFS_CUDA_OK(cudaGetLastError());
   return VFS_OK;
 }

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+  pdl_wait();   // launched with launch_pdl: everything above overlaps the tail of the previous kernel
 
   const int nb = p.bn / 64;                                        // Cin boxes per stage (1 or 2)
   const uint32_t stage_tx = (2 + nb) * kWgBoxBytes;                // bytes landing per stage
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 // [Cout][taps][Cin] fp32 -> OIHW fp32 (optionally accumulating into an existing gradient)
 __global__ void wgrad_unpack_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin, int kk,
                                     int accumulate, float out_scale) {
+  pdl_wait();
   const size_t total = static_cast<size_t>(Cout) * Cin * kk;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -360,13 +362,12 @@ int conv_wgrad_tc(const VfsConvDesc* d, const void* x_split, const void* dz_spli
     configured = true;
   }
   const int grid = p.num_units < sms ? p.num_units : sms;
-  wgrad_tc_kernel<<<grid, kWgThreads, kWgSmemBytes, stream>>>(p);
-  VFS_CUDA_OK(cudaGetLastError());
+  VFS_CUDA_OK(launch_pdl(wgrad_tc_kernel, dim3(grid), dim3(kWgThreads), kWgSmemBytes, stream, p));
   if (direct) return VFS_OK;
   const size_t total = static_cast<size_t>(Cout) * Cin * k * k;
   const int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
-  wgrad_unpack_kernel<<<blocks, 256, 0, stream>>>(p.dw, dw_oihw, Cout, Cin, k * k, accumulate, out_scale);
-  VFS_CUDA_OK(cudaGetLastError());
+  VFS_CUDA_OK(launch_pdl(wgrad_unpack_kernel, dim3(blocks), dim3(256), 0, stream, static_cast<const float*>(p.dw), dw_oihw,
+                         Cout, Cin, k * k, accumulate, out_scale));
   return VFS_OK;
 }
 
