@@ -519,10 +519,53 @@ def test_attention_general_masks_and_dense_softmax_match_oracle(case):
     out = masked_attention_efficient(q.cuda(), k.cuda(), v.cuda(), mask.cuda() if torch.is_tensor(mask) else mask,
                                      temperature=0.07 if mode == 'softmax' else 1.0, topk=topk, non_mask_len=nml,
                                      mode=mode)
-    ref = stable_oracle(lambda: oracle.masked_attention_efficient(
-        q, k, v, ref_mask, temperature=0.07 if mode == 'softmax' else 1.0, topk=topk, non_mask_len=nml, mode=mode))
+    temp = 0.07 if mode == 'softmax' else 1.0
+    ref = stable_oracle(lambda: oracle.masked_attention_efficient(q, k, v, ref_mask, temperature=temp, topk=topk,
+                                                                  non_mask_len=nml, mode=mode))
     assert tuple(out.shape) == tuple(ref.shape) == (N, Cv, Hq, Wq)
-    assert rel_err(out, ref) < REL_TOL
+    err = rel_err(out, ref)
+    if err >= REL_TOL and topk is None:
+        # The torch-CPU oracle has given a wrong answer for this very case in ~1 of 10 fresh processes on the GPU boxes
+        # (tools/dense_flake_probe.py: the CUDA output matched an fp64 re-evaluation of the same inputs to 1e-7 while
+        # two oracle evaluations disagreed by 0.12).  Arbitrate with an independent fp64 evaluation written out below
+        # (mask from integer arithmetic): the CUDA path must match it; the oracle's deviation is reported.
+        ref64 = _dense_attention_fp64(q, k, v, ref_mask if kind != 'window' else _window_mask_int(Hk, Wk, 8), temp, nml,
+                                      mode)
+        again = oracle.masked_attention_efficient(q, k, v, ref_mask, temperature=temp, topk=topk, non_mask_len=nml,
+                                                  mode=mode)
+        print(f'[oracle glitch?] {case[0]}: cuda vs oracle {err:.3e}, cuda vs fp64 {rel_err(out, ref64):.3e}, '
+              f'oracle vs fp64 {rel_err(ref, ref64):.3e}, oracle re-evaluated vs fp64 {rel_err(again, ref64):.3e}')
+        assert rel_err(ref, ref64) >= REL_TOL, 'the oracle agrees with fp64 but the CUDA path does not'
+        err = rel_err(out, ref64)
+    assert err < REL_TOL
+
+
+def _window_mask_int(h, w, neighbor_range):
+    """spatial_neighbor (circle) in integer arithmetic: dy^2 + dx^2 < (neighbor_range // 2)^2, bool [HW, HW]."""
+    r = neighbor_range // 2
+    ys, xs = torch.arange(h).view(h, 1, 1, 1), torch.arange(w).view(1, w, 1, 1)
+    d2 = (ys - torch.arange(h).view(1, 1, h, 1))**2 + (xs - torch.arange(w).view(1, 1, 1, w))**2
+    return (d2 < r * r).reshape(h * w, h * w)
+
+
+def _dense_attention_fp64(q, k, v, mask, temperature, non_mask_len, mode):
+    """masked_attention_efficient with topk=None written out in float64, one batch item at a time (independent of the
+    oracle's chunked einsum formulation): rows = keys (t, y, x), columns = queries."""
+    N, C, Hq, Wq = q.shape
+    T, Hk, Wk = k.shape[2:]
+    qn = torch.nn.functional.normalize(q.double(), p=2, dim=1).reshape(N, C, Hq * Wq)
+    kn = torch.nn.functional.normalize(k.double(), p=2, dim=1).reshape(N, C, T * Hk * Wk)
+    out = torch.zeros(N, v.shape[1], Hq * Wq, dtype=torch.float64)
+    for n in range(N):
+        aff = kn[n].t() @ qn[n] / temperature                              # [T*HWk, HWq]
+        if mask is not None:
+            m = (mask if mask.ndim == 2 else mask[n]).bool()               # [HWk, HWq]
+            full = m.repeat(T, 1)
+            full[:non_mask_len * Hk * Wk] = True
+            aff = aff.masked_fill(~full, float('-inf'))
+        wgt = aff.softmax(dim=0) if mode == 'softmax' else aff.clamp(min=0)**2
+        out[n] = v[n].double().reshape(v.shape[1], -1) @ wgt
+    return out.reshape(N, v.shape[1], Hq, Wq)
 
 
 ATTN_FORM_CASES = [
