@@ -19,11 +19,12 @@ REL_TOL = 1e-3  # north_star: "within 1e-3 rel fp32"
 
 
 def stable_oracle(fn, tries=5):
-    """Evaluate a CPU-oracle expression until two consecutive evaluations are bit-identical.  On the GPU boxes the
-    FIRST torch-CPU evaluation of the dense-softmax oracle in a fresh process came back wrong in about 1 of 30
-    processes (tools/dense_flake_probe.py: the CUDA output matched an fp64 re-evaluation of the same inputs to 1e-7,
-    the oracle's own second evaluation differed from its first by 0.12 -- a host-side torch threading artefact, not
-    reproducible in 40 cold processes in the build container).  The GPU result is not involved in the vote."""
+    """Evaluate a CPU-oracle expression until two consecutive evaluations are bit-identical (a cheap guard against
+    host-side nondeterminism of torch-CPU; the GPU result is not involved in the vote).  History: the dense-softmax
+    window case failed in ~1 of 10 fresh processes on the GPU boxes with the CUDA output right (1e-7 from an fp64
+    re-evaluation) and the oracle 0.32 off; the vote did not catch it because the wrong value was reproducible inside
+    the process -- the float32 ``(dy**2 + dx**2)**0.5 < r`` neighbour mask came out different in those processes.
+    oracle.spatial_neighbor now uses integer arithmetic; the fp64 arbiter in the test below reports any recurrence."""
     prev = fn()
     for _ in range(tries):
         cur = fn()
