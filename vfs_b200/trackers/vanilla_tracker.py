@@ -70,7 +70,6 @@ class VanillaTracker(BaseTracker):
         super().__init__(*args, **kwargs)
         self.save_np = self.test_cfg.get('save_np', False)
         self._result_pool = {}
-        self._d2h_stream = None
 
     @property
     def stride(self):
@@ -298,21 +297,10 @@ class VanillaTracker(BaseTracker):
         # one device->host copy per call, into pinned memory (a pageable destination makes the copy several times
         # slower); deferred calls stage through recycled buffers, see _stage
         host = _stage(self._result_pool, preds.shape, preds.dtype)
-        if defer:
-            # the copy runs on a side stream behind an event: the kernels of the next enqueued call do not queue up
-            # behind the PCIe transfer on the compute stream
-            cur = torch.cuda.current_stream(imgs.device)
-            if self._d2h_stream is None:
-                self._d2h_stream = torch.cuda.Stream(device=imgs.device)
-            ready = torch.cuda.Event()
-            ready.record(cur)
-            self._d2h_stream.wait_event(ready)
-            with torch.cuda.stream(self._d2h_stream):
-                host.copy_(preds, non_blocking=True)
-                done = torch.cuda.Event()
-                done.record(self._d2h_stream)
-            preds.record_stream(self._d2h_stream)
-            return host, done
         host.copy_(preds, non_blocking=True)
+        if defer:
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(imgs.device))
+            return host, done
         torch.cuda.current_stream(imgs.device).synchronize()
         return _unstage(host, self._result_pool)
