@@ -498,3 +498,24 @@ def test_evaluation_driver_coalesces_only_batches_of_identical_layout():
     assert [d['imgs'].shape[0] for d in _coalesced(batches[:3], 1)] == [1, 2, 1]
     odd = dict(imgs=torch.zeros(1, 1, 3, 3, 4, 4), extra=7)                           # a non-list, non-tensor entry
     assert list(_coalesced([mk(1), odd, mk(1)], 8))[1] is odd
+
+
+def test_pending_predictions_handle_and_cpu_driver_loop():
+    """Host logic of the evaluation driver without a GPU: a finished handle returns its value unchanged (paths that
+    cannot be deferred), and single_gpu_test on a CPU model is the reference's plain loop (list results flattened,
+    other results appended, no device feed, no merging)."""
+    import torch
+    from vfs_b200.apis import single_gpu_test
+    from vfs_b200.trackers.vanilla_tracker import PendingPredictions
+
+    value = [1, 2, 3]
+    handle = PendingPredictions.finished(value)
+    assert handle.result() is value and handle.result() is value
+
+    class Echo(torch.nn.Module):
+        def forward(self, imgs, return_loss=True, **kw):
+            assert return_loss is False and not imgs.is_cuda
+            return [int(x) for x in imgs] if imgs.numel() > 1 else {'single': int(imgs)}
+
+    loader = [dict(imgs=torch.tensor([1, 2])), dict(imgs=torch.tensor([3])), dict(imgs=torch.tensor([4, 5, 6]))]
+    assert single_gpu_test(Echo(), loader) == [1, 2, {'single': 3}, 4, 5, 6]
